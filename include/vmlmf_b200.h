@@ -1,0 +1,112 @@
+/* vmlmf_b200.h -- C ABI of libvmlmf_b200.so (sm_100a).
+ *
+ * Drop-in boundary for the VMLMF compressed-LSTM hot path.  The reference
+ * (snudm-starlab/VMLMF) has no FFI / plugin interface: its boundary is the Python
+ * nn.Module API.  Each entry point below replaces a piece of reference Python that runs
+ * once per timestep (or its autograd replay); the file:line being replaced is cited.
+ * "V/" = rnn_compression_factorization_vmlmf/src/ in the reference tree.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is DEVICE memory owned by the caller
+ *    (PyTorch); the library never allocates, frees, retains pointers or synchronises.
+ *  - all tensors fp32, innermost dimension contiguous; x / y / dy / dx carry explicit
+ *    element strides for their (time, batch) axes so batch-first (MyLSTM) and time-major
+ *    (MyVMLSTM) callers share one kernel.
+ *  - `stream` is a cudaStream_t passed as void*.  Entry points are re-entrant (autograd
+ *    calls backward from its own thread); there is no global mutable state.
+ *  - return 0 on success, a negative VMLMF_E* code for bad arguments / unsupported shapes,
+ *    a positive cudaError_t for a launch failure.  vmlmf_strerror() maps either to text.
+ *
+ * Canonical parameters (see DESIGN.md "canonical recurrence"; gate order k = i,f,o,n):
+ *   Ux[I,RX]  Vx[4H,RX]  Dx[4,I]   input side  (Dx = dia_x - diag(Ux Vx_k^T))
+ *   A [H,RH]  Bm[4H,RH]  Dh[4,H]   hidden side (Dh = dia_h - diag(A  Bm_k^T))
+ *   bias[4H] = b_x + b_h
+ *   pre_t[b,k,j] = (x_t Ux) Vx[kH+j,:] + [j<I] x_t[b,j] Dx[k,j]
+ *                + (h_{t-1} A) Bm[kH+j,:] + h_{t-1}[b,j] Dh[k,j] + bias[kH+j]
+ */
+#ifndef VMLMF_B200_H_
+#define VMLMF_B200_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VMLMF_ABI_VERSION 1
+
+enum {
+  VMLMF_OK = 0,
+  VMLMF_EINVAL = -1,       /* null pointer / non-positive size / bad stride            */
+  VMLMF_ESHAPE = -2,       /* hidden_size < input_size: the reference raises TypeError
+                              here too (V/models/vmlmf.py:92-94,117)                    */
+  VMLMF_EUNSUPPORTED = -3, /* shape outside every compiled regime                       */
+  VMLMF_EWORKSPACE = -4,   /* workspace too small (see vmlmf_seq_plan)                  */
+  VMLMF_EPLAN = -5         /* plan does not match the arguments                         */
+};
+
+/* regimes (vmlmf_plan.path) */
+enum {
+  VMLMF_PATH_R1 = 1, /* persistent, factors register-resident, one CTA per batch tile   */
+  VMLMF_PATH_G = 2   /* generic: time-parallel XP GEMM + one fused launch per timestep  */
+};
+
+typedef struct vmlmf_plan {
+  int path;                  /* VMLMF_PATH_*                                            */
+  int zx_pitch;              /* row pitch (floats) of zx[T*B, zx_pitch]  (x_t Ux)       */
+  int z_pitch;               /* row pitch (floats) of z [T*B, z_pitch]   (h_{t-1} A)    */
+  int xp_cols;               /* PATH_G: columns of xp[T*B, xp_cols] (=4H), else 0       */
+  long long fwd_workspace_bytes;
+  long long bwd_workspace_bytes;
+  int reserved[8];
+} vmlmf_plan;
+
+int vmlmf_abi_version(void);
+const char* vmlmf_strerror(int code);
+
+/* Which regime runs these sizes, and how big the caller-owned scratch buffers must be. */
+int vmlmf_seq_plan(int T, int B, int I, int H, int RX, int RH, vmlmf_plan* plan);
+
+/* K1: zx[t,b,:] = x[t,b,:] Ux for every timestep at once (time-parallel half of
+ * `torch.matmul(x, self.u_x)`, V/models/vmlmf.py:98, vmlmf_group.py:98, vmlmf_lm.py:246).
+ * zx is [T*B, plan.zx_pitch], pad columns written as 0.                               */
+int vmlmf_xproj_fwd(const float* x, long long xs_t, long long xs_b, const float* Ux,
+                    float* zx, int T, int B, int I, int RX, int zx_pitch, void* stream);
+
+/* K2: the whole time loop of one layer -- replaces `for t in range(seqlen): h,c = cell(...)`
+ * (V/models/vmlmf.py:308-310 with the cell body :78-125; vmlmf_group.py:85-155;
+ * vmlmf_lm.py:272-280 with lstm_step :222-269).
+ *   h0,c0      [B,H] or NULL (= zeros, MyLSTM.forward :302-303)
+ *   y          h_t for every t, strides (ys_t, ys_b)
+ *   hT,cT      [B,H] final state
+ *   gates,cs,z saved for backward: gates[T,B,4,H] (i,f,o,n), cs[T,B,H], z[T*B,z_pitch];
+ *              all three NULL = inference (nothing saved)
+ *   workspace  plan.fwd_workspace_bytes (may be NULL when that is 0)                   */
+int vmlmf_seq_fwd(const vmlmf_plan* plan, const float* x, long long xs_t, long long xs_b,
+                  const float* zx, const float* Ux, const float* Vx, const float* Dx,
+                  const float* A, const float* Bm, const float* Dh, const float* bias,
+                  const float* h0, const float* c0, float* y, long long ys_t, long long ys_b,
+                  float* hT, float* cT, float* gates, float* cs, float* z, void* workspace,
+                  int T, int B, int I, int H, int RX, int RH, void* stream);
+
+/* K3: fused backward-through-time of the same loop (replaces the autograd replay of the
+ * per-step ATen ops).  Accumulates every factor gradient on chip; no [H,4H] matrix or its
+ * gradient is formed.  dy (strides dys_t,dys_b), dhT, dcT may each be NULL (= zeros).
+ * Outputs: dx (strides dxs_t,dxs_b; may be NULL), dh0,dc0 [B,H] (may be NULL) and the
+ * canonical-parameter gradients dUx,dVx,dDx,dA,dBm,dDh,dbias (overwritten, not added).
+ * The sum over CTAs is a fixed-order tree: results are bit-reproducible run to run.     */
+int vmlmf_seq_bwd(const vmlmf_plan* plan, const float* x, long long xs_t, long long xs_b,
+                  const float* zx, const float* Ux, const float* Vx, const float* Dx,
+                  const float* A, const float* Bm, const float* Dh,
+                  const float* h0, const float* c0, const float* y, long long ys_t,
+                  long long ys_b, const float* gates, const float* cs, const float* z,
+                  const float* dy, long long dys_t, long long dys_b, const float* dhT,
+                  const float* dcT, float* dx, long long dxs_t, long long dxs_b, float* dh0,
+                  float* dc0, float* dUx, float* dVx, float* dDx, float* dA, float* dBm,
+                  float* dDh, float* dbias, void* workspace, int T, int B, int I, int H,
+                  int RX, int RH, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VMLMF_B200_H_ */

@@ -1,0 +1,248 @@
+"""GPU: parity of the fused sm_100a path against (a) golden vectors from the live reference,
+(b) the CPU oracle on seeded inputs, (c) size-independent properties at full benchmark sizes.
+
+Tolerance: 1e-5 relative (norm-relative AND max-normalised) against the reference's fp32 results,
+as BASELINE.json's north_star states.  Everything goes through the C ABI via the autograd.Function.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import assert_close, load_golden, rel_err
+from oracle import canonical_numpy as cn
+from oracle import vmlmf_oracle as vo
+
+import vmlmf_b200 as vb
+from vmlmf_b200.functional import vmlmf_sequence
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+DEV = "cuda:0"
+
+
+def _load(module, g):
+    sd = {k[len("param/"):]: torch.from_numpy(v) for k, v in g.items() if k.startswith("param/")}
+    module.load_state_dict(sd)
+    return module.to(DEV)
+
+
+def _inp(g, k, grad=True):
+    t = torch.from_numpy(g[f"in/{k}"]).to(DEV)
+    return t.requires_grad_(True) if (grad and t.is_floating_point()) else t
+
+
+def _check(g, module, outs, ins, tol=TOL):
+    worst = 0.0
+    for k, v in outs.items():
+        assert_close(v.detach().cpu().numpy(), g[f"out/{k}"], tol, f"out {k}")
+        worst = max(worst, *rel_err(v.detach().cpu().numpy(), g[f"out64/{k}"]))
+    n = 0
+    for k, p in module.named_parameters():
+        if f"grad/{k}" in g:
+            assert p.grad is not None, k
+            assert_close(p.grad.cpu().numpy(), g[f"grad/{k}"], tol, f"grad {k}")
+            n += 1
+        else:
+            assert p.grad is None, f"{k} must not receive a gradient"
+    for k, v in ins.items():
+        if f"grad/in.{k}" in g:
+            assert_close(v.grad.cpu().numpy(), g[f"grad/in.{k}"], tol, f"grad in.{k}")
+    assert n > 0
+    return worst
+
+
+def _weighted(outs, g):
+    return sum((outs[k] * torch.from_numpy(g[f"in/w.{k}"]).to(DEV)).sum() for k in outs)
+
+
+# ----------------------------- (a) golden vectors ----------------------------- #
+
+def test_golden_plain_cell_single_step():
+    g = load_golden("plain_cell")
+    m = _load(vb.MyVMLMFCell(9, 16, w_rank=3, u_ranks=2), g)
+    ins = {k: _inp(g, k) for k in ("x", "h", "c")}
+    h, c = m(ins["x"], (ins["h"], ins["c"]))
+    outs = {"h": h, "c": c}
+    _weighted(outs, g).backward()
+    _check(g, m, outs, ins)
+
+
+@pytest.mark.parametrize("case,build", [
+    ("net_plain", lambda: vb.Net(9, [32], w_rank=8, u_rank=[6], cell=vb.MyVMLMFCell)),
+    ("net_opp_h180", lambda: vb.Net(77, [180], w_rank=8, u_rank=[6], cell=vb.MyVMLMFCell)),
+    ("net_group", lambda: vb.Net(9, [16], w_rank=4, u_rank=[2, 3], cell=vb.MyVMLMFCellg2)),
+    ("net_group_h180", lambda: vb.Net(77, [180], w_rank=8, u_rank=[2, 4], cell=vb.MyVMLMFCellg2)),
+])
+def test_golden_net(case, build):
+    g = load_golden(case)
+    m = _load(build(), g)
+    x = _inp(g, "x")
+    logits = m(x)
+    torch.nn.functional.cross_entropy(logits, _inp(g, "label")).backward()
+    _check(g, m, {"logits": logits}, {"x": x})
+
+
+@pytest.mark.parametrize("case,build", [
+    ("mylstm_2layer", lambda: vb.MyLSTM(9, [16, 24], w_rank=4, u_ranks=[3], cell=vb.MyVMLMFCell)),
+    ("group_ablation", lambda: vb.MyLSTM(9, [16], w_rank=4, u_ranks=[2, 3], cell=vb.MyVMLMFgCellg2)),
+    ("group_g4", lambda: vb.MyLSTM(6, [16], w_rank=3, u_ranks=[2, 1, 3, 2], cell=vb.MyVMLMFCellg2, g=4)),
+])
+def test_golden_layer_stack(case, build):
+    g = load_golden(case)
+    m = _load(build(), g)
+    x = _inp(g, "x")
+    seq, hcat = m(x)
+    outs = {"seq": seq, "hcat": hcat}
+    _weighted(outs, g).backward()
+    _check(g, m, outs, {"x": x})
+
+
+def test_golden_lm_layer_carried_state():
+    g = load_golden("lm_layer")
+    m = _load(vb.MyVMLSTM(24, 24, w_rank=5, u_ranks=7), g)
+    ins = {k: _inp(g, k) for k in ("x", "h0", "c0")}
+    out, (h, c) = m(ins["x"], (ins["h0"], ins["c0"]))
+    outs = {"out": out, "hT": h, "cT": c}
+    _weighted(outs, g).backward()
+    _check(g, m, outs, ins)
+
+
+def test_golden_lm_model():
+    g = load_golden("lm_model")
+    m = _load(vb.Model(50, 16, 2, 0.0, 0.25, w_rank=4, u_ranks=[5], lstm_type="vmlmf"), g)
+    st = [(_inp(g, "h0a"), _inp(g, "c0a")), (_inp(g, "h0b"), _inp(g, "c0b"))]
+    scores, new = m(_inp(g, "tok"), st)
+    y = _inp(g, "y")
+    p = torch.softmax(scores, 1)[torch.arange(y.numel(), device=DEV), y.reshape(-1)]
+    torch.mean(-torch.log(p) * y.size(1)).backward()
+    outs = {"scores": scores, "hTa": new[0][0], "cTa": new[0][1], "hTb": new[1][0], "cTb": new[1][1]}
+    _check(g, m, outs, {})
+
+
+# ------------------ (b) canonical kernels vs the numpy spec, ragged shapes ------------------ #
+
+def _rand_canon(rng, I, H, RX, RH, scale=0.3):
+    f = lambda *s: (rng.standard_normal(s) * scale).astype(np.float32)
+    return dict(Ux=f(I, RX), Vx=f(4 * H, RX), Dx=f(4, I), A=f(H, RH), Bm=f(4 * H, RH), Dh=f(4, H), bias=f(4 * H))
+
+
+@pytest.mark.parametrize("T,B,I,H,RX,RH,bf,state", [
+    (1, 1, 3, 5, 1, 1, True, False),        # smallest everything
+    (7, 5, 9, 33, 8, 6, True, True),        # H not a multiple of 32, ragged batch tile
+    (5, 13, 16, 16, 3, 2, False, True),     # I == H, time-major
+    (24, 81, 77, 180, 8, 6, True, False),   # reference unit-test shape
+    (9, 3, 30, 256, 16, 8, False, True),    # widest compiled ranks at H=256
+    (6, 7, 4, 64, 4, 16, True, True),
+])
+def test_canonical_kernels_vs_numpy_spec(T, B, I, H, RX, RH, bf, state):
+    rng = np.random.default_rng(T * 1000 + B)
+    cp = _rand_canon(rng, I, H, RX, RH)
+    x = rng.standard_normal((T, B, I)).astype(np.float32)
+    h0 = (rng.standard_normal((B, H)) * .5).astype(np.float32) if state else None
+    c0 = (rng.standard_normal((B, H)) * .5).astype(np.float32) if state else None
+    dy = rng.standard_normal((T, B, H)).astype(np.float32)
+    dhT = rng.standard_normal((B, H)).astype(np.float32)
+    dcT = rng.standard_normal((B, H)).astype(np.float32)
+    # fp64 spec
+    cp64 = {k: v.astype(np.float64) for k, v in cp.items()}
+    d = lambda a: None if a is None else a.astype(np.float64)
+    y64, hT64, cT64, saved = cn.forward(cp64, d(x), d(h0), d(c0))
+    g64 = cn.backward(cp64, d(x), y64, saved, d(dy), d(dhT), d(dcT), d(h0), d(c0))
+    # fused kernels
+    tp = [torch.from_numpy(cp[k]).to(DEV).requires_grad_(True) for k in ("Ux", "Vx", "Dx", "A", "Bm", "Dh", "bias")]
+    xt = torch.from_numpy(x if not bf else np.ascontiguousarray(x.transpose(1, 0, 2))).to(DEV).requires_grad_(True)
+    h0t = None if h0 is None else torch.from_numpy(h0).to(DEV).requires_grad_(True)
+    c0t = None if c0 is None else torch.from_numpy(c0).to(DEV).requires_grad_(True)
+    y, hT, cT = vmlmf_sequence(xt, h0t, c0t, tp, batch_first=bf)
+    dyt = torch.from_numpy(dy if not bf else np.ascontiguousarray(dy.transpose(1, 0, 2))).to(DEV)
+    torch.autograd.backward([y, hT, cT], [dyt, torch.from_numpy(dhT).to(DEV), torch.from_numpy(dcT).to(DEV)])
+    un = (lambda a: a.transpose(1, 0, 2)) if bf else (lambda a: a)
+    assert_close(un(y.detach().cpu().numpy()), y64, TOL, "y")
+    assert_close(hT.detach().cpu().numpy(), hT64, TOL, "hT")
+    assert_close(cT.detach().cpu().numpy(), cT64, TOL, "cT")
+    for k, t in zip(("Ux", "Vx", "Dx", "A", "Bm", "Dh", "bias"), tp):
+        assert_close(t.grad.cpu().numpy(), g64[k], TOL, f"d{k}")
+    assert_close(un(xt.grad.cpu().numpy()), g64["dx"], TOL, "dx")
+    if state:
+        assert_close(h0t.grad.cpu().numpy(), g64["dh0"], TOL, "dh0")
+        assert_close(c0t.grad.cpu().numpy(), g64["dc0"], TOL, "dc0")
+
+
+def test_inference_mode_matches_training_forward_and_noncontiguous_upstream():
+    torch.manual_seed(5)
+    m = vb.MyLSTM(9, [64], w_rank=8, u_ranks=[6], cell=vb.MyVMLMFCell).to(DEV)
+    x = torch.randn(10, 12, 9, device=DEV)
+    with torch.no_grad():
+        y0, h0 = m(x)
+    xg = x.clone().requires_grad_(True)
+    y1, h1 = m(xg)
+    assert torch.equal(y0, y1) and torch.equal(h0, h1)          # same kernel math with / without saving
+    (y1[:, ::2, 1::3].sum() * 2.0).backward()                    # strided / expanded upstream gradient
+    g1 = xg.grad.clone()
+    xg2 = x.clone().requires_grad_(True)
+    y2, _ = m(xg2)
+    w = torch.zeros_like(y2)
+    w[:, ::2, 1::3] = 2.0
+    (y2 * w).sum().backward()
+    assert torch.equal(g1, xg2.grad)
+
+
+# ------------------ (c) oracle at benchmark shapes + size-independent properties ------------------ #
+
+def _oracle_net(net_cpu_sd, x, label, kind="plain"):
+    sd = {k: v.clone().requires_grad_(True) for k, v in net_cpu_sd.items()}
+    pre = "rnn.rnncells.0." + ("layers." if kind == "group" else "")
+    cell = vo.split_state_dict(sd, pre)
+    xo = x.clone().requires_grad_(True)
+    logits = vo.net_forward([cell], sd["lin.weight"], sd["lin.bias"], xo, kind=kind)
+    torch.nn.functional.cross_entropy(logits, label).backward()
+    return logits, xo.grad, {k: v.grad for k, v in sd.items()}
+
+
+@pytest.mark.parametrize("name,build,shape,classes,kind", [
+    ("cfg1", lambda: vb.Net(9, [128], w_rank=8, u_rank=[6], cell=vb.MyVMLMFCell), (64, 128, 9), 6, "plain"),
+    ("cfg2", lambda: vb.Net(77, [256], w_rank=8, u_rank=[6], cell=vb.MyVMLMFCell), (81, 24, 77), 18, "plain"),
+    ("cfg3", lambda: vb.Net(9, [128], w_rank=8, u_rank=[2, 4], cell=vb.MyVMLMFCellg2), (96, 128, 9), 6, "group"),
+])
+def test_benchmark_configs_vs_cpu_oracle(name, build, shape, classes, kind):
+    torch.manual_seed(3)                                   # demo.sh seed
+    net = build()
+    x = torch.randn(*shape)
+    label = torch.randint(0, classes, (shape[0],))
+    lo, dxo, go = _oracle_net(net.state_dict(), x, label, kind)
+    net = net.to(DEV)
+    xg = x.to(DEV).requires_grad_(True)
+    lg = net(xg)
+    torch.nn.functional.cross_entropy(lg, label.to(DEV)).backward()
+    assert_close(lg.detach().cpu().numpy(), lo.detach().numpy(), TOL, "logits")
+    assert_close(xg.grad.cpu().numpy(), dxo.numpy(), TOL, "dx")
+    for k, p in net.named_parameters():
+        if go[k] is None:
+            assert p.grad is None
+        else:
+            assert_close(p.grad.cpu().numpy(), go[k].numpy(), TOL, k)
+
+
+def test_full_size_properties_cfg2():
+    """B=8192 (the bench workload): batch independence, run-to-run bit reproducibility, and
+    linearity of every gradient in the upstream gradient."""
+    torch.manual_seed(3)
+    net = vb.Net(77, [256], w_rank=8, u_rank=[6], cell=vb.MyVMLMFCell).to(DEV)
+    x = torch.randn(8192, 24, 77, device=DEV)
+    with torch.no_grad():
+        full = net(x)
+        sub = net(x[1000:1037])
+    assert torch.equal(full[1000:1037], sub)               # sequences never interact in forward
+
+    def grads(scale):
+        net.zero_grad()
+        xg = x.clone().requires_grad_(True)
+        (net(xg) * w).sum().mul(scale).backward()
+        return [xg.grad] + [p.grad.clone() for p in net.parameters() if p.grad is not None]
+
+    w = torch.randn(8192, 18, device=DEV) / 8192
+    g1, g1b, g3 = grads(1.0), grads(1.0), grads(3.0)
+    for a, b in zip(g1, g1b):
+        assert torch.equal(a, b)                           # fixed-order reductions: bitwise reproducible
+    for a, b in zip(g1, g3):
+        assert_close(b.cpu().numpy(), 3.0 * a.cpu().numpy(), 2e-6, "linearity")

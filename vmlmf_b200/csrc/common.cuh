@@ -1,0 +1,66 @@
+// common.cuh -- small device helpers shared by the VMLMF kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vmlmf {
+
+constexpr int kWarp = 32;
+
+__host__ __device__ constexpr int ceil_div(int a, int b) { return (a + b - 1) / b; }
+__host__ __device__ constexpr int round_up(int a, int b) { return ceil_div(a, b) * b; }
+__host__ __device__ constexpr int next_pow2(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+__host__ __device__ constexpr int ilog2(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return l;
+}
+
+// fp32-accurate gate non-linearities.  The parity budget is 1e-5 relative against the
+// reference's fp32 eager ops, whose own fp32-vs-fp64 noise is ~1e-7: expf/tanhf (<=2 ulp)
+// keep us at that floor; tanh.approx / ex2.approx-only forms do not.
+__device__ __forceinline__ float sigmoidf_acc(float v) { return __frcp_rn(1.0f + expf(-v)); }
+__device__ __forceinline__ float tanhf_acc(float v) { return tanhf(v); }
+
+// Sum N (power of two, <= 32) per-lane values across the 32 lanes of a warp with
+// N-1 + log2(32/N) shuffles instead of 5N ("transposing" butterfly: every stage halves the
+// number of live values, each lane keeps the half selected by one of its lane-id bits).
+// On return, v[0] in lane l is the warp-wide sum of value index  bitrev_{log2 N}(l mod N).
+template <int N>
+__device__ __forceinline__ float warp_multi_reduce(float (&v)[N], int lane) {
+  static_assert(N >= 1 && N <= 32 && (N & (N - 1)) == 0, "N must be a power of two <= 32");
+  int mask = 1;
+#pragma unroll
+  for (int cur = N; cur > 1; cur >>= 1) {
+    const int half = cur >> 1;
+    const bool upper = (lane & mask) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float send = upper ? v[i] : v[i + half];
+      const float keep = upper ? v[i + half] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
+    }
+    mask <<= 1;
+  }
+#pragma unroll
+  for (; mask < 32; mask <<= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], mask);
+  return v[0];
+}
+
+// value index held by `lane` after warp_multi_reduce<N>
+template <int N>
+__device__ __forceinline__ int warp_multi_reduce_index(int lane) {
+  constexpr int L = ilog2(N);
+  int idx = 0;
+#pragma unroll
+  for (int b = 0; b < L; ++b) idx |= ((lane >> b) & 1) << (L - 1 - b);
+  return idx;
+}
+
+__device__ __forceinline__ float ldg_f(const float* p) { return __ldg(p); }
+
+}  // namespace vmlmf

@@ -1,0 +1,165 @@
+// vmlmf_api.cu -- the C ABI (include/vmlmf_b200.h): argument checks, regime selection, launches.
+#include "../../include/vmlmf_b200.h"
+
+#include <cuda_runtime.h>
+
+#include "generic.cuh"
+#include "seq_r1_launch.cuh"
+#include "xproj.cuh"
+
+using namespace vmlmf;
+
+namespace {
+
+// smallest compiled template rank >= r, or -1
+int pick(const int* list, int n, int r) {
+  for (int i = 0; i < n; ++i)
+    if (list[i] >= r) return list[i];
+  return -1;
+}
+const int kRH[] = {2, 4, 6, 8, 12, 16};
+const int kRX[] = {4, 8, 16};
+
+struct R1Choice { int rh_t, rx_t; bool ok; };
+
+R1Choice choose_r1(int I, int H, int RX, int RH) {
+  R1Choice c{pick(kRH, 6, RH), pick(kRX, 3, RX), false};
+  c.ok = c.rh_t > 0 && c.rx_t > 0 && (c.rh_t + c.rx_t) <= 24 && H <= 256 && I <= H;
+  return c;
+}
+
+int check_dims(int T, int B, int I, int H, int RX, int RH) {
+  if (T <= 0 || B <= 0 || I <= 0 || H <= 0 || RX <= 0 || RH <= 0) return VMLMF_EINVAL;
+  if (H < I) return VMLMF_ESHAPE;
+  return VMLMF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int vmlmf_abi_version(void) { return VMLMF_ABI_VERSION; }
+
+const char* vmlmf_strerror(int code) {
+  switch (code) {
+    case VMLMF_OK: return "ok";
+    case VMLMF_EINVAL: return "vmlmf: invalid argument (null pointer, non-positive size or bad stride)";
+    case VMLMF_ESHAPE: return "vmlmf: hidden_size must be >= input_size";
+    case VMLMF_EUNSUPPORTED: return "vmlmf: shape outside every compiled regime";
+    case VMLMF_EWORKSPACE: return "vmlmf: workspace missing or too small";
+    case VMLMF_EPLAN: return "vmlmf: plan does not match the arguments";
+    default: break;
+  }
+  if (code > 0) return cudaGetErrorString((cudaError_t)code);
+  return "vmlmf: unknown error";
+}
+
+int vmlmf_seq_plan(int T, int B, int I, int H, int RX, int RH, vmlmf_plan* plan) {
+  if (!plan) return VMLMF_EINVAL;
+  const int rc = check_dims(T, B, I, H, RX, RH);
+  if (rc) return rc;
+  *plan = vmlmf_plan{};
+  const R1Choice c = choose_r1(I, H, RX, RH);
+  if (c.ok) {
+    plan->path = VMLMF_PATH_R1;
+    plan->zx_pitch = round_up(c.rx_t, 4);
+    plan->z_pitch = next_pow2(c.rh_t);
+    plan->xp_cols = 0;
+    plan->fwd_workspace_bytes = 0;
+    const GradLayout L(I, H, RX, RH);
+    const long long ntiles = ceil_div(B, kBwdBT);
+    const long long cap = (long long)kNumSMs * kMaxCtasPerSM;
+    plan->bwd_workspace_bytes = (ntiles < cap ? ntiles : cap) * L.total * (long long)sizeof(float);
+    plan->reserved[0] = c.rh_t;
+    plan->reserved[1] = c.rx_t;
+    return VMLMF_OK;
+  }
+  return generic_plan(T, B, I, H, RX, RH, plan);
+}
+
+int vmlmf_xproj_fwd(const float* x, long long xs_t, long long xs_b, const float* Ux, float* zx, int T,
+                    int B, int I, int RX, int zx_pitch, void* stream) {
+  if (!x || !Ux || !zx || T <= 0 || B <= 0 || I <= 0 || RX <= 0) return VMLMF_EINVAL;
+  if (zx_pitch < RX || (zx_pitch & 3)) return VMLMF_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int G = zx_pitch / 4;
+  if (G <= 128 && (size_t)I * zx_pitch * 4 <= 64 * 1024 && I <= 512) {
+    const int rows = 128 / G;
+    const size_t smem = ((size_t)I * zx_pitch + (size_t)rows * (I + 1)) * sizeof(float);
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(xproj_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+    }
+    const long long nrows = (long long)T * B;
+    long long grid = (nrows + rows - 1) / rows;
+    if (grid > kNumSMs * 16) grid = kNumSMs * 16;
+    xproj_small_kernel<<<(int)grid, 128, smem, st>>>(x, xs_t, xs_b, Ux, zx, T, B, I, RX, zx_pitch);
+    return (int)cudaGetLastError();
+  }
+  return generic_xproj(x, xs_t, xs_b, Ux, zx, T, B, I, RX, zx_pitch, st);
+}
+
+int vmlmf_seq_fwd(const vmlmf_plan* plan, const float* x, long long xs_t, long long xs_b, const float* zx,
+                  const float* Ux, const float* Vx, const float* Dx, const float* A, const float* Bm,
+                  const float* Dh, const float* bias, const float* h0, const float* c0, float* y,
+                  long long ys_t, long long ys_b, float* hT, float* cT, float* gates, float* cs, float* z,
+                  void* workspace, int T, int B, int I, int H, int RX, int RH, void* stream) {
+  if (!plan || !x || !zx || !Ux || !Vx || !Dx || !A || !Bm || !Dh || !bias || !y || !hT || !cT) return VMLMF_EINVAL;
+  const int rc = check_dims(T, B, I, H, RX, RH);
+  if (rc) return rc;
+  const bool save = gates || cs || z;
+  if (save && !(gates && cs && z)) return VMLMF_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (plan->path == VMLMF_PATH_R1) {
+    const R1Choice c = choose_r1(I, H, RX, RH);
+    if (!c.ok || plan->zx_pitch != round_up(c.rx_t, 4) || plan->z_pitch != next_pow2(c.rh_t)) return VMLMF_EPLAN;
+    SeqFwdArgs a{x, xs_t, xs_b, zx, Vx, Dx, A, Bm, Dh, bias, h0, c0, y, ys_t, ys_b, hT, cT, gates, cs, z,
+                 T, B, I, H, RX, RH};
+    switch (c.rx_t) {
+      case 4: return launch_fwd_r1_rx4(c.rh_t, a, save, st);
+      case 8: return launch_fwd_r1_rx8(c.rh_t, a, save, st);
+      case 16: return launch_fwd_r1_rx16(c.rh_t, a, save, st);
+    }
+    return VMLMF_EUNSUPPORTED;
+  }
+  if (plan->path == VMLMF_PATH_G)
+    return generic_seq_fwd(plan, x, xs_t, xs_b, zx, Ux, Vx, Dx, A, Bm, Dh, bias, h0, c0, y, ys_t, ys_b, hT, cT,
+                           gates, cs, z, workspace, T, B, I, H, RX, RH, st);
+  return VMLMF_EPLAN;
+}
+
+int vmlmf_seq_bwd(const vmlmf_plan* plan, const float* x, long long xs_t, long long xs_b, const float* zx,
+                  const float* Ux, const float* Vx, const float* Dx, const float* A, const float* Bm,
+                  const float* Dh, const float* h0, const float* c0, const float* y, long long ys_t,
+                  long long ys_b, const float* gates, const float* cs, const float* z, const float* dy,
+                  long long dys_t, long long dys_b, const float* dhT, const float* dcT, float* dx,
+                  long long dxs_t, long long dxs_b, float* dh0, float* dc0, float* dUx, float* dVx,
+                  float* dDx, float* dA, float* dBm, float* dDh, float* dbias, void* workspace, int T, int B,
+                  int I, int H, int RX, int RH, void* stream) {
+  if (!plan || !x || !zx || !Ux || !Vx || !Dx || !A || !Bm || !Dh || !y || !gates || !cs || !z) return VMLMF_EINVAL;
+  if (!dUx || !dVx || !dDx || !dA || !dBm || !dDh || !dbias) return VMLMF_EINVAL;
+  const int rc = check_dims(T, B, I, H, RX, RH);
+  if (rc) return rc;
+  if (plan->bwd_workspace_bytes > 0 && !workspace) return VMLMF_EWORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (plan->path == VMLMF_PATH_R1) {
+    const R1Choice c = choose_r1(I, H, RX, RH);
+    if (!c.ok || plan->zx_pitch != round_up(c.rx_t, 4) || plan->z_pitch != next_pow2(c.rh_t)) return VMLMF_EPLAN;
+    SeqBwdArgs a{x, xs_t, xs_b, zx, Ux, Vx, Dx, A, Bm, Dh, h0, c0, y, ys_t, ys_b, gates, cs, z,
+                 dy, dys_t, dys_b, dhT, dcT, dx, dxs_t, dxs_b, dh0, dc0, (float*)workspace, T, B, I, H, RX, RH};
+    GradOut o{dUx, dVx, dDx, dA, dBm, dDh, dbias};
+    switch (c.rx_t) {
+      case 4: return launch_bwd_r1_rx4(c.rh_t, a, o, st);
+      case 8: return launch_bwd_r1_rx8(c.rh_t, a, o, st);
+      case 16: return launch_bwd_r1_rx16(c.rh_t, a, o, st);
+    }
+    return VMLMF_EUNSUPPORTED;
+  }
+  if (plan->path == VMLMF_PATH_G)
+    return generic_seq_bwd(plan, x, xs_t, xs_b, zx, Ux, Vx, Dx, A, Bm, Dh, h0, c0, y, ys_t, ys_b, gates, cs, z,
+                           dy, dys_t, dys_b, dhT, dcT, dx, dxs_t, dxs_b, dh0, dc0, dUx, dVx, dDx, dA, dBm, dDh,
+                           dbias, workspace, T, B, I, H, RX, RH, st);
+  return VMLMF_EPLAN;
+}
+
+}  // extern "C"

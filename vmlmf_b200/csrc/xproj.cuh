@@ -1,0 +1,56 @@
+// xproj.cuh -- K1 (small-shape variant): zx[t,b,:] = x[t,b,:] Ux for all T*B rows at once.
+// Time-parallel half of `torch.matmul(x, self.u_x)` (V/models/vmlmf.py:98, vmlmf_group.py:98,
+// vmlmf_lm.py:246).  In regime R1 the contraction is [T*B, I<=256] x [I, RX<=16]: K and N are
+// far below one tcgen05 tile, the op is bound by reading x once (I floats/row) and SIMT FMAs,
+// so it is a shared-memory tiled SIMT kernel; the large-shape x projection (regime G) goes
+// through the GEMM path instead.
+#pragma once
+#include "common.cuh"
+
+namespace vmlmf {
+
+// block = 128 threads; each thread produces 4 consecutive outputs of one row.
+// smem: Us[I][pitch] | xs[ROWS][I+1]
+static __global__ void __launch_bounds__(128) xproj_small_kernel(const float* __restrict__ x, long long xs_t,
+                                                          long long xs_b, const float* __restrict__ Ux,
+                                                          float* __restrict__ zx, int T, int B, int I,
+                                                          int RX, int pitch) {
+  extern __shared__ __align__(16) float smem[];
+  const int G = pitch >> 2;                 // threads per row
+  const int ROWS = blockDim.x / G;          // rows per block
+  float* Us = smem;                         // [I][pitch], zero padded
+  float* xs = smem + I * pitch;             // [ROWS][I+1]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = blockDim.x >> 5;
+  for (int i = tid; i < I * pitch; i += blockDim.x) {
+    const int jj = i / pitch, r = i % pitch;
+    Us[i] = r < RX ? __ldg(Ux + (size_t)jj * RX + r) : 0.f;
+  }
+  const long long nrows = (long long)T * B;
+  for (long long row0 = (long long)blockIdx.x * ROWS; row0 < nrows; row0 += (long long)gridDim.x * ROWS) {
+    __syncthreads();
+    for (int rr = warp; rr < ROWS; rr += NW) {
+      const long long row = row0 + rr;
+      if (row < nrows) {
+        const long long t = row / B, b = row % B;
+        const float* src = x + t * xs_t + b * xs_b;
+        for (int jj = lane; jj < I; jj += 32) xs[rr * (I + 1) + jj] = __ldg(src + jj);
+      }
+    }
+    __syncthreads();
+    const int rr = tid / G, rg = tid % G;
+    const long long row = row0 + rr;
+    if (rr < ROWS && row < nrows) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float* xr = xs + rr * (I + 1);
+      for (int jj = 0; jj < I; ++jj) {
+        const float xv = xr[jj];
+        const float4 u = *reinterpret_cast<const float4*>(Us + jj * pitch + 4 * rg);
+        acc.x = fmaf(xv, u.x, acc.x); acc.y = fmaf(xv, u.y, acc.y);
+        acc.z = fmaf(xv, u.z, acc.z); acc.w = fmaf(xv, u.w, acc.w);
+      }
+      *reinterpret_cast<float4*>(zx + row * pitch + 4 * rg) = acc;
+    }
+  }
+}
+
+}  // namespace vmlmf

@@ -1,0 +1,117 @@
+"""torch.autograd.Function over the C ABI: one fused call per layer per direction.
+
+    y, hT, cT = vmlmf_sequence(x, h0, c0, Ux, Vx, Dx, A, Bm, Dh, bias, batch_first)
+
+replaces the reference's python time loop and everything inside it
+(V/models/vmlmf.py:308-310, V/models/vmlmf_lm.py:277-279).  PyTorch owns every buffer (inputs,
+outputs, saved activations, scratch); the library only launches kernels on the current stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _row_contig(t):
+    return t if t.stride(-1) == 1 else t.contiguous()
+
+
+def _tb_strides(t, batch_first):
+    """(time stride, batch stride) in elements of a [B,T,F] / [T,B,F] tensor"""
+    return (t.stride(1), t.stride(0)) if batch_first else (t.stride(0), t.stride(1))
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("vmlmf_b200: tensors must live on a CUDA device (no CPU fallback exists)")
+        if t is not None and t.dtype != torch.float32:
+            raise RuntimeError("vmlmf_b200: fp32 only (the reference computes in fp32)")
+
+
+class VmlmfSeqFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, h0, c0, Ux, Vx, Dx, A, Bm, Dh, bias, batch_first):
+        _require_cuda(x, h0, c0, Ux, Vx, Dx, A, Bm, Dh, bias)
+        x = _row_contig(x)
+        params = [p.contiguous() for p in (Ux, Vx, Dx, A, Bm, Dh, bias)]
+        Ux, Vx, Dx, A, Bm, Dh, bias = params
+        if batch_first:
+            B, T, I = x.shape
+        else:
+            T, B, I = x.shape
+        H, RH = A.shape
+        RX = Ux.shape[1]
+        h0 = None if h0 is None else h0.contiguous()
+        c0 = None if c0 is None else c0.contiguous()
+        plan = _lib.plan(T, B, I, H, RX, RH)
+        lib = _lib.lib()
+        new = x.new_empty
+        y = new((B, T, H)) if batch_first else new((T, B, H))
+        hT, cT = new((B, H)), new((B, H))
+        zx = new((T * B, plan.zx_pitch))
+        need_grad = any(ctx.needs_input_grad)
+        if need_grad:
+            gates, cs, z = new((T, B, 4, H)), new((T, B, H)), new((T * B, plan.z_pitch))
+        else:
+            gates = cs = z = None
+        ws = new((plan.fwd_workspace_bytes + 3) // 4) if plan.fwd_workspace_bytes else None
+        xs_t, xs_b = _tb_strides(x, batch_first)
+        ys_t, ys_b = _tb_strides(y, batch_first)
+        with torch.cuda.device_of(x):
+            st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            _lib.check(lib.vmlmf_xproj_fwd(_ptr(x), xs_t, xs_b, _ptr(Ux), _ptr(zx), T, B, I, RX, plan.zx_pitch, st))
+            _lib.check(lib.vmlmf_seq_fwd(C.byref(plan), _ptr(x), xs_t, xs_b, _ptr(zx), _ptr(Ux), _ptr(Vx), _ptr(Dx),
+                                         _ptr(A), _ptr(Bm), _ptr(Dh), _ptr(bias), _ptr(h0), _ptr(c0), _ptr(y), ys_t,
+                                         ys_b, _ptr(hT), _ptr(cT), _ptr(gates), _ptr(cs), _ptr(z), _ptr(ws),
+                                         T, B, I, H, RX, RH, st))
+        if need_grad:
+            ctx.save_for_backward(x, zx, Ux, Vx, Dx, A, Bm, Dh, h0, c0, y, gates, cs, z)
+            ctx.plan = plan
+            ctx.batch_first = batch_first
+            ctx.dims = (T, B, I, H, RX, RH)
+            ctx.set_materialize_grads(False)
+        return y, hT, cT
+
+    @staticmethod
+    def backward(ctx, dy, dhT, dcT):
+        x, zx, Ux, Vx, Dx, A, Bm, Dh, h0, c0, y, gates, cs, z = ctx.saved_tensors
+        T, B, I, H, RX, RH = ctx.dims
+        plan, bf = ctx.plan, ctx.batch_first
+        lib = _lib.lib()
+        new = x.new_empty
+        dy = None if dy is None else _row_contig(dy)
+        dhT = None if dhT is None else dhT.contiguous()
+        dcT = None if dcT is None else dcT.contiguous()
+        need = ctx.needs_input_grad
+        dx = torch.empty_like(x, memory_format=torch.contiguous_format) if need[0] else None
+        dh0 = new((B, H)) if (h0 is not None and need[1]) else None
+        dc0 = new((B, H)) if (c0 is not None and need[2]) else None
+        dUx, dVx, dDx, dA, dBm, dDh = (torch.empty_like(p) for p in (Ux, Vx, Dx, A, Bm, Dh))
+        dbias = new((4 * H,))
+        ws = new((plan.bwd_workspace_bytes + 3) // 4) if plan.bwd_workspace_bytes else None
+        xs = _tb_strides(x, bf)
+        ys = _tb_strides(y, bf)
+        dys = _tb_strides(dy, bf) if dy is not None else (0, 0)
+        dxs = _tb_strides(dx, bf) if dx is not None else (0, 0)
+        with torch.cuda.device_of(x):
+            st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            _lib.check(lib.vmlmf_seq_bwd(C.byref(plan), _ptr(x), xs[0], xs[1], _ptr(zx), _ptr(Ux), _ptr(Vx), _ptr(Dx),
+                                         _ptr(A), _ptr(Bm), _ptr(Dh), _ptr(h0), _ptr(c0), _ptr(y), ys[0], ys[1],
+                                         _ptr(gates), _ptr(cs), _ptr(z), _ptr(dy), dys[0], dys[1], _ptr(dhT),
+                                         _ptr(dcT), _ptr(dx), dxs[0], dxs[1], _ptr(dh0), _ptr(dc0), _ptr(dUx),
+                                         _ptr(dVx), _ptr(dDx), _ptr(dA), _ptr(dBm), _ptr(dDh), _ptr(dbias), _ptr(ws),
+                                         T, B, I, H, RX, RH, st))
+        return dx, dh0, dc0, dUx, dVx, dDx, dA, dBm, dDh, dbias, None
+
+
+def vmlmf_sequence(x, h0, c0, canon, batch_first=True):
+    """Run one VMLMF layer over a whole sequence.  canon = (Ux,Vx,Dx,A,Bm,Dh,bias)."""
+    return VmlmfSeqFunction.apply(x, h0, c0, *canon, batch_first)

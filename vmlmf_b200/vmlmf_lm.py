@@ -1,0 +1,158 @@
+"""Drop-in replacements for V/models/vmlmf_lm.py: the language-model VMLMF layer and network.
+
+MyVMLSTM.forward runs its whole [T,B,X] window in one fused call with the carried (h,c) state
+(reference: python loop over lstm_step, V/models/vmlmf_lm.py:272-280).  Embedding gather, dropout and
+the vocabulary projection are ordinary dense ops around the path and stay in PyTorch."""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from . import packing
+from .functional import vmlmf_sequence
+
+
+class Embed(nn.Module):
+    """index -> row of w (V/models/vmlmf_lm.py:33-51)"""
+
+    def __init__(self, vocab_size, embed_size):
+        super().__init__()
+        self.vocab_size, self.embed_size = vocab_size, embed_size
+        self.w = nn.Parameter(torch.Tensor(vocab_size, embed_size))
+
+    def forward(self, x):
+        return self.w[x]
+
+    def __repr__(self):
+        return f"Embedding(vocab: {self.vocab_size}, embedding: {self.embed_size})"
+
+
+class MyVMLSTM(nn.Module):
+    """VMLMF LSTM layer for the LM (V/models/vmlmf_lm.py:178-280); needs input_size == hidden_size
+    because the reference adds a [B,4I] tensor to a [B,4H] one (:243,:256).  Parameters are created
+    uninitialised like the reference; Model.reset_parameters fills them."""
+
+    def __init__(self, input_size, hidden_size, dropout=0, w_rank=None, u_ranks=None):
+        super().__init__()
+        self.input_size, self.hidden_size, self.dropout = input_size, hidden_size, dropout
+        self.w_rank, self.u_ranks = w_rank, u_ranks
+        self.u_x = nn.Parameter(torch.Tensor(input_size, w_rank))
+        self.u_h = nn.Parameter(torch.Tensor(hidden_size, u_ranks))
+        self.w_x = nn.Parameter(torch.Tensor(4 * hidden_size, w_rank))
+        self.w_h = nn.Parameter(torch.Tensor(4 * hidden_size, u_ranks))
+        self.b_x = nn.Parameter(torch.Tensor(4 * hidden_size))
+        self.b_h = nn.Parameter(torch.Tensor(4 * hidden_size))
+        self.dia_x = nn.Parameter(torch.Tensor(1, input_size))
+        self.dia_h = nn.Parameter(torch.Tensor(1, hidden_size))
+        self.cnt = 0
+
+    def __repr__(self):
+        return f"LSTM(input: {self.input_size}, hidden: {self.hidden_size})"
+
+    def canonical(self):
+        if self.input_size != self.hidden_size:
+            raise RuntimeError("MyVMLSTM requires input_size == hidden_size (as the reference does)")
+        return packing.pack_plain(self.u_x, self.u_h, self.w_x, self.w_h, self.b_x, self.b_h, self.dia_x, self.dia_h)
+
+    def lstm_step(self, x, h, c):
+        _, h1, c1 = vmlmf_sequence(x.unsqueeze(0), h, c, self.canonical(), batch_first=False)
+        return h1, c1
+
+    def forward(self, x, states):
+        """x[T,B,X], (h,c) -> (out[T,B,H], (h_T, c_T))"""
+        h, c = states
+        out, h1, c1 = vmlmf_sequence(x, h, c, self.canonical(), batch_first=False)
+        return out, (h1, c1)
+
+
+class LSTM(nn.Module):
+    """Plain dense LSTM layer, the reference's "custom" baseline (V/models/vmlmf_lm.py:283-339).
+    Eager PyTorch; not part of the accelerated path."""
+
+    def __init__(self, input_size, hidden_size, dropout=0):
+        super().__init__()
+        self.input_size, self.hidden_size, self.dropout = input_size, hidden_size, dropout
+        self.w_x = nn.Parameter(torch.Tensor(4 * hidden_size, input_size))
+        self.w_h = nn.Parameter(torch.Tensor(4 * hidden_size, hidden_size))
+        self.b_x = nn.Parameter(torch.Tensor(4 * hidden_size))
+        self.b_h = nn.Parameter(torch.Tensor(4 * hidden_size))
+
+    def __repr__(self):
+        return f"LSTM(input: {self.input_size}, hidden: {self.hidden_size})"
+
+    def forward(self, x, states):
+        h, c = states
+        gx_all = torch.addmm(self.b_x, x.reshape(-1, x.size(2)), self.w_x.t()).view(x.size(0), x.size(1), -1)
+        outs = []
+        for gx in gx_all.unbind(0):
+            i, f, o, n = (gx + torch.addmm(self.b_h, h, self.w_h.t())).chunk(4, 1)
+            c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(n)
+            h = torch.sigmoid(o) * torch.tanh(c)
+            outs.append(h)
+        return torch.stack(outs), (h, c)
+
+
+class Linear(nn.Module):
+    """[T,B,H] -> [T*B, V] projection (V/models/vmlmf_lm.py:341-361)"""
+
+    def __init__(self, input_size, hidden_size):
+        super().__init__()
+        self.input_size, self.hidden_size = input_size, hidden_size
+        self.w = nn.Parameter(torch.Tensor(hidden_size, input_size))
+        self.b = nn.Parameter(torch.Tensor(hidden_size))
+
+    def forward(self, x):
+        return torch.addmm(self.b, x.reshape(-1, x.size(2)), self.w.t())
+
+    def __repr__(self):
+        return f"FC(input: {self.input_size}, output: {self.hidden_size})"
+
+
+class Model(nn.Module):
+    """Embed -> dropout -> L x LSTM layers -> dropout -> FC (V/models/vmlmf_lm.py:363-441).
+
+    lstm_type "vmlmf" selects the fused VMLMF layers.  "custom" / "pytorch" build the reference's
+    dense baselines.  The reference's "vmgroup"/"vm_group" branch is unreachable as shipped
+     and is rejected here with an explicit error."""
+
+    def __init__(self, vocab_size, hidden_size, layer_num, dropout, winit, w_rank=None, u_ranks=None,
+                 lstm_type="pytorch"):
+        super().__init__()
+        self.vocab_size, self.hidden_size, self.layer_num = vocab_size, hidden_size, layer_num
+        self.winit, self.lstm_type = winit, lstm_type
+        self.embed = Embed(vocab_size, hidden_size)
+        if lstm_type in ("vmgroup", "vm_group"):
+            raise NotImplementedError("the reference's group LM layer is unreachable through Model "
+                                      "(vmlmf_lm.py:387-393); use lstm_type='vmlmf'")
+        if u_ranks is not None:
+            u_ranks = u_ranks[-1]
+        if lstm_type == "vmlmf":
+            rnns = [MyVMLSTM(hidden_size, hidden_size, w_rank=w_rank, u_ranks=u_ranks) for _ in range(layer_num)]
+        elif lstm_type == "custom":
+            rnns = [LSTM(hidden_size, hidden_size) for _ in range(layer_num)]
+        else:
+            rnns = [nn.LSTM(hidden_size, hidden_size) for _ in range(layer_num)]
+        self.rnns = nn.ModuleList(rnns)
+        self.fc = Linear(hidden_size, vocab_size)
+        self.dropout = nn.Dropout(p=dropout)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        for param in self.parameters():
+            nn.init.uniform_(param, -self.winit, self.winit)
+
+    def state_init(self, batch_size):
+        dev = next(self.parameters()).device
+        flat = self.lstm_type in ("custom", "vmlmf", "vmgroup", "hmd")
+        shape = (lambda l: (batch_size, l.hidden_size)) if flat else (lambda l: (1, batch_size, l.hidden_size))
+        return [(torch.zeros(*shape(l), device=dev), torch.zeros(*shape(l), device=dev)) for l in self.rnns]
+
+    def detach(self, states):
+        return [(h.detach(), c.detach()) for (h, c) in states]
+
+    def forward(self, x, states):
+        x = self.dropout(self.embed(x))
+        for i, rnn in enumerate(self.rnns):
+            x, states[i] = rnn(x, states[i])
+            x = self.dropout(x)
+        return self.fc(x), states
