@@ -1,14 +1,506 @@
-// generic.cuh -- regime G (any shape): placeholder until the per-step GEMM path lands.
+// generic.cuh -- regime G: any (T,B,I,H,RX,RH) with I <= H.  Used when the factors do not fit the
+// register-resident regime R1 (LM layer H=650 r=300, the H>=1024 sweep, wide group packings).
+//
+// Structure (fp32 SIMT throughout; fp32 parity, no TF32):
+//   time-parallel   ZX = X Ux                    (vmlmf_xproj_fwd)            [T*B, RX]
+//                   XP = ZX Vx^T + bias + x(.)Dx (epilogue-fused)             [T*B, 4H]
+//   per timestep    z_t = h_{t-1} A              (GEMM, K=H)
+//                   gates/c/h = f(XP_t + z_t Bm^T + h_{t-1}(.)Dh)  (GEMM K=RH + gate epilogue)
+//   backward        per step: dPre_t (pointwise) ; dz_t = dPre_t Bm ; dh_{t-1} += dz_t A^T
+//                   time-parallel, split-K, fixed-order: dBm = dPre^T Z, dA = Hprev^T dZ,
+//                   dVx = dPre^T ZX, dZX = dPre Vx, dUx = X^T dZX, dX = dZX Ux^T + dPre(.)Dx,
+//                   column reductions dDh, dDx, dbias.
+// One 64x64x16 register-tiled GEMM template serves every contraction; operands are addressed
+// through RowView so batch-first and time-major tensors need no copies.
 #pragma once
 #include "../../include/vmlmf_b200.h"
 #include "common.cuh"
 
 namespace vmlmf {
 
-inline int generic_plan(int, int, int, int, int, int, vmlmf_plan*) { return VMLMF_EUNSUPPORTED; }
-inline int generic_xproj(const float*, long long, long long, const float*, float*, int, int, int, int, int,
-                         cudaStream_t) { return VMLMF_EUNSUPPORTED; }
-template <class... Ts> inline int generic_seq_fwd(Ts...) { return VMLMF_EUNSUPPORTED; }
-template <class... Ts> inline int generic_seq_bwd(Ts...) { return VMLMF_EUNSUPPORTED; }
+// rows of a [rows, cols] matrix whose row r lives at p + (r / bdiv) * s_t + (r % bdiv) * s_b
+struct RowView {
+  float* p; long long s_t, s_b; int bdiv;
+  __host__ __device__ float* row(long long r) const { return p + (r / bdiv) * s_t + (r % bdiv) * s_b; }
+};
+inline RowView plain_view(const float* p, long long ld) { return RowView{const_cast<float*>(p), 0, ld, 0x7fffffff}; }
+inline RowView tb_view(const float* p, long long s_t, long long s_b, int B) { return RowView{const_cast<float*>(p), s_t, s_b, B}; }
+
+constexpr int GBM = 64, GBN = 64, GBK = 16;
+
+struct NIdent { __device__ long long operator()(int n) const { return n; } };
+// gate-interleaved column order n' = j*4 + k  ->  stored row k*H + j of a [4H, R] factor
+struct NGate { int H; __device__ long long operator()(int n) const { return (long long)(n & 3) * H + (n >> 2); } };
+
+// ---- epilogues: called once per (row m, 4 consecutive columns n..n+3) ----
+struct EpiStore {           // C = acc (+ C)
+  RowView C; int beta;
+  __device__ void operator()(int m, int n, int N, const float (&v)[4]) const {
+    float* c = C.row(m) + n;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (n + q < N) c[q] = beta ? c[q] + v[q] : v[q];
+  }
+};
+struct EpiPartial {         // raw partial tile for split-K: part[z][m][n]
+  float* part; int M, N;
+  __device__ void operator()(int m, int n, int, const float (&v)[4]) const {
+    float* c = part + ((size_t)blockIdx.z * M + m) * N + n;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (n + q < N) c[q] = v[q];
+  }
+};
+struct EpiXP {              // XP[m, kH+j] = acc + bias[kH+j] + [j<I] x[m,j] Dx[k,j]
+  float* xp; const float* bias; RowView X; const float* Dx; int H, I;
+  __device__ void operator()(int m, int n, int N, const float (&v)[4]) const {
+    const float* xr = X.row(m);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int nn = n + q;
+      if (nn < N) {
+        const int k = nn / H, j = nn - k * H;
+        float r = v[q] + bias[nn];
+        if (j < I) r = fmaf(xr[j], Dx[k * I + j], r);
+        xp[(size_t)m * N + nn] = r;
+      }
+    }
+  }
+};
+struct EpiGate {            // columns are gate-interleaved: n = 4*j + k  (needs N = 4H, n % 4 == 0)
+  const float* xp_t;        // XP rows of this step   [B, 4H]
+  const float* hprev; long long hp_sb;    // h_{t-1}[b] = hprev + b*hp_sb (null = zeros)
+  const float* cprev;                     // [B,H] or null
+  const float* Dh;
+  float* y_t; long long y_sb;             // h_t[b] = y_t + b*y_sb
+  float* c_out;                           // [B,H]  (cs[t] when saving, else the running cT buffer)
+  float* gates_t;                         // [B,4,H] or null
+  float *hT, *cT;                         // written on the last step only (else null)
+  int H;
+  __device__ void operator()(int m, int n, int N, const float (&v)[4]) const {
+    if (n >= N) return;
+    const int j = n >> 2;
+    const float hp = hprev ? hprev[(size_t)m * hp_sb + j] : 0.f;
+    const float cp = cprev ? cprev[(size_t)m * H + j] : 0.f;
+    const float* xr = xp_t + (size_t)m * 4 * H + j;
+    float pre[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) pre[k] = v[k] + xr[(size_t)k * H] + hp * Dh[k * H + j];
+    const float gi = sigmoidf_acc(pre[0]), gf = sigmoidf_acc(pre[1]);
+    const float go = sigmoidf_acc(pre[2]), gn = tanhf_acc(pre[3]);
+    const float c = fmaf(gf, cp, gi * gn);
+    const float h = go * tanhf_acc(c);
+    y_t[(size_t)m * y_sb + j] = h;
+    c_out[(size_t)m * H + j] = c;
+    if (gates_t) {
+      float* g = gates_t + (size_t)m * 4 * H + j;
+      g[0] = gi; g[H] = gf; g[2 * H] = go; g[3 * H] = gn;
+    }
+    if (hT) { hT[(size_t)m * H + j] = h; cT[(size_t)m * H + j] = c; }
+  }
+};
+struct EpiDX {              // dX[m,j] = acc + sum_k dPre[m,kH+j] Dx[k,j]
+  RowView dX; const float* dpre; const float* Dx; int H, I;
+  __device__ void operator()(int m, int n, int N, const float (&v)[4]) const {
+    float* o = dX.row(m);
+    const float* dp = dpre + (size_t)m * 4 * H;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int j = n + q;
+      if (j < N) {
+        float r = v[q];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) r = fmaf(dp[k * H + j], Dx[k * I + j], r);
+        o[j] = r;
+      }
+    }
+  }
+};
+
+// C[m,n] = sum_k Aop(m,k) Bop(k,n).
+//   A_T=false: A stored [M rows][K cols]   A_T=true: stored [K rows][M cols]
+//   B_T=false: B stored [K rows][N cols]   B_T=true: stored [N rows][K cols], row = nmap(n)
+// grid = (n tiles, m tiles, k splits); each split covers k_chunk consecutive k.
+template <bool A_T, bool B_T, class NMap, class Epi>
+__global__ void __launch_bounds__(256) gemm_kernel(RowView A, RowView Bv, int M, int N, long long K,
+                                                   long long k_chunk, NMap nmap, Epi epi) {
+  __shared__ __align__(16) float As[GBK][GBM + 4];
+  __shared__ __align__(16) float Bs[GBK][GBN + 4];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * GBM, n0 = blockIdx.x * GBN;
+  const long long kbeg = (long long)blockIdx.z * k_chunk;
+  const long long kend = (kbeg + k_chunk < K) ? kbeg + k_chunk : K;
+  float acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+
+  for (long long k0 = kbeg; k0 < kend; k0 += GBK) {
+#pragma unroll
+    for (int e = 0; e < (GBM * GBK) / 256; ++e) {
+      const int idx = e * 256 + tid;
+      if constexpr (!A_T) {
+        const int mm = idx / GBK, kk = idx % GBK;
+        const int m = m0 + mm; const long long k = k0 + kk;
+        As[kk][mm] = (m < M && k < kend) ? A.row(m)[k] : 0.f;
+      } else {
+        const int kk = idx / GBM, mm = idx % GBM;
+        const int m = m0 + mm; const long long k = k0 + kk;
+        As[kk][mm] = (m < M && k < kend) ? A.row(k)[m] : 0.f;
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < (GBN * GBK) / 256; ++e) {
+      const int idx = e * 256 + tid;
+      if constexpr (B_T) {
+        const int nn = idx / GBK, kk = idx % GBK;
+        const int n = n0 + nn; const long long k = k0 + kk;
+        Bs[kk][nn] = (n < N && k < kend) ? Bv.row(nmap(n))[k] : 0.f;
+      } else {
+        const int kk = idx / GBN, nn = idx % GBN;
+        const int n = n0 + nn; const long long k = k0 + kk;
+        Bs[kk][nn] = (n < N && k < kend) ? Bv.row(k)[n] : 0.f;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < GBK; ++kk) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(av[a], bv[b], acc[a][b]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int m = m0 + ty * 4 + a;
+    if (m < M) epi(m, n0 + tx * 4, N, acc[a]);
+  }
+}
+
+template <bool A_T, bool B_T, class NMap, class Epi>
+inline int gemm_launch(RowView A, RowView Bv, int M, int N, long long K, int splits, NMap nmap, Epi epi,
+                       cudaStream_t st) {
+  if (M <= 0 || N <= 0) return 0;
+  long long chunk = (K + splits - 1) / splits;
+  chunk = (chunk + GBK - 1) / GBK * GBK;
+  dim3 grid(ceil_div(N, GBN), ceil_div(M, GBM), splits);
+  gemm_kernel<A_T, B_T, NMap, Epi><<<grid, 256, 0, st>>>(A, Bv, M, N, K, chunk, nmap, epi);
+  return (int)cudaGetLastError();
+}
+
+// out[i] = sum_z part[z][i]   (fixed order)
+static __global__ void splitk_reduce_kernel(const float* __restrict__ part, int nsplit, long long n, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int z = 0; z < nsplit; ++z) s += part[(size_t)z * n + i];
+  out[i] = s;
+}
+
+// ---- backward, pointwise part of one timestep ----
+struct DpreArgs {
+  const float* gates_t;      // [B,4,H]
+  const float* c_t;          // [B,H]
+  const float* c_prev;       // [B,H] or null
+  const float* dy_t; long long dy_sb;     // or null
+  const float* Dh;
+  float* dh;                 // [B,H] in: dh_next   out: sum_k dpre_k Dh_k   (seed of dh_{t-1})
+  float* dc;                 // [B,H] in: dc_next   out: dc_next for t-1
+  float* dpre_t;             // [B,4,H]
+  int B, H;
+};
+static __global__ void dpre_step_kernel(const DpreArgs a) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)a.B * a.H) return;
+  const int b = (int)(i / a.H), j = (int)(i % a.H);
+  const float* g = a.gates_t + (size_t)b * 4 * a.H + j;
+  const float gi = g[0], gf = g[a.H], go = g[2 * a.H], gn = g[3 * a.H];
+  const float dh = a.dh[i] + (a.dy_t ? a.dy_t[(size_t)b * a.dy_sb + j] : 0.f);
+  const float tc = tanhf_acc(a.c_t[i]);
+  const float cp = a.c_prev ? a.c_prev[i] : 0.f;
+  const float dc = fmaf(dh * go, 1.f - tc * tc, a.dc[i]);
+  float d[4];
+  d[0] = dc * gn * gi * (1.f - gi);
+  d[1] = dc * cp * gf * (1.f - gf);
+  d[2] = dh * tc * go * (1.f - go);
+  d[3] = dc * gi * (1.f - gn * gn);
+  float* o = a.dpre_t + (size_t)b * 4 * a.H + j;
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    o[(size_t)k * a.H] = d[k];
+    s = fmaf(d[k], a.Dh[k * a.H + j], s);
+  }
+  a.dc[i] = dc * gf;
+  a.dh[i] = s;
+}
+
+// ---- column reductions over all T*B rows: dbias, dDh, dDx (split over rows, fixed order) ----
+struct ColRedArgs {
+  const float* dpre;         // [T*B, 4H]
+  RowView Y; const float* h0; // h_{t-1}: t>0 -> Y.row((t-1)*B+b), t==0 -> h0[b] (null = 0)
+  RowView X;
+  float* part;               // [nsplit][4H + 4H + 4I]
+  int T, B, H, I; long long rows_per_split;
+};
+static __global__ void colreduce_kernel(const ColRedArgs a) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;          // column of dPre
+  if (n >= 4 * a.H) return;
+  const int k = n / a.H, j = n - k * a.H;
+  const long long rows = (long long)a.T * a.B;
+  const long long r0 = (long long)blockIdx.y * a.rows_per_split;
+  const long long r1 = r0 + a.rows_per_split < rows ? r0 + a.rows_per_split : rows;
+  float sb = 0.f, sh = 0.f, sx = 0.f;
+  for (long long r = r0; r < r1; ++r) {
+    const float d = a.dpre[(size_t)r * 4 * a.H + n];
+    sb += d;
+    float hp = 0.f;
+    if (r >= a.B) hp = a.Y.row(r - a.B)[j];
+    else if (a.h0) hp = a.h0[(size_t)r * a.H + j];
+    sh = fmaf(d, hp, sh);
+    if (j < a.I) sx = fmaf(d, a.X.row(r)[j], sx);
+  }
+  float* p = a.part + (size_t)blockIdx.y * (8 * a.H + 4 * a.I);
+  p[n] = sb;
+  p[4 * a.H + n] = sh;
+  if (j < a.I) p[8 * a.H + k * a.I + j] = sx;
+}
+static __global__ void colreduce_final_kernel(const float* __restrict__ part, int nsplit, int H, int I,
+                                              float* dbias, float* dDh, float* dDx) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, tot = 8 * H + 4 * I;
+  if (i >= tot) return;
+  float s = 0.f;
+  for (int z = 0; z < nsplit; ++z) s += part[(size_t)z * tot + i];
+  if (i < 4 * H) dbias[i] = s;
+  else if (i < 8 * H) dDh[i - 4 * H] = s;
+  else dDx[i - 8 * H] = s;
+}
+
+// --------------------------------------------------------------------------------------------- //
+// host side
+// --------------------------------------------------------------------------------------------- //
+inline int g_splits(int M, int N, long long K) {
+  const long long tiles = (long long)ceil_div(M, GBM) * ceil_div(N, GBN);
+  long long s = (2LL * 148 + tiles - 1) / tiles;
+  const long long kmax = (K + 255) / 256;
+  if (s > kmax) s = kmax;
+  if (s > 128) s = 128;
+  if (s < 1) s = 1;
+  return (int)s;
+}
+constexpr int kColSplits = 64;
+
+struct GenericSizes {
+  int zxp, zp;
+  long long n_xp, n_dpre, n_dz, n_dzx, n_state, n_part;
+};
+inline GenericSizes generic_sizes(int T, int B, int I, int H, int RX, int RH) {
+  GenericSizes s;
+  s.zxp = round_up(RX, 4);
+  s.zp = round_up(RH, 4);
+  const long long rows = (long long)T * B;
+  s.n_xp = rows * 4 * H;
+  s.n_dpre = rows * 4 * H;
+  s.n_dz = rows * s.zp;
+  s.n_dzx = rows * s.zxp;
+  s.n_state = (long long)B * H;
+  long long p = (long long)(g_splits(4 * H, RH, rows) + 1) * 4 * H * RH;       // dBm
+  long long q = (long long)(g_splits(H, RH, rows) + 1) * H * RH; if (q > p) p = q;   // dA (+1: h0 slice)
+  q = (long long)g_splits(4 * H, RX, rows) * 4 * H * RX; if (q > p) p = q;     // dVx
+  q = (long long)g_splits(I, RX, rows) * I * RX; if (q > p) p = q;             // dUx
+  q = (long long)kColSplits * (8 * H + 4 * I); if (q > p) p = q;               // column reductions
+  s.n_part = p;
+  return s;
+}
+
+inline int generic_plan(int T, int B, int I, int H, int RX, int RH, vmlmf_plan* plan) {
+  const GenericSizes s = generic_sizes(T, B, I, H, RX, RH);
+  plan->path = VMLMF_PATH_G;
+  plan->zx_pitch = s.zxp;
+  plan->z_pitch = s.zp;
+  plan->xp_cols = 4 * H;
+  plan->fwd_workspace_bytes = (s.n_xp + 2 * s.n_state) * (long long)sizeof(float);
+  plan->bwd_workspace_bytes = (s.n_dpre + s.n_dz + s.n_dzx + 2 * s.n_state + s.n_part) * (long long)sizeof(float);
+  return VMLMF_OK;
+}
+
+// ZX = X Ux, pad columns zeroed
+static __global__ void zero_pad_cols_kernel(float* z, long long rows, int pitch, int R) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int pad = pitch - R;
+  if (pad <= 0 || i >= rows * pad) return;
+  z[(i / pad) * pitch + R + (i % pad)] = 0.f;
+}
+inline int generic_xproj(const float* x, long long xs_t, long long xs_b, const float* Ux, float* zx, int T, int B,
+                         int I, int RX, int zx_pitch, cudaStream_t st) {
+  const long long rows = (long long)T * B;
+  if (rows > 0x7fffffff) return VMLMF_EUNSUPPORTED;
+  if (zx_pitch > RX) {
+    const long long n = rows * (zx_pitch - RX);
+    zero_pad_cols_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(zx, rows, zx_pitch, RX);
+  }
+  return gemm_launch<false, false>(tb_view(x, xs_t, xs_b, B), plain_view(Ux, RX), (int)rows, RX, I, 1, NIdent{},
+                                   EpiStore{plain_view(zx, zx_pitch), 0}, st);
+}
+
+#define G_TRY(expr) do { int rc__ = (expr); if (rc__) return rc__; } while (0)
+
+inline int generic_seq_fwd(const vmlmf_plan* plan, const float* x, long long xs_t, long long xs_b, const float* zx,
+                           const float* Ux, const float* Vx, const float* Dx, const float* A, const float* Bm,
+                           const float* Dh, const float* bias, const float* h0, const float* c0, float* y,
+                           long long ys_t, long long ys_b, float* hT, float* cT, float* gates, float* cs, float* z,
+                           void* workspace, int T, int B, int I, int H, int RX, int RH, cudaStream_t st) {
+  (void)Ux;
+  const GenericSizes s = generic_sizes(T, B, I, H, RX, RH);
+  if (plan->zx_pitch != s.zxp || plan->z_pitch != s.zp) return VMLMF_EPLAN;
+  if (!workspace) return VMLMF_EWORKSPACE;
+  const long long rows = (long long)T * B;
+  if (rows * 4 * H > (1LL << 40) || rows > 0x7fffffff) return VMLMF_EUNSUPPORTED;
+  float* xp = (float*)workspace;
+  float* cbuf[2] = {xp + s.n_xp, xp + s.n_xp + s.n_state};      // running c when not saving
+  float* zrow = nullptr;                                         // z_t when not saving
+  // time-parallel: XP = ZX Vx^T + bias + x (.) Dx
+  G_TRY((gemm_launch<false, true>(plain_view(zx, s.zxp), plain_view(Vx, RX), (int)rows, 4 * H, RX, 1, NIdent{},
+                                  EpiXP{xp, bias, tb_view(x, xs_t, xs_b, B), Dx, H, I}, st)));
+  const bool save = gates != nullptr;
+  for (int t = 0; t < T; ++t) {
+    const float* hprev = t ? y + (size_t)(t - 1) * ys_t : h0;
+    const long long hp_sb = t ? ys_b : H;
+    const float* cprev = save ? (t ? cs + (size_t)(t - 1) * B * H : c0) : (t ? cbuf[(t - 1) & 1] : c0);
+    float* cout = save ? cs + (size_t)t * B * H : cbuf[t & 1];
+    // z_t = h_{t-1} A  (zero when there is no initial state)
+    float* zt = save ? z + (size_t)t * B * s.zp : (zrow ? zrow : (zrow = cbuf[0] /*placeholder*/, nullptr));
+    (void)zt;
+    float* zdst = save ? z + (size_t)t * B * s.zp : nullptr;
+    if (!zdst) return VMLMF_EUNSUPPORTED;   // replaced below (inference scratch) -- see generic_seq_fwd_infer
+    if (hprev) {
+      if (s.zp > RH) {
+        const long long n = (long long)B * (s.zp - RH);
+        zero_pad_cols_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(zdst, B, s.zp, RH);
+      }
+      G_TRY((gemm_launch<false, false>(RowView{const_cast<float*>(hprev), 0, hp_sb, 0x7fffffff}, plain_view(A, RH), B, RH,
+                                       H, 1, NIdent{}, EpiStore{plain_view(zdst, s.zp), 0}, st)));
+    } else {
+      G_TRY((int)cudaMemsetAsync(zdst, 0, (size_t)B * s.zp * sizeof(float), st));
+    }
+    const bool last = (t == T - 1);
+    EpiGate eg{xp + (size_t)t * B * 4 * H, hprev, hp_sb, cprev, Dh, y + (size_t)t * ys_t, ys_b, cout,
+               save ? gates + (size_t)t * B * 4 * H : nullptr, last ? hT : nullptr, last ? cT : nullptr, H};
+    G_TRY((gemm_launch<false, true>(plain_view(zdst, s.zp), plain_view(Bm, RH), B, 4 * H, RH, 1, NGate{H}, eg, st)));
+  }
+  return VMLMF_OK;
+}
+
+inline int generic_seq_bwd(const vmlmf_plan* plan, const float* x, long long xs_t, long long xs_b, const float* zx,
+                           const float* Ux, const float* Vx, const float* Dx, const float* A, const float* Bm,
+                           const float* Dh, const float* h0, const float* c0, const float* y, long long ys_t,
+                           long long ys_b, const float* gates, const float* cs, const float* z, const float* dy,
+                           long long dys_t, long long dys_b, const float* dhT, const float* dcT, float* dx,
+                           long long dxs_t, long long dxs_b, float* dh0, float* dc0, float* dUx, float* dVx,
+                           float* dDx, float* dA, float* dBm, float* dDh, float* dbias, void* workspace, int T,
+                           int B, int I, int H, int RX, int RH, cudaStream_t st) {
+  const GenericSizes s = generic_sizes(T, B, I, H, RX, RH);
+  if (plan->zx_pitch != s.zxp || plan->z_pitch != s.zp) return VMLMF_EPLAN;
+  if (!workspace) return VMLMF_EWORKSPACE;
+  const long long rows = (long long)T * B;
+  if (rows > 0x7fffffff) return VMLMF_EUNSUPPORTED;
+  float* dpre = (float*)workspace;
+  float* dz = dpre + s.n_dpre;
+  float* dzx = dz + s.n_dz;
+  float* dh = dzx + s.n_dzx;
+  float* dc = dh + s.n_state;
+  float* part = dc + s.n_state;
+  const size_t sb = (size_t)B * H * sizeof(float);
+  if (dhT) G_TRY((int)cudaMemcpyAsync(dh, dhT, sb, cudaMemcpyDeviceToDevice, st));
+  else G_TRY((int)cudaMemsetAsync(dh, 0, sb, st));
+  if (dcT) G_TRY((int)cudaMemcpyAsync(dc, dcT, sb, cudaMemcpyDeviceToDevice, st));
+  else G_TRY((int)cudaMemsetAsync(dc, 0, sb, st));
+  if (s.zp > RH) G_TRY((int)cudaMemsetAsync(dz, 0, (size_t)s.n_dz * sizeof(float), st));
+
+  const int nel = B * H;
+  for (int t = T - 1; t >= 0; --t) {
+    DpreArgs da{gates + (size_t)t * B * 4 * H, cs + (size_t)t * B * H, t ? cs + (size_t)(t - 1) * B * H : c0,
+                dy ? dy + (size_t)t * dys_t : nullptr, dys_b, Dh, dh, dc, dpre + (size_t)t * B * 4 * H, B, H};
+    dpre_step_kernel<<<ceil_div(nel, 256), 256, 0, st>>>(da);
+    G_TRY((int)cudaGetLastError());
+    float* dzt = dz + (size_t)t * B * s.zp;
+    // dz_t = dPre_t Bm        [B,4H] x [4H,RH]
+    G_TRY((gemm_launch<false, false>(plain_view(dpre + (size_t)t * B * 4 * H, 4 * H), plain_view(Bm, RH), B, RH, 4 * H, 1,
+                                     NIdent{}, EpiStore{plain_view(dzt, s.zp), 0}, st)));
+    // dh_{t-1} = (sum_k dpre_k Dh_k) + dz_t A^T
+    G_TRY((gemm_launch<false, true>(plain_view(dzt, s.zp), plain_view(A, RH), B, H, RH, 1, NIdent{},
+                                    EpiStore{plain_view(dh, H), 1}, st)));
+  }
+  if (dh0) G_TRY((int)cudaMemcpyAsync(dh0, dh, sb, cudaMemcpyDeviceToDevice, st));
+  if (dc0) G_TRY((int)cudaMemcpyAsync(dc0, dc, sb, cudaMemcpyDeviceToDevice, st));
+
+  const RowView Xv = tb_view(x, xs_t, xs_b, B), Yv = tb_view(y, ys_t, ys_b, B);
+  const RowView dPv = plain_view(dpre, 4 * H), Zv = plain_view(z, s.zp), ZXv = plain_view(zx, s.zxp);
+  auto reduce_to = [&](int nsplit, long long n, float* out) -> int {
+    splitk_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(part, nsplit, n, out);
+    return (int)cudaGetLastError();
+  };
+  // dBm = dPre^T Z   [4H,RH]
+  {
+    const int sp = g_splits(4 * H, RH, rows);
+    G_TRY((gemm_launch<true, false>(dPv, Zv, 4 * H, RH, rows, sp, NIdent{}, EpiPartial{part, 4 * H, RH}, st)));
+    G_TRY(reduce_to(sp, (long long)4 * H * RH, dBm));
+  }
+  // dA = Hprev^T dZ  [H,RH]: rows t>=1 pair y[t-1] with dz[t]; rows of t=0 pair h0 with dz[0]
+  {
+    const long long r1 = rows - B;
+    int sp = 0;
+    if (r1 > 0) {
+      sp = g_splits(H, RH, r1);
+      G_TRY((gemm_launch<true, false>(Yv, plain_view(dz + (size_t)B * s.zp, s.zp), H, RH, r1, sp, NIdent{},
+                                      EpiPartial{part, H, RH}, st)));
+    }
+    if (h0) {
+      G_TRY((gemm_launch<true, false>(plain_view(h0, H), plain_view(dz, s.zp), H, RH, B, 1, NIdent{},
+                                      EpiPartial{part + (size_t)sp * H * RH, H, RH}, st)));
+      ++sp;
+    }
+    if (sp == 0) G_TRY((int)cudaMemsetAsync(dA, 0, (size_t)H * RH * sizeof(float), st));
+    else G_TRY(reduce_to(sp, (long long)H * RH, dA));
+  }
+  // dVx = dPre^T ZX  [4H,RX]
+  {
+    const int sp = g_splits(4 * H, RX, rows);
+    G_TRY((gemm_launch<true, false>(dPv, ZXv, 4 * H, RX, rows, sp, NIdent{}, EpiPartial{part, 4 * H, RX}, st)));
+    G_TRY(reduce_to(sp, (long long)4 * H * RX, dVx));
+  }
+  // dZX = dPre Vx    [T*B,RX]
+  if (s.zxp > RX) G_TRY((int)cudaMemsetAsync(dzx, 0, (size_t)s.n_dzx * sizeof(float), st));
+  G_TRY((gemm_launch<false, false>(dPv, plain_view(Vx, RX), (int)rows, RX, 4 * H, 1, NIdent{},
+                                   EpiStore{plain_view(dzx, s.zxp), 0}, st)));
+  // dUx = X^T dZX    [I,RX]
+  {
+    const int sp = g_splits(I, RX, rows);
+    G_TRY((gemm_launch<true, false>(Xv, plain_view(dzx, s.zxp), I, RX, rows, sp, NIdent{}, EpiPartial{part, I, RX}, st)));
+    G_TRY(reduce_to(sp, (long long)I * RX, dUx));
+  }
+  // dX = dZX Ux^T + sum_k dPre[:, kH:kH+I] (.) Dx_k
+  if (dx)
+    G_TRY((gemm_launch<false, true>(plain_view(dzx, s.zxp), plain_view(Ux, RX), (int)rows, I, RX, 1, NIdent{},
+                                    EpiDX{tb_view(dx, dxs_t, dxs_b, B), dpre, Dx, H, I}, st)));
+  // dbias, dDh, dDx
+  {
+    long long rps = (rows + kColSplits - 1) / kColSplits;
+    if (rps < 1) rps = 1;
+    const int nsp = (int)((rows + rps - 1) / rps);
+    ColRedArgs ca{dpre, Yv, h0, Xv, part, T, B, H, I, rps};
+    colreduce_kernel<<<dim3(ceil_div(4 * H, 128), nsp), 128, 0, st>>>(ca);
+    G_TRY((int)cudaGetLastError());
+    colreduce_final_kernel<<<ceil_div(8 * H + 4 * I, 256), 256, 0, st>>>(part, nsp, H, I, dbias, dDh, dDx);
+    G_TRY((int)cudaGetLastError());
+  }
+  return VMLMF_OK;
+}
 
 }  // namespace vmlmf
