@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""bench.py -- VMLMF-LSTM training throughput (sequences/s) on B200, with kernel roofline and the
+same-run host-CPU baseline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): VMLMF LSTM on synthetic Opportunity-shaped windows --
+Net(77, [256], w_rank=8, u_rank=[6], cell=MyVMLMFCell), x[B,24,77] ~ N(0,1), 18 classes, fp32,
+weights from the reference initialisers under torch.manual_seed(3).  One "step" is the reference's
+training iteration (V/train_test/train.py:58-65): zero_grad, forward, cross-entropy, backward,
+Adam(lr=0.002) step; with N>1 the batch is sharded over ranks (fixed per-GPU batch => weak scaling) and
+the live factor gradients are averaged with one flat-bucket NCCL all-reduce before the optimizer.
+
+One JSON line on stdout (rank 0).  `value` = whole-job train sequences/s with inputs resident in
+HBM; `e2e` = same step driven from pinned HOST buffers through the public nn.Module API, H2D copy of
+every batch and a D2H read of every loss inside the timed region; `roofline` = the dominant kernel
+(fused BPTT) timed live with CUDA events inside the timed steps; `cpu_baseline` = the CPU oracle port
+of the reference (oracle/vmlmf_oracle.py, torch eager, all host threads) on a bounded sample.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+T_STEPS, N_IN, HIDDEN, W_RANK, U_RANK, N_CLASS = 24, 77, 256, 8, 6, 18
+WORKLOAD = "cfg2: VMLMF LSTM Net(77,[256],w_rank=8,u_rank=[6]) on synthetic Opportunity windows [B,24,77], 18 classes, train step (fwd+CE+bwd+Adam)"
+METRIC = "vmlmf_lstm_train_sequences_per_sec"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=8192, help="sequences per GPU per step")
+    ap.add_argument("--cpu-batch", type=int, default=1024, help="sequences per CPU-baseline step (bounded sample)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------- #
+# CPU arm: the oracle port of the reference, timed on the host cores
+# ----------------------------------------------------------------------------------------------- #
+
+def cpu_train_rate(batch, steps, warmup, budget_s=60.0):
+    """sequences/s of the reference training iteration on CPU (oracle port, torch eager, all threads)."""
+    import torch
+
+    import vmlmf_b200 as vb
+    from oracle import vmlmf_oracle as vo
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(3)
+    net = vb.Net(N_IN, [HIDDEN], w_rank=W_RANK, u_rank=[U_RANK], cell=vb.MyVMLMFCell)     # parameters only (CPU)
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in net.state_dict().items() if not k.startswith("cell.")}
+    cell = vo.split_state_dict(sd, "rnn.rnncells.0.")
+    opt = torch.optim.Adam(list(sd.values()), lr=0.002)
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randn(batch, T_STEPS, N_IN, generator=g)
+    y = torch.randint(0, N_CLASS, (batch,), generator=g)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        logits = vo.net_forward([cell], sd["lin.weight"], sd["lin.bias"], x)
+        loss = torch.nn.functional.cross_entropy(logits, y)
+        loss.backward()
+        opt.step()
+        return loss.item()
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(steps):
+        step()
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return done * batch / dt, dt / done * 1e3, done, torch.get_num_threads()
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle port; the reference is pure Python and does not
+    travel to the GPU box), all host threads, same metric/config, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rate, ms, done, threads = cpu_train_rate(args.cpu_batch, args.steps, max(1, min(args.warmup, 3)), budget_s=150.0)
+    sample = f"{done} steps x {args.cpu_batch} sequences of the cfg2 train step on CPU (oracle port, torch eager)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": "sequences/s", "n_gpus": args.gpus,
+        "steps": done, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "per_step_batch": args.cpu_batch},
+        "cpu_baseline": {"value": rate, "unit": "sequences/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": "sequences/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ----------------------------------------------------------------------------------------------- #
+# GPU arm
+# ----------------------------------------------------------------------------------------------- #
+
+class ClockSampler:
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.QUERY}",
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            pass
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [s.strip() for s in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        # idle samples (before the first kernel ramps the clock) sit at the bottom; report the median
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "sm_mhz_max_seen": max(sm) if sm else None, "power_w_max": max(pw) if pw else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import vmlmf_b200 as vb
+    from vmlmf_b200 import functional as F
+    from vmlmf_b200.parallel import GradBucket, broadcast_parameters
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the fused path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    B, K, W = args.batch, args.steps, max(args.warmup, 3)
+    torch.manual_seed(3)
+    net = vb.Net(N_IN, [HIDDEN], w_rank=W_RANK, u_rank=[U_RANK], cell=vb.MyVMLMFCell).to(dev)
+    broadcast_parameters(net)
+    opt = torch.optim.Adam(net.parameters(), lr=0.002, fused=True)
+    bucket = GradBucket(net, average=True)
+    ce = torch.nn.functional.cross_entropy
+
+    POOL = 4                                   # distinct resident batches, rotated (each step's set >> L2)
+    g = torch.Generator().manual_seed(1234 + rank)
+    host_x = [torch.randn(B, T_STEPS, N_IN, generator=g).pin_memory() for _ in range(POOL)]
+    host_y = [torch.randint(0, N_CLASS, (B,), generator=g).pin_memory() for _ in range(POOL)]
+    dev_x = [t.to(dev) for t in host_x]
+    dev_y = [t.to(dev) for t in host_y]
+
+    def train_step(x, y):
+        bucket.zero()
+        loss = ce(net(x), y)
+        loss.backward()
+        bucket.all_reduce()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world > 1:
+            t = torch.tensor([v], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return t.item()
+        return v
+
+    # ---------------- value: inputs resident in HBM ----------------
+    for i in range(W):
+        train_step(dev_x[i % POOL], dev_y[i % POOL])
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    F.EVENT_LOG = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(K):
+        train_step(dev_x[i % POOL], dev_y[i % POOL])
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    log, F.EVENT_LOG = F.EVENT_LOG, None
+    kt = {}
+    for name, a, b in log:
+        kt.setdefault(name, []).append(a.elapsed_time(b))
+    kernel_ms = {k: sum(v) / len(v) for k, v in kt.items()}
+    ms_step = ms_total / K
+    value = world * B * K / (ms_total * 1e-3)
+
+    # ---------------- e2e: pinned host buffers, H2D + D2H every step, public API ----------------
+    copy_stream = torch.cuda.Stream()
+    stage_x = [torch.empty_like(dev_x[0]) for _ in range(2)]
+    stage_y = [torch.empty_like(dev_y[0]) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    freed = [torch.cuda.Event() for _ in range(2)]
+
+    def issue_copy(i):
+        s = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(freed[s])
+            stage_x[s].copy_(host_x[i % POOL], non_blocking=True)
+            stage_y[s].copy_(host_y[i % POOL], non_blocking=True)
+            ready[s].record(copy_stream)
+
+    def e2e_loop(n):
+        for s in range(2):
+            freed[s].record()
+        issue_copy(0)
+        last = 0.0
+        for i in range(n):
+            s = i % 2
+            if i + 1 < n:
+                issue_copy(i + 1)                       # overlaps with this step's compute
+            torch.cuda.current_stream().wait_event(ready[s])
+            loss = train_step(stage_x[s], stage_y[s])
+            freed[s].record()
+            last = loss.item()                          # D2H read of the step's result (syncs, as train.py:66 does)
+        return last
+
+    e2e_loop(min(W, 5))
+    barrier()
+    t0 = time.perf_counter()
+    e2e_loop(K)
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = world * B * K / e2e_s
+    h2d = host_x[0].numel() * 4 + host_y[0].numel() * 8
+
+    # ---------------- inference (no_grad) throughput, resident inputs ----------------
+    net.eval()
+    with torch.no_grad():
+        for i in range(3):
+            net(dev_x[i % POOL])
+        barrier()
+        e0.record()
+        for i in range(K):
+            net(dev_x[i % POOL])
+        e1.record()
+        barrier()
+    inf_ms = max_over_ranks(e0.elapsed_time(e1))
+    inf_value = world * B * K / (inf_ms * 1e-3)
+    net.train()
+    clocks = sampler.stop() if sampler else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- per-step recurrence latency at the reference's own batch (cfg1: B=64, T=128) ----------------
+    torch.manual_seed(3)
+    net1 = vb.Net(9, [128], w_rank=8, u_rank=[6], cell=vb.MyVMLMFCell).to(dev)
+    x1 = torch.randn(64, 128, 9, device=dev)
+    y1 = torch.randint(0, 6, (64,), device=dev)
+    for _ in range(5):
+        ce(net1(x1), y1).backward()
+    F.EVENT_LOG = []
+    for _ in range(20):
+        net1.zero_grad()
+        ce(net1(x1), y1).backward()
+    torch.cuda.synchronize()
+    lat = {}
+    for name, a, b in F.EVENT_LOG:
+        lat.setdefault(name, []).append(a.elapsed_time(b))
+    F.EVENT_LOG = None
+    latency = {"config": "cfg1 Net(9,[128],8,[6]) B=64 T=128",
+               "fwd_us_per_timestep": statistics.median(lat["seq_fwd"]) * 1e3 / 128,
+               "bwd_us_per_timestep": statistics.median(lat["seq_bwd"]) * 1e3 / 128}
+
+    # ---------------- roofline of the dominant kernel ----------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        pass
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    units = B * T_STEPS                                   # sequence-timesteps per launch
+    q_bwd = 4 * (7 * HIDDEN + 2 * N_IN)                   # bwd share of Q_train (saved 6H + dY H, x I, dX I)
+    q_fwd = 4 * (N_IN + 6 * HIDDEN)                       # fwd share: read x, write h,c,i,f,o,n
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except (OSError, ValueError):
+        pass
+
+    def roof(name, q):
+        ms = kernel_ms.get(name)
+        if not ms:
+            return None
+        ach = q * units / (ms * 1e-3) / 1e9
+        return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+                "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)",
+                "ms_per_launch": ms, "algorithmic_bytes_per_launch": q * units,
+                "traffic": (traffic or {}).get(name)}
+
+    r_bwd, r_fwd = roof("seq_bwd", q_bwd), roof("seq_fwd", q_fwd)
+    roofline = dict(r_bwd or {})
+    roofline["other_kernels"] = [r_fwd, {"kernel": "xproj_fwd", "ms_per_launch": kernel_ms.get("xproj_fwd")}]
+    roofline["step_share"] = {k: v / ms_step for k, v in kernel_ms.items()}
+
+    # ---------------- CPU baseline (bounded sample) ----------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        rate, ms, done, threads = cpu_train_rate(args.cpu_batch, 40, 1, budget_s=20.0)
+        cpu = {"value": rate, "unit": "sequences/s", "cores": threads, "kind": "port",
+               "sample": f"{done} steps x {args.cpu_batch} sequences of the same cfg2 train step (oracle port, torch eager, "
+                         f"{ms:.0f} ms/step)"}
+
+    out = {
+        "metric": METRIC, "value": value, "unit": "sequences/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": B * world, "seq_len": T_STEPS,
+                   "parallelism": f"dp{world}", "l2_policy": "inputs larger than L2 (x 60 MB + 1.5 GB saved state per step, 4 rotating batches)"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "sequences/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": e2e_s * 1e3 / K},
+        "gpu_launches": 4 * K,          # per step: xproj_small, seq_fwd_r1, seq_bwd_r1, reduce_partials
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "inference": {"value": inf_value, "unit": "sequences/s", "ms_per_step": inf_ms / K},
+        "recurrence_latency": latency,
+        "grad_allreduce_bytes": bucket.nbytes,
+    }
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

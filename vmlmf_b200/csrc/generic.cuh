@@ -325,7 +325,7 @@ inline int generic_plan(int T, int B, int I, int H, int RX, int RH, vmlmf_plan* 
   plan->zx_pitch = s.zxp;
   plan->z_pitch = s.zp;
   plan->xp_cols = 4 * H;
-  plan->fwd_workspace_bytes = (s.n_xp + 2 * s.n_state) * (long long)sizeof(float);
+  plan->fwd_workspace_bytes = (s.n_xp + 2 * s.n_state + (long long)B * s.zp) * (long long)sizeof(float);
   plan->bwd_workspace_bytes = (s.n_dpre + s.n_dz + s.n_dzx + 2 * s.n_state + s.n_part) * (long long)sizeof(float);
   return VMLMF_OK;
 }
@@ -364,7 +364,7 @@ inline int generic_seq_fwd(const vmlmf_plan* plan, const float* x, long long xs_
   if (rows * 4 * H > (1LL << 40) || rows > 0x7fffffff) return VMLMF_EUNSUPPORTED;
   float* xp = (float*)workspace;
   float* cbuf[2] = {xp + s.n_xp, xp + s.n_xp + s.n_state};      // running c when not saving
-  float* zrow = nullptr;                                         // z_t when not saving
+  float* zscratch = xp + s.n_xp + 2 * s.n_state;                 // z_t when not saving  [B, zp]
   // time-parallel: XP = ZX Vx^T + bias + x (.) Dx
   G_TRY((gemm_launch<false, true>(plain_view(zx, s.zxp), plain_view(Vx, RX), (int)rows, 4 * H, RX, 1, NIdent{},
                                   EpiXP{xp, bias, tb_view(x, xs_t, xs_b, B), Dx, H, I}, st)));
@@ -374,11 +374,7 @@ inline int generic_seq_fwd(const vmlmf_plan* plan, const float* x, long long xs_
     const long long hp_sb = t ? ys_b : H;
     const float* cprev = save ? (t ? cs + (size_t)(t - 1) * B * H : c0) : (t ? cbuf[(t - 1) & 1] : c0);
     float* cout = save ? cs + (size_t)t * B * H : cbuf[t & 1];
-    // z_t = h_{t-1} A  (zero when there is no initial state)
-    float* zt = save ? z + (size_t)t * B * s.zp : (zrow ? zrow : (zrow = cbuf[0] /*placeholder*/, nullptr));
-    (void)zt;
-    float* zdst = save ? z + (size_t)t * B * s.zp : nullptr;
-    if (!zdst) return VMLMF_EUNSUPPORTED;   // replaced below (inference scratch) -- see generic_seq_fwd_infer
+    float* zdst = save ? z + (size_t)t * B * s.zp : zscratch;   // z_t = h_{t-1} A (zero without initial state)
     if (hprev) {
       if (s.zp > RH) {
         const long long n = (long long)B * (s.zp - RH);

@@ -15,6 +15,29 @@ import torch
 from . import _lib
 
 
+# bench.py sets this to a list; each C-ABI call then appends (name, start_event, end_event) recorded on the
+# launching stream.  None (the default) adds no work.
+EVENT_LOG = None
+
+
+class _timed:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if EVENT_LOG is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        if EVENT_LOG is not None:
+            self.b.record()
+            EVENT_LOG.append((self.name, self.a, self.b))
+        return False
+
+
 def _ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
@@ -67,8 +90,10 @@ class VmlmfSeqFunction(torch.autograd.Function):
         ys_t, ys_b = _tb_strides(y, batch_first)
         with torch.cuda.device_of(x):
             st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-            _lib.check(lib.vmlmf_xproj_fwd(_ptr(x), xs_t, xs_b, _ptr(Ux), _ptr(zx), T, B, I, RX, plan.zx_pitch, st))
-            _lib.check(lib.vmlmf_seq_fwd(C.byref(plan), _ptr(x), xs_t, xs_b, _ptr(zx), _ptr(Ux), _ptr(Vx), _ptr(Dx),
+            with _timed("xproj_fwd"):
+                _lib.check(lib.vmlmf_xproj_fwd(_ptr(x), xs_t, xs_b, _ptr(Ux), _ptr(zx), T, B, I, RX, plan.zx_pitch, st))
+            with _timed("seq_fwd"):
+              _lib.check(lib.vmlmf_seq_fwd(C.byref(plan), _ptr(x), xs_t, xs_b, _ptr(zx), _ptr(Ux), _ptr(Vx), _ptr(Dx),
                                          _ptr(A), _ptr(Bm), _ptr(Dh), _ptr(bias), _ptr(h0), _ptr(c0), _ptr(y), ys_t,
                                          ys_b, _ptr(hT), _ptr(cT), _ptr(gates), _ptr(cs), _ptr(z), _ptr(ws),
                                          T, B, I, H, RX, RH, st))
@@ -103,7 +128,8 @@ class VmlmfSeqFunction(torch.autograd.Function):
         dxs = _tb_strides(dx, bf) if dx is not None else (0, 0)
         with torch.cuda.device_of(x):
             st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-            _lib.check(lib.vmlmf_seq_bwd(C.byref(plan), _ptr(x), xs[0], xs[1], _ptr(zx), _ptr(Ux), _ptr(Vx), _ptr(Dx),
+            with _timed("seq_bwd"):
+              _lib.check(lib.vmlmf_seq_bwd(C.byref(plan), _ptr(x), xs[0], xs[1], _ptr(zx), _ptr(Ux), _ptr(Vx), _ptr(Dx),
                                          _ptr(A), _ptr(Bm), _ptr(Dh), _ptr(h0), _ptr(c0), _ptr(y), ys[0], ys[1],
                                          _ptr(gates), _ptr(cs), _ptr(z), _ptr(dy), dys[0], dys[1], _ptr(dhT),
                                          _ptr(dcT), _ptr(dx), dxs[0], dxs[1], _ptr(dh0), _ptr(dc0), _ptr(dUx),

@@ -1,0 +1,75 @@
+"""Batch-sharded data parallelism for the VMLMF nets: one process per GPU, replicated parameters,
+one flat-bucket all-reduce of the (small) factor gradients per step.
+
+The reference has no multi-device code at all (single `cuda:{gpu_id}`, V/train_test/main.py:109-110).
+Sequences are independent in forward and backward, so the only exchange is the gradient sum
+(SURVEY 8e).  Loss semantics to preserve: HAR uses a batch-MEAN cross entropy (train.py:63) =>
+gradients are averaged over ranks; the LM loss is token-mean x batch size (lm_test.py:147,153) =>
+callers that shard B pass average=False and scale the local loss themselves.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+class GradBucket:
+    """Flat view of every live parameter gradient; `.grad` tensors alias slices of one buffer so the
+    all-reduce needs no packing copies.  Parameters that never receive a gradient (the reference's
+    dead `Net.cell`, V/models/vmlmf.py:348-350) are left out -- found from the first backward."""
+
+    def __init__(self, module, average=True):
+        self.module = module
+        self.average = average
+        self.flat = None
+        self.params = []
+
+    def _build(self):
+        self.params = [p for p in self.module.parameters() if p.grad is not None]
+        n = sum(p.numel() for p in self.params)
+        ref = self.params[0]
+        self.flat = torch.zeros(n, dtype=ref.dtype, device=ref.device)
+        off = 0
+        for p in self.params:
+            view = self.flat[off:off + p.numel()].view_as(p)
+            view.copy_(p.grad)
+            p.grad = view
+            off += p.numel()
+
+    def zero(self):
+        """call instead of module.zero_grad(): keeps the aliasing alive"""
+        if self.flat is not None:
+            self.flat.zero_()
+        else:
+            self.module.zero_grad(set_to_none=True)
+
+    def all_reduce(self):
+        """sum (or mean) the bucket over all ranks; no-op for a single process"""
+        if self.flat is None:
+            self._build()
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+            if self.average:
+                self.flat.div_(dist.get_world_size())
+        return self.flat
+
+    @property
+    def nbytes(self):
+        return 0 if self.flat is None else self.flat.numel() * self.flat.element_size()
+
+
+def broadcast_parameters(module, src=0):
+    """make every rank start from rank `src`'s weights"""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        for t in list(module.parameters()) + list(module.buffers()):
+            dist.broadcast(t.data, src)
+
+
+def shard_batch(x, dim=0):
+    """this rank's contiguous slice of a global batch along `dim`"""
+    if not (dist.is_available() and dist.is_initialized()):
+        return x
+    w, r = dist.get_world_size(), dist.get_rank()
+    n = x.size(dim)
+    assert n % w == 0, "global batch must divide evenly over ranks"
+    return x.narrow(dim, r * (n // w), n // w)
