@@ -59,6 +59,33 @@ __global__ void k(float* out, long long* cyc, float seed) {
       for (int r = 0; r < 4; ++r)
 #pragma unroll
         for (int i = 0; i < 16; ++i) a[i] = fmaf(a[i], w[r], a[i]);
+    } else if (MODE == 7 || MODE == 8) {   // 16 mma.m16n8k8 tf32: 8 independent accumulators (7) / 1 dependent chain (8)
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        const int c = (MODE == 7) ? (r & 3) * 4 : 0;
+        asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(a[c]), "+f"(a[c + 1]), "+f"(a[c + 2]), "+f"(a[c + 3])
+                     : "r"(__float_as_uint(w[0])), "r"(__float_as_uint(w[1])), "r"(__float_as_uint(w[2])),
+                       "r"(__float_as_uint(w[3])), "r"(__float_as_uint(w[4])), "r"(__float_as_uint(w[5])));
+      }
+    } else if (MODE == 9) {   // 16 mma.m16n8k16 bf16, 4 independent accumulators
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        const int c = (r & 3) * 4;
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(a[c]), "+f"(a[c + 1]), "+f"(a[c + 2]), "+f"(a[c + 3])
+                     : "r"(__float_as_uint(w[0])), "r"(__float_as_uint(w[1])), "r"(__float_as_uint(w[2])),
+                       "r"(__float_as_uint(w[3])), "r"(__float_as_uint(w[4])), "r"(__float_as_uint(w[5])));
+      }
+    } else if (MODE == 10) {  // 32 cvt.rna.tf32
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          unsigned u;
+          asm volatile("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(a[i]));
+          a[i] = __uint_as_float(u) + w[r];
+        }
     } else if (MODE == 6) {     // mix: 56 FFMA + 5 ex2 + 5 rcp (one unit-step of the forward)
 #pragma unroll
       for (int r = 0; r < 4; ++r)
@@ -106,6 +133,10 @@ int main() {
   run<3>("SHFL (32/iter)", 32, out, cyc);
   run<4>("LDS.128 bcast (16/iter)", 16, out, cyc);
   run<6>("mix 56 FFMA+10 MUFU (66)", 66, out, cyc);
+  run<7>("HMMA tf32 m16n8k8 x4acc (16)", 16, out, cyc);
+  run<8>("HMMA tf32 m16n8k8 chain (16)", 16, out, cyc);
+  run<9>("HMMA bf16 m16n8k16 x4acc(16)", 16, out, cyc);
+  run<10>("cvt.rna.tf32+FADD (64)", 64, out, cyc);
   printf("err=%s\n", cudaGetErrorString(cudaGetLastError()));
   return 0;
 }

@@ -25,17 +25,21 @@ int launch_fwd_r1(const SeqFwdArgs& a, bool save, cudaStream_t st) {
   const int NT = round_up(a.H, 32);
   const int smem = r1_fwd_smem_bytes(RH_T, RX_T, NT);
   const int ntiles = ceil_div(a.B, kFwdBT);
-  auto go = [&](auto kern) -> int {
-    int occ = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem);
-    if (e != cudaSuccess) return (int)e;
-    if (occ < 1) occ = 1;
+  auto go = [&](auto kern, int variant) -> int {
+    static int occ_cache[2][9] = {{0}};                 // [variant][NT/32]; benign race
+    int occ = occ_cache[variant][NT / 32];
+    if (occ == 0) {
+      cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem);
+      if (e != cudaSuccess) return (int)e;
+      if (occ < 1) occ = 1;
+      occ_cache[variant][NT / 32] = occ;
+    }
     const int grid = ntiles < kNumSMs * occ ? ntiles : kNumSMs * occ;
     kern<<<grid, NT, smem, st>>>(a);
     return (int)cudaGetLastError();
   };
-  if (save) return go(seq_fwd_r1_kernel<RH_T, RX_T, kFwdBT, true, 256, 1>);
-  return go(seq_fwd_r1_kernel<RH_T, RX_T, kFwdBT, false, 256, 1>);
+  if (save) return go(seq_fwd_r1_kernel<RH_T, RX_T, kFwdBT, true, 256, 1>, 1);
+  return go(seq_fwd_r1_kernel<RH_T, RX_T, kFwdBT, false, 256, 1>, 0);
 }
 
 template <int RH_T, int RX_T>
@@ -44,11 +48,16 @@ int launch_bwd_r1(const SeqBwdArgs& a, const GradOut& out, cudaStream_t st) {
   const int smem = r1_bwd_smem_bytes(RH_T, RX_T, NT);
   const int ntiles = ceil_div(a.B, kBwdBT);
   auto kern = seq_bwd_r1_kernel<RH_T, RX_T, kBwdBT, 256, 1>;
-  int occ = 0;
-  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem);
-  if (e != cudaSuccess) return (int)e;
-  if (occ < 1) occ = 1;
-  if (occ > kMaxCtasPerSM) occ = kMaxCtasPerSM;
+  static int occ_cache[9] = {0};
+  int occ = occ_cache[NT / 32];
+  cudaError_t e;
+  if (occ == 0) {
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem);
+    if (e != cudaSuccess) return (int)e;
+    if (occ < 1) occ = 1;
+    if (occ > kMaxCtasPerSM) occ = kMaxCtasPerSM;
+    occ_cache[NT / 32] = occ;
+  }
   const int grid = ntiles < kNumSMs * occ ? ntiles : kNumSMs * occ;
   kern<<<grid, NT, smem, st>>>(a);
   e = cudaGetLastError();

@@ -2,8 +2,10 @@
 #include "../../include/vmlmf_b200.h"
 
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include "generic.cuh"
+#include "seq_mma.cuh"
 #include "seq_r1_launch.cuh"
 #include "xproj.cuh"
 
@@ -26,6 +28,17 @@ R1Choice choose_r1(int I, int H, int RX, int RH) {
   R1Choice c{pick(kRH, 6, RH), pick(kRX, 3, RX), false};
   c.ok = c.rh_t > 0 && c.rx_t > 0 && (c.rh_t + c.rx_t) <= 24 && H <= 256 && I <= H;
   return c;
+}
+
+// VMLMF_R1_SIMT=1 forces the SIMT R1 kernels (A/B measurements); read once
+bool simt_only() {
+  static const bool v = [] { const char* e = getenv("VMLMF_R1_SIMT"); return e && e[0] == '1'; }();
+  return v;
+}
+
+int dbg_flags() {
+  static const int v = [] { const char* e = getenv("VMLMF_DBG"); return e ? atoi(e) : 0; }();
+  return v;
 }
 
 int check_dims(int T, int B, int I, int H, int RX, int RH) {
@@ -115,6 +128,10 @@ int vmlmf_seq_fwd(const vmlmf_plan* plan, const float* x, long long xs_t, long l
     if (!c.ok || plan->zx_pitch != round_up(c.rx_t, 4) || plan->z_pitch != next_pow2(c.rh_t)) return VMLMF_EPLAN;
     SeqFwdArgs a{x, xs_t, xs_b, zx, Vx, Dx, A, Bm, Dh, bias, h0, c0, y, ys_t, ys_b, hT, cT, gates, cs, z,
                  T, B, I, H, RX, RH};
+    if (!simt_only()) {              // warp-MMA kernel first; shapes it does not cover fall through to SIMT
+      const int rc2 = launch_fwd_mma(SeqFwdMmaArgs{a, plan->z_pitch, plan->zx_pitch, dbg_flags()}, save, st);
+      if (rc2 != kMmaNoFit) return rc2;
+    }
     switch (c.rx_t) {
       case 4: return launch_fwd_r1_rx4(c.rh_t, a, save, st);
       case 8: return launch_fwd_r1_rx8(c.rh_t, a, save, st);

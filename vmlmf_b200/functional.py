@@ -80,7 +80,7 @@ class VmlmfSeqFunction(torch.autograd.Function):
         y = new((B, T, H)) if batch_first else new((T, B, H))
         hT, cT = new((B, H)), new((B, H))
         zx = new((T * B, plan.zx_pitch))
-        need_grad = any(ctx.needs_input_grad)
+        need_grad = torch.is_grad_enabled() and any(ctx.needs_input_grad)
         if need_grad:
             gates, cs, z = new((T, B, 4, H)), new((T, B, H)), new((T * B, plan.z_pitch))
         else:
