@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define VMLMF_ABI_VERSION 1
+#define VMLMF_ABI_VERSION 2
 
 enum {
   VMLMF_OK = 0,
@@ -47,8 +47,10 @@ enum {
 
 /* regimes (vmlmf_plan.path) */
 enum {
-  VMLMF_PATH_R1 = 1, /* persistent, factors register-resident, one CTA per batch tile   */
-  VMLMF_PATH_G = 2   /* generic: time-parallel XP GEMM + one fused launch per timestep  */
+  VMLMF_PATH_R1 = 1,  /* persistent SIMT, factors register-resident, thread = hidden unit      */
+  VMLMF_PATH_G = 2,   /* generic: time-parallel XP GEMM + one fused launch per timestep        */
+  VMLMF_PATH_R1M = 3  /* persistent warp-MMA (mma.sync 3xTF32) recurrence, CTA = 16 sequences;
+                         needs H % 4 == 0, H <= 256, RH <= 16, RH + RX + 1 <= 32               */
 };
 
 typedef struct vmlmf_plan {
@@ -58,6 +60,10 @@ typedef struct vmlmf_plan {
   int xp_cols;               /* PATH_G: columns of xp[T*B, xp_cols] (=4H), else 0       */
   long long fwd_workspace_bytes;
   long long bwd_workspace_bytes;
+  long long gates_bytes;     /* size of the saved `gates` buffer (PATH_R1M pads it to whole
+                                16-sequence x 16-unit fragments and stores it fragment-major;
+                                the other paths use [T,B,4,H]); opaque to the caller          */
+  long long cs_bytes;        /* size of the saved `cs` buffer, same remark                     */
   int reserved[8];
 } vmlmf_plan;
 
@@ -79,8 +85,10 @@ int vmlmf_xproj_fwd(const float* x, long long xs_t, long long xs_b, const float*
  *   h0,c0      [B,H] or NULL (= zeros, MyLSTM.forward :302-303)
  *   y          h_t for every t, strides (ys_t, ys_b)
  *   hT,cT      [B,H] final state
- *   gates,cs,z saved for backward: gates[T,B,4,H] (i,f,o,n), cs[T,B,H], z[T*B,z_pitch];
+ *   gates,cs,z saved for backward: plan.gates_bytes / plan.cs_bytes / T*B*z_pitch floats, written by
+ *              this call and read back only by vmlmf_seq_bwd (layout is private to the path);
  *              all three NULL = inference (nothing saved)
+ *   PATH_R1M additionally needs y rows 8-byte aligned (ys_t, ys_b even)
  *   workspace  plan.fwd_workspace_bytes (may be NULL when that is 0)                   */
 int vmlmf_seq_fwd(const vmlmf_plan* plan, const float* x, long long xs_t, long long xs_b,
                   const float* zx, const float* Ux, const float* Vx, const float* Dx,

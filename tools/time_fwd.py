@@ -58,7 +58,16 @@ def loop_ms(mode, n=30):
     return e0.elapsed_time(e1) / n
 
 
+import subprocess
+def clk():
+    try:
+        return subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.mem,power.draw,temperature.gpu,clocks_event_reasons.active", "--format=csv,noheader"], capture_output=True, text=True).stdout.strip()
+    except OSError:
+        return "n/a"
+run("fwd", 5)
+print("clocks under load:", clk())
 print("loop infer ms/call", loop_ms("infer"), " loop fwd-train ms/call", loop_ms("fwd"))
 print("infer", run("infer"))
 print("fwd-train", run("fwd"))
 print("train", run("train"))
+print("clocks after:", clk())

@@ -10,16 +10,16 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvmlmf_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
-PATH_R1, PATH_G = 1, 2
+PATH_R1, PATH_G, PATH_R1M = 1, 2, 3
 
 
 class Plan(C.Structure):
     """mirror of struct vmlmf_plan"""
     _fields_ = [("path", C.c_int), ("zx_pitch", C.c_int), ("z_pitch", C.c_int), ("xp_cols", C.c_int),
                 ("fwd_workspace_bytes", C.c_longlong), ("bwd_workspace_bytes", C.c_longlong),
-                ("reserved", C.c_int * 8)]
+                ("gates_bytes", C.c_longlong), ("cs_bytes", C.c_longlong), ("reserved", C.c_int * 8)]
 
 
 _P, _LL, _I = C.c_void_p, C.c_longlong, C.c_int

@@ -31,6 +31,13 @@ static int launch_fwd_mma_t(const SeqFwdMmaArgs& a, bool save, cudaStream_t st) 
   return go(seq_fwd_mma_kernel<KS, NZ, false>, 0);
 }
 
+bool fwd_mma_fits(int I, int H, int RX, int RH) {
+  if (H > 256 || (H & 3) || I > H || RH > 16) return false;
+  const int KS = ceil_div(RH + RX + 1, 8), NZ = ceil_div(RH, 8);
+  if (KS > 4 || (NZ == 1 && KS > 3) || (NZ == 2 && KS < 2)) return false;
+  return seq_fwd_mma_smem_bytes(ceil_div(H, 16), KS, NZ) <= 227 * 1024;
+}
+
 int launch_fwd_mma(const SeqFwdMmaArgs& a, bool save, cudaStream_t st) {
   const int RH = a.s.RH, RX = a.s.RX;
   if (a.s.H > 256 || RH > 16) return kMmaNoFit;

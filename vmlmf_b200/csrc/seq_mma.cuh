@@ -35,7 +35,6 @@ namespace vmlmf {
 struct SeqFwdMmaArgs {
   SeqFwdArgs s;
   int zp, zxp;      // row pitch of saved z / of zx (floats)
-  int dbg;          // development toggles (VMLMF_DBG): 1 = skip stores, 2 = skip gate MMAs, 4 = skip MUFU
 };
 
 __device__ __forceinline__ float tf32_rna(float v) {
@@ -66,8 +65,25 @@ __device__ __forceinline__ void split4(const float (&v)[4], float (&hi)[4], floa
   }
 }
 
+// asynchronous prefetch of a contiguous global range into L2 (bytes: multiple of 16, p: 16-byte aligned)
+__device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 constexpr float kNegLog2e = -1.4426950408889634f;
 constexpr float kNeg2Log2e = -2.8853900817779268f;
+
+// Fragment-major layout of the tensors that only the warp-MMA kernels exchange (saved gates and c of the forward,
+// dPre of the backward).  One block per (timestep t, 16-sequence tile): blk = t * ntiles + tile.  Inside a
+// block, quantity Q of NQ, warp w (16 hidden units), P (8-unit half), hf (sequence half) hold 32 lanes x 2 floats:
+// lane (g,q) = units 16w + 8P + 2q + {0,1} of sequence 16*tile + g + 8*hf  -- exactly the MMA accumulator
+// fragment, so every warp-level load/store is one contiguous 256-byte segment.
+__host__ __device__ inline size_t frag_addr(size_t blk, int NQ, int Q, int NW, int w, int P, int hf, int lane) {
+  return ((((blk * NQ + Q) * NW + w) * 4 + P * 2 + hf) * 64) + lane * 2;
+}
+__host__ __device__ inline size_t frag_floats(int T, int B, int H, int NQ) {       // buffer size incl. padding
+  return (size_t)T * ((B + 15) / 16) * NQ * ((H + 15) / 16) * 256;
+}
 
 __host__ __device__ constexpr int mma_pp(int NZ) { return 8 * NZ + 4; }    // pitch of a z-partial row
 __host__ __device__ constexpr int mma_sp(int KS) { return 8 * KS + 4; }    // pitch of an A row
@@ -145,8 +161,6 @@ __global__ void __launch_bounds__(512, 1) seq_fwd_mma_kernel(const SeqFwdMmaArgs
   for (int i = tid; i < 16 * SP; i += blockDim.x) Ar[i] = ((i % SP) == RH + RX) ? 1.f : 0.f;
 
   const bool xwarp = ubase < I;                          // this warp has units with an x term
-  const bool vec2 = ((H & 1) == 0) && ((aa.s.ys_t & 1) == 0) && ((aa.s.ys_b & 1) == 0) &&
-                    ((reinterpret_cast<uintptr_t>(aa.s.y) & 7) == 0);
   const int ntiles = ceil_div(B, 16);
   const int j0 = ubase + 2 * q;                          // this lane's units: j0 + 8P + e
   const int nthreads = blockDim.x;
@@ -156,14 +170,16 @@ __global__ void __launch_bounds__(512, 1) seq_fwd_mma_kernel(const SeqFwdMmaArgs
     const int sq[2] = {b0 + g, b0 + g + 8};
     const bool ok[2] = {sq[0] < B, sq[1] < B};
     // per-lane row pointers (advanced by one timestep at the end of every step)
-    float* yrow[2]; float* crow[2]; float* grow[2]; const float* xrow[2];
+    float* yrow[2]; const float* xrow[2];
 #pragma unroll
     for (int hf = 0; hf < 2; ++hf) {
       yrow[hf] = aa.s.y + (size_t)sq[hf] * aa.s.ys_b + j0;
-      crow[hf] = SAVE ? aa.s.cs + (size_t)sq[hf] * H + j0 : nullptr;
-      grow[hf] = SAVE ? aa.s.gates + (size_t)sq[hf] * 4 * H + j0 : nullptr;
       xrow[hf] = aa.s.x + (size_t)sq[hf] * aa.s.xs_b + j0;
     }
+    // fragment-major saved state (frag_addr): block = (t, tile); this lane's slot of quantity 0, P = 0, hf = 0
+    float* gfrag = SAVE ? aa.s.gates + frag_addr((size_t)tile, 4, 0, NW, warp, 0, 0, lane) : nullptr;
+    float* cfrag = SAVE ? aa.s.cs + frag_addr((size_t)tile, 1, 0, NW, warp, 0, 0, lane) : nullptr;
+    const size_t gstep = (size_t)ntiles * 4 * NW * 256, cstep = (size_t)ntiles * NW * 256;
     float c[2][2][2], hp[2][2][2], xn[2][2][2];          // [P][e][hf]
 #pragma unroll
     for (int P = 0; P < 2; ++P)
@@ -273,7 +289,7 @@ __global__ void __launch_bounds__(512, 1) seq_fwd_mma_kernel(const SeqFwdMmaArgs
         for (int e = 0; e < 2; ++e)
 #pragma unroll
           for (int hf = 0; hf < 2; ++hf) xv[P][e][hf] = xn[P][e][hf];
-      if (more && !(aa.dbg & 8)) {
+      if (more) {
         if (warp == NW - 1) fetch_zx(t + 1);
         if (xwarp) {
 #pragma unroll
@@ -302,7 +318,6 @@ __global__ void __launch_bounds__(512, 1) seq_fwd_mma_kernel(const SeqFwdMmaArgs
         for (int k = 0; k < 4; ++k)
 #pragma unroll
           for (int i = 0; i < 4; ++i) acc[k][i] = 0.f;
-        if (!(aa.dbg & 2))
 #pragma unroll
         for (int s = 0; s < KS; ++s) {                  // 4 independent accumulators per MMA round
           float4 b[4];
@@ -324,12 +339,6 @@ __global__ void __launch_bounds__(512, 1) seq_fwd_mma_kernel(const SeqFwdMmaArgs
         }
         float hnew[2][2];                                // [e][hf]
         float gsave[4][2][2];
-        if (aa.dbg & 16) {
-#pragma unroll
-          for (int hf = 0; hf < 2; ++hf)
-#pragma unroll
-            for (int e = 0; e < 2; ++e) { hnew[e][hf] = acc[0][2 * hf + e] + acc[1][2 * hf + e] + acc[2][2 * hf + e] + acc[3][2 * hf + e]; hp[P][e][hf] = hnew[e][hf]; }
-        } else
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf)
 #pragma unroll
@@ -342,54 +351,34 @@ __global__ void __launch_bounds__(512, 1) seq_fwd_mma_kernel(const SeqFwdMmaArgs
               const float dhk = e ? dh[k].y : dh[k].x, dxk = e ? dx[k].y : dx[k].x;
               pre[k] = fmaf(dxk, xx, fmaf(dhk, hprev, acc[k][i]));     // = -log2e * pre-activation (x2 for n)
             }
-            float gi, gf, go, gn, cn, tc;
-            if (aa.dbg & 4) {
-              gi = pre[0] * 0.5f; gf = pre[1] * 0.25f; go = pre[2] * 0.125f; gn = pre[3] * 0.1f;
-              cn = fmaf(gf, c[P][e][hf], gi * gn); tc = cn * 0.3f;
-            } else {
-            gi = rcp_approx(1.f + ex2_approx(pre[0]));
-            gf = rcp_approx(1.f + ex2_approx(pre[1]));
-            go = rcp_approx(1.f + ex2_approx(pre[2]));
-            gn = fmaf(2.f, rcp_approx(1.f + ex2_approx(pre[3])), -1.f);
-            cn = fmaf(gf, c[P][e][hf], gi * gn);
-            tc = fmaf(2.f, rcp_approx(1.f + ex2_approx(cn * kNeg2Log2e)), -1.f);
-            }
+            const float gi = rcp_approx(1.f + ex2_approx(pre[0]));
+            const float gf = rcp_approx(1.f + ex2_approx(pre[1]));
+            const float go = rcp_approx(1.f + ex2_approx(pre[2]));
+            const float gn = fmaf(2.f, rcp_approx(1.f + ex2_approx(pre[3])), -1.f);
+            const float cn = fmaf(gf, c[P][e][hf], gi * gn);
+            const float tc = fmaf(2.f, rcp_approx(1.f + ex2_approx(cn * kNeg2Log2e)), -1.f);
             const float hn = go * tc;
             c[P][e][hf] = cn;
             hp[P][e][hf] = hn;
             hnew[e][hf] = hn;
             if (SAVE) { gsave[0][e][hf] = gi; gsave[1][e][hf] = gf; gsave[2][e][hf] = go; gsave[3][e][hf] = gn; }
           }
-        // ---- stores ----
-        const bool live = (j0 + 8 * P) < H && !(aa.dbg & 1);
+        // ---- stores: y in the caller's layout (8 rows x 32 B per instruction); saved gates / c in the
+        //      fragment-major layout (each warp instruction writes 256 contiguous bytes) ----
+        if (ok[0] && (j0 + 8 * P) < H) *reinterpret_cast<float2*>(yrow[0] + 8 * P) = make_float2(hnew[0][0], hnew[1][0]);
+        if (ok[1] && (j0 + 8 * P) < H) *reinterpret_cast<float2*>(yrow[1] + 8 * P) = make_float2(hnew[0][1], hnew[1][1]);
+        if (SAVE) {
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          if (!ok[hf]) continue;
-          if (vec2) {
-            if (live) {
-              *reinterpret_cast<float2*>(yrow[hf] + 8 * P) = make_float2(hnew[0][hf], hnew[1][hf]);
-              if (SAVE) {
-                *reinterpret_cast<float2*>(crow[hf] + 8 * P) = make_float2(c[P][0][hf], c[P][1][hf]);
+          for (int hf = 0; hf < 2; ++hf) {
+            *reinterpret_cast<float2*>(cfrag + (P * 2 + hf) * 64) = make_float2(c[P][0][hf], c[P][1][hf]);
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  *reinterpret_cast<float2*>(grow[hf] + (size_t)k * H + 8 * P) = make_float2(gsave[k][0][hf], gsave[k][1][hf]);
-              }
-            }
-          } else {
-#pragma unroll
-            for (int e = 0; e < 2; ++e)
-              if (j0 + 8 * P + e < H) {
-                yrow[hf][8 * P + e] = hnew[e][hf];
-                if (SAVE) {
-                  crow[hf][8 * P + e] = c[P][e][hf];
-#pragma unroll
-                  for (int k = 0; k < 4; ++k) grow[hf][(size_t)k * H + 8 * P + e] = gsave[k][e][hf];
-                }
-              }
+            for (int k = 0; k < 4; ++k)
+              *reinterpret_cast<float2*>(gfrag + (size_t)k * NW * 256 + (P * 2 + hf) * 64) =
+                  make_float2(gsave[k][0][hf], gsave[k][1][hf]);
           }
         }
         // ---- z GEMM k-step P: A fragment = (h[g][u0], h[g+8][u0], h[g][u1], h[g+8][u1]) ----
-        if (more && !(aa.dbg & 32)) {
+        if (more) {
           const float hv[4] = {hnew[0][0], hnew[0][1], hnew[1][0], hnew[1][1]};
           z_mma(zacc, P, hv);
         }
@@ -397,14 +386,14 @@ __global__ void __launch_bounds__(512, 1) seq_fwd_mma_kernel(const SeqFwdMmaArgs
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
         yrow[hf] += aa.s.ys_t;
-        if (SAVE) { crow[hf] += (size_t)B * H; grow[hf] += (size_t)B * 4 * H; }
       }
+      if (SAVE) { gfrag += gstep; cfrag += cstep; }
       if (more) {
         z_partial_store(zacc);
-        if (!(aa.dbg & 128)) __syncthreads();            // partials complete; every warp is done reading Ar
+        __syncthreads();                                 // partials complete; every warp is done reading Ar
         if (warp == NW - 1) stage_zx();
-        if (!(aa.dbg & 64)) z_reduce(t + 1);
-        if (!(aa.dbg & 128)) __syncthreads();
+        z_reduce(t + 1);
+        __syncthreads();
       }
     }
     // ---- final state ----
@@ -426,5 +415,6 @@ __global__ void __launch_bounds__(512, 1) seq_fwd_mma_kernel(const SeqFwdMmaArgs
 // host launcher: returns kMmaNoFit when the shape is outside this kernel (caller falls back to the SIMT R1 kernel)
 constexpr int kMmaNoFit = -1000;
 int launch_fwd_mma(const SeqFwdMmaArgs& a, bool save, cudaStream_t st);
+bool fwd_mma_fits(int I, int H, int RX, int RH);
 
 }  // namespace vmlmf

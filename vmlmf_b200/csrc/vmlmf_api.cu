@@ -2,9 +2,11 @@
 #include "../../include/vmlmf_b200.h"
 
 #include <cuda_runtime.h>
+#include <stdint.h>
 #include <stdlib.h>
 
 #include "generic.cuh"
+#include "seq_bwd_mma.cuh"
 #include "seq_mma.cuh"
 #include "seq_r1_launch.cuh"
 #include "xproj.cuh"
@@ -33,11 +35,6 @@ R1Choice choose_r1(int I, int H, int RX, int RH) {
 // VMLMF_R1_SIMT=1 forces the SIMT R1 kernels (A/B measurements); read once
 bool simt_only() {
   static const bool v = [] { const char* e = getenv("VMLMF_R1_SIMT"); return e && e[0] == '1'; }();
-  return v;
-}
-
-int dbg_flags() {
-  static const int v = [] { const char* e = getenv("VMLMF_DBG"); return e ? atoi(e) : 0; }();
   return v;
 }
 
@@ -72,6 +69,17 @@ int vmlmf_seq_plan(int T, int B, int I, int H, int RX, int RH, vmlmf_plan* plan)
   const int rc = check_dims(T, B, I, H, RX, RH);
   if (rc) return rc;
   *plan = vmlmf_plan{};
+  plan->gates_bytes = (long long)T * B * 4 * H * (long long)sizeof(float);
+  plan->cs_bytes = (long long)T * B * H * (long long)sizeof(float);
+  if (!simt_only() && fwd_mma_fits(I, H, RX, RH) && bwd_mma_fits(I, H, RX, RH)) {
+    plan->path = VMLMF_PATH_R1M;
+    plan->zx_pitch = round_up(RX, 4);
+    plan->z_pitch = 8 * ceil_div(RH, 8);
+    plan->gates_bytes = (long long)frag_floats(T, B, H, 4) * (long long)sizeof(float);
+    plan->cs_bytes = (long long)frag_floats(T, B, H, 1) * (long long)sizeof(float);
+    plan->bwd_workspace_bytes = bwd_mma_workspace_floats(T, B, I, H, RX, RH) * (long long)sizeof(float);
+    return VMLMF_OK;
+  }
   const R1Choice c = choose_r1(I, H, RX, RH);
   if (c.ok) {
     plan->path = VMLMF_PATH_R1;
@@ -128,16 +136,20 @@ int vmlmf_seq_fwd(const vmlmf_plan* plan, const float* x, long long xs_t, long l
     if (!c.ok || plan->zx_pitch != round_up(c.rx_t, 4) || plan->z_pitch != next_pow2(c.rh_t)) return VMLMF_EPLAN;
     SeqFwdArgs a{x, xs_t, xs_b, zx, Vx, Dx, A, Bm, Dh, bias, h0, c0, y, ys_t, ys_b, hT, cT, gates, cs, z,
                  T, B, I, H, RX, RH};
-    if (!simt_only()) {              // warp-MMA kernel first; shapes it does not cover fall through to SIMT
-      const int rc2 = launch_fwd_mma(SeqFwdMmaArgs{a, plan->z_pitch, plan->zx_pitch, dbg_flags()}, save, st);
-      if (rc2 != kMmaNoFit) return rc2;
-    }
     switch (c.rx_t) {
       case 4: return launch_fwd_r1_rx4(c.rh_t, a, save, st);
       case 8: return launch_fwd_r1_rx8(c.rh_t, a, save, st);
       case 16: return launch_fwd_r1_rx16(c.rh_t, a, save, st);
     }
     return VMLMF_EUNSUPPORTED;
+  }
+  if (plan->path == VMLMF_PATH_R1M) {
+    if (!fwd_mma_fits(I, H, RX, RH) || plan->z_pitch != 8 * ceil_div(RH, 8) || plan->zx_pitch != round_up(RX, 4))
+      return VMLMF_EPLAN;
+    if ((ys_t & 1) || (ys_b & 1) || (reinterpret_cast<uintptr_t>(y) & 7)) return VMLMF_EINVAL;
+    SeqFwdArgs a{x, xs_t, xs_b, zx, Vx, Dx, A, Bm, Dh, bias, h0, c0, y, ys_t, ys_b, hT, cT, gates, cs, z,
+                 T, B, I, H, RX, RH};
+    return launch_fwd_mma(SeqFwdMmaArgs{a, plan->z_pitch, plan->zx_pitch}, save, st);
   }
   if (plan->path == VMLMF_PATH_G)
     return generic_seq_fwd(plan, x, xs_t, xs_b, zx, Ux, Vx, Dx, A, Bm, Dh, bias, h0, c0, y, ys_t, ys_b, hT, cT,
@@ -171,6 +183,18 @@ int vmlmf_seq_bwd(const vmlmf_plan* plan, const float* x, long long xs_t, long l
       case 16: return launch_bwd_r1_rx16(c.rh_t, a, o, st);
     }
     return VMLMF_EUNSUPPORTED;
+  }
+  if (plan->path == VMLMF_PATH_R1M) {
+    if (!bwd_mma_fits(I, H, RX, RH) || plan->z_pitch != 8 * ceil_div(RH, 8) || plan->zx_pitch != round_up(RX, 4))
+      return VMLMF_EPLAN;
+    if ((ys_t & 1) || (ys_b & 1) || (reinterpret_cast<uintptr_t>(y) & 7)) return VMLMF_EINVAL;
+    // reverse-time recurrence (K3a) + time-parallel gradient accumulation (K3b)
+    SeqBwdMmaArgs ba{gates, cs, c0, dy, dys_t, dys_b, dhT, dcT, Vx, A, Bm, Dh, nullptr, nullptr, dh0, dc0, T, B, H, RX, RH};
+    GradRowsArgs gr{nullptr, nullptr, z, zx, plan->z_pitch, plan->zx_pitch, y, ys_t, ys_b, h0, x, xs_t, xs_b, Ux, Dx,
+                    dx, dxs_t, dxs_b, nullptr, T, B, I, H, RX, RH, 0};
+    GradOut o{dUx, dVx, dDx, dA, dBm, dDh, dbias};
+    int nparts = 0;
+    return launch_bwd_mma(ba, gr, o, workspace, &nparts, st);
   }
   if (plan->path == VMLMF_PATH_G)
     return generic_seq_bwd(plan, x, xs_t, xs_b, zx, Ux, Vx, Dx, A, Bm, Dh, h0, c0, y, ys_t, ys_b, gates, cs, z,

@@ -80,9 +80,9 @@ class VmlmfSeqFunction(torch.autograd.Function):
         y = new((B, T, H)) if batch_first else new((T, B, H))
         hT, cT = new((B, H)), new((B, H))
         zx = new((T * B, plan.zx_pitch))
-        need_grad = torch.is_grad_enabled() and any(ctx.needs_input_grad)
+        need_grad = any(ctx.needs_input_grad)
         if need_grad:
-            gates, cs, z = new((T, B, 4, H)), new((T, B, H)), new((T * B, plan.z_pitch))
+            gates, cs, z = new((plan.gates_bytes // 4,)), new((plan.cs_bytes // 4,)), new((T * B, plan.z_pitch))
         else:
             gates = cs = z = None
         ws = new((plan.fwd_workspace_bytes + 3) // 4) if plan.fwd_workspace_bytes else None
