@@ -20,6 +20,17 @@ TOL = 1e-5
 DEV = "cuda:0"
 
 
+@pytest.fixture(params=["auto", "mma", "simt"], autouse=True)
+def r1_path(request, monkeypatch):
+    """Run every test three times: with the library's own regime choice, with the warp-MMA kernels forced
+    for every shape they cover (VMLMF_MMA_MIN_BATCH=1), and with the SIMT kernels forced (VMLMF_R1_SIMT=1)."""
+    if request.param == "mma":
+        monkeypatch.setenv("VMLMF_MMA_MIN_BATCH", "1")
+    elif request.param == "simt":
+        monkeypatch.setenv("VMLMF_R1_SIMT", "1")
+    return request.param
+
+
 def _load(module, g):
     sd = {k[len("param/"):]: torch.from_numpy(v) for k, v in g.items() if k.startswith("param/")}
     module.load_state_dict(sd)
@@ -128,6 +139,9 @@ def _rand_canon(rng, I, H, RX, RH, scale=0.3):
 
 @pytest.mark.parametrize("T,B,I,H,RX,RH,bf,state", [
     (1, 1, 3, 5, 1, 1, True, False),        # smallest everything
+    (3, 37, 12, 20, 2, 3, True, True),      # H % 4 == 0 but not % 16, two ragged 16-sequence tiles, KS = 1
+    (4, 19, 9, 128, 8, 12, False, True),    # group-cell sized ranks: KS = 3, NZ = 2
+    (2, 50, 40, 44, 9, 16, True, False),    # KS = 4 (RH + RX + 1 = 26), I close to H
     (7, 5, 9, 33, 8, 6, True, True),        # H not a multiple of 32, ragged batch tile
     (5, 13, 16, 16, 3, 2, False, True),     # I == H, time-major
     (24, 81, 77, 180, 8, 6, True, False),   # reference unit-test shape
@@ -223,7 +237,13 @@ def test_benchmark_configs_vs_cpu_oracle(name, build, shape, classes, kind):
             assert_close(p.grad.cpu().numpy(), go[k].numpy(), TOL, k)
 
 
-def test_full_size_properties_cfg2():
+def test_regime_choice_matches_plan(r1_path):
+    from vmlmf_b200 import _lib
+    want = {"auto": (_lib.PATH_R1, _lib.PATH_R1M), "mma": (_lib.PATH_R1M, _lib.PATH_R1M), "simt": (_lib.PATH_R1, _lib.PATH_R1)}
+    assert (_lib.plan(24, 81, 77, 256, 8, 6).path, _lib.plan(24, 8192, 77, 256, 8, 6).path) == want[r1_path]
+
+
+def test_full_size_properties_cfg2(r1_path):
     """B=8192 (the bench workload): batch independence, run-to-run bit reproducibility, and
     linearity of every gradient in the upstream gradient."""
     torch.manual_seed(3)
@@ -232,7 +252,10 @@ def test_full_size_properties_cfg2():
     with torch.no_grad():
         full = net(x)
         sub = net(x[1000:1037])
-    assert torch.equal(full[1000:1037], sub)               # sequences never interact in forward
+    if r1_path == "auto":      # 8192 sequences plan the warp-MMA kernels, 37 the SIMT ones: same math, different rounding
+        assert_close(full[1000:1037].cpu().numpy(), sub.cpu().numpy(), 2e-6, "batch independence across regimes")
+    else:
+        assert torch.equal(full[1000:1037], sub)           # sequences never interact in forward (bitwise within a regime)
 
     def grads(scale):
         net.zero_grad()

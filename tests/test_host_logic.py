@@ -28,6 +28,14 @@ def test_library_exports_every_declared_symbol():
 def test_plan_and_error_codes():
     p = _lib.plan(24, 81, 77, 256, 8, 6)
     assert p.path == _lib.PATH_R1 and p.zx_pitch == 8 and p.z_pitch == 8 and p.bwd_workspace_bytes > 0
+    assert p.gates_bytes == 24 * 81 * 4 * 256 * 4 and p.cs_bytes == 24 * 81 * 256 * 4
+    # large batches plan the warp-MMA path: saved state padded to whole 16-sequence x 16-unit fragments
+    p = _lib.plan(24, 8200, 77, 180, 8, 6)
+    assert p.path == _lib.PATH_R1M and p.zx_pitch == 8 and p.z_pitch == 8
+    assert p.gates_bytes == 24 * 513 * 4 * 12 * 256 * 4 and p.cs_bytes * 4 == p.gates_bytes
+    assert p.bwd_workspace_bytes >= p.gates_bytes
+    assert _lib.plan(24, 8200, 77, 181, 8, 6).path == _lib.PATH_R1          # H % 4 != 0 stays on the SIMT kernels
+    assert _lib.plan(35, 4096, 650, 650, 300, 300).path == _lib.PATH_G
     with pytest.raises(TypeError):                       # H < I: the reference raises TypeError too
         _lib.plan(4, 2, 20, 10, 4, 4)
     with pytest.raises(RuntimeError):

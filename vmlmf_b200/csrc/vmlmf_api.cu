@@ -15,6 +15,8 @@ using namespace vmlmf;
 
 namespace {
 
+const int kMmaMinBatch = 1536;
+
 // smallest compiled template rank >= r, or -1
 int pick(const int* list, int n, int r) {
   for (int i = 0; i < n; ++i)
@@ -32,10 +34,15 @@ R1Choice choose_r1(int I, int H, int RX, int RH) {
   return c;
 }
 
-// VMLMF_R1_SIMT=1 forces the SIMT R1 kernels (A/B measurements); read once
+// VMLMF_R1_SIMT=1 forces the SIMT R1 kernels (A/B measurements, tests); read at plan time
 bool simt_only() {
-  static const bool v = [] { const char* e = getenv("VMLMF_R1_SIMT"); return e && e[0] == '1'; }();
-  return v;
+  const char* e = getenv("VMLMF_R1_SIMT");
+  return e && e[0] == '1';
+}
+// VMLMF_MMA_MIN_BATCH overrides the batch size from which the warp-MMA path is planned (tests force it to 1)
+int mma_min_batch() {
+  const char* e = getenv("VMLMF_MMA_MIN_BATCH");
+  return e ? atoi(e) : kMmaMinBatch;
 }
 
 int check_dims(int T, int B, int I, int H, int RX, int RH) {
@@ -71,7 +78,10 @@ int vmlmf_seq_plan(int T, int B, int I, int H, int RX, int RH, vmlmf_plan* plan)
   *plan = vmlmf_plan{};
   plan->gates_bytes = (long long)T * B * 4 * H * (long long)sizeof(float);
   plan->cs_bytes = (long long)T * B * H * (long long)sizeof(float);
-  if (!simt_only() && fwd_mma_fits(I, H, RX, RH) && bwd_mma_fits(I, H, RX, RH)) {
+  // warp-MMA kernels tile 16 sequences per CTA: they win once the batch fills most SMs (measured crossover
+  // on B200 between B = 1024 and 2048 at H = 256); below that the SIMT kernels (4 / 2
+  // sequences per CTA) have the lower per-step latency.
+  if (!simt_only() && B >= mma_min_batch() && fwd_mma_fits(I, H, RX, RH) && bwd_mma_fits(I, H, RX, RH)) {
     plan->path = VMLMF_PATH_R1M;
     plan->zx_pitch = round_up(RX, 4);
     plan->z_pitch = 8 * ceil_div(RH, 8);
