@@ -61,7 +61,7 @@ def _require_cuda(*ts):
 
 class VmlmfSeqFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, h0, c0, Ux, Vx, Dx, A, Bm, Dh, bias, batch_first):
+    def forward(ctx, x, h0, c0, Ux, Vx, Dx, A, Bm, Dh, bias, batch_first, save=True):
         _require_cuda(x, h0, c0, Ux, Vx, Dx, A, Bm, Dh, bias)
         x = _row_contig(x)
         params = [p.contiguous() for p in (Ux, Vx, Dx, A, Bm, Dh, bias)]
@@ -80,7 +80,9 @@ class VmlmfSeqFunction(torch.autograd.Function):
         y = new((B, T, H)) if batch_first else new((T, B, H))
         hT, cT = new((B, H)), new((B, H))
         zx = new((T * B, plan.zx_pitch))
-        need_grad = any(ctx.needs_input_grad)
+        # grad mode is always off inside Function.forward and needs_input_grad ignores torch.no_grad():
+        # the caller (vmlmf_sequence) decides whether anything has to be kept for backward
+        need_grad = save and any(ctx.needs_input_grad)
         if need_grad:
             gates, cs, z = new((plan.gates_bytes // 4,)), new((plan.cs_bytes // 4,)), new((T * B, plan.z_pitch))
         else:
@@ -135,9 +137,10 @@ class VmlmfSeqFunction(torch.autograd.Function):
                                          _ptr(dcT), _ptr(dx), dxs[0], dxs[1], _ptr(dh0), _ptr(dc0), _ptr(dUx),
                                          _ptr(dVx), _ptr(dDx), _ptr(dA), _ptr(dBm), _ptr(dDh), _ptr(dbias), _ptr(ws),
                                          T, B, I, H, RX, RH, st))
-        return dx, dh0, dc0, dUx, dVx, dDx, dA, dBm, dDh, dbias, None
+        return dx, dh0, dc0, dUx, dVx, dDx, dA, dBm, dDh, dbias, None, None
 
 
 def vmlmf_sequence(x, h0, c0, canon, batch_first=True):
     """Run one VMLMF layer over a whole sequence.  canon = (Ux,Vx,Dx,A,Bm,Dh,bias)."""
-    return VmlmfSeqFunction.apply(x, h0, c0, *canon, batch_first)
+    save = torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (x, h0, c0, *canon))
+    return VmlmfSeqFunction.apply(x, h0, c0, *canon, batch_first, save)
