@@ -1,0 +1,427 @@
+// gemm_tc.cuh -- fp32-accurate GEMM on the 5th-generation tensor cores (sm_100a):
+//     C[M,N] (+epilogue) = A[M,K] * B[N,K]^T          A, B fp32, K-major (row pitch in floats, % 4 == 0)
+// TMA (cp.async.bulk.tensor, 128-byte swizzle) stages raw fp32 tiles in shared memory; four "split" warps turn
+// every tile into a tf32 hi part (in place) and a lo part (second buffer, same swizzled offsets); one elected
+// thread issues tcgen05.mma.kind::tf32 three times per 8-deep k-step (lo*hi, hi*lo, hi*hi -- 3xTF32 error
+// compensation, fp32 accumulate in TMEM); the same four warps read the accumulator back with tcgen05.ld and run
+// the epilogue functor.  Pipeline: kStages smem stages, mbarriers  full (TMA landed) -> split (hi/lo ready) ->
+// empty (MMAs that read the stage have completed, via tcgen05.commit).
+//
+// This is the time-parallel x-side product of the VMLMF cells ((x U_x) V_x^T with bias and the vector-
+// multiplication term fused in the epilogue: V/models/vmlmf.py:98,103-104,109; vmlmf_lm.py:246,256) and the
+// per-timestep hidden-side products of the generic regime (V/models/vmlmf_lm.py:247; vmlmf.py:99).
+//
+// B can also be a rank-3 view [4][H][K] (the four gate blocks of a [4H,K] factor): the tile then holds
+// 4 gates x 32 units, so one accumulator row carries i,f,o,n of 32 hidden units and the LSTM cell update runs in
+// the epilogue (EpiGate32).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace vmlmf {
+namespace tc {
+
+constexpr int BM = 128, BN = 128, BK = 32;          // tile: 128 x 128, 32 fp32 (= 128 bytes, one swizzle row) deep
+constexpr int kStages = 3;
+constexpr int kTileBytes = BM * BK * 4;             // 16 KB per operand tile (BN == BM)
+constexpr int kStageBytes = 4 * kTileBytes;         // A hi | A lo | B hi | B lo
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+constexpr int kThreads = 192;                       // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: split + epilogue
+constexpr int kAcc = 4;                             // accumulators: hi*hi round-robin over 3, cross terms in the 4th
+constexpr int kTmemCols = kAcc * BN;                // 4 x (128 lanes x 128 fp32 columns) = all 512 TMEM columns
+
+// ------------------------------------------------------------------------------------------------- PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ float tf32r(float v) {       // round to nearest tf32, returned as fp32 bits
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// shared-memory matrix descriptor: K-major tile, rows of 128 bytes, SWIZZLE_128B, 8-row groups 1024 bytes apart
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);            // start address
+  d |= (uint64_t)1 << 16;                            // leading byte offset (unused with 128B swizzle, K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                            // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
+  return d;
+}
+// instruction descriptor: D = f32, A = B = tf32, both K-major, M = 128, N = BN
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_tf32_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 8 consecutive fp32 columns of one accumulator -> 8 registers per thread
+__device__ __forceinline__ void tmem_ld8_raw(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// sum of the `nacc` accumulators that were written (column offset BN apart); waits for the loads
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, int nhi, float (&v)[8]) {
+  float a[8], b[8];
+  tmem_ld8_raw(taddr, v);                 // hi*hi accumulator 0
+  tmem_ld8_raw(taddr + 3 * 128, a);       // cross terms
+  tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] += a[i];
+  if (nhi > 1) {
+    tmem_ld8_raw(taddr + 128, a);
+    if (nhi > 2) tmem_ld8_raw(taddr + 256, b);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] += a[i];
+    if (nhi > 2) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] += b[i];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------- epilogues
+// Plain epilogues get (row m, first column n0 of 8 consecutive columns, the 8 values).
+struct EpiStoreTC {                      // C[m, n] = v (+ C[m, n] when beta)
+  float* C; long long ldc; int beta;
+  static constexpr bool kGate = false;
+  __device__ void operator()(int m, int n0, int N, const float (&v)[8]) const {
+    float* c = C + (size_t)m * ldc + n0;
+    if (!beta && n0 + 8 <= N && ((reinterpret_cast<uintptr_t>(c) & 15) == 0)) {
+      reinterpret_cast<float4*>(c)[0] = make_float4(v[0], v[1], v[2], v[3]);
+      reinterpret_cast<float4*>(c)[1] = make_float4(v[4], v[5], v[6], v[7]);
+      return;
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      if (n0 + q < N) c[q] = beta ? c[q] + v[q] : v[q];
+  }
+};
+struct EpiXPTC {                         // XP[m, kH+j] = v + bias[kH+j] + [j<I] x[m,j] Dx[k,j]
+  float* xp; const float* bias; const float* x; long long xs_t, xs_b; int Bsz; const float* Dx; int H, I;
+  static constexpr bool kGate = false;
+  __device__ void operator()(int m, int n0, int N, const float (&v)[8]) const {
+    const float* xr = x + (long long)(m / Bsz) * xs_t + (long long)(m % Bsz) * xs_b;
+    float out[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int nn = n0 + q;
+      float r = 0.f;
+      if (nn < N) {
+        const int k = nn / H, j = nn - k * H;
+        r = v[q] + __ldg(bias + nn);
+        if (j < I) r = fmaf(__ldg(xr + j), __ldg(Dx + k * I + j), r);
+      }
+      out[q] = r;
+    }
+    float* c = xp + (size_t)m * N + n0;
+    if (n0 + 8 <= N && ((reinterpret_cast<uintptr_t>(c) & 15) == 0)) {
+      reinterpret_cast<float4*>(c)[0] = make_float4(out[0], out[1], out[2], out[3]);
+      reinterpret_cast<float4*>(c)[1] = make_float4(out[4], out[5], out[6], out[7]);
+    } else {
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (n0 + q < N) c[q] = out[q];
+    }
+  }
+};
+// Gate epilogue (B is the rank-3 view): called with the four gates of 8 consecutive hidden units j0..j0+7 of row m.
+struct EpiGate32 {
+  const float* xp_t;        // XP rows of this step   [B, 4H]
+  const float* hprev; long long hp_sb;    // h_{t-1}[b] = hprev + b*hp_sb (null = zeros)
+  const float* cprev;                     // [B,H] or null
+  const float* Dh;
+  float* y_t; long long y_sb;
+  float* c_out;                           // [B,H]
+  float* gates_t;                         // [B,4,H] or null
+  float *hT, *cT;                         // written on the last step only (else null)
+  int H;
+  static constexpr bool kGate = true;
+  __device__ void operator()(int m, int j0, const float (&g)[4][8]) const {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int j = j0 + q;
+      if (j >= H) continue;
+      const float hp = hprev ? hprev[(size_t)m * hp_sb + j] : 0.f;
+      const float cp = cprev ? cprev[(size_t)m * H + j] : 0.f;
+      const float* xr = xp_t + (size_t)m * 4 * H + j;
+      float pre[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) pre[k] = g[k][q] + xr[(size_t)k * H] + hp * __ldg(Dh + k * H + j);
+      const float gi = sigmoidf_acc(pre[0]), gf = sigmoidf_acc(pre[1]);
+      const float go = sigmoidf_acc(pre[2]), gn = tanhf_acc(pre[3]);
+      const float c = fmaf(gf, cp, gi * gn);
+      const float h = go * tanhf_acc(c);
+      y_t[(size_t)m * y_sb + j] = h;
+      c_out[(size_t)m * H + j] = c;
+      if (gates_t) {
+        float* gp = gates_t + (size_t)m * 4 * H + j;
+        gp[0] = gi; gp[H] = gf; gp[2 * H] = go; gp[3 * H] = gn;
+      }
+      if (hT) { hT[(size_t)m * H + j] = h; cT[(size_t)m * H + j] = c; }
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------- kernel
+// grid = (ceil(N / BN) [or ceil(H / 32) for the gate view], ceil(M / BM)); one output tile per CTA.
+template <class Epi>
+__global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                              const __grid_constant__ CUtensorMap mapB, int M, int N,
+                                                              int K, Epi epi) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* full = bars;                        // [kStages] TMA bytes landed
+  uint64_t* split = bars + kStages;             // [kStages] hi/lo tiles written (4 warps arrive)
+  uint64_t* empty = bars + 2 * kStages;         // [kStages] MMAs reading the stage completed
+  uint64_t* accf = bars + 3 * kStages;          // accumulator complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kStages + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BM;
+  const int n_tile = blockIdx.x;
+  const int nkb = (K + BK - 1) / BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&split[s], 4); mbar_init(&empty[s], 1); }
+    mbar_init(accf, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % kStages, it = kb / kStages;
+        if (it > 0) mbar_wait(&empty[s], (it - 1) & 1);
+        uint8_t* st = smem + s * kStageBytes;
+        mbar_arrive_expect_tx(&full[s], 2 * kTileBytes);
+        tma_load_2d(st, &mapA, kb * BK, m0, &full[s]);
+        if (Epi::kGate) tma_load_3d(st + 2 * kTileBytes, &mapB, kb * BK, n_tile * 32, 0, &full[s]);
+        else tma_load_2d(st + 2 * kTileBytes, &mapB, kb * BK, n_tile * BN, &full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(BM, BN);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % kStages, it = kb / kStages;
+        mbar_wait(&split[s], it & 1);
+        tc_fence_after();
+        const uint32_t a_hi = smem_u32(smem + s * kStageBytes), a_lo = a_hi + kTileBytes;
+        const uint32_t b_hi = a_hi + 2 * kTileBytes, b_lo = a_hi + 3 * kTileBytes;
+        // The tensor core adds into the fp32 accumulator with truncation, so the error grows with the number of
+        // accumulations into one accumulator (measured ~3e-8 relative per add).  The large hi*hi products are
+        // spread round-robin over three accumulators, the small cross terms go to a fourth; the epilogue adds
+        // the four in fp32.
+#pragma unroll
+        for (int k = 0; k < BK / 8; ++k) {               // 8 tf32 = 32 bytes per k-step inside the 128-byte swizzle row
+          const uint32_t off = k * 32;
+          const int kk = kb * (BK / 8) + k;
+          mma_tf32_ss(tmem_d + 3 * BN, make_desc(a_lo + off), make_desc(b_hi + off), idesc, kk ? 1u : 0u);
+          mma_tf32_ss(tmem_d + 3 * BN, make_desc(a_hi + off), make_desc(b_lo + off), idesc, 1u);
+          mma_tf32_ss(tmem_d + (kk % 3) * BN, make_desc(a_hi + off), make_desc(b_hi + off), idesc, kk >= 3 ? 1u : 0u);
+        }
+        mma_commit(&empty[s]);                           // stage reusable once these MMAs have read it
+      }
+      mma_commit(accf);                                  // accumulator complete
+    }
+  } else {
+    // ================= split warps, then epilogue =================
+    const int sw = warp - 2;                             // 0..3
+    const int st_tid = sw * 32 + lane;                   // 0..127
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % kStages, it = kb / kStages;
+      mbar_wait(&full[s], it & 1);
+      float4* a_hi = reinterpret_cast<float4*>(smem + s * kStageBytes);
+      float4* a_lo = a_hi + kTileBytes / 16;
+      float4* b_hi = a_hi + 2 * kTileBytes / 16;
+      float4* b_lo = a_hi + 3 * kTileBytes / 16;
+      // elementwise at identical offsets: the swizzle pattern of the TMA write is preserved
+#pragma unroll 4
+      for (int i = st_tid; i < kTileBytes / 16; i += 128) {
+        const float4 va = a_hi[i], vb = b_hi[i];
+        float4 ha, la, hb, lb;
+        ha.x = tf32r(va.x); ha.y = tf32r(va.y); ha.z = tf32r(va.z); ha.w = tf32r(va.w);
+        la.x = tf32r(va.x - ha.x); la.y = tf32r(va.y - ha.y); la.z = tf32r(va.z - ha.z); la.w = tf32r(va.w - ha.w);
+        hb.x = tf32r(vb.x); hb.y = tf32r(vb.y); hb.z = tf32r(vb.z); hb.w = tf32r(vb.w);
+        lb.x = tf32r(vb.x - hb.x); lb.y = tf32r(vb.y - hb.y); lb.z = tf32r(vb.z - hb.z); lb.w = tf32r(vb.w - hb.w);
+        a_hi[i] = ha; a_lo[i] = la; b_hi[i] = hb; b_lo[i] = lb;
+      }
+      fence_proxy_async();                               // generic-proxy writes -> visible to the tensor-core (async) proxy
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&split[s]);
+    }
+    // ---- epilogue: warp sw reads TMEM lanes [32*(warp%4), +32) = rows m0 + 32*(warp%4) + lane ----
+    mbar_wait(accf, 0);
+    tc_fence_after();
+    const int lane_grp = warp & 3;                       // TMEM lane quarter this warp may access
+    const int m = m0 + lane_grp * 32 + lane;
+    const uint32_t tbase = tmem_d + ((uint32_t)(lane_grp * 32) << 16);
+    const int nks = nkb * (BK / 8);
+    const int nhi = nks < 3 ? nks : 3;                   // hi*hi accumulators that received at least one product
+    if constexpr (Epi::kGate) {
+#pragma unroll 1
+      for (int ub = 0; ub < 4; ++ub) {                   // 8 hidden units at a time: columns k*32 + 8*ub .. +7 of gate k
+        float g[4][8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) tmem_ld8(tbase + k * 32 + ub * 8, nhi, g[k]);
+        if (m < M) epi(m, n_tile * 32 + ub * 8, g);
+      }
+    } else {
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 8) {
+        float v[8];
+        tmem_ld8(tbase + c, nhi, v);
+        if (m < M && n_tile * BN + c < N) epi(m, n_tile * BN + c, N, v);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(kTmemCols));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------- host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess) p = nullptr;
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+constexpr int kTcNoFit = -1001;
+
+// rows x K fp32 matrix, row pitch ld floats: box = 32 (K) x 128 rows
+inline int make_map_2d(CUtensorMap* map, const float* p, long long rows, long long K, long long ld) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return kTcNoFit;
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {BK, BM};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(p), dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : kTcNoFit;
+}
+// [4][H][K] view of a [4H, K] factor (row pitch ld): box = 32 (K) x 32 units x 4 gates
+inline int make_map_gate3d(CUtensorMap* map, const float* p, long long H, long long K, long long ld) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return kTcNoFit;
+  cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)H, 4};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)H * ld * 4};
+  cuuint32_t box[3] = {BK, 32, 4};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(p), dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : kTcNoFit;
+}
+inline bool tc_operand_ok(const float* p, long long ld) {
+  return ((reinterpret_cast<uintptr_t>(p) & 15) == 0) && (ld % 4 == 0) && ld > 0;
+}
+
+// C = A[M,K] B[N,K]^T with a plain epilogue.  Returns kTcNoFit when an operand does not meet the TMA constraints.
+template <class Epi>
+inline int gemm_tc(const float* A, long long lda, const float* Bm, long long ldb, int M, int N, int K, Epi epi,
+                   cudaStream_t st) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if (!tc_operand_ok(A, lda) || !tc_operand_ok(Bm, ldb)) return kTcNoFit;
+  CUtensorMap ma, mb;
+  int rc = make_map_2d(&ma, A, M, K, lda);
+  if (rc) return rc;
+  rc = Epi::kGate ? make_map_gate3d(&mb, Bm, N / 4, K, ldb) : make_map_2d(&mb, Bm, N, K, ldb);
+  if (rc) return rc;
+  auto kern = gemm_tc_kernel<Epi>;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) return (int)e;
+    attr = true;
+  }
+  const int ntn = Epi::kGate ? ceil_div(N / 4, 32) : ceil_div(N, BN);
+  dim3 grid(ntn, ceil_div(M, BM));
+  kern<<<grid, kThreads, kSmemBytes, st>>>(ma, mb, M, N, K, epi);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace tc
+}  // namespace vmlmf
