@@ -148,9 +148,9 @@ def _rand_canon(rng, I, H, RX, RH, scale=0.3):
     (9, 3, 30, 256, 16, 8, False, True),    # widest compiled ranks at H=256
     (6, 7, 4, 64, 4, 16, True, True),
 ])
-def test_canonical_kernels_vs_numpy_spec(T, B, I, H, RX, RH, bf, state):
+def test_canonical_kernels_vs_numpy_spec(T, B, I, H, RX, RH, bf, state, scale=0.3):
     rng = np.random.default_rng(T * 1000 + B)
-    cp = _rand_canon(rng, I, H, RX, RH)
+    cp = _rand_canon(rng, I, H, RX, RH, scale)
     x = rng.standard_normal((T, B, I)).astype(np.float32)
     h0 = (rng.standard_normal((B, H)) * .5).astype(np.float32) if state else None
     c0 = (rng.standard_normal((B, H)) * .5).astype(np.float32) if state else None
@@ -180,6 +180,23 @@ def test_canonical_kernels_vs_numpy_spec(T, B, I, H, RX, RH, bf, state):
     if state:
         assert_close(h0t.grad.cpu().numpy(), g64["dh0"], TOL, "dh0")
         assert_close(c0t.grad.cpu().numpy(), g64["dc0"], TOL, "dc0")
+
+
+@pytest.mark.parametrize("gemm", ["tcgen05", "simt"])
+@pytest.mark.parametrize("T,B,I,H,RX,RH,bf,state", [
+    (4, 20, 650, 650, 300, 300, False, True),    # the LM layer (V/models/vmlmf_lm.py, hidden 650, ranks 300), carried state
+    (3, 150, 12, 40, 20, 24, True, False),       # ranks beyond R1, ragged 128-row tile, H < one 128-column tile
+    (2, 9, 8, 300, 8, 8, False, True),           # H > 256 with small ranks: K = 8 (one tf32 k-step)
+])
+def test_generic_regime_vs_numpy_spec(T, B, I, H, RX, RH, bf, state, gemm, monkeypatch):
+    """Regime G (time-parallel XP GEMM + per-step GEMMs): with the tcgen05/TMA 3xTF32 GEMM and with the SIMT GEMM."""
+    from vmlmf_b200 import _lib
+    if gemm == "simt":
+        monkeypatch.setenv("VMLMF_G_SIMT", "1")
+    assert _lib.plan(T, B, I, H, RX, RH).path == _lib.PATH_G
+    # the LM initialises U(-0.05, 0.05) (V/train_test/lm_test.py:57); 0.3-scale factors at H = 650 would drive every
+    # pre-activation to |40| and make the comparison a test of saturation, not of the kernels
+    test_canonical_kernels_vs_numpy_spec(T, B, I, H, RX, RH, bf, state, scale=0.05 if H >= 300 else 0.3)
 
 
 def test_inference_mode_matches_training_forward_and_noncontiguous_upstream():

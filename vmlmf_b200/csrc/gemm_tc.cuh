@@ -194,6 +194,7 @@ struct EpiGate32 {
   float* c_out;                           // [B,H]
   float* gates_t;                         // [B,4,H] or null
   float *hT, *cT;                         // written on the last step only (else null)
+  float* hpad; int hp4;                   // padded copy of h_t, row pitch hp4 (% 4 == 0): next step's TMA operand
   int H;
   static constexpr bool kGate = true;
   __device__ void operator()(int m, int j0, const float (&g)[4][8]) const {
@@ -212,6 +213,7 @@ struct EpiGate32 {
       const float c = fmaf(gf, cp, gi * gn);
       const float h = go * tanhf_acc(c);
       y_t[(size_t)m * y_sb + j] = h;
+      hpad[(size_t)m * hp4 + j] = h;
       c_out[(size_t)m * H + j] = c;
       if (gates_t) {
         float* gp = gates_t + (size_t)m * 4 * H + j;

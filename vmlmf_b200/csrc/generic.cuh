@@ -14,7 +14,10 @@
 // through RowView so batch-first and time-major tensors need no copies.
 #pragma once
 #include "../../include/vmlmf_b200.h"
+#include <stdlib.h>
+
 #include "common.cuh"
+#include "gemm_tc.cuh"
 
 namespace vmlmf {
 
@@ -299,6 +302,9 @@ constexpr int kColSplits = 64;
 struct GenericSizes {
   int zxp, zp;
   long long n_xp, n_dpre, n_dz, n_dzx, n_state, n_part;
+  long long n_at, n_uxt;        // forward: A^T [RH, Hp], Ux^T [RX, Ip]   (B operands of the tensor-core GEMMs are K-major)
+  long long n_bmt, n_vxt;       // backward: Bm^T [RH, 4H], Vx^T [RX, 4H]
+  int hp4, ip4;
 };
 inline GenericSizes generic_sizes(int T, int B, int I, int H, int RX, int RH) {
   GenericSizes s;
@@ -316,6 +322,12 @@ inline GenericSizes generic_sizes(int T, int B, int I, int H, int RX, int RH) {
   q = (long long)g_splits(I, RX, rows) * I * RX; if (q > p) p = q;             // dUx
   q = (long long)kColSplits * (8 * H + 4 * I); if (q > p) p = q;               // column reductions
   s.n_part = p;
+  s.hp4 = round_up(H, 4);
+  s.ip4 = round_up(I, 4);
+  s.n_at = (long long)RH * s.hp4;
+  s.n_uxt = (long long)RX * s.ip4;
+  s.n_bmt = (long long)RH * 4 * H;
+  s.n_vxt = (long long)RX * 4 * H;
   return s;
 }
 
@@ -325,10 +337,36 @@ inline int generic_plan(int T, int B, int I, int H, int RX, int RH, vmlmf_plan* 
   plan->zx_pitch = s.zxp;
   plan->z_pitch = s.zp;
   plan->xp_cols = 4 * H;
-  plan->fwd_workspace_bytes = (s.n_xp + 2 * s.n_state + (long long)B * s.zp) * (long long)sizeof(float);
-  plan->bwd_workspace_bytes = (s.n_dpre + s.n_dz + s.n_dzx + 2 * s.n_state + s.n_part) * (long long)sizeof(float);
+  plan->fwd_workspace_bytes = (s.n_xp + 2 * s.n_state + (long long)B * s.zp + s.n_at + s.n_uxt + 2 * (long long)B * s.hp4 + 16) * (long long)sizeof(float);
+  plan->bwd_workspace_bytes = (s.n_dpre + s.n_dz + s.n_dzx + 2 * s.n_state + s.n_part + s.n_bmt + s.n_vxt + 8) * (long long)sizeof(float);
   return VMLMF_OK;
 }
+
+// dst[c, r] = src[r, c]  (src [R, C] row-major, dst row pitch ldd >= R); tiny factors only
+static __global__ void transpose_kernel(const float* __restrict__ src, int R, int Cc, float* __restrict__ dst, int ldd) {
+  __shared__ float tile[32][33];
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < R && c < Cc) ? src[(size_t)r * Cc + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (c < Cc && r < ldd) dst[(size_t)c * ldd + r] = (r < R) ? tile[threadIdx.x][i] : 0.f;
+  }
+}
+inline int transpose_launch(const float* src, int R, int Cc, float* dst, int ldd, cudaStream_t st) {
+  dim3 grid(ceil_div(Cc, 32), ceil_div(ldd, 32));
+  transpose_kernel<<<grid, dim3(32, 8), 0, st>>>(src, R, Cc, dst, ldd);
+  return (int)cudaGetLastError();
+}
+// VMLMF_G_SIMT=1 keeps every GEMM of the generic regime on the SIMT kernel (A/B measurements, tests)
+inline bool g_simt_only() {
+  const char* e = getenv("VMLMF_G_SIMT");
+  return e && e[0] == '1';
+}
+inline float* align4(float* p) { return reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(p) + 15) & ~(uintptr_t)15); }
 
 // ZX = X Ux, pad columns zeroed
 static __global__ void zero_pad_cols_kernel(float* z, long long rows, int pitch, int R) {
@@ -364,10 +402,25 @@ inline int generic_seq_fwd(const vmlmf_plan* plan, const float* x, long long xs_
   if (rows * 4 * H > (1LL << 40) || rows > 0x7fffffff) return VMLMF_EUNSUPPORTED;
   float* xp = (float*)workspace;
   float* cbuf[2] = {xp + s.n_xp, xp + s.n_xp + s.n_state};      // running c when not saving
-  float* zscratch = xp + s.n_xp + 2 * s.n_state;                 // z_t when not saving  [B, zp]
-  // time-parallel: XP = ZX Vx^T + bias + x (.) Dx
-  G_TRY((gemm_launch<false, true>(plain_view(zx, s.zxp), plain_view(Vx, RX), (int)rows, 4 * H, RX, 1, NIdent{},
-                                  EpiXP{xp, bias, tb_view(x, xs_t, xs_b, B), Dx, H, I}, st)));
+  float* zscratch = align4(xp + s.n_xp + 2 * s.n_state);         // z_t when not saving  [B, zp], 16-byte aligned (TMA operand)
+  const bool use_tc = !g_simt_only();
+  float* at = align4(zscratch + (size_t)B * s.zp);               // A^T [RH, hp4] for the tensor-core z GEMM
+  // time-parallel: XP = ZX Vx^T + bias + x (.) Dx   (tcgen05 3xTF32 GEMM; SIMT when an operand misses the TMA constraints)
+  {
+    int rc = tc::kTcNoFit;
+    if (use_tc) rc = tc::gemm_tc(zx, s.zxp, Vx, RX, (int)rows, 4 * H, RX, tc::EpiXPTC{xp, bias, x, xs_t, xs_b, B, Dx, H, I}, st);
+    if (rc == tc::kTcNoFit)
+      rc = gemm_launch<false, true>(plain_view(zx, s.zxp), plain_view(Vx, RX), (int)rows, 4 * H, RX, 1, NIdent{},
+                                    EpiXP{xp, bias, tb_view(x, xs_t, xs_b, B), Dx, H, I}, st);
+    G_TRY(rc);
+  }
+  float* hpad[2] = {align4(at + s.n_at), nullptr};               // padded h_t ping-pong [B, hp4]
+  hpad[1] = hpad[0] + (size_t)B * s.hp4;
+  const bool tc_step = use_tc && tc::tc_operand_ok(Bm, RH) && (!z || tc::tc_operand_ok(z, s.zp)) && tc::encode_fn() != nullptr;
+  if (tc_step) {
+    G_TRY(transpose_launch(A, H, RH, at, s.hp4, st));
+    if (h0) G_TRY((int)cudaMemcpy2DAsync(hpad[1], (size_t)s.hp4 * 4, h0, (size_t)H * 4, (size_t)H * 4, B, cudaMemcpyDeviceToDevice, st));
+  }
   const bool save = gates != nullptr;
   for (int t = 0; t < T; ++t) {
     const float* hprev = t ? y + (size_t)(t - 1) * ys_t : h0;
@@ -380,15 +433,30 @@ inline int generic_seq_fwd(const vmlmf_plan* plan, const float* x, long long xs_
         const long long n = (long long)B * (s.zp - RH);
         zero_pad_cols_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(zdst, B, s.zp, RH);
       }
-      G_TRY((gemm_launch<false, false>(RowView{const_cast<float*>(hprev), 0, hp_sb, 0x7fffffff}, plain_view(A, RH), B, RH,
-                                       H, 1, NIdent{}, EpiStore{plain_view(zdst, s.zp), 0}, st)));
+      int rc = tc::kTcNoFit;
+      if (tc_step) rc = tc::gemm_tc(hpad[(t + 1) & 1], s.hp4, at, s.hp4, B, RH, H, tc::EpiStoreTC{zdst, s.zp, 0}, st);
+      if (rc == tc::kTcNoFit) {
+        if (tc_step) return VMLMF_EUNSUPPORTED;
+        rc = gemm_launch<false, false>(RowView{const_cast<float*>(hprev), 0, hp_sb, 0x7fffffff}, plain_view(A, RH), B, RH, H,
+                                       1, NIdent{}, EpiStore{plain_view(zdst, s.zp), 0}, st);
+      }
+      G_TRY(rc);
     } else {
       G_TRY((int)cudaMemsetAsync(zdst, 0, (size_t)B * s.zp * sizeof(float), st));
     }
     const bool last = (t == T - 1);
     EpiGate eg{xp + (size_t)t * B * 4 * H, hprev, hp_sb, cprev, Dh, y + (size_t)t * ys_t, ys_b, cout,
                save ? gates + (size_t)t * B * 4 * H : nullptr, last ? hT : nullptr, last ? cT : nullptr, H};
-    G_TRY((gemm_launch<false, true>(plain_view(zdst, s.zp), plain_view(Bm, RH), B, 4 * H, RH, 1, NGate{H}, eg, st)));
+    int rc = tc::kTcNoFit;
+    if (tc_step) {
+      tc::EpiGate32 eg32{eg.xp_t, eg.hprev, eg.hp_sb, eg.cprev, eg.Dh, eg.y_t, eg.y_sb, eg.c_out, eg.gates_t, eg.hT, eg.cT, hpad[t & 1], s.hp4, H};
+      rc = tc::gemm_tc(zdst, s.zp, Bm, RH, B, 4 * H, RH, eg32, st);       // B = [4][H][RH] view: tile = 4 gates x 32 units
+    }
+    if (rc == tc::kTcNoFit) {
+      if (tc_step) return VMLMF_EUNSUPPORTED;            // the padded h copy is only maintained by the tensor-core epilogue
+      rc = gemm_launch<false, true>(plain_view(zdst, s.zp), plain_view(Bm, RH), B, 4 * H, RH, 1, NGate{H}, eg, st);
+    }
+    G_TRY(rc);
   }
   return VMLMF_OK;
 }
