@@ -120,6 +120,25 @@ struct EpiDX {              // dX[m,j] = acc + sum_k dPre[m,kH+j] Dx[k,j]
   }
 };
 
+struct EpiDXTC {            // tensor-core epilogue of dX = dZX Ux^T + sum_k dPre_k Dx_k  (8 columns per call)
+  float* dx; long long dxs_t, dxs_b; int Bsz; const float* dpre; const float* Dx; int H, I;
+  static constexpr bool kGate = false;
+  __device__ void operator()(int m, int n0, int N, const float (&v)[8]) const {
+    float* o = dx + (long long)(m / Bsz) * dxs_t + (long long)(m % Bsz) * dxs_b;
+    const float* dp = dpre + (size_t)m * 4 * H;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int j = n0 + q;
+      if (j < N) {
+        float r = v[q];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) r = fmaf(dp[k * H + j], Dx[k * I + j], r);
+        o[j] = r;
+      }
+    }
+  }
+};
+
 // C[m,n] = sum_k Aop(m,k) Bop(k,n).
 //   A_T=false: A stored [M rows][K cols]   A_T=true: stored [K rows][M cols]
 //   B_T=false: B stored [K rows][N cols]   B_T=true: stored [N rows][K cols], row = nmap(n)
@@ -487,6 +506,11 @@ inline int generic_seq_bwd(const vmlmf_plan* plan, const float* x, long long xs_
   else G_TRY((int)cudaMemsetAsync(dc, 0, sb, st));
   if (s.zp > RH) G_TRY((int)cudaMemsetAsync(dz, 0, (size_t)s.n_dz * sizeof(float), st));
 
+  const bool use_tc = !g_simt_only() && tc::encode_fn() != nullptr;
+  float* bmt = align4(part + s.n_part);                          // Bm^T [RH, 4H]
+  float* vxt = align4(bmt + s.n_bmt);                            // Vx^T [RX, 4H]
+  const bool tc_step = use_tc && tc::tc_operand_ok(dpre, 4 * H) && tc::tc_operand_ok(dz, s.zp) && tc::tc_operand_ok(A, RH);
+  if (tc_step) G_TRY(transpose_launch(Bm, 4 * H, RH, bmt, 4 * H, st));
   const int nel = B * H;
   for (int t = T - 1; t >= 0; --t) {
     DpreArgs da{gates + (size_t)t * B * 4 * H, cs + (size_t)t * B * H, t ? cs + (size_t)(t - 1) * B * H : c0,
@@ -495,11 +519,19 @@ inline int generic_seq_bwd(const vmlmf_plan* plan, const float* x, long long xs_
     G_TRY((int)cudaGetLastError());
     float* dzt = dz + (size_t)t * B * s.zp;
     // dz_t = dPre_t Bm        [B,4H] x [4H,RH]
-    G_TRY((gemm_launch<false, false>(plain_view(dpre + (size_t)t * B * 4 * H, 4 * H), plain_view(Bm, RH), B, RH, 4 * H, 1,
-                                     NIdent{}, EpiStore{plain_view(dzt, s.zp), 0}, st)));
+    int rc = tc::kTcNoFit;
+    if (tc_step) rc = tc::gemm_tc(dpre + (size_t)t * B * 4 * H, 4 * H, bmt, 4 * H, B, RH, 4 * H, tc::EpiStoreTC{dzt, s.zp, 0}, st);
+    if (rc == tc::kTcNoFit)
+      rc = gemm_launch<false, false>(plain_view(dpre + (size_t)t * B * 4 * H, 4 * H), plain_view(Bm, RH), B, RH, 4 * H, 1,
+                                     NIdent{}, EpiStore{plain_view(dzt, s.zp), 0}, st);
+    G_TRY(rc);
     // dh_{t-1} = (sum_k dpre_k Dh_k) + dz_t A^T
-    G_TRY((gemm_launch<false, true>(plain_view(dzt, s.zp), plain_view(A, RH), B, H, RH, 1, NIdent{},
-                                    EpiStore{plain_view(dh, H), 1}, st)));
+    rc = tc::kTcNoFit;
+    if (tc_step) rc = tc::gemm_tc(dzt, s.zp, A, RH, B, H, RH, tc::EpiStoreTC{dh, H, 1}, st);
+    if (rc == tc::kTcNoFit)
+      rc = gemm_launch<false, true>(plain_view(dzt, s.zp), plain_view(A, RH), B, H, RH, 1, NIdent{},
+                                    EpiStore{plain_view(dh, H), 1}, st);
+    G_TRY(rc);
   }
   if (dh0) G_TRY((int)cudaMemcpyAsync(dh0, dh, sb, cudaMemcpyDeviceToDevice, st));
   if (dc0) G_TRY((int)cudaMemcpyAsync(dc0, dc, sb, cudaMemcpyDeviceToDevice, st));
@@ -541,8 +573,17 @@ inline int generic_seq_bwd(const vmlmf_plan* plan, const float* x, long long xs_
   }
   // dZX = dPre Vx    [T*B,RX]
   if (s.zxp > RX) G_TRY((int)cudaMemsetAsync(dzx, 0, (size_t)s.n_dzx * sizeof(float), st));
-  G_TRY((gemm_launch<false, false>(dPv, plain_view(Vx, RX), (int)rows, RX, 4 * H, 1, NIdent{},
-                                   EpiStore{plain_view(dzx, s.zxp), 0}, st)));
+  {
+    int rc = tc::kTcNoFit;
+    if (use_tc && tc::tc_operand_ok(dpre, 4 * H) && tc::tc_operand_ok(dzx, s.zxp)) {
+      G_TRY(transpose_launch(Vx, 4 * H, RX, vxt, 4 * H, st));
+      rc = tc::gemm_tc(dpre, 4 * H, vxt, 4 * H, (int)rows, RX, 4 * H, tc::EpiStoreTC{dzx, s.zxp, 0}, st);
+    }
+    if (rc == tc::kTcNoFit)
+      rc = gemm_launch<false, false>(dPv, plain_view(Vx, RX), (int)rows, RX, 4 * H, 1, NIdent{},
+                                     EpiStore{plain_view(dzx, s.zxp), 0}, st);
+    G_TRY(rc);
+  }
   // dUx = X^T dZX    [I,RX]
   {
     const int sp = g_splits(I, RX, rows);
@@ -550,9 +591,15 @@ inline int generic_seq_bwd(const vmlmf_plan* plan, const float* x, long long xs_
     G_TRY(reduce_to(sp, (long long)I * RX, dUx));
   }
   // dX = dZX Ux^T + sum_k dPre[:, kH:kH+I] (.) Dx_k
-  if (dx)
-    G_TRY((gemm_launch<false, true>(plain_view(dzx, s.zxp), plain_view(Ux, RX), (int)rows, I, RX, 1, NIdent{},
-                                    EpiDX{tb_view(dx, dxs_t, dxs_b, B), dpre, Dx, H, I}, st)));
+  if (dx) {
+    int rc = tc::kTcNoFit;
+    if (use_tc && tc::tc_operand_ok(dzx, s.zxp) && tc::tc_operand_ok(Ux, RX))
+      rc = tc::gemm_tc(dzx, s.zxp, Ux, RX, (int)rows, I, RX, EpiDXTC{dx, dxs_t, dxs_b, B, dpre, Dx, H, I}, st);
+    if (rc == tc::kTcNoFit)
+      rc = gemm_launch<false, true>(plain_view(dzx, s.zxp), plain_view(Ux, RX), (int)rows, I, RX, 1, NIdent{},
+                                    EpiDX{tb_view(dx, dxs_t, dxs_b, B), dpre, Dx, H, I}, st);
+    G_TRY(rc);
+  }
   // dbias, dDh, dDx
   {
     long long rps = (rows + kColSplits - 1) / kColSplits;
