@@ -163,6 +163,11 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly one JSON line: anything a library prints meanwhile (e.g. NCCL's version banner) goes
+    # to stderr; the line itself is written to the saved descriptor at the end
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the fused path has no CPU fallback")
     torch.cuda.set_device(local)
@@ -366,7 +371,8 @@ def run_ours(args):
         "recurrence_latency": latency,
         "grad_allreduce_bytes": bucket.nbytes,
     }
-    print(json.dumps(out))
+    sys.stdout.flush()
+    os.write(json_fd, (json.dumps(out) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
