@@ -184,13 +184,15 @@ def test_canonical_kernels_vs_numpy_spec(T, B, I, H, RX, RH, bf, state, scale=0.
 
 @pytest.mark.parametrize("gemm", ["tcgen05", "simt"])
 @pytest.mark.parametrize("T,B,I,H,RX,RH,bf,state", [
-    (4, 20, 650, 650, 300, 300, False, True),    # the LM layer (V/models/vmlmf_lm.py, hidden 650, ranks 300), carried state
+    (3, 20, 650, 650, 300, 300, False, True),    # the LM layer (V/models/vmlmf_lm.py, hidden 650, ranks 300), carried state
     (3, 150, 12, 40, 20, 24, True, False),       # ranks beyond R1, ragged 128-row tile, H < one 128-column tile
     (2, 9, 8, 300, 8, 8, False, True),           # H > 256 with small ranks: K = 8 (one tf32 k-step)
 ])
-def test_generic_regime_vs_numpy_spec(T, B, I, H, RX, RH, bf, state, gemm, monkeypatch):
+def test_generic_regime_vs_numpy_spec(T, B, I, H, RX, RH, bf, state, gemm, monkeypatch, r1_path):
     """Regime G (time-parallel XP GEMM + per-step GEMMs): with the tcgen05/TMA 3xTF32 GEMM and with the SIMT GEMM."""
     from vmlmf_b200 import _lib
+    if r1_path != "auto":
+        pytest.skip("regime G does not depend on the R1 kernel choice")
     if gemm == "simt":
         monkeypatch.setenv("VMLMF_G_SIMT", "1")
     assert _lib.plan(T, B, I, H, RX, RH).path == _lib.PATH_G

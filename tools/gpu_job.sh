@@ -1,2 +1,9 @@
-timeout 600 python -m pytest tests -q -m gpu -k "generic_regime or lm or group_g4" 2>&1 | tail -4
-for B in 20 512; do python tools/time_lm.py $B; VMLMF_G_SIMT=1 python tools/time_lm.py $B; done
+python -m pytest tests -q -m gpu -x 2>&1 | tail -4
+python tools/time_fwd.py 2>&1 | grep -E "clocks under|^train"
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"seq_|grad_rows|reduce_partials|xproj" -s 8 -c 5 --csv --log-file gpurun_out/launches_mma.csv python tools/prof_step.py 8192 3 > /dev/null 2>&1
+grep -v "^==" gpurun_out/launches_mma.csv | python -c "
+import csv,sys
+for r in csv.DictReader(sys.stdin):
+    print(r['Kernel Name'][:70], r['Metric Value'])
+"
+build/test_gemm_tc | grep -E "rel|ms per|OK|FAIL"

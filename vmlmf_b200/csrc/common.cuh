@@ -50,6 +50,13 @@ __device__ __forceinline__ float tanhf_acc(float v) {
 }
 #endif
 
+// Round an fp32 value to the nearest tf32 (10 explicit mantissa bits, ties away from zero, like cvt.rna.tf32.f32),
+// returned as an fp32 bit pattern with the low 13 bits cleared.  Two integer instructions; ptxas expands
+// cvt.rna.tf32.f32 into five (it also canonicalises NaN, which never reaches these kernels).
+__device__ __forceinline__ float tf32_rna(float v) {
+  return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
+}
+
 // Sum N (power of two, <= 32) per-lane values across the 32 lanes of a warp with
 // N-1 + log2(32/N) shuffles instead of 5N ("transposing" butterfly: every stage halves the
 // number of live values, each lane keeps the half selected by one of its lane-id bits).

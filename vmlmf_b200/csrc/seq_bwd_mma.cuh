@@ -351,34 +351,38 @@ __global__ void __launch_bounds__(NT_MAX, 1) grad_rows_kernel(const GradRowsArgs
     const int b0 = tile * 16;
     const int nvalid = (B - b0) < 16 ? (B - b0) : 16;
     const float* dblk = a.dpre + frag_addr((size_t)blk, 4, 0, NW, warp, 0, 0, 0);
+    // per-block bases (row rr of the block = sequence b0 + rr at timestep t); everything below adds small constants
+    const size_t rbase = (size_t)t * B + b0;
+    const float* hbase = nullptr;                        // h_{t-1} row of sequence b0, this lane's unit pair
+    long long hstride = 0;
+    if (uin) {
+      if (t > 0) { hbase = a.y + (size_t)(t - 1) * a.ys_t + (size_t)b0 * a.ys_b + ju; hstride = a.ys_b; }
+      else if (a.h0) { hbase = a.h0 + (size_t)b0 * H + ju; hstride = H; }
+    }
+    const float* xbase = a.x + (size_t)t * a.xs_t + (size_t)b0 * a.xs_b + ju;
+    const float* dlane = dblk + (Pg * 2) * 64 + (q * 4 + qq) * 2;          // + k*qstride + ks*64 (+32 for row q+4)
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks) {                     // k-step = 8 sequences (hf = ks): lane holds rows q and q+4 of it
       const int rr0 = 8 * ks + q, rr1 = rr0 + 4;
       const bool v0 = rr0 < nvalid, v1 = rr1 < nvalid;
-      const size_t r0 = (size_t)t * B + b0 + rr0, r1 = r0 + 4;
+      const size_t r0 = rbase + rr0, r1 = r0 + 4;
       // dPre pieces: (gate k, P = g>>2, hf = ks, source lane = row-in-half * 4 + qq)
       float2 d0[4], d1[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const float* base = dblk + (size_t)k * qstride + (Pg * 2 + ks) * 64;
-        d0[k] = __ldg(reinterpret_cast<const float2*>(base + (q * 4 + qq) * 2));
-        d1[k] = __ldg(reinterpret_cast<const float2*>(base + ((q + 4) * 4 + qq) * 2));
+        d0[k] = __ldg(reinterpret_cast<const float2*>(dlane + (size_t)k * qstride + ks * 64));
+        d1[k] = __ldg(reinterpret_cast<const float2*>(dlane + (size_t)k * qstride + ks * 64 + 32));
       }
       // h_{t-1} pairs of this lane's units (same for the four gates)
       float2 h0v = make_float2(0.f, 0.f), h1v = h0v;
-      if (uin) {
-        if (t > 0) {
-          if (v0) h0v = __ldg(reinterpret_cast<const float2*>(a.y + (size_t)(t - 1) * a.ys_t + (size_t)(b0 + rr0) * a.ys_b + ju));
-          if (v1) h1v = __ldg(reinterpret_cast<const float2*>(a.y + (size_t)(t - 1) * a.ys_t + (size_t)(b0 + rr1) * a.ys_b + ju));
-        } else if (a.h0) {
-          if (v0) h0v = __ldg(reinterpret_cast<const float2*>(a.h0 + (size_t)(b0 + rr0) * H + ju));
-          if (v1) h1v = __ldg(reinterpret_cast<const float2*>(a.h0 + (size_t)(b0 + rr1) * H + ju));
-        }
+      if (hbase) {
+        if (v0) h0v = __ldg(reinterpret_cast<const float2*>(hbase + (long long)rr0 * hstride));
+        if (v1) h1v = __ldg(reinterpret_cast<const float2*>(hbase + (long long)rr1 * hstride));
       }
       float2 x0v = make_float2(0.f, 0.f), x1v = x0v;
       if (xcols) {
-        const float* xp0 = a.x + (size_t)t * a.xs_t + (size_t)(b0 + rr0) * a.xs_b + ju;
-        const float* xp1 = a.x + (size_t)t * a.xs_t + (size_t)(b0 + rr1) * a.xs_b + ju;
+        const float* xp0 = xbase + (long long)rr0 * a.xs_b;
+        const float* xp1 = xbase + (long long)rr1 * a.xs_b;
         if (ju < I) { if (v0) x0v.x = __ldg(xp0); if (v1) x1v.x = __ldg(xp1); }
         if (ju + 1 < I) { if (v0) x0v.y = __ldg(xp0 + 1); if (v1) x1v.y = __ldg(xp1 + 1); }
       }

@@ -37,12 +37,6 @@ struct SeqFwdMmaArgs {
   int zp, zxp;      // row pitch of saved z / of zx (floats)
 };
 
-__device__ __forceinline__ float tf32_rna(float v) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-  return __uint_as_float(r);
-}
-
 // d += a(16x8, row) * b(8x8, col), tf32 inputs (fp32 bit patterns), fp32 accumulate
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const float (&a)[4], float b0, float b1) {
   asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
