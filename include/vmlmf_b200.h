@@ -73,6 +73,15 @@ const char* vmlmf_strerror(int code);
 /* Which regime runs these sizes, and how big the caller-owned scratch buffers must be. */
 int vmlmf_seq_plan(int T, int B, int I, int H, int RX, int RH, vmlmf_plan* plan);
 
+/* K0 / K5: the loop-invariant diagonal corrections, hoisted out of the time loop (the reference recomputes them
+ * in every step: V/models/vmlmf.py:102-106, vmlmf_lm.py:250-255) and their chain rule.
+ *   D[k,j] = dia[j] - sum_r u[j,r] v[kH+j,r]          u[n,R]  v[4H,R]  dia[n]  D[4,n]   (n = I or H, n <= H)
+ *   du[j,r] = -sum_k dD[k,j] v[kH+j,r]    dv[kH+j,r] = -dD[k,j] u[j,r] (0 for j >= n)    ddia[j] = sum_k dD[k,j]   */
+int vmlmf_diag_fwd(const float* u, const float* v, const float* dia, float* D, int n, int H, int R,
+                   void* stream);
+int vmlmf_diag_bwd(const float* u, const float* v, const float* dD, float* du, float* dv, float* ddia,
+                   int n, int H, int R, void* stream);
+
 /* K1: zx[t,b,:] = x[t,b,:] Ux for every timestep at once (time-parallel half of
  * `torch.matmul(x, self.u_x)`, V/models/vmlmf.py:98, vmlmf_group.py:98, vmlmf_lm.py:246).
  * zx is [T*B, plan.zx_pitch], pad columns written as 0.                               */

@@ -256,6 +256,27 @@ def test_benchmark_configs_vs_cpu_oracle(name, build, shape, classes, kind):
             assert_close(p.grad.cpu().numpy(), go[k].numpy(), TOL, k)
 
 
+@pytest.mark.parametrize("n,H,R", [(9, 128, 8), (77, 180, 6), (650, 650, 300), (1, 1, 1)])
+def test_fused_diag_correction_matches_torch(n, H, R, r1_path):
+    """K0 / K5 (vmlmf_diag_fwd / _bwd) against the torch formula of packing._diag_corr, values and chain rule."""
+    if r1_path != "auto":
+        pytest.skip("independent of the recurrence regime")
+    from vmlmf_b200 import packing
+    from vmlmf_b200.functional import diag_correction
+    g = torch.Generator(device=DEV).manual_seed(n * 7 + R)
+    mk = lambda *s: torch.randn(*s, device=DEV, generator=g, dtype=torch.float64)
+    u64, v64, d64, w64 = mk(n, R), mk(4 * H, R), mk(1, n), mk(4, n)
+    ref_in = [t.clone().requires_grad_(True) for t in (u64, v64, d64)]
+    ref = ref_in[2].reshape(1, n) - packing._diag_corr(ref_in[0], ref_in[1], n)
+    (ref * w64).sum().backward()
+    got_in = [t.float().requires_grad_(True) for t in (u64, v64, d64)]
+    got = diag_correction(*got_in)
+    (got * w64.float()).sum().backward()
+    assert_close(got.detach().cpu().numpy(), ref.detach().cpu().numpy(), 2e-6, "D")
+    for a, b, name in zip(got_in, ref_in, ("du", "dv", "ddia")):
+        assert_close(a.grad.cpu().numpy(), b.grad.cpu().numpy(), 2e-6, name)
+
+
 def test_regime_choice_matches_plan(r1_path):
     from vmlmf_b200 import _lib
     want = {"auto": (_lib.PATH_R1, _lib.PATH_R1M), "mma": (_lib.PATH_R1M, _lib.PATH_R1M), "simt": (_lib.PATH_R1, _lib.PATH_R1)}

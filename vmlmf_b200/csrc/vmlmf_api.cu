@@ -108,6 +108,23 @@ int vmlmf_seq_plan(int T, int B, int I, int H, int RX, int RH, vmlmf_plan* plan)
   return generic_plan(T, B, I, H, RX, RH, plan);
 }
 
+int vmlmf_diag_fwd(const float* u, const float* v, const float* dia, float* D, int n, int H, int R, void* stream) {
+  if (!u || !v || !dia || !D || n <= 0 || H <= 0 || R <= 0) return VMLMF_EINVAL;
+  if (n > H) return VMLMF_ESHAPE;
+  const long long threads = 4LL * n * 32;
+  diag_fwd_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(u, v, dia, D, n, H, R);
+  return (int)cudaGetLastError();
+}
+
+int vmlmf_diag_bwd(const float* u, const float* v, const float* dD, float* du, float* dv, float* ddia, int n, int H,
+                   int R, void* stream) {
+  if (!u || !v || !dD || !du || !dv || !ddia || n <= 0 || H <= 0 || R <= 0) return VMLMF_EINVAL;
+  if (n > H) return VMLMF_ESHAPE;
+  const long long threads = 4LL * H * R;
+  diag_bwd_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(u, v, dD, du, dv, ddia, n, H, R);
+  return (int)cudaGetLastError();
+}
+
 int vmlmf_xproj_fwd(const float* x, long long xs_t, long long xs_b, const float* Ux, float* zx, int T,
                     int B, int I, int RX, int zx_pitch, void* stream) {
   if (!x || !Ux || !zx || T <= 0 || B <= 0 || I <= 0 || RX <= 0) return VMLMF_EINVAL;

@@ -53,4 +53,37 @@ static __global__ void __launch_bounds__(128) xproj_small_kernel(const float* __
   }
 }
 
+// ---- K0 / K5: diagonal corrections of the vector-multiplication terms and their chain rule ----
+// one warp per (gate k, row j): D[k,j] = dia[j] - <u[j,:], v[kH+j,:]>
+static __global__ void diag_fwd_kernel(const float* __restrict__ u, const float* __restrict__ v,
+                                       const float* __restrict__ dia, float* __restrict__ D, int n, int H, int R) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= 4 * n) return;
+  const int k = w / n, j = w - k * n;
+  const float* ur = u + (size_t)j * R;
+  const float* vr = v + ((size_t)k * H + j) * R;
+  float s = 0.f;
+  for (int r = lane; r < R; r += 32) s = fmaf(__ldg(ur + r), __ldg(vr + r), s);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) D[w] = __ldg(dia + j) - s;
+}
+// one thread per element of dv [4H, R]; the first n*R threads also produce du, the first n ddia
+static __global__ void diag_bwd_kernel(const float* __restrict__ u, const float* __restrict__ v,
+                                       const float* __restrict__ dD, float* __restrict__ du, float* __restrict__ dv,
+                                       float* __restrict__ ddia, int n, int H, int R) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)4 * H * R) return;
+  const int row = (int)(i / R), r = (int)(i - (long long)row * R);
+  const int k = row / H, j = row - k * H;
+  dv[i] = j < n ? -__ldg(dD + k * n + j) * __ldg(u + (size_t)j * R + r) : 0.f;
+  if (i < (long long)n * R) {                 // here row = j < n <= H (k == 0), column r
+    float s = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) s = fmaf(__ldg(dD + kk * n + row), __ldg(v + ((size_t)kk * H + row) * R + r), s);
+    du[i] = -s;
+  }
+  if (i < n) ddia[i] = __ldg(dD + i) + __ldg(dD + n + i) + __ldg(dD + 2 * n + i) + __ldg(dD + 3 * n + i);
+}
+
 }  // namespace vmlmf

@@ -140,6 +140,42 @@ class VmlmfSeqFunction(torch.autograd.Function):
         return dx, dh0, dc0, dUx, dVx, dDx, dA, dBm, dDh, dbias, None, None
 
 
+class DiagCorrFunction(torch.autograd.Function):
+    """D[k,j] = dia[j] - sum_r u[j,r] v[kH+j,r]  and its chain rule, one kernel each way (K0 / K5).
+    The reference recomputes this inside every timestep (V/models/vmlmf.py:102-106)."""
+
+    @staticmethod
+    def forward(ctx, u, v, dia):
+        _require_cuda(u, v, dia)
+        u, v, d1 = u.contiguous(), v.contiguous(), dia.reshape(-1).contiguous()
+        n, r = u.shape
+        hidden = v.shape[0] // 4
+        out = u.new_empty((4, n))
+        with torch.cuda.device_of(u):
+            st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            _lib.check(_lib.lib().vmlmf_diag_fwd(_ptr(u), _ptr(v), _ptr(d1), _ptr(out), n, hidden, r, st))
+        ctx.save_for_backward(u, v)
+        ctx.dia_shape = dia.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        u, v = ctx.saved_tensors
+        n, r = u.shape
+        hidden = v.shape[0] // 4
+        d_out = d_out.contiguous()
+        du, dv, ddia = torch.empty_like(u), torch.empty_like(v), u.new_empty((n,))
+        with torch.cuda.device_of(u):
+            st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            _lib.check(_lib.lib().vmlmf_diag_bwd(_ptr(u), _ptr(v), _ptr(d_out), _ptr(du), _ptr(dv), _ptr(ddia), n, hidden, r, st))
+        return du, dv, ddia.view(ctx.dia_shape)
+
+
+def diag_correction(u, v, dia):
+    """[4,n] vector-multiplication coefficients of one side (n = rows of u)."""
+    return DiagCorrFunction.apply(u, v, dia)
+
+
 def vmlmf_sequence(x, h0, c0, canon, batch_first=True):
     """Run one VMLMF layer over a whole sequence.  canon = (Ux,Vx,Dx,A,Bm,Dh,bias)."""
     save = torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (x, h0, c0, *canon))

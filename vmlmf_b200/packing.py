@@ -24,8 +24,12 @@ def _diag_corr(u, v, n):
 def pack_plain(u_x, u_h, v_x, v_h, b_x, b_h, dia_x, dia_h):
     """MyVMLMFCell (V/models/vmlmf.py:78-125) and MyVMLSTM (vmlmf_lm.py:222-269, v=w_x/w_h)."""
     n_in, hidden = u_x.shape[0], u_h.shape[0]
-    dx = dia_x.reshape(1, n_in) - _diag_corr(u_x, v_x, n_in)
-    dh = dia_h.reshape(1, hidden) - _diag_corr(u_h, v_h, hidden)
+    if u_x.is_cuda:                      # fused: one kernel per side each way (host-side tests use the torch form below)
+        from .functional import diag_correction
+        dx, dh = diag_correction(u_x, v_x, dia_x), diag_correction(u_h, v_h, dia_h)
+    else:
+        dx = dia_x.reshape(1, n_in) - _diag_corr(u_x, v_x, n_in)
+        dh = dia_h.reshape(1, hidden) - _diag_corr(u_h, v_h, hidden)
     return u_x, v_x, dx, u_h, v_h, dh, b_x.reshape(-1) + b_h.reshape(-1)
 
 
