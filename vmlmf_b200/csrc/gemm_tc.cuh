@@ -29,6 +29,7 @@ constexpr int kStages = 3;
 constexpr int kTileBytes = BM * BK * 4;             // 16 KB per operand tile (BN == BM)
 constexpr int kStageBytes = 4 * kTileBytes;         // A hi | A lo | B hi | B lo
 constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+constexpr int kEpiPitch = BN + 4;                    // staged accumulator row pitch (floats): conflict-free both ways
 constexpr int kThreads = 192;                       // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: split + epilogue
 constexpr int kAcc = 4;                             // accumulators: hi*hi round-robin over 3, cross terms in the 4th
 constexpr int kTmemCols = kAcc * BN;                // 4 x (128 lanes x 128 fp32 columns) = all 512 TMEM columns
@@ -136,51 +137,38 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, int nhi, float (&v)[8])
 }
 
 // ------------------------------------------------------------------------------------------------- epilogues
-// Plain epilogues get (row m, first column n0 of 8 consecutive columns, the 8 values).
+// The accumulator tile is staged in shared memory and handed out one ROW per call to a whole warp:
+// lane l receives the four values of columns n0 + l + 32*i (i = 0..3), so every global access is a contiguous
+// 128-byte segment per warp instruction.
 struct EpiStoreTC {                      // C[m, n] = v (+ C[m, n] when beta)
   float* C; long long ldc; int beta;
   static constexpr bool kGate = false;
-  __device__ void operator()(int m, int n0, int N, const float (&v)[8]) const {
-    float* c = C + (size_t)m * ldc + n0;
-    if (!beta && n0 + 8 <= N && ((reinterpret_cast<uintptr_t>(c) & 15) == 0)) {
-      reinterpret_cast<float4*>(c)[0] = make_float4(v[0], v[1], v[2], v[3]);
-      reinterpret_cast<float4*>(c)[1] = make_float4(v[4], v[5], v[6], v[7]);
-      return;
-    }
+  __device__ void operator()(int m, int n0, int N, int lane, const float (&v)[4]) const {
+    float* c = C + (size_t)m * ldc + n0 + lane;
 #pragma unroll
-    for (int q = 0; q < 8; ++q)
-      if (n0 + q < N) c[q] = beta ? c[q] + v[q] : v[q];
+    for (int i = 0; i < 4; ++i)
+      if (n0 + lane + 32 * i < N) c[32 * i] = beta ? c[32 * i] + v[i] : v[i];
   }
 };
 struct EpiXPTC {                         // XP[m, kH+j] = v + bias[kH+j] + [j<I] x[m,j] Dx[k,j]
   float* xp; const float* bias; const float* x; long long xs_t, xs_b; int Bsz; const float* Dx; int H, I;
   static constexpr bool kGate = false;
-  __device__ void operator()(int m, int n0, int N, const float (&v)[8]) const {
+  __device__ void operator()(int m, int n0, int N, int lane, const float (&v)[4]) const {
     const float* xr = x + (long long)(m / Bsz) * xs_t + (long long)(m % Bsz) * xs_b;
-    float out[8];
+    float* c = xp + (size_t)m * N;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const int nn = n0 + q;
-      float r = 0.f;
+    for (int i = 0; i < 4; ++i) {
+      const int nn = n0 + lane + 32 * i;
       if (nn < N) {
         const int k = nn / H, j = nn - k * H;
-        r = v[q] + __ldg(bias + nn);
+        float r = v[i] + __ldg(bias + nn);
         if (j < I) r = fmaf(__ldg(xr + j), __ldg(Dx + k * I + j), r);
+        c[nn] = r;
       }
-      out[q] = r;
-    }
-    float* c = xp + (size_t)m * N + n0;
-    if (n0 + 8 <= N && ((reinterpret_cast<uintptr_t>(c) & 15) == 0)) {
-      reinterpret_cast<float4*>(c)[0] = make_float4(out[0], out[1], out[2], out[3]);
-      reinterpret_cast<float4*>(c)[1] = make_float4(out[4], out[5], out[6], out[7]);
-    } else {
-#pragma unroll
-      for (int q = 0; q < 8; ++q)
-        if (n0 + q < N) c[q] = out[q];
     }
   }
 };
-// Gate epilogue (B is the rank-3 view): called with the four gates of 8 consecutive hidden units j0..j0+7 of row m.
+// Gate epilogue (B is the rank-3 view, tile = 4 gates x 32 units): lane l receives i,f,o,n of hidden unit j0 + l.
 struct EpiGate32 {
   const float* xp_t;        // XP rows of this step   [B, 4H]
   const float* hprev; long long hp_sb;    // h_{t-1}[b] = hprev + b*hp_sb (null = zeros)
@@ -193,30 +181,31 @@ struct EpiGate32 {
   float* hpad; int hp4;                   // padded copy of h_t, row pitch hp4 (% 4 == 0): next step's TMA operand
   int H;
   static constexpr bool kGate = true;
-  __device__ void operator()(int m, int j0, const float (&g)[4][8]) const {
+  struct In { float xp[4], hp, cp; };
+  // global operands of (row m, unit j): issued for several rows before any of them is consumed
+  __device__ void load(int m, int j, In& in) const {
+    const float* xr = xp_t + (size_t)m * 4 * H + j;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const int j = j0 + q;
-      if (j >= H) continue;
-      const float hp = hprev ? hprev[(size_t)m * hp_sb + j] : 0.f;
-      const float cp = cprev ? cprev[(size_t)m * H + j] : 0.f;
-      const float* xr = xp_t + (size_t)m * 4 * H + j;
-      float pre[4];
+    for (int k = 0; k < 4; ++k) in.xp[k] = __ldg(xr + (size_t)k * H);
+    in.hp = hprev ? hprev[(size_t)m * hp_sb + j] : 0.f;
+    in.cp = cprev ? cprev[(size_t)m * H + j] : 0.f;
+  }
+  __device__ void finish(int m, int j, const float (&g)[4], const In& in, const float (&dh)[4]) const {
+    float pre[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) pre[k] = g[k][q] + xr[(size_t)k * H] + hp * __ldg(Dh + k * H + j);
-      const float gi = sigmoidf_acc(pre[0]), gf = sigmoidf_acc(pre[1]);
-      const float go = sigmoidf_acc(pre[2]), gn = tanhf_acc(pre[3]);
-      const float c = fmaf(gf, cp, gi * gn);
-      const float h = go * tanhf_acc(c);
-      y_t[(size_t)m * y_sb + j] = h;
-      hpad[(size_t)m * hp4 + j] = h;
-      c_out[(size_t)m * H + j] = c;
-      if (gates_t) {
-        float* gp = gates_t + (size_t)m * 4 * H + j;
-        gp[0] = gi; gp[H] = gf; gp[2 * H] = go; gp[3 * H] = gn;
-      }
-      if (hT) { hT[(size_t)m * H + j] = h; cT[(size_t)m * H + j] = c; }
+    for (int k = 0; k < 4; ++k) pre[k] = g[k] + in.xp[k] + in.hp * dh[k];
+    const float gi = sigmoidf_acc(pre[0]), gf = sigmoidf_acc(pre[1]);
+    const float go = sigmoidf_acc(pre[2]), gn = tanhf_acc(pre[3]);
+    const float c = fmaf(gf, in.cp, gi * gn);
+    const float h = go * tanhf_acc(c);
+    y_t[(size_t)m * y_sb + j] = h;
+    hpad[(size_t)m * hp4 + j] = h;
+    c_out[(size_t)m * H + j] = c;
+    if (gates_t) {
+      float* gp = gates_t + (size_t)m * 4 * H + j;
+      gp[0] = gi; gp[H] = gf; gp[2 * H] = go; gp[3 * H] = gn;
     }
+    if (hT) { hT[(size_t)m * H + j] = h; cT[(size_t)m * H + j] = c; }
   }
 };
 
@@ -319,28 +308,55 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       __syncwarp();
       if (lane == 0) mbar_arrive(&split[s]);
     }
-    // ---- epilogue: warp sw reads TMEM lanes [32*(warp%4), +32) = rows m0 + 32*(warp%4) + lane ----
+    // ---- epilogue: TMEM -> registers -> shared memory (row per thread), then one row per warp with lane <-> column
     mbar_wait(accf, 0);
     tc_fence_after();
     const int lane_grp = warp & 3;                       // TMEM lane quarter this warp may access
-    const int m = m0 + lane_grp * 32 + lane;
     const uint32_t tbase = tmem_d + ((uint32_t)(lane_grp * 32) << 16);
     const int nks = nkb * (BK / 8);
     const int nhi = nks < 3 ? nks : 3;                   // hi*hi accumulators that received at least one product
-    if constexpr (Epi::kGate) {
-#pragma unroll 1
-      for (int ub = 0; ub < 4; ++ub) {                   // 8 hidden units at a time: columns k*32 + 8*ub .. +7 of gate k
-        float g[4][8];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) tmem_ld8(tbase + k * 32 + ub * 8, nhi, g[k]);
-        if (m < M) epi(m, n_tile * 32 + ub * 8, g);
-      }
-    } else {
+    float* S = reinterpret_cast<float*>(smem);           // [128][kEpiPitch]: the pipeline stages are idle by now
+    {
+      float* srow = S + (size_t)(lane_grp * 32 + lane) * kEpiPitch;
 #pragma unroll 1
       for (int c = 0; c < BN; c += 8) {
         float v[8];
         tmem_ld8(tbase + c, nhi, v);
-        if (m < M && n_tile * BN + c < N) epi(m, n_tile * BN + c, N, v);
+        reinterpret_cast<float4*>(srow + c)[0] = make_float4(v[0], v[1], v[2], v[3]);
+        reinterpret_cast<float4*>(srow + c)[1] = make_float4(v[4], v[5], v[6], v[7]);
+      }
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");       // the four epilogue warps only
+    const int n0 = Epi::kGate ? n_tile * 32 : n_tile * BN;
+    if constexpr (Epi::kGate) {
+      // four rows in flight per warp: all global operands are requested before the first row is finished
+      const int j = n0 + lane;
+      if (j < epi.H) {
+        float dh[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) dh[k] = __ldg(epi.Dh + k * epi.H + j);
+#pragma unroll 1
+        for (int r = sw; r < BM; r += 16) {
+          typename Epi::In in[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (m0 + r + 4 * u < M) epi.load(m0 + r + 4 * u, j, in[u]);
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (m0 + r + 4 * u < M) {
+              const float* srow = S + (size_t)(r + 4 * u) * kEpiPitch + lane;
+              const float g[4] = {srow[0], srow[32], srow[64], srow[96]};
+              epi.finish(m0 + r + 4 * u, j, g, in[u], dh);
+            }
+        }
+      }
+    } else {
+      for (int r = sw; r < BM; r += 4) {
+        const int m = m0 + r;
+        if (m >= M) break;
+        const float* srow = S + (size_t)r * kEpiPitch + lane;
+        const float v[4] = {srow[0], srow[32], srow[64], srow[96]};
+        epi(m, n0, N, lane, v);
       }
     }
   }

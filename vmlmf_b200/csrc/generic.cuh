@@ -120,17 +120,17 @@ struct EpiDX {              // dX[m,j] = acc + sum_k dPre[m,kH+j] Dx[k,j]
   }
 };
 
-struct EpiDXTC {            // tensor-core epilogue of dX = dZX Ux^T + sum_k dPre_k Dx_k  (8 columns per call)
+struct EpiDXTC {            // tensor-core epilogue of dX = dZX Ux^T + sum_k dPre_k Dx_k  (lane <-> column, see gemm_tc.cuh)
   float* dx; long long dxs_t, dxs_b; int Bsz; const float* dpre; const float* Dx; int H, I;
   static constexpr bool kGate = false;
-  __device__ void operator()(int m, int n0, int N, const float (&v)[8]) const {
+  __device__ void operator()(int m, int n0, int N, int lane, const float (&v)[4]) const {
     float* o = dx + (long long)(m / Bsz) * dxs_t + (long long)(m % Bsz) * dxs_b;
     const float* dp = dpre + (size_t)m * 4 * H;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const int j = n0 + q;
+    for (int i = 0; i < 4; ++i) {
+      const int j = n0 + lane + 32 * i;
       if (j < N) {
-        float r = v[q];
+        float r = v[i];
 #pragma unroll
         for (int k = 0; k < 4; ++k) r = fmaf(dp[k * H + j], Dx[k * I + j], r);
         o[j] = r;
