@@ -150,6 +150,16 @@ struct EpiStoreTC {                      // C[m, n] = v (+ C[m, n] when beta)
       if (n0 + lane + 32 * i < N) c[32 * i] = beta ? c[32 * i] + v[i] : v[i];
   }
 };
+struct EpiPartialTC {                    // split-K partial: part[blockIdx.z][m][n] = v  (summed later in a fixed order)
+  float* part; int M, N;
+  static constexpr bool kGate = false;
+  __device__ void operator()(int m, int n0, int, int lane, const float (&v)[4]) const {
+    float* c = part + ((size_t)blockIdx.z * M + m) * N + n0 + lane;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (n0 + lane + 32 * i < N) c[32 * i] = v[i];
+  }
+};
 struct EpiXPTC {                         // XP[m, kH+j] = v + bias[kH+j] + [j<I] x[m,j] Dx[k,j]
   float* xp; const float* bias; const float* x; long long xs_t, xs_b; int Bsz; const float* Dx; int H, I;
   static constexpr bool kGate = false;
@@ -214,7 +224,7 @@ struct EpiGate32 {
 template <class Epi>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA,
                                                               const __grid_constant__ CUtensorMap mapB, int M, int N,
-                                                              int K, Epi epi) {
+                                                              int K, int kb_per_split, Epi epi) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
@@ -227,7 +237,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * BM;
   const int n_tile = blockIdx.x;
-  const int nkb = (K + BK - 1) / BK;
+  // split-K: blockIdx.z owns k-blocks [kb0, kb0 + nkb)
+  const int nkb_total = (K + BK - 1) / BK;
+  const int kb0 = blockIdx.z * kb_per_split;
+  const int nkb = (nkb_total - kb0) < kb_per_split ? (nkb_total - kb0) : kb_per_split;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&split[s], 4); mbar_init(&empty[s], 1); }
@@ -251,9 +264,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         if (it > 0) mbar_wait(&empty[s], (it - 1) & 1);
         uint8_t* st = smem + s * kStageBytes;
         mbar_arrive_expect_tx(&full[s], 2 * kTileBytes);
-        tma_load_2d(st, &mapA, kb * BK, m0, &full[s]);
-        if (Epi::kGate) tma_load_3d(st + 2 * kTileBytes, &mapB, kb * BK, n_tile * 32, 0, &full[s]);
-        else tma_load_2d(st + 2 * kTileBytes, &mapB, kb * BK, n_tile * BN, &full[s]);
+        tma_load_2d(st, &mapA, (kb0 + kb) * BK, m0, &full[s]);
+        if (Epi::kGate) tma_load_3d(st + 2 * kTileBytes, &mapB, (kb0 + kb) * BK, n_tile * 32, 0, &full[s]);
+        else tma_load_2d(st + 2 * kTileBytes, &mapB, (kb0 + kb) * BK, n_tile * BN, &full[s]);
       }
     }
   } else if (warp == 1) {
@@ -414,9 +427,20 @@ inline bool tc_operand_ok(const float* p, long long ld) {
 }
 
 // C = A[M,K] B[N,K]^T with a plain epilogue.  Returns kTcNoFit when an operand does not meet the TMA constraints.
+// k-blocks per split so that the grid has about one wave of CTAs (never more than `max_splits` splits)
+inline int tc_splits(int M, int N, int K, int max_splits) {
+  const long long tiles = (long long)ceil_div(M, BM) * ceil_div(N, BN);
+  const int nkb = ceil_div(K, BK);
+  long long s = (148 + tiles - 1) / tiles;
+  if (s > nkb / 4) s = nkb / 4;                      // keep at least 4 k-blocks per split
+  if (s > max_splits) s = max_splits;
+  if (s < 1) s = 1;
+  return (int)s;
+}
+
 template <class Epi>
 inline int gemm_tc(const float* A, long long lda, const float* Bm, long long ldb, int M, int N, int K, Epi epi,
-                   cudaStream_t st) {
+                   cudaStream_t st, int splits = 1) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if (!tc_operand_ok(A, lda) || !tc_operand_ok(Bm, ldb)) return kTcNoFit;
   CUtensorMap ma, mb;
@@ -432,8 +456,10 @@ inline int gemm_tc(const float* A, long long lda, const float* Bm, long long ldb
     attr = true;
   }
   const int ntn = Epi::kGate ? ceil_div(N / 4, 32) : ceil_div(N, BN);
-  dim3 grid(ntn, ceil_div(M, BM));
-  kern<<<grid, kThreads, kSmemBytes, st>>>(ma, mb, M, N, K, epi);
+  const int nkb = ceil_div(K, BK);
+  const int kbs = ceil_div(nkb, splits);
+  dim3 grid(ntn, ceil_div(M, BM), ceil_div(nkb, kbs));
+  kern<<<grid, kThreads, kSmemBytes, st>>>(ma, mb, M, N, K, kbs, epi);
   return (int)cudaGetLastError();
 }
 

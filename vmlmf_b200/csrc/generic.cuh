@@ -224,6 +224,17 @@ static __global__ void splitk_reduce_kernel(const float* __restrict__ part, int 
   for (int z = 0; z < nsplit; ++z) s += part[(size_t)z * n + i];
   out[i] = s;
 }
+// out[m*ldo + c] (+)= sum_z part[z][m*N + c]   (fixed order; rows of the output may be padded)
+static __global__ void splitk_reduce_rows_kernel(const float* __restrict__ part, int nsplit, int M, int N,
+                                                 float* __restrict__ out, long long ldo, int accumulate) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)M * N) return;
+  const int m = (int)(i / N), c = (int)(i - (long long)m * N);
+  float s = 0.f;
+  for (int z = 0; z < nsplit; ++z) s += part[(size_t)z * M * N + i];
+  float* o = out + (size_t)m * ldo + c;
+  *o = accumulate ? *o + s : s;
+}
 
 // ---- backward, pointwise part of one timestep ----
 struct DpreArgs {
@@ -323,6 +334,7 @@ struct GenericSizes {
   long long n_xp, n_dpre, n_dz, n_dzx, n_state, n_part;
   long long n_at, n_uxt;        // forward: A^T [RH, Hp], Ux^T [RX, Ip]   (B operands of the tensor-core GEMMs are K-major)
   long long n_bmt, n_vxt;       // backward: Bm^T [RH, 4H], Vx^T [RX, 4H]
+  long long n_tcpart;           // split-K partials of the per-timestep tensor-core GEMMs
   int hp4, ip4;
 };
 inline GenericSizes generic_sizes(int T, int B, int I, int H, int RX, int RH) {
@@ -347,6 +359,7 @@ inline GenericSizes generic_sizes(int T, int B, int I, int H, int RX, int RH) {
   s.n_uxt = (long long)RX * s.ip4;
   s.n_bmt = (long long)RH * 4 * H;
   s.n_vxt = (long long)RX * 4 * H;
+  s.n_tcpart = 16LL * B * (RH > H ? RH : H);
   return s;
 }
 
@@ -356,8 +369,8 @@ inline int generic_plan(int T, int B, int I, int H, int RX, int RH, vmlmf_plan* 
   plan->zx_pitch = s.zxp;
   plan->z_pitch = s.zp;
   plan->xp_cols = 4 * H;
-  plan->fwd_workspace_bytes = (s.n_xp + 2 * s.n_state + (long long)B * s.zp + s.n_at + s.n_uxt + 2 * (long long)B * s.hp4 + 16) * (long long)sizeof(float);
-  plan->bwd_workspace_bytes = (s.n_dpre + s.n_dz + s.n_dzx + 2 * s.n_state + s.n_part + s.n_bmt + s.n_vxt + 8) * (long long)sizeof(float);
+  plan->fwd_workspace_bytes = (s.n_xp + 2 * s.n_state + (long long)B * s.zp + s.n_at + s.n_uxt + 2 * (long long)B * s.hp4 + s.n_tcpart + 32) * (long long)sizeof(float);
+  plan->bwd_workspace_bytes = (s.n_dpre + s.n_dz + s.n_dzx + 2 * s.n_state + s.n_part + s.n_bmt + s.n_vxt + s.n_tcpart + 32) * (long long)sizeof(float);
   return VMLMF_OK;
 }
 
@@ -386,6 +399,21 @@ inline bool g_simt_only() {
   return e && e[0] == '1';
 }
 inline float* align4(float* p) { return reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(p) + 15) & ~(uintptr_t)15); }
+
+// out[M, N] (row pitch ldo) (+)= A[M,K] B[N,K]^T on the tensor cores, split over K when the tile grid alone would
+// leave most SMs idle (per-timestep GEMMs: M = batch, N = rank).  `part` holds up to part_cap floats of partials.
+inline int tc_gemm_rows(const float* A, long long lda, const float* Bm, long long ldb, int M, int N, int K, float* out,
+                        long long ldo, int accumulate, float* part, long long part_cap, cudaStream_t st) {
+  int splits = tc::tc_splits(M, N, K, 16);
+  while (splits > 1 && (long long)splits * M * N > part_cap) --splits;
+  if (splits <= 1) return tc::gemm_tc(A, lda, Bm, ldb, M, N, K, tc::EpiStoreTC{out, ldo, accumulate}, st);
+  const int nkb = ceil_div(K, tc::BK), kbs = ceil_div(nkb, splits), nz = ceil_div(nkb, kbs);
+  int rc = tc::gemm_tc(A, lda, Bm, ldb, M, N, K, tc::EpiPartialTC{part, M, N}, st, splits);
+  if (rc) return rc;
+  const long long n = (long long)M * N;
+  splitk_reduce_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(part, nz, M, N, out, ldo, accumulate);
+  return (int)cudaGetLastError();
+}
 
 // ZX = X Ux, pad columns zeroed
 static __global__ void zero_pad_cols_kernel(float* z, long long rows, int pitch, int R) {
@@ -435,6 +463,7 @@ inline int generic_seq_fwd(const vmlmf_plan* plan, const float* x, long long xs_
   }
   float* hpad[2] = {align4(at + s.n_at), nullptr};               // padded h_t ping-pong [B, hp4]
   hpad[1] = hpad[0] + (size_t)B * s.hp4;
+  float* tcpart = align4(hpad[1] + (size_t)B * s.hp4);
   const bool tc_step = use_tc && tc::tc_operand_ok(Bm, RH) && (!z || tc::tc_operand_ok(z, s.zp)) && tc::encode_fn() != nullptr;
   if (tc_step) {
     G_TRY(transpose_launch(A, H, RH, at, s.hp4, st));
@@ -453,7 +482,7 @@ inline int generic_seq_fwd(const vmlmf_plan* plan, const float* x, long long xs_
         zero_pad_cols_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(zdst, B, s.zp, RH);
       }
       int rc = tc::kTcNoFit;
-      if (tc_step) rc = tc::gemm_tc(hpad[(t + 1) & 1], s.hp4, at, s.hp4, B, RH, H, tc::EpiStoreTC{zdst, s.zp, 0}, st);
+      if (tc_step) rc = tc_gemm_rows(hpad[(t + 1) & 1], s.hp4, at, s.hp4, B, RH, H, zdst, s.zp, 0, tcpart, s.n_tcpart, st);
       if (rc == tc::kTcNoFit) {
         if (tc_step) return VMLMF_EUNSUPPORTED;
         rc = gemm_launch<false, false>(RowView{const_cast<float*>(hprev), 0, hp_sb, 0x7fffffff}, plain_view(A, RH), B, RH, H,
@@ -509,6 +538,7 @@ inline int generic_seq_bwd(const vmlmf_plan* plan, const float* x, long long xs_
   const bool use_tc = !g_simt_only() && tc::encode_fn() != nullptr;
   float* bmt = align4(part + s.n_part);                          // Bm^T [RH, 4H]
   float* vxt = align4(bmt + s.n_bmt);                            // Vx^T [RX, 4H]
+  float* tcpart = align4(vxt + s.n_vxt);
   const bool tc_step = use_tc && tc::tc_operand_ok(dpre, 4 * H) && tc::tc_operand_ok(dz, s.zp) && tc::tc_operand_ok(A, RH);
   if (tc_step) G_TRY(transpose_launch(Bm, 4 * H, RH, bmt, 4 * H, st));
   const int nel = B * H;
@@ -520,14 +550,14 @@ inline int generic_seq_bwd(const vmlmf_plan* plan, const float* x, long long xs_
     float* dzt = dz + (size_t)t * B * s.zp;
     // dz_t = dPre_t Bm        [B,4H] x [4H,RH]
     int rc = tc::kTcNoFit;
-    if (tc_step) rc = tc::gemm_tc(dpre + (size_t)t * B * 4 * H, 4 * H, bmt, 4 * H, B, RH, 4 * H, tc::EpiStoreTC{dzt, s.zp, 0}, st);
+    if (tc_step) rc = tc_gemm_rows(dpre + (size_t)t * B * 4 * H, 4 * H, bmt, 4 * H, B, RH, 4 * H, dzt, s.zp, 0, tcpart, s.n_tcpart, st);
     if (rc == tc::kTcNoFit)
       rc = gemm_launch<false, false>(plain_view(dpre + (size_t)t * B * 4 * H, 4 * H), plain_view(Bm, RH), B, RH, 4 * H, 1,
                                      NIdent{}, EpiStore{plain_view(dzt, s.zp), 0}, st);
     G_TRY(rc);
     // dh_{t-1} = (sum_k dpre_k Dh_k) + dz_t A^T
     rc = tc::kTcNoFit;
-    if (tc_step) rc = tc::gemm_tc(dzt, s.zp, A, RH, B, H, RH, tc::EpiStoreTC{dh, H, 1}, st);
+    if (tc_step) rc = tc_gemm_rows(dzt, s.zp, A, RH, B, H, RH, dh, H, 1, tcpart, s.n_tcpart, st);
     if (rc == tc::kTcNoFit)
       rc = gemm_launch<false, true>(plain_view(dzt, s.zp), plain_view(A, RH), B, H, RH, 1, NIdent{},
                                     EpiStore{plain_view(dh, H), 1}, st);
