@@ -184,7 +184,7 @@ def test_canonical_kernels_vs_numpy_spec(T, B, I, H, RX, RH, bf, state, scale=0.
 
 @pytest.mark.parametrize("gemm", ["tcgen05", "simt"])
 @pytest.mark.parametrize("T,B,I,H,RX,RH,bf,state", [
-    (3, 20, 650, 650, 300, 300, False, True),    # the LM layer (V/models/vmlmf_lm.py, hidden 650, ranks 300), carried state
+    (3, 96, 650, 650, 300, 300, False, True),    # the LM layer (V/models/vmlmf_lm.py, hidden 650, ranks 300), carried state
     (3, 150, 12, 40, 20, 24, True, False),       # ranks beyond R1, ragged 128-row tile, H < one 128-column tile
     (2, 9, 8, 300, 8, 8, False, True),           # H > 256 with small ranks: K = 8 (one tf32 k-step)
 ])

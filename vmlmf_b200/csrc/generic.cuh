@@ -335,6 +335,7 @@ struct GenericSizes {
   long long n_at, n_uxt;        // forward: A^T [RH, Hp], Ux^T [RX, Ip]   (B operands of the tensor-core GEMMs are K-major)
   long long n_bmt, n_vxt;       // backward: Bm^T [RH, 4H], Vx^T [RX, 4H]
   long long n_tcpart;           // split-K partials of the per-timestep tensor-core GEMMs
+  long long ldt, n_tA, n_tB;    // transposed time-parallel operands: [4H, ldt] and [max(RH,RX), ldt], ldt = round_up(T*B, 4)
   int hp4, ip4;
 };
 inline GenericSizes generic_sizes(int T, int B, int I, int H, int RX, int RH) {
@@ -360,6 +361,9 @@ inline GenericSizes generic_sizes(int T, int B, int I, int H, int RX, int RH) {
   s.n_bmt = (long long)RH * 4 * H;
   s.n_vxt = (long long)RX * 4 * H;
   s.n_tcpart = 16LL * B * (RH > H ? RH : H);
+  s.ldt = (rows + 3) / 4 * 4;
+  s.n_tA = 4LL * H * s.ldt;
+  s.n_tB = (long long)(RH > RX ? RH : RX) * s.ldt;
   return s;
 }
 
@@ -370,7 +374,7 @@ inline int generic_plan(int T, int B, int I, int H, int RX, int RH, vmlmf_plan* 
   plan->z_pitch = s.zp;
   plan->xp_cols = 4 * H;
   plan->fwd_workspace_bytes = (s.n_xp + 2 * s.n_state + (long long)B * s.zp + s.n_at + s.n_uxt + 2 * (long long)B * s.hp4 + s.n_tcpart + 32) * (long long)sizeof(float);
-  plan->bwd_workspace_bytes = (s.n_dpre + s.n_dz + s.n_dzx + 2 * s.n_state + s.n_part + s.n_bmt + s.n_vxt + s.n_tcpart + 32) * (long long)sizeof(float);
+  plan->bwd_workspace_bytes = (s.n_dpre + s.n_dz + s.n_dzx + 2 * s.n_state + s.n_part + s.n_bmt + s.n_vxt + s.n_tcpart + s.n_tA + s.n_tB + 48) * (long long)sizeof(float);
   return VMLMF_OK;
 }
 
@@ -387,6 +391,36 @@ static __global__ void transpose_kernel(const float* __restrict__ src, int R, in
     const int c = c0 + i, r = r0 + threadIdx.x;
     if (c < Cc && r < ldd) dst[(size_t)c * ldd + r] = (r < R) ? tile[threadIdx.x][i] : 0.f;
   }
+}
+// dst[c, r] = row_r[c] for r < rows, c < C, where row_r = head + r*head_ld for r < head_n (zeros when head is null)
+// and src.row(r - head_n) otherwise; dst row pitch ldd (pad columns r >= rows are not written).
+static __global__ void transpose_rows_kernel(RowView src, const float* __restrict__ head, long long head_ld, int head_n,
+                                             long long rows, int C, float* __restrict__ dst, long long ldd) {
+  __shared__ float tile[32][33];
+  const long long r0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const long long r = r0 + i;
+    const int c = c0 + threadIdx.x;
+    float v = 0.f;
+    if (r < rows && c < C) {
+      if (r < head_n) v = head ? head[r * head_ld + c] : 0.f;
+      else v = src.row(r - head_n)[c];
+    }
+    tile[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i;
+    const long long r = r0 + threadIdx.x;
+    if (c < C && r < rows) dst[(size_t)c * ldd + r] = tile[threadIdx.x][i];
+  }
+}
+inline int transpose_rows_launch(RowView src, const float* head, long long head_ld, int head_n, long long rows, int C,
+                                 float* dst, long long ldd, cudaStream_t st) {
+  dim3 grid((unsigned)((rows + 31) / 32), ceil_div(C, 32));
+  transpose_rows_kernel<<<grid, dim3(32, 8), 0, st>>>(src, head, head_ld, head_n, rows, C, dst, ldd);
+  return (int)cudaGetLastError();
 }
 inline int transpose_launch(const float* src, int R, int Cc, float* dst, int ldd, cudaStream_t st) {
   dim3 grid(ceil_div(Cc, 32), ceil_div(ldd, 32));
@@ -572,34 +606,59 @@ inline int generic_seq_bwd(const vmlmf_plan* plan, const float* x, long long xs_
     splitk_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(part, nsplit, n, out);
     return (int)cudaGetLastError();
   };
+  float* tA = align4(tcpart + s.n_tcpart);                       // transposed A-side operand [<=4H, ldt]
+  float* tB = align4(tA + s.n_tA);                               // transposed B-side operand [<=max(RH,RX), ldt]
+  const bool tc_tp = use_tc && rows >= 256;                      // K = rows contractions on the tensor cores
+  // C[M,N] = At[M, rows] Bt[N, rows]^T, split over K with a fixed-order reduce into `out`
+  auto tc_tn = [&](int M, int N, float* out) -> int {
+    int splits = tc::tc_splits(M, N, (int)rows, 32);
+    while (splits > 1 && (long long)splits * M * N > s.n_part) --splits;
+    const int nkb = ceil_div((int)rows, tc::BK), kbs = ceil_div(nkb, splits), nz = ceil_div(nkb, kbs);
+    int rc = tc::gemm_tc(tA, s.ldt, tB, s.ldt, M, N, (int)rows, tc::EpiPartialTC{part, M, N}, st, splits);
+    if (rc) return rc;
+    return reduce_to(nz, (long long)M * N, out);
+  };
+  if (tc_tp) {
+    // dBm = dPre^T Z, dVx = dPre^T ZX share the transposed dPre
+    G_TRY(transpose_rows_launch(dPv, nullptr, 0, 0, rows, 4 * H, tA, s.ldt, st));
+    G_TRY(transpose_rows_launch(Zv, nullptr, 0, 0, rows, RH, tB, s.ldt, st));
+    G_TRY(tc_tn(4 * H, RH, dBm));
+    G_TRY(transpose_rows_launch(ZXv, nullptr, 0, 0, rows, RX, tB, s.ldt, st));
+    G_TRY(tc_tn(4 * H, RX, dVx));
+    // dA = Hprev^T dZ: row (t,b) of Hprev is y[t-1,b], or h0[b] / 0 at t = 0
+    G_TRY(transpose_rows_launch(Yv, h0, H, B, rows, H, tA, s.ldt, st));
+    G_TRY(transpose_rows_launch(plain_view(dz, s.zp), nullptr, 0, 0, rows, RH, tB, s.ldt, st));
+    G_TRY(tc_tn(H, RH, dA));
+  } else {
   // dBm = dPre^T Z   [4H,RH]
-  {
-    const int sp = g_splits(4 * H, RH, rows);
-    G_TRY((gemm_launch<true, false>(dPv, Zv, 4 * H, RH, rows, sp, NIdent{}, EpiPartial{part, 4 * H, RH}, st)));
-    G_TRY(reduce_to(sp, (long long)4 * H * RH, dBm));
-  }
-  // dA = Hprev^T dZ  [H,RH]: rows t>=1 pair y[t-1] with dz[t]; rows of t=0 pair h0 with dz[0]
-  {
-    const long long r1 = rows - B;
-    int sp = 0;
-    if (r1 > 0) {
-      sp = g_splits(H, RH, r1);
-      G_TRY((gemm_launch<true, false>(Yv, plain_view(dz + (size_t)B * s.zp, s.zp), H, RH, r1, sp, NIdent{},
-                                      EpiPartial{part, H, RH}, st)));
+    {
+      const int sp = g_splits(4 * H, RH, rows);
+      G_TRY((gemm_launch<true, false>(dPv, Zv, 4 * H, RH, rows, sp, NIdent{}, EpiPartial{part, 4 * H, RH}, st)));
+      G_TRY(reduce_to(sp, (long long)4 * H * RH, dBm));
     }
-    if (h0) {
-      G_TRY((gemm_launch<true, false>(plain_view(h0, H), plain_view(dz, s.zp), H, RH, B, 1, NIdent{},
-                                      EpiPartial{part + (size_t)sp * H * RH, H, RH}, st)));
-      ++sp;
+    // dA = Hprev^T dZ  [H,RH]: rows t>=1 pair y[t-1] with dz[t]; rows of t=0 pair h0 with dz[0]
+    {
+      const long long r1 = rows - B;
+      int sp = 0;
+      if (r1 > 0) {
+        sp = g_splits(H, RH, r1);
+        G_TRY((gemm_launch<true, false>(Yv, plain_view(dz + (size_t)B * s.zp, s.zp), H, RH, r1, sp, NIdent{},
+                                        EpiPartial{part, H, RH}, st)));
+      }
+      if (h0) {
+        G_TRY((gemm_launch<true, false>(plain_view(h0, H), plain_view(dz, s.zp), H, RH, B, 1, NIdent{},
+                                        EpiPartial{part + (size_t)sp * H * RH, H, RH}, st)));
+        ++sp;
+      }
+      if (sp == 0) G_TRY((int)cudaMemsetAsync(dA, 0, (size_t)H * RH * sizeof(float), st));
+      else G_TRY(reduce_to(sp, (long long)H * RH, dA));
     }
-    if (sp == 0) G_TRY((int)cudaMemsetAsync(dA, 0, (size_t)H * RH * sizeof(float), st));
-    else G_TRY(reduce_to(sp, (long long)H * RH, dA));
-  }
-  // dVx = dPre^T ZX  [4H,RX]
-  {
-    const int sp = g_splits(4 * H, RX, rows);
-    G_TRY((gemm_launch<true, false>(dPv, ZXv, 4 * H, RX, rows, sp, NIdent{}, EpiPartial{part, 4 * H, RX}, st)));
-    G_TRY(reduce_to(sp, (long long)4 * H * RX, dVx));
+    // dVx = dPre^T ZX  [4H,RX]
+    {
+      const int sp = g_splits(4 * H, RX, rows);
+      G_TRY((gemm_launch<true, false>(dPv, ZXv, 4 * H, RX, rows, sp, NIdent{}, EpiPartial{part, 4 * H, RX}, st)));
+      G_TRY(reduce_to(sp, (long long)4 * H * RX, dVx));
+    }
   }
   // dZX = dPre Vx    [T*B,RX]
   if (s.zxp > RX) G_TRY((int)cudaMemsetAsync(dzx, 0, (size_t)s.n_dzx * sizeof(float), st));
@@ -615,6 +674,11 @@ inline int generic_seq_bwd(const vmlmf_plan* plan, const float* x, long long xs_
     G_TRY(rc);
   }
   // dUx = X^T dZX    [I,RX]
+  if (tc_tp) {
+    G_TRY(transpose_rows_launch(Xv, nullptr, 0, 0, rows, I, tA, s.ldt, st));
+    G_TRY(transpose_rows_launch(plain_view(dzx, s.zxp), nullptr, 0, 0, rows, RX, tB, s.ldt, st));
+    G_TRY(tc_tn(I, RX, dUx));
+  } else
   {
     const int sp = g_splits(I, RX, rows);
     G_TRY((gemm_launch<true, false>(Xv, plain_view(dzx, s.zxp), I, RX, rows, sp, NIdent{}, EpiPartial{part, I, RX}, st)));
