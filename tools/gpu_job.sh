@@ -1,2 +1,1 @@
-timeout 600 python -m pytest tests -q -m gpu -x -k "generic_regime or lm or group_g4" 2>&1 | tail -3
-for B in 20 512; do python tools/time_lm.py $B; done
+timeout 900 python tools/config_sweep.py gpurun_out/r01_configs.json 2>&1 | tail -80
