@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=8192, help="sequences per GPU per step")
     ap.add_argument("--cpu-batch", type=int, default=1024, help="sequences per CPU-baseline step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel of the step eagerly instead of replaying a CUDA graph")
     return ap.parse_args()
 
 
@@ -179,9 +180,10 @@ def run_ours(args):
     torch.manual_seed(3)
     net = vb.Net(N_IN, [HIDDEN], w_rank=W_RANK, u_rank=[U_RANK], cell=vb.MyVMLMFCell).to(dev)
     broadcast_parameters(net)
-    opt = torch.optim.Adam(net.parameters(), lr=0.002, fused=True)
+    opt = torch.optim.Adam(net.parameters(), lr=0.002, fused=True, capturable=True)
     bucket = GradBucket(net, average=True)
     ce = torch.nn.functional.cross_entropy
+    use_graph = (world == 1) and not args.no_graph          # with N > 1 the NCCL all-reduce stays outside a graph
 
     POOL = 4                                   # distinct resident batches, rotated (each step's set >> L2)
     g = torch.Generator().manual_seed(1234 + rank)
@@ -190,13 +192,18 @@ def run_ours(args):
     dev_x = [t.to(dev) for t in host_x]
     dev_y = [t.to(dev) for t in host_y]
 
-    def train_step(x, y):
+    def eager_step(x, y):
         bucket.zero()
         loss = ce(net(x), y)
         loss.backward()
         bucket.all_reduce()
         opt.step()
         return loss
+
+    graphed = None
+
+    def train_step(x, y):
+        return graphed(x, y) if graphed is not None else eager_step(x, y)
 
     def barrier():
         if world > 1:
@@ -212,10 +219,21 @@ def run_ours(args):
 
     # ---------------- value: inputs resident in HBM ----------------
     for i in range(W):
-        train_step(dev_x[i % POOL], dev_y[i % POOL])
+        eager_step(dev_x[i % POOL], dev_y[i % POOL])
+    # per-kernel times for the roofline come from a few eager steps (CUDA events around the C-ABI calls); the
+    # timed region below replays the same step as ONE CUDA graph when running on a single GPU
+    F.EVENT_LOG = []
+    for i in range(10):
+        eager_step(dev_x[i % POOL], dev_y[i % POOL])
+    torch.cuda.synchronize()
+    log, F.EVENT_LOG = F.EVENT_LOG, None
+    if use_graph:
+        from vmlmf_b200.graphs import GraphedTrainStep
+        graphed = GraphedTrainStep(net, opt, ce, dev_x[0], dev_y[0], zero_fn=bucket.zero)
+        for i in range(3):
+            train_step(dev_x[i % POOL], dev_y[i % POOL])
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
-    F.EVENT_LOG = []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -224,7 +242,6 @@ def run_ours(args):
     e1.record()
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
-    log, F.EVENT_LOG = F.EVENT_LOG, None
     kt = {}
     for name, a, b in log:
         kt.setdefault(name, []).append(a.elapsed_time(b))
@@ -359,7 +376,7 @@ def run_ours(args):
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": B * world, "seq_len": T_STEPS,
-                   "parallelism": f"dp{world}", "l2_policy": "inputs larger than L2 (x 60 MB + 1.5 GB saved state per step, 4 rotating batches)"},
+                   "parallelism": f"dp{world}", "cuda_graph": bool(use_graph), "l2_policy": "inputs larger than L2 (x 60 MB + 1.5 GB saved state per step, 4 rotating batches)"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "sequences/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": e2e_s * 1e3 / K},

@@ -277,6 +277,39 @@ def test_fused_diag_correction_matches_torch(n, H, R, r1_path):
         assert_close(a.grad.cpu().numpy(), b.grad.cpu().numpy(), 2e-6, name)
 
 
+def test_cuda_graph_train_step_matches_eager(r1_path):
+    """GraphedTrainStep (one CUDA graph per training step) follows the same trajectory as eager steps."""
+    from vmlmf_b200.graphs import GraphedTrainStep
+    ce = torch.nn.functional.cross_entropy
+    g = torch.Generator(device=DEV).manual_seed(9)
+    xs = [torch.randn(48, 12, 9, device=DEV, generator=g) for _ in range(4)]
+    ys = [torch.randint(0, 6, (48,), device=DEV, generator=g) for _ in range(4)]
+
+    def make():
+        torch.manual_seed(4)
+        net = vb.Net(9, [32], w_rank=8, u_rank=[6], cell=vb.MyVMLMFCell).to(DEV)
+        # plain SGD: Adam's g/sqrt(v) turns the last-bit differences of cuBLAS' capture-time algorithm choice
+        # (Linear head) into 1e-4 trajectory differences, which would hide what this test is about
+        return net, torch.optim.SGD(net.parameters(), lr=0.05)
+
+    net_e, opt_e = make()
+    net_g, opt_g = make()
+    step = GraphedTrainStep(net_g, opt_g, ce, xs[0], ys[0], warmup=2)      # 2 warm-up steps on (xs[0], ys[0]); capture only records
+    for _ in range(2):
+        opt_e.zero_grad()
+        ce(net_e(xs[0]), ys[0]).backward()
+        opt_e.step()
+    for x, y in zip(xs[1:], ys[1:]):
+        opt_e.zero_grad()
+        le = ce(net_e(x), y)
+        le.backward()
+        opt_e.step()
+        lg = step(x, y)
+        assert abs(float(lg) - float(le)) <= 1e-5 * max(1.0, abs(float(le)))
+    for (k, a), (_, b) in zip(net_g.state_dict().items(), net_e.state_dict().items()):
+        assert_close(a.cpu().numpy(), b.cpu().numpy(), 1e-5, f"param {k} after graphed vs eager steps")
+
+
 def test_regime_choice_matches_plan(r1_path):
     from vmlmf_b200 import _lib
     want = {"auto": (_lib.PATH_R1, _lib.PATH_R1M), "mma": (_lib.PATH_R1M, _lib.PATH_R1M), "simt": (_lib.PATH_R1, _lib.PATH_R1)}

@@ -1,1 +1,1 @@
-timeout 900 python tools/config_sweep.py gpurun_out/r01_configs.json 2>&1 | tail -80
+python -m pytest tests -q -m gpu -x 2>&1 | tail -3

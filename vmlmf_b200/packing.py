@@ -30,7 +30,10 @@ def pack_plain(u_x, u_h, v_x, v_h, b_x, b_h, dia_x, dia_h):
     else:
         dx = dia_x.reshape(1, n_in) - _diag_corr(u_x, v_x, n_in)
         dh = dia_h.reshape(1, hidden) - _diag_corr(u_h, v_h, hidden)
-    return u_x, v_x, dx, u_h, v_h, dh, b_x.reshape(-1) + b_h.reshape(-1)
+    # b_h passes through a multiply so that autograd hands b_x and b_h two DIFFERENT gradient tensors: a bare
+    # `b_x + b_h` gives both AccumulateGrad nodes the same tensor, they alias .grad, and any in-place accumulation
+    # into persistent .grad buffers (zero_grad(set_to_none=False), CUDA-graph training) then doubles the bias gradient
+    return u_x, v_x, dx, u_h, v_h, dh, b_x.reshape(-1) + b_h.reshape(-1) * 1.0
 
 
 def _gate_perm(hidden, device):
