@@ -123,6 +123,16 @@ int vmlmf_seq_bwd(const vmlmf_plan* plan, const float* x, long long xs_t, long l
                   float* dDh, float* dbias, void* workspace, int T, int B, int I, int H,
                   int RX, int RH, void* stream);
 
+/* fp32-accurate GEMM on the tensor cores (tcgen05, 3xTF32, TMA):  C[M,N] (+)= A[M,K] B[N,K]^T (+ bias[N]).
+ * Row pitches in floats; A and B need 16-byte aligned rows (pitch % 4 == 0, base % 16 == 0) -- other operands
+ * run on the SIMT fallback.  Used for the LM vocabulary projection around the path
+ * (V/models/vmlmf_lm.py:341-361, `torch.addmm(self.b, x, self.w.t())`) and its backward.  K contractions longer
+ * than a tile wave are split and summed in a fixed order; `workspace` (workspace_bytes >= 16*M*N*4 lets every
+ * split configuration through, 0 disables splitting) holds the partials.                                      */
+int vmlmf_gemm_nt(const float* A, long long lda, const float* B, long long ldb, float* C, long long ldc,
+                  const float* bias, int M, int N, int K, int accumulate, void* workspace,
+                  long long workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

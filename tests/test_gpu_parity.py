@@ -310,6 +310,27 @@ def test_cuda_graph_train_step_matches_eager(r1_path):
         assert_close(a.cpu().numpy(), b.cpu().numpy(), 1e-5, f"param {k} after graphed vs eager steps")
 
 
+@pytest.mark.parametrize("M,N,K", [(700, 1000, 650), (513, 130, 36), (64, 48, 1024)])
+def test_tensor_core_linear_matches_fp64(M, N, K, r1_path):
+    """vmlmf_gemm_nt / LinearTCFunction (LM head) against an fp64 product: forward, dX, dW, db."""
+    if r1_path != "auto":
+        pytest.skip("independent of the recurrence regime")
+    from vmlmf_b200.functional import linear_tc
+    g = torch.Generator(device=DEV).manual_seed(M + N)
+    x64 = torch.randn(M, K, device=DEV, generator=g, dtype=torch.float64)
+    w64 = torch.randn(N, K, device=DEV, generator=g, dtype=torch.float64) * 0.05
+    b64 = torch.randn(N, device=DEV, generator=g, dtype=torch.float64)
+    u64 = torch.randn(M, N, device=DEV, generator=g, dtype=torch.float64)
+    ref_in = [t.clone().requires_grad_(True) for t in (x64, w64, b64)]
+    (torch.addmm(ref_in[2], ref_in[0], ref_in[1].t()) * u64).sum().backward()
+    got_in = [t.float().requires_grad_(True) for t in (x64, w64, b64)]
+    y = linear_tc(*got_in)
+    (y * u64.float()).sum().backward()
+    assert_close(y.detach().cpu().numpy(), torch.addmm(b64, x64, w64.t()).cpu().numpy(), 3e-6, "y")
+    for a, b, name in zip(got_in, ref_in, ("dx", "dw", "db")):
+        assert_close(a.grad.cpu().numpy(), b.grad.cpu().numpy(), 3e-6, name)
+
+
 def test_regime_choice_matches_plan(r1_path):
     from vmlmf_b200 import _lib
     want = {"auto": (_lib.PATH_R1, _lib.PATH_R1M), "mma": (_lib.PATH_R1M, _lib.PATH_R1M), "simt": (_lib.PATH_R1, _lib.PATH_R1)}

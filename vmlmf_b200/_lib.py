@@ -31,6 +31,7 @@ SIGNATURES = {
     "vmlmf_seq_plan": [_I] * 6 + [C.POINTER(Plan)],
     "vmlmf_diag_fwd": [_P, _P, _P, _P, _I, _I, _I, _P],
     "vmlmf_diag_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
+    "vmlmf_gemm_nt": [_P, _LL, _P, _LL, _P, _LL, _P, _I, _I, _I, _I, _P, _LL, _P],
     "vmlmf_xproj_fwd": [_P, _LL, _LL, _P, _P, _I, _I, _I, _I, _I, _P],
     "vmlmf_seq_fwd": [C.POINTER(Plan), _P, _LL, _LL] + [_P] * 10 + [_P, _LL, _LL] + [_P] * 6 + [_I] * 6 + [_P],
     "vmlmf_seq_bwd": [C.POINTER(Plan), _P, _LL, _LL] + [_P] * 9 + [_P, _LL, _LL] + [_P] * 3 + [_P, _LL, _LL]

@@ -150,6 +150,21 @@ struct EpiStoreTC {                      // C[m, n] = v (+ C[m, n] when beta)
       if (n0 + lane + 32 * i < N) c[32 * i] = beta ? c[32 * i] + v[i] : v[i];
   }
 };
+struct EpiBiasTC {                       // C[m, n] = v + bias[n] (+ C[m, n] when beta); bias may be null
+  float* C; long long ldc; const float* bias; int beta;
+  static constexpr bool kGate = false;
+  __device__ void operator()(int m, int n0, int N, int lane, const float (&v)[4]) const {
+    float* c = C + (size_t)m * ldc + n0 + lane;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int n = n0 + lane + 32 * i;
+      if (n < N) {
+        const float r = v[i] + (bias ? __ldg(bias + n) : 0.f);
+        c[32 * i] = beta ? c[32 * i] + r : r;
+      }
+    }
+  }
+};
 struct EpiPartialTC {                    // split-K partial: part[blockIdx.z][m][n] = v  (summed later in a fixed order)
   float* part; int M, N;
   static constexpr bool kGate = false;

@@ -449,6 +449,48 @@ inline int tc_gemm_rows(const float* A, long long lda, const float* Bm, long lon
   return (int)cudaGetLastError();
 }
 
+struct EpiBias {            // SIMT fallback of EpiBiasTC
+  RowView C; const float* bias; int beta;
+  __device__ void operator()(int m, int n, int N, const float (&v)[4]) const {
+    float* c = C.row(m) + n;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (n + q < N) {
+        const float r = v[q] + (bias ? bias[n + q] : 0.f);
+        c[q] = beta ? c[q] + r : r;
+      }
+  }
+};
+static __global__ void splitk_reduce_bias_kernel(const float* __restrict__ part, int nsplit, int M, int N,
+                                                 const float* __restrict__ bias, float* __restrict__ out, long long ldo,
+                                                 int accumulate) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)M * N) return;
+  const int m = (int)(i / N), c = (int)(i - (long long)m * N);
+  float s = bias ? bias[c] : 0.f;
+  for (int z = 0; z < nsplit; ++z) s += part[(size_t)z * M * N + i];
+  float* o = out + (size_t)m * ldo + c;
+  *o = accumulate ? *o + s : s;
+}
+// public GEMM (vmlmf_gemm_nt): tensor cores when the operands meet the TMA constraints, SIMT otherwise
+inline int gemm_nt_public(const float* A, long long lda, const float* Bm, long long ldb, float* C, long long ldc,
+                          const float* bias, int M, int N, int K, int accumulate, float* part, long long part_floats,
+                          cudaStream_t st) {
+  if (!g_simt_only() && tc::encode_fn() && tc::tc_operand_ok(A, lda) && tc::tc_operand_ok(Bm, ldb)) {
+    int splits = tc::tc_splits(M, N, K, 16);
+    while (splits > 1 && (!part || (long long)splits * M * N > part_floats)) --splits;
+    if (splits <= 1) return tc::gemm_tc(A, lda, Bm, ldb, M, N, K, tc::EpiBiasTC{C, ldc, bias, accumulate}, st);
+    const int nkb = ceil_div(K, tc::BK), kbs = ceil_div(nkb, splits), nz = ceil_div(nkb, kbs);
+    int rc = tc::gemm_tc(A, lda, Bm, ldb, M, N, K, tc::EpiPartialTC{part, M, N}, st, splits);
+    if (rc) return rc;
+    const long long n = (long long)M * N;
+    splitk_reduce_bias_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(part, nz, M, N, bias, C, ldc, accumulate);
+    return (int)cudaGetLastError();
+  }
+  return gemm_launch<false, true>(plain_view(A, lda), plain_view(Bm, ldb), M, N, K, 1, NIdent{},
+                                  EpiBias{plain_view(C, ldc), bias, accumulate}, st);
+}
+
 // ZX = X Ux, pad columns zeroed
 static __global__ void zero_pad_cols_kernel(float* z, long long rows, int pitch, int R) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -125,6 +125,14 @@ int vmlmf_diag_bwd(const float* u, const float* v, const float* dD, float* du, f
   return (int)cudaGetLastError();
 }
 
+int vmlmf_gemm_nt(const float* A, long long lda, const float* B, long long ldb, float* C, long long ldc,
+                  const float* bias, int M, int N, int K, int accumulate, void* workspace, long long workspace_bytes,
+                  void* stream) {
+  if (!A || !B || !C || M <= 0 || N <= 0 || K <= 0 || lda < K || ldb < K || ldc < N) return VMLMF_EINVAL;
+  return gemm_nt_public(A, lda, B, ldb, C, ldc, bias, M, N, K, accumulate, (float*)workspace,
+                        workspace ? workspace_bytes / (long long)sizeof(float) : 0, (cudaStream_t)stream);
+}
+
 int vmlmf_xproj_fwd(const float* x, long long xs_t, long long xs_b, const float* Ux, float* zx, int T,
                     int B, int I, int RX, int zx_pitch, void* stream) {
   if (!x || !Ux || !zx || T <= 0 || B <= 0 || I <= 0 || RX <= 0) return VMLMF_EINVAL;

@@ -176,6 +176,56 @@ def diag_correction(u, v, dia):
     return DiagCorrFunction.apply(u, v, dia)
 
 
+def _pad4(t):
+    """copy of a 2-D tensor whose row pitch is a multiple of 4 floats and whose base is 16-byte aligned (TMA operand)"""
+    rows, cols = t.shape
+    if t.stride(1) == 1 and t.stride(0) % 4 == 0 and t.data_ptr() % 16 == 0:
+        return t, t.stride(0)
+    ld = (cols + 3) // 4 * 4
+    buf = t.new_zeros((rows, ld))
+    buf[:, :cols].copy_(t)
+    return buf, ld
+
+
+def gemm_nt(a, b, bias=None, out=None, accumulate=False):
+    """out[M,N] (+)= a[M,K] @ b[N,K]^T (+ bias) on the tcgen05 3xTF32 GEMM (vmlmf_gemm_nt); fp32-accurate."""
+    _require_cuda(a, b, bias)
+    (m, k), n = a.shape, b.shape[0]
+    a2, lda = _pad4(a)
+    b2, ldb = _pad4(b)
+    if out is None:
+        out = a.new_empty((m, n))
+    ws = a.new_empty((min(16, max(1, -(-k // 128))) * m * n,)) if m * n <= (1 << 24) else None
+    with torch.cuda.device_of(a):
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _lib.check(_lib.lib().vmlmf_gemm_nt(_ptr(a2), lda, _ptr(b2), ldb, _ptr(out), out.stride(0), _ptr(bias), m, n, k,
+                                            1 if accumulate else 0, _ptr(ws), 0 if ws is None else ws.numel() * 4, st))
+    return out
+
+
+class LinearTCFunction(torch.autograd.Function):
+    """y = x w^T + b with all three GEMMs (forward, dX, dW) on the tensor-core kernel.
+    Replaces `torch.addmm(self.b, x, self.w.t())` of the LM head (V/models/vmlmf_lm.py:357) and its autograd."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        ctx.save_for_backward(x, w)
+        return gemm_nt(x, w, b)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = gemm_nt(dy, w.t().contiguous()) if ctx.needs_input_grad[0] else None          # [M,N] x [K,N]^T
+        dw = gemm_nt(dy.t().contiguous(), x.t().contiguous()) if ctx.needs_input_grad[1] else None   # [N,M] x [K,M]^T
+        db = dy.sum(0) if ctx.needs_input_grad[2] else None
+        return dx, dw, db
+
+
+def linear_tc(x, w, b):
+    return LinearTCFunction.apply(x, w, b)
+
+
 def vmlmf_sequence(x, h0, c0, canon, batch_first=True):
     """Run one VMLMF layer over a whole sequence.  canon = (Ux,Vx,Dx,A,Bm,Dh,bias)."""
     save = torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (x, h0, c0, *canon))

@@ -102,7 +102,12 @@ class Linear(nn.Module):
         self.b = nn.Parameter(torch.Tensor(hidden_size))
 
     def forward(self, x):
-        return torch.addmm(self.b, x.reshape(-1, x.size(2)), self.w.t())
+        x2 = x.reshape(-1, x.size(2))
+        if x2.is_cuda and x2.dtype == torch.float32 and x2.size(0) >= 512:
+            # large vocabulary projection: fp32-accurate tcgen05 GEMMs (forward, dX, dW)
+            from .functional import linear_tc
+            return linear_tc(x2, self.w, self.b)
+        return torch.addmm(self.b, x2, self.w.t())
 
     def __repr__(self):
         return f"FC(input: {self.input_size}, output: {self.hidden_size})"
