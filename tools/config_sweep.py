@@ -24,7 +24,7 @@ def timeit(fn, n, warm=3):
     return e0.elapsed_time(e1) / n
 
 
-def har(name, I, H, wr, ur, cell, B, T, classes, n=20):
+def har(name, I, H, wr, ur, cell, B, T, classes, n=20, graph=False):
     torch.manual_seed(3)
     net = vb.Net(I, [H], w_rank=wr, u_rank=ur, cell=cell).to(dev)
     opt = torch.optim.Adam(net.parameters(), lr=0.002, fused=True)
@@ -41,11 +41,18 @@ def har(name, I, H, wr, ur, cell, B, T, classes, n=20):
             net(x)
 
     tr, inf = timeit(train, n), timeit(infer, n)
-    return {"config": name, "batch": B, "seq_len": T, "train_ms": tr, "train_seq_per_s": B / tr * 1e3,
-            "infer_ms": inf, "infer_seq_per_s": B / inf * 1e3}
+    out = {"config": name, "batch": B, "seq_len": T, "train_ms": tr, "train_seq_per_s": B / tr * 1e3,
+           "infer_ms": inf, "infer_seq_per_s": B / inf * 1e3}
+    if graph:                                  # same step replayed as one CUDA graph (vmlmf_b200.graphs)
+        from vmlmf_b200.graphs import GraphedTrainStep
+        opt_g = torch.optim.Adam(net.parameters(), lr=0.002, capturable=True, foreach=True)
+        step = GraphedTrainStep(net, opt_g, ce, x, y)
+        trg = timeit(lambda: step(x, y), n)
+        out.update({"train_graph_ms": trg, "train_graph_seq_per_s": B / trg * 1e3})
+    return out
 
 
-def lm(B, n=10):
+def lm(B, n=10, graph=False):
     torch.manual_seed(3)
     model = vb.Model(10000, 650, 2, 0.5, 0.05, 300, [300], "vmlmf").to(dev)
     x = torch.randint(0, 10000, (35, B), device=dev)
@@ -63,15 +70,46 @@ def lm(B, n=10):
                 p -= 1.0 * p.grad
 
     tr = timeit(train, n)
-    return {"config": "cfg4 LM Model(10000,650,2,0.5,0.05,300,[300],'vmlmf') bptt 35", "batch": B, "seq_len": 35,
-            "train_ms": tr, "train_seq_per_s": B / tr * 1e3, "train_tokens_per_s": 35 * B / tr * 1e3}
+    out = {"config": "cfg4 LM Model(10000,650,2,0.5,0.05,300,[300],'vmlmf') bptt 35", "batch": B, "seq_len": 35,
+           "train_ms": tr, "train_seq_per_s": B / tr * 1e3, "train_tokens_per_s": 35 * B / tr * 1e3}
+    if graph:
+        # the same step as one CUDA graph: carried (h, c) live in static buffers that the graph updates in place;
+        # gradient clipping and the manual SGD update (V/train_test/lm_test.py:203-209) are captured too
+        from vmlmf_b200.graphs import GraphedCallable
+        static = model.state_init(B)
+        model.zero_grad(set_to_none=True)      # .grad buffers must be created during the side-stream warm-up
+
+        def gstep():
+            for p in model.parameters():
+                if p.grad is not None:
+                    p.grad.zero_()
+            cur = [(h.detach(), c.detach()) for h, c in static]
+            scores, new = model(x, cur)
+            loss = ce(scores, y)
+            loss.backward()
+            with torch.no_grad():
+                grads = [p.grad for p in model.parameters()]
+                total = torch.linalg.vector_norm(torch.stack(torch._foreach_norm(grads)))      # no host sync: capture-safe
+                coef = torch.clamp(5.0 / (total + 1e-6), max=1.0)
+                for gr in grads:
+                    gr.mul_(coef)
+                torch._foreach_add_(list(model.parameters()), grads, alpha=-1.0)
+                for (h, c), (h1, c1) in zip(static, new):
+                    h.copy_(h1)
+                    c.copy_(c1)
+            return loss.detach()
+
+        g = GraphedCallable(gstep)
+        trg = timeit(g, n)
+        out.update({"train_graph_ms": trg, "train_graph_seq_per_s": B / trg * 1e3, "train_graph_tokens_per_s": 35 * B / trg * 1e3})
+    return out
 
 
 out = {"gpu": torch.cuda.get_device_name(0), "results": []}
 R = out["results"]
-R.append(har("cfg1 UCI Net(9,[128],8,[6]) B=64 (reference batch)", 9, 128, 8, [6], vb.MyVMLMFCell, 64, 128, 6))
+R.append(har("cfg1 UCI Net(9,[128],8,[6]) B=64 (reference batch)", 9, 128, 8, [6], vb.MyVMLMFCell, 64, 128, 6, graph=True))
 R.append(har("cfg1 UCI shape, B=8192", 9, 128, 8, [6], vb.MyVMLMFCell, 8192, 128, 6))
-R.append(har("cfg2 OPP Net(77,[256],8,[6]) B=81 (reference batch)", 77, 256, 8, [6], vb.MyVMLMFCell, 81, 24, 18))
+R.append(har("cfg2 OPP Net(77,[256],8,[6]) B=81 (reference batch)", 77, 256, 8, [6], vb.MyVMLMFCell, 81, 24, 18, graph=True))
 R.append(har("cfg2 OPP Net(77,[256],8,[6]) B=8192", 77, 256, 8, [6], vb.MyVMLMFCell, 8192, 24, 18))
 R.append(har("cfg2 OPP Net(77,[256],32,[32]) B=8192 (generic regime)", 77, 256, 32, [32], vb.MyVMLMFCell, 8192, 24, 18, n=5))
 R.append(har("cfg3 group Net(9,[128],8,[2,4],MyVMLMFCellg2) B=8192", 9, 128, 8, [2, 4], vb.MyVMLMFCellg2, 8192, 128, 6, n=10))

@@ -1,2 +1,1 @@
-python -m pytest tests -q -m gpu -x -k "tensor_core_linear or lm" 2>&1 | tail -4
-for B in 20 512; do python tools/time_lm.py $B; done
+timeout 900 python tools/config_sweep.py gpurun_out/r01_configs.json 2>&1 | grep -E "config|train_seq|graph_seq|tokens|Error|error|Traceback" | head -40

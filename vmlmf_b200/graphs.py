@@ -11,6 +11,27 @@ from __future__ import annotations
 import torch
 
 
+class GraphedCallable:
+    """Capture `fn()` (a closure over static tensors that launches only on the current stream) into one CUDA graph.
+    `fn` is run `warmup` times eagerly on a side stream first; calling the object replays the graph and returns
+    what `fn` returned at capture time (static output tensors)."""
+
+    def __init__(self, fn, warmup=3):
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                fn()
+        torch.cuda.current_stream().wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = fn()
+
+    def __call__(self):
+        self.graph.replay()
+        return self.out
+
+
 class GraphedTrainStep:
     """step = GraphedTrainStep(net, opt, loss_fn, x_example, y_example);  loss = step(x, y)
 
@@ -23,6 +44,10 @@ class GraphedTrainStep:
         self.module, self.opt, self.loss_fn = module, opt, loss_fn
         self.static_x = x_example.clone()
         self.static_y = y_example.clone()
+        if zero_fn is None:
+            # .grad buffers created earlier on another stream would make autograd synchronise with that stream
+            # during capture (cudaErrorStreamCaptureImplicit): let the side-stream warm-up create them
+            opt.zero_grad(set_to_none=True)
         self.zero_fn = zero_fn or (lambda: opt.zero_grad(set_to_none=False))
         self.after_backward = after_backward
         side = torch.cuda.Stream()
