@@ -40,7 +40,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=8192, help="sequences per GPU per step")
+    # 9472 = 4 x 148 SMs x 16: the warp-MMA kernels tile 16 sequences per CTA, so this batch is a whole number of waves
+    ap.add_argument("--batch", type=int, default=9472, help="sequences per GPU per step")
     ap.add_argument("--cpu-batch", type=int, default=1024, help="sequences per CPU-baseline step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel of the step eagerly instead of replaying a CUDA graph")
@@ -376,7 +377,7 @@ def run_ours(args):
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": B * world, "seq_len": T_STEPS,
-                   "parallelism": f"dp{world}", "cuda_graph": bool(use_graph), "l2_policy": "inputs larger than L2 (x 60 MB + 1.5 GB saved state per step, 4 rotating batches)"},
+                   "parallelism": f"dp{world}", "cuda_graph": bool(use_graph), "l2_policy": "inputs larger than L2 (x 70 MB + 1.4 GB saved state + 0.9 GB dPre per step, 4 rotating batches)"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "sequences/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": e2e_s * 1e3 / K},

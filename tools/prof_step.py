@@ -9,7 +9,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import vmlmf_b200 as vb  # noqa: E402
 
-B = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 9472
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 dev = torch.device("cuda:0")
 torch.manual_seed(3)
