@@ -362,4 +362,4 @@ def test_full_size_properties_cfg2(r1_path):
     for a, b in zip(g1, g1b):
         assert torch.equal(a, b)                           # fixed-order reductions: bitwise reproducible
     for a, b in zip(g1, g3):
-        assert_close(b.cpu().numpy(), 3.0 * a.cpu().numpy(), 2e-6, "linearity")
+        assert_close(b.cpu().numpy(), 3.0 * a.cpu().numpy(), 5e-6, "linearity")     # x3 is not exact in fp32: rounding only

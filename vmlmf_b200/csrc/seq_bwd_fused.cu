@@ -1,0 +1,62 @@
+// seq_bwd_fused.cu -- instantiations and host launcher of the fused R1M backward (seq_bwd_fused.cuh).
+#include "seq_bwd_fused.cuh"
+#include "seq_r1_launch.cuh"
+
+namespace vmlmf {
+
+namespace {
+int ks_of(int RX, int RH) { return ceil_div(RH + RX + 1, 8); }
+int nz_of(int RH) { return ceil_div(RH, 8); }
+int grid_of(int B) { const int nt = ceil_div(B, 16); return nt < kNumSMs ? nt : kNumSMs; }
+int tmem_cols_of(int NW) {
+  int c = kFusedCols * ceil_div(NW, 4), p = 32;
+  while (p < c) p <<= 1;
+  return p;
+}
+}  // namespace
+
+bool bwd_fused_fits(int I, int H, int RX, int RH) {
+  if (H > 256 || (H & 3) || I > H || RH > 16) return false;
+  const int KS = ks_of(RX, RH), NZ = nz_of(RH);
+  if (KS > 2 || NZ > KS) return false;
+  return seq_bwd_fused_smem_bytes(ceil_div(H, 16), KS, I, RX) <= 227 * 1024;
+}
+
+long long bwd_fused_workspace_floats(int T, int B, int I, int H, int RX, int RH) {
+  if (!bwd_fused_fits(I, H, RX, RH)) return 0;
+  const GradLayout L(I, H, RX, RH);
+  (void)T;
+  return (long long)grid_of(B) * L.total + 8;
+}
+
+template <int KS, int NZ>
+static int launch_t(const SeqBwdFusedArgs& a, int NW, int G, cudaStream_t st) {
+  auto kern = seq_bwd_fused_kernel<KS, NZ>;
+  const size_t smem = seq_bwd_fused_smem_bytes(NW, KS, a.I, a.RX);
+  static bool attr_done = false;                        // benign race
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr_done = true;
+  }
+  kern<<<G, NW * 32, smem, st>>>(a, tmem_cols_of(NW));
+  return (int)cudaGetLastError();
+}
+
+int launch_bwd_fused(const SeqBwdFusedArgs& a0, const GradOut& out, void* workspace, cudaStream_t st) {
+  const int KS = ks_of(a0.RX, a0.RH), NZ = nz_of(a0.RH), NW = ceil_div(a0.H, 16);
+  const int G = grid_of(a0.B);
+  const GradLayout L(a0.I, a0.H, a0.RX, a0.RH);
+  SeqBwdFusedArgs a = a0;
+  a.dzc = nullptr;
+  a.partial = (float*)workspace;
+  int rc = kMmaNoFit;
+  if (KS == 1) rc = launch_t<1, 1>(a, NW, G, st);
+  else if (KS == 2 && NZ == 1) rc = launch_t<2, 1>(a, NW, G, st);
+  else if (KS == 2 && NZ == 2) rc = launch_t<2, 2>(a, NW, G, st);
+  if (rc) return rc;
+  reduce_partials_kernel<<<ceil_div(L.total, 256), 256, 0, st>>>(a.partial, G, L, out);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace vmlmf

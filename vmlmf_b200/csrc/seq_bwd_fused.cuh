@@ -1,0 +1,684 @@
+// seq_bwd_fused.cuh -- regime R1M backward with the weight-gradient accumulation fused into the reverse-time
+// recurrence: dPre never leaves the SM.
+//
+// Same tiling as seq_bwd_mma_kernel (K3a): CTA = 16 sequences, warp w = hidden units [16w,16w+16), lane (g,q) =
+// units 16w+8P+2q+{0,1} of sequences g, g+8.  The split design wrote dPre[T*B,4H] to HBM for a second kernel
+// (0.8 GB out + 0.8 GB in at the bench workload: traffic twice the algorithmic bytes).  Here the gradient
+// accumulators do not fit the register file next to the recurrence state (the kernel already runs at the
+// 128-register cap of a 512-thread CTA), so they live in TENSOR MEMORY: every warp owns 64 TMEM columns x 32 lanes
+// and moves accumulator fragments with tcgen05.ld / tcgen05.st around its mma.sync products:
+//   columns  0..31  [z|zx|1]^T dPre   (dBm | dVx | dbias)   8 n-tiles (gate k, half P) x 4 registers
+//   columns 32..47  dDh partial sums of the lane's 8 (unit, gate) pairs... per half P: 8 registers
+//   columns 48..63  dDx partial sums (x-side warps)
+// Per step and half P: dPre fragments -> per-warp shared tile (accumulator layout) -> read back transposed as the
+// B operand (K = the 16 sequences) of the [z|zx|1]^T dPre product; A = the step's [z|zx|1] rows, brought in one
+// step ahead with cp.async.  dX = dzx Ux^T + sum_k dPre_k Dx_k is finished in the same kernel (x-side warps).
+// What remains for a second pass are the two products that need h_{t-1} and x TRANSPOSED against the reduced dzc
+// (dA = Hprev^T dz, dUx = X^T dzx): grad_hx_kernel streams y, x and dzc only (0.3 GB).
+#pragma once
+#include "gemm_tc.cuh"
+#include "seq_bwd_mma.cuh"
+
+namespace vmlmf {
+
+struct SeqBwdFusedArgs {
+  const float *gates, *cs, *c0;
+  const float* dy; long long dys_t, dys_b;
+  const float *dhT, *dcT;
+  const float *Ux, *Vx, *Dx, *A, *Bm, *Dh;
+  const float* x; long long xs_t, xs_b;
+  const float* y; long long ys_t, ys_b;
+  const float* h0;
+  const float *z, *zx; int zp, zxp;
+  float* dzc;                              // [T*B, 8*KS] reduced [dz | dzx] rows (for grad_hx_kernel)
+  float* dx; long long dxs_t, dxs_b;       // may be null
+  float *dh0, *dc0;
+  float* partial;                          // [gridDim.x, GradLayout.total]; this kernel writes dVx, dDx, dBm, dDh, dbias
+  int T, B, I, H, RX, RH;
+};
+
+constexpr int kFusedTP = 40;               // pitch of the per-warp dPre tile (16 sequences x 32 columns of one half P)
+constexpr int kFusedCols = 80;             // TMEM columns per warp: 32 dW, 16 dDh, 16 dDx, 8 dA, 8 dUx (+ 8 spare with KS = 1)
+constexpr int kFusedAP = 17;               // pitch of a staged [z|zx|1] row (<= 16 slots: KS <= 2)
+
+inline size_t seq_bwd_fused_smem_bytes(int NW, int KS, int I, int RX) {
+  size_t fl = (size_t)NW * 8 * KS * 32 * 4             // B fragments of [Bm|Vx]
+              + (size_t)NW * 16 * kFusedTP             // per-warp dPre tiles
+              + (size_t)NW * 16 * bwd_pitch(KS)        // dzc partials
+              + (size_t)16 * bwd_pitch(KS)             // reduced dzc rows
+              + 2 * 4 * (size_t)NW * 16                // Dh, Dx [4][HP]
+              + 2 * 16 * (size_t)kFusedAP              // [z|zx|1] rows, double buffered
+              + (size_t)I * RX                         // Ux
+              + 4;                                     // TMEM base address slot
+  return fl * sizeof(float);
+}
+
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const float (&v)[4]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(__float_as_uint(v[0])),
+               "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3]))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
+  uint32_t r0, r1, r2, r3;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(taddr) : "memory");
+  v[0] = __uint_as_float(r0); v[1] = __uint_as_float(r1); v[2] = __uint_as_float(r2); v[3] = __uint_as_float(r3);
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cp_async4(float* dst_smem, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
+// KS <= 2 (one 16-slot m-tile of [z|zx|1]); NZ: n-tiles of the dh GEMM
+template <int KS, int NZ>
+__global__ void __launch_bounds__(512, 1) seq_bwd_fused_kernel(const SeqBwdFusedArgs a, const int tmem_cols) {
+  constexpr int PP = bwd_pitch(KS), TP = kFusedTP, AP = kFusedAP;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = blockDim.x >> 5;
+  const int g = lane >> 2, q = lane & 3;
+  const int H = a.H, I = a.I, B = a.B, T = a.T, RH = a.RH, RX = a.RX;
+  const int HP = NW * 16;
+  const int ubase = warp * 16;
+  const int j0 = ubase + 2 * q;                          // this lane's units: j0 + 8P + e
+  const bool xwarp = ubase < I;
+
+  extern __shared__ __align__(16) float smem[];
+  float4* Bf = reinterpret_cast<float4*>(smem);          // [NW][2 P][4 k][KS][32]
+  float* Tt = smem + (size_t)NW * 8 * KS * 32 * 4;       // [NW][16][TP]
+  float* Pz = Tt + (size_t)NW * 16 * TP;                 // [NW][16][PP]
+  float* Dz = Pz + (size_t)NW * 16 * PP;                 // [16][PP]
+  float* DhS = Dz + 16 * PP;                             // [4][HP]
+  float* DxS = DhS + 4 * HP;                             // [4][HP] (zero beyond I)
+  float* Ar = DxS + 4 * HP;                              // [2][16][AP]
+  float* UxS = Ar + 2 * 16 * AP;                         // [I][RX]
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(UxS + I * RX);
+
+  // ---- tensor memory: accumulator space, 64 columns per warp ----
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(tslot)), "r"(tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  // ---- prologue (as K3a) ----
+  auto wc = [&](int k, int j, int slot) -> float {
+    if (j >= H) return 0.f;
+    const size_t row = (size_t)k * H + j;
+    if (slot < RH) return __ldg(a.Bm + row * RH + slot);
+    if (slot < RH + RX) return __ldg(a.Vx + row * RX + (slot - RH));
+    return 0.f;
+  };
+  float4* myB = Bf + (size_t)warp * 8 * KS * 32 + lane;
+#pragma unroll 1
+  for (int pk = 0; pk < 8; ++pk) {
+    const int P = pk >> 2, k = pk & 3;
+#pragma unroll
+    for (int s = 0; s < KS; ++s) {
+      const float b0 = wc(k, j0 + 8 * P, 8 * s + g), b1 = wc(k, j0 + 8 * P + 1, 8 * s + g);
+      const float b0h = tf32_rna(b0), b1h = tf32_rna(b1);
+      myB[(pk * KS + s) * 32] = make_float4(b0h, b1h, tf32_rna(b0 - b0h), tf32_rna(b1 - b1h));
+    }
+  }
+  for (int i = tid; i < 4 * HP; i += blockDim.x) {
+    const int k = i / HP, j = i - k * HP;
+    DhS[i] = (j < H) ? __ldg(a.Dh + k * H + j) : 0.f;
+    DxS[i] = (j < I) ? __ldg(a.Dx + k * I + j) : 0.f;
+  }
+  for (int i = tid; i < I * RX; i += blockDim.x) UxS[i] = __ldg(a.Ux + i);
+  for (int i = tid; i < 2 * 16 * AP; i += blockDim.x) Ar[i] = ((i % AP) == RH + RX) ? 1.f : 0.f;
+  float Ath[2][NZ][2], Atl[2][NZ][2];
+#pragma unroll
+  for (int P = 0; P < 2; ++P)
+#pragma unroll
+    for (int s = 0; s < NZ; ++s)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int j = ubase + 8 * P + g, r = 8 * s + q + 4 * e;
+        const float v = (j < H && r < RH) ? __ldg(a.A + (size_t)j * RH + r) : 0.f;
+        Ath[P][s][e] = tf32_rna(v);
+        Atl[P][s][e] = tf32_rna(v - Ath[P][s][e]);
+      }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tbase = *tslot + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * kFusedCols);
+  {
+    const float zero4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < kFusedCols; c += 4) tmem_st4(tbase + c, zero4);
+    tmem_wait_st();
+  }
+
+  const int ntiles = ceil_div(B, 16);
+  const int nthreads = blockDim.x;
+  const size_t gstep = (size_t)ntiles * 4 * NW * 256, cstep = (size_t)ntiles * NW * 256, qstride = (size_t)NW * 256;
+  const bool dy_vec = a.dy && ((reinterpret_cast<uintptr_t>(a.dy) & 7) == 0) && !(a.dys_t & 1) && !(a.dys_b & 1);
+  float* myT = Tt + (size_t)warp * 16 * TP;
+
+  // staging of the [z|zx] part of the [z|zx|1] rows: thread i < 16*(RH+RX) owns element (row i / (RH+RX), slot i % (RH+RX))
+  // and walks its source pointer backwards in time (one 4-byte cp.async per step)
+  // (CTAs with fewer threads than elements -- H < 128 -- let a thread take the further elements tid + k*nthreads
+  //  through the slower generic path)
+  const int st_rr = tid / (RH + RX), st_slot = tid - st_rr * (RH + RX);
+  const bool st_own = tid < 16 * (RH + RX);
+  const long long st_pitch = st_slot < RH ? a.zp : a.zxp;
+  const float* st_base = st_slot < RH ? a.z + st_slot : a.zx + (st_slot - RH);
+  const bool st_more = 16 * (RH + RX) > (int)blockDim.x;
+
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int b0 = tile * 16;
+    const int sq[2] = {b0 + g, b0 + g + 8};
+    bool ok[2][2];                                       // [hf][P]
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+      for (int P = 0; P < 2; ++P) ok[hf][P] = sq[hf] < B && (j0 + 8 * P) < H;
+    float dhn[2][2][2], dcn[2][2][2];                    // [P][e][hf]
+#pragma unroll
+    for (int P = 0; P < 2; ++P)
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        float2 v = make_float2(0.f, 0.f), w = v;
+        if (ok[hf][P] && a.dhT) v = __ldg(reinterpret_cast<const float2*>(a.dhT + (size_t)sq[hf] * H + j0 + 8 * P));
+        if (ok[hf][P] && a.dcT) w = __ldg(reinterpret_cast<const float2*>(a.dcT + (size_t)sq[hf] * H + j0 + 8 * P));
+        dhn[P][0][hf] = v.x; dhn[P][1][hf] = v.y;
+        dcn[P][0][hf] = w.x; dcn[P][1][hf] = w.y;
+      }
+    const float* gfrag = a.gates + frag_addr((size_t)(T - 1) * ntiles + tile, 4, 0, NW, warp, 0, 0, lane);
+    const float* cfrag = a.cs + frag_addr((size_t)(T - 1) * ntiles + tile, 1, 0, NW, warp, 0, 0, lane);
+    auto prefetch_step = [&](int tp) {
+      if (tid != 0 || tp < 0) return;
+      l2_prefetch_bulk(a.gates + frag_addr((size_t)tp * ntiles + tile, 4, 0, NW, 0, 0, 0, 0), (uint32_t)(4 * NW * 256 * sizeof(float)));
+      if (tp > 0) l2_prefetch_bulk(a.cs + frag_addr((size_t)(tp - 1) * ntiles + tile, 1, 0, NW, 0, 0, 0, 0), (uint32_t)(NW * 256 * sizeof(float)));
+    };
+    if (tid == 0) l2_prefetch_bulk(a.cs + frag_addr((size_t)(T - 1) * ntiles + tile, 1, 0, NW, 0, 0, 0, 0), (uint32_t)(NW * 256 * sizeof(float)));
+    prefetch_step(T - 1);
+    prefetch_step(T - 2);
+    __syncthreads();                                     // previous tile finished with every shared buffer
+    const bool st_valid = st_own && (b0 + st_rr) < B;
+    const float* st_src = st_base + ((size_t)(T - 1) * B + b0 + st_rr) * st_pitch;      // row (T-1, b0 + st_rr)
+    auto stage_rows = [&](int ts) {                      // rows of timestep ts -> buffer ts & 1
+      if (ts < 0 || !st_own) return;
+      float* dst = Ar + (size_t)(ts & 1) * 16 * AP + st_rr * AP + st_slot;
+      if (st_valid) cp_async4(dst, st_src);
+      else *dst = 0.f;
+      st_src -= (size_t)B * st_pitch;
+      if (st_more)
+        for (int i = tid + nthreads; i < 16 * (RH + RX); i += nthreads) {
+          const int rr = i / (RH + RX), slot = i - rr * (RH + RX);
+          float* d2 = Ar + (size_t)(ts & 1) * 16 * AP + rr * AP + slot;
+          if (b0 + rr < B) {
+            const size_t r = (size_t)ts * B + b0 + rr;
+            cp_async4(d2, slot < RH ? a.z + r * a.zp + slot : a.zx + r * a.zxp + (slot - RH));
+          } else {
+            *d2 = 0.f;
+          }
+        }
+    };
+    stage_rows(T - 1);
+    cp_async_commit_wait_all();
+    // per-lane row pointers of the caller-layout tensors at the LAST timestep (walked backwards)
+    const float* yrow[2]; const float* xrow[2]; const float* dyrow[2]; float* dxrow[2];
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      yrow[hf] = a.y + (size_t)(T - 2) * a.ys_t + (size_t)sq[hf] * a.ys_b + j0;          // h_{t-1} of step t = T-1
+      xrow[hf] = a.x + (size_t)(T - 1) * a.xs_t + (size_t)sq[hf] * a.xs_b + j0;
+      dyrow[hf] = a.dy ? a.dy + (size_t)(T - 1) * a.dys_t + (size_t)sq[hf] * a.dys_b + j0 : nullptr;
+      dxrow[hf] = a.dx ? a.dx + (size_t)(T - 1) * a.dxs_t + (size_t)sq[hf] * a.dxs_b + j0 : nullptr;
+    }
+    // L2 prefetch of the h_{t-1} rows two steps ahead (16 lanes of warp 1, one row each)
+    auto prefetch_y = [&](int tp) {
+      if (warp != 1 || lane >= 16 || tp < 1 || (b0 + lane) >= B) return;
+      l2_prefetch_bulk(a.y + (size_t)(tp - 1) * a.ys_t + (size_t)(b0 + lane) * a.ys_b, (uint32_t)(H * sizeof(float)));
+    };
+    prefetch_y(T - 1);
+    prefetch_y(T - 2);
+    __syncthreads();
+
+    for (int t = T - 1; t >= 0; --t) {
+      prefetch_step(t - 2);
+      prefetch_y(t - 2);
+      stage_rows(t - 1);                                 // rows of the NEXT (earlier) step, visible after this step's barriers
+      const float* arow = Ar + (size_t)(t & 1) * 16 * AP;
+      // A operand of the [z|zx|1]^T dPre product for this step: (m = slot g / g+8, k = sequence q / q+4) x two k-steps
+      float wah[2][4], wal[2][4];
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        const float av[4] = {arow[(8 * ks + q) * AP + g], arow[(8 * ks + q) * AP + g + 8], arow[(8 * ks + q + 4) * AP + g],
+                             arow[(8 * ks + q + 4) * AP + g + 8]};
+        split4(av, wah[ks], wal[ks]);
+      }
+      float dz[KS][4];
+#pragma unroll
+      for (int s = 0; s < KS; ++s)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dz[s][i] = 0.f;
+      float sd[2][2][2];                                 // [P][e][hf]  sum_k dPre_k Dh_k
+      float sx[2][2][2];                                 // [P][e][hf]  sum_k dPre_k Dx_k (x-side warps)
+#pragma unroll
+      for (int P = 0; P < 2; ++P) {
+        float dpre[4][2][2];                             // [k][e][hf]
+        float2 hp2[2], xv2[2];
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          const int o = (P * 2 + hf) * 64;
+          float2 G[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) G[k] = __ldg(reinterpret_cast<const float2*>(gfrag + (size_t)k * qstride + o));
+          const float2 ct2 = __ldg(reinterpret_cast<const float2*>(cfrag + o));
+          float2 cp2 = make_float2(0.f, 0.f), dy2 = cp2;
+          hp2[hf] = cp2; xv2[hf] = cp2;
+          if (t > 0) cp2 = __ldg(reinterpret_cast<const float2*>(cfrag - cstep + o));
+          else if (ok[hf][P] && a.c0) cp2 = __ldg(reinterpret_cast<const float2*>(a.c0 + (size_t)sq[hf] * H + j0 + 8 * P));
+          if (ok[hf][P]) {
+            if (a.dy) {
+              const float* dp = dyrow[hf] + 8 * P;
+              if (dy_vec) dy2 = __ldg(reinterpret_cast<const float2*>(dp));
+              else { dy2.x = __ldg(dp); dy2.y = __ldg(dp + 1); }
+            }
+            if (t > 0) hp2[hf] = __ldg(reinterpret_cast<const float2*>(yrow[hf] + 8 * P));
+            else if (a.h0) hp2[hf] = __ldg(reinterpret_cast<const float2*>(a.h0 + (size_t)sq[hf] * H + j0 + 8 * P));
+          }
+          if (xwarp && sq[hf] < B) {
+            const float* xp = xrow[hf] + 8 * P;
+            if (j0 + 8 * P < I) xv2[hf].x = __ldg(xp);
+            if (j0 + 8 * P + 1 < I) xv2[hf].y = __ldg(xp + 1);
+          }
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const float gi = e ? G[0].y : G[0].x, gf = e ? G[1].y : G[1].x, go = e ? G[2].y : G[2].x, gn = e ? G[3].y : G[3].x;
+            const float ct = e ? ct2.y : ct2.x, cp = e ? cp2.y : cp2.x, dyv = e ? dy2.y : dy2.x;
+            const float dh = dhn[P][e][hf] + dyv;
+            const float tc = fmaf(2.f, rcp_approx(1.f + ex2_approx(ct * kNeg2Log2e)), -1.f);
+            const float dc = fmaf(dh * go, fmaf(-tc, tc, 1.f), dcn[P][e][hf]);
+            dpre[0][e][hf] = dc * gn * gi * (1.f - gi);
+            dpre[1][e][hf] = dc * cp * gf * (1.f - gf);
+            dpre[2][e][hf] = dh * tc * go * (1.f - go);
+            dpre[3][e][hf] = dc * gi * fmaf(-gn, gn, 1.f);
+            dcn[P][e][hf] = dc * gf;
+          }
+          // dPre of this half -> per-warp tile, accumulator layout: row = sequence, column = k*8 + unit-in-half
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            *reinterpret_cast<float2*>(myT + (g + 8 * hf) * TP + k * 8 + 2 * q) = make_float2(dpre[k][0][hf], dpre[k][1][hf]);
+        }
+        // ---- vector-multiplication terms: dh seed, dx seed, and the dDh / dDx sums (accumulators in tensor memory) ----
+        {
+          float gd[2][4];                                // [e][k] running sums of dPre_k * h_{t-1} over this lane's sequences
+          tmem_ld4(tbase + 32 + 8 * P, gd[0]);
+          tmem_ld4(tbase + 36 + 8 * P, gd[1]);
+#pragma unroll
+          for (int e = 0; e < 2; ++e)
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) sd[P][e][hf] = sx[P][e][hf] = 0.f;
+          tmem_wait_ld();
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 d2 = *reinterpret_cast<const float2*>(DhS + k * HP + j0 + 8 * P);
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+              sd[P][0][hf] = fmaf(dpre[k][0][hf], d2.x, sd[P][0][hf]);
+              sd[P][1][hf] = fmaf(dpre[k][1][hf], d2.y, sd[P][1][hf]);
+              gd[0][k] = fmaf(dpre[k][0][hf], hp2[hf].x, gd[0][k]);
+              gd[1][k] = fmaf(dpre[k][1][hf], hp2[hf].y, gd[1][k]);
+            }
+          }
+          tmem_st4(tbase + 32 + 8 * P, gd[0]);
+          tmem_st4(tbase + 36 + 8 * P, gd[1]);
+          if (xwarp) {
+            float gx[2][4];
+            tmem_ld4(tbase + 48 + 8 * P, gx[0]);
+            tmem_ld4(tbase + 52 + 8 * P, gx[1]);
+            tmem_wait_ld();
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float2 d2 = *reinterpret_cast<const float2*>(DxS + k * HP + j0 + 8 * P);
+#pragma unroll
+              for (int hf = 0; hf < 2; ++hf) {
+                sx[P][0][hf] = fmaf(dpre[k][0][hf], d2.x, sx[P][0][hf]);
+                sx[P][1][hf] = fmaf(dpre[k][1][hf], d2.y, sx[P][1][hf]);
+                gx[0][k] = fmaf(dpre[k][0][hf], xv2[hf].x, gx[0][k]);
+                gx[1][k] = fmaf(dpre[k][1][hf], xv2[hf].y, gx[1][k]);
+              }
+            }
+            tmem_st4(tbase + 48 + 8 * P, gx[0]);
+            tmem_st4(tbase + 52 + 8 * P, gx[1]);
+          }
+        }
+        // ---- partial dzc GEMM of this half (dPre registers are the A fragments) ----
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float av[4] = {dpre[k][0][0], dpre[k][0][1], dpre[k][1][0], dpre[k][1][1]};
+          float ah[4], al[4];
+          split4(av, ah, al);
+#pragma unroll
+          for (int s = 0; s < KS; ++s) {
+            const float4 b = myB[((P * 4 + k) * KS + s) * 32];
+            mma_3x(dz[s], ah, al, b.x, b.y, b.z, b.w);
+          }
+        }
+        // ---- [z|zx|1]^T dPre of this half: B = dPre tile read back transposed (k = sequence, n = unit 8P+g of gate k) ----
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float acc[4];
+          tmem_ld4(tbase + 4 * (P * 4 + k), acc);
+          const float* tc0 = myT + k * 8 + g;
+          const float b[4] = {tc0[q * TP], tc0[(q + 4) * TP], tc0[(q + 8) * TP], tc0[(q + 12) * TP]};
+          float bh[4], bl[4];
+          split4(b, bh, bl);
+          tmem_wait_ld();
+          mma_3x(acc, wah[0], wal[0], bh[0], bh[1], bl[0], bl[1]);
+          mma_3x(acc, wah[1], wal[1], bh[2], bh[3], bl[2], bl[3]);
+          tmem_st4(tbase + 4 * (P * 4 + k), acc);
+        }
+        __syncwarp();                                    // tile reads done before the next half overwrites it
+      }
+      {
+        float* pw = Pz + (size_t)warp * 16 * PP;
+#pragma unroll
+        for (int s = 0; s < KS; ++s) {
+          *reinterpret_cast<float2*>(pw + g * PP + 8 * s + 2 * q) = make_float2(dz[s][0], dz[s][1]);
+          *reinterpret_cast<float2*>(pw + (g + 8) * PP + 8 * s + 2 * q) = make_float2(dz[s][2], dz[s][3]);
+        }
+      }
+      gfrag -= gstep; cfrag -= cstep;
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        yrow[hf] -= a.ys_t; xrow[hf] -= a.xs_t;
+        if (a.dy) dyrow[hf] -= a.dys_t;
+      }
+      cp_async_commit_wait_all();                        // this thread's staged element of step t-1 has landed
+      __syncthreads();
+      // ---- fixed-order sum over warps -> Dz rows (and the global dzc rows grad_hx_kernel reads) ----
+      for (int idx = tid; idx < 16 * 8 * KS * 4; idx += nthreads) {
+        const int el = idx >> 2, part = idx & 3, seq = el / (8 * KS), slot = el - seq * (8 * KS);
+        float s = 0.f;
+        for (int w = part; w < NW; w += 4) s += Pz[((size_t)w * 16 + seq) * PP + slot];
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        if (part == 0) {
+          Dz[seq * PP + slot] = s;
+        }
+      }
+      __syncthreads();
+      // ---- dh_{t-1} = dz A^T + sum_k dPre_k Dh_k ; dx_t = dzx Ux^T + sum_k dPre_k Dx_k ----
+      float acc[2][4];
+#pragma unroll
+      for (int P = 0; P < 2; ++P) {
+        acc[P][0] = sd[P][0][0]; acc[P][1] = sd[P][1][0]; acc[P][2] = sd[P][0][1]; acc[P][3] = sd[P][1][1];
+      }
+#pragma unroll
+      for (int s = 0; s < NZ; ++s) {
+        const float av[4] = {Dz[g * PP + 8 * s + q], Dz[(g + 8) * PP + 8 * s + q], Dz[g * PP + 8 * s + q + 4],
+                             Dz[(g + 8) * PP + 8 * s + q + 4]};
+        float ah[4], al[4];
+        split4(av, ah, al);
+#pragma unroll
+        for (int P = 0; P < 2; ++P) mma_3x(acc[P], ah, al, Ath[P][s][0], Ath[P][s][1], Atl[P][s][0], Atl[P][s][1]);
+      }
+#pragma unroll
+      for (int P = 0; P < 2; ++P) {
+        dhn[P][0][0] = acc[P][0]; dhn[P][1][0] = acc[P][1]; dhn[P][0][1] = acc[P][2]; dhn[P][1][1] = acc[P][3];
+      }
+      if (xwarp && a.dx) {
+        float ax[2][4];
+#pragma unroll
+        for (int P = 0; P < 2; ++P) {
+          ax[P][0] = sx[P][0][0]; ax[P][1] = sx[P][1][0]; ax[P][2] = sx[P][0][1]; ax[P][3] = sx[P][1][1];
+        }
+#pragma unroll
+        for (int s = 0; s < KS; ++s) {
+          const int s0 = 8 * s + q, s1 = s0 + 4;
+          const float av[4] = {Dz[g * PP + s0], Dz[(g + 8) * PP + s0], Dz[g * PP + s1], Dz[(g + 8) * PP + s1]};
+          float ah[4], al[4];
+          split4(av, ah, al);
+#pragma unroll
+          for (int P = 0; P < 2; ++P) {                  // B = Ux^T restricted to the zx slots: (k = slot, n = g <-> unit 8P+g)
+            const int j = ubase + 8 * P + g;
+            const float b0 = (j < I && s0 >= RH && s0 < RH + RX) ? UxS[j * RX + (s0 - RH)] : 0.f;
+            const float b1 = (j < I && s1 >= RH && s1 < RH + RX) ? UxS[j * RX + (s1 - RH)] : 0.f;
+            const float b0h = tf32_rna(b0), b1h = tf32_rna(b1);
+            mma_3x(ax[P], ah, al, b0h, b1h, b0 - b0h, b1 - b1h);
+          }
+        }
+#pragma unroll
+        for (int P = 0; P < 2; ++P)
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            const int j = j0 + 8 * P;
+            if (sq[hf] < B) {
+              float* o = dxrow[hf] + 8 * P;
+              if (j < I) o[0] = ax[P][2 * hf];
+              if (j + 1 < I) o[1] = ax[P][2 * hf + 1];
+            }
+          }
+      }
+      if (a.dx) { dxrow[0] -= a.dxs_t; dxrow[1] -= a.dxs_t; }
+      // ---- dA += Hprev^T dz, dUx += X^T dzx: A = (m = g: unit ju, m = g+8: unit ju+1; k = sequence q / q+4) read transposed
+      //      from the rows this warp touched in phase 1 (L1/L2 hits), B = the reduced dzc rows (k = sequence, n = slot) ----
+      {
+        const int ju = ubase + 8 * (g >> 2) + 2 * (g & 3);
+        const bool uin = ju < H;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          const int rr0 = 8 * ks + q, rr1 = rr0 + 4;
+          const bool v0 = (b0 + rr0) < B, v1 = (b0 + rr1) < B;
+          float2 h0v = make_float2(0.f, 0.f), h1v = h0v, x0v = h0v, x1v = h0v;
+          if (uin) {
+            if (t > 0) {
+              const float* yb = a.y + (size_t)(t - 1) * a.ys_t + (size_t)b0 * a.ys_b + ju;
+              if (v0) h0v = __ldg(reinterpret_cast<const float2*>(yb + (size_t)rr0 * a.ys_b));
+              if (v1) h1v = __ldg(reinterpret_cast<const float2*>(yb + (size_t)rr1 * a.ys_b));
+            } else if (a.h0) {
+              if (v0) h0v = __ldg(reinterpret_cast<const float2*>(a.h0 + (size_t)(b0 + rr0) * H + ju));
+              if (v1) h1v = __ldg(reinterpret_cast<const float2*>(a.h0 + (size_t)(b0 + rr1) * H + ju));
+            }
+          }
+          if (xwarp) {
+            const float* xb = a.x + (size_t)t * a.xs_t + (size_t)b0 * a.xs_b + ju;
+            if (ju < I) { if (v0) x0v.x = __ldg(xb + (size_t)rr0 * a.xs_b); if (v1) x1v.x = __ldg(xb + (size_t)rr1 * a.xs_b); }
+            if (ju + 1 < I) { if (v0) x0v.y = __ldg(xb + (size_t)rr0 * a.xs_b + 1); if (v1) x1v.y = __ldg(xb + (size_t)rr1 * a.xs_b + 1); }
+          }
+          const float hv[4] = {h0v.x, h0v.y, h1v.x, h1v.y};
+          float hh[4], hl[4], xh[4], xl[4];
+          split4(hv, hh, hl);
+          if (xwarp) {
+            const float xv[4] = {x0v.x, x0v.y, x1v.x, x1v.y};
+            split4(xv, xh, xl);
+          }
+#pragma unroll
+          for (int s = 0; s < KS; ++s) {
+            float ag[4], au[4];
+            tmem_ld4(tbase + 64 + 4 * s, ag);
+            if (xwarp) tmem_ld4(tbase + 72 + 4 * s, au);
+            const float d0 = Dz[rr0 * PP + 8 * s + g], d1 = Dz[rr1 * PP + 8 * s + g];
+            const float b0h = tf32_rna(d0), b1h = tf32_rna(d1);
+            tmem_wait_ld();
+            mma_3x(ag, hh, hl, b0h, b1h, d0 - b0h, d1 - b1h);
+            tmem_st4(tbase + 64 + 4 * s, ag);
+            if (xwarp) {
+              mma_3x(au, xh, xl, b0h, b1h, d0 - b0h, d1 - b1h);
+              tmem_st4(tbase + 72 + 4 * s, au);
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int P = 0; P < 2; ++P)
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf)
+        if (ok[hf][P]) {
+          if (a.dh0) *reinterpret_cast<float2*>(a.dh0 + (size_t)sq[hf] * H + j0 + 8 * P) = make_float2(dhn[P][0][hf], dhn[P][1][hf]);
+          if (a.dc0) *reinterpret_cast<float2*>(a.dc0 + (size_t)sq[hf] * H + j0 + 8 * P) = make_float2(dcn[P][0][hf], dcn[P][1][hf]);
+        }
+  }
+
+  // ---- this CTA's partial: accumulators out of tensor memory ----
+  tmem_wait_st();
+  const GradLayout L(I, H, RX, RH);
+  float* Pout = a.partial + (size_t)blockIdx.x * L.total;
+  // [z|zx|1]^T dPre, n-tile (k, P): C fragment (slot g, unit 8P+2q / +1), (slot g+8, same)
+#pragma unroll
+  for (int P = 0; P < 2; ++P)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float acc[4];
+      tmem_ld4(tbase + 4 * (P * 4 + k), acc);
+      tmem_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int slot = g + 8 * (i >> 1), j = j0 + 8 * P + (i & 1);
+        if (j >= H) continue;
+        const size_t row = (size_t)k * H + j;
+        if (slot < RH) Pout[L.oBm + row * RH + slot] = acc[i];
+        else if (slot < RH + RX) Pout[L.oVx + row * RX + (slot - RH)] = acc[i];
+        else if (slot == RH + RX) Pout[L.oBias + row] = acc[i];
+      }
+    }
+  // dDh / dDx: sum over the eight g lanes (sequences), lanes g == 0 store units j0 + 8P + e
+#pragma unroll
+  for (int P = 0; P < 2; ++P)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      float gd[4], gx[4];
+      tmem_ld4(tbase + 32 + 8 * P + 4 * e, gd);
+      tmem_ld4(tbase + 48 + 8 * P + 4 * e, gx);
+      tmem_wait_ld();
+      const int j = j0 + 8 * P + e;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float v = gd[k], w = gx[k];
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+          v += __shfl_xor_sync(0xffffffffu, v, o);
+          w += __shfl_xor_sync(0xffffffffu, w, o);
+        }
+        if (g == 0 && j < H) Pout[L.oDh + k * H + j] = v;
+        if (g == 0 && j < I) Pout[L.oDx + k * I + j] = w;
+      }
+    }
+  // dA / dUx: C fragment (m = g [+8] <-> unit ju [+1], n = slot 8s + 2q [+1])
+  {
+    const int ju = ubase + 8 * (g >> 2) + 2 * (g & 3);
+#pragma unroll
+    for (int s = 0; s < KS; ++s) {
+      float ag[4], au[4];
+      tmem_ld4(tbase + 64 + 4 * s, ag);
+      tmem_ld4(tbase + 72 + 4 * s, au);
+      tmem_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int j = ju + (i >> 1), slot = 8 * s + 2 * q + (i & 1);
+        if (j < H && slot < RH) Pout[L.oA + (size_t)j * RH + slot] = ag[i];
+        if (j < I && slot >= RH && slot < RH + RX) Pout[L.oUx + (size_t)j * RX + (slot - RH)] = au[i];
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc::tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tslot), "r"(tmem_cols));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------- //
+// dA = Hprev^T dz and dUx = X^T dzx over all rows (the two products that need h_{t-1} / x transposed)
+// ------------------------------------------------------------------------------------------------- //
+struct GradHxArgs {
+  const float* dzc;                        // [T*B, 8*KS]
+  const float* y; long long ys_t, ys_b;
+  const float* h0;
+  const float* x; long long xs_t, xs_b;
+  float* partial;                          // [gridDim.x, GradLayout.total]; this kernel writes dUx and dA
+  int T, B, I, H, RX, RH;
+  int blocks_per_cta;
+};
+
+// blockDim = 32 * ceil(H/16): warp w owns units [16w,16w+16); lane (g,q) = unit pair 16w + 8(g>>2) + 2(g&3) + {0,1},
+// rows q, q+4 (+8, +12) of each 16-sequence block -- the mapping of grad_rows_kernel without its dPre part.
+template <int KS>
+__global__ void __launch_bounds__(512, 1) grad_hx_kernel(const GradHxArgs a) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, q = lane & 3;
+  const int H = a.H, I = a.I, B = a.B, RH = a.RH, RX = a.RX;
+  const int ntiles = ceil_div(B, 16);
+  const long long nblocks = (long long)a.T * ntiles;
+  const int ju = warp * 16 + 8 * (g >> 2) + 2 * (g & 3);
+  const bool uin = ju < H, xcols = warp * 16 < I;
+  float accG[KS][4], accU[KS][4];
+#pragma unroll
+  for (int s = 0; s < KS; ++s)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) accG[s][i] = accU[s][i] = 0.f;
+  const long long blk_begin = (long long)blockIdx.x * a.blocks_per_cta;
+  long long blk_end = blk_begin + a.blocks_per_cta;
+  if (blk_end > nblocks) blk_end = nblocks;
+  auto prefetch_blk = [&](long long pb) {                // h_{t-1} rows of a block into L2 (16 lanes of warp 0)
+    if (pb >= blk_end || warp != 0 || lane >= 16) return;
+    const int tp = (int)(pb / ntiles), bp = (int)(pb % ntiles) * 16;
+    if (tp > 0 && bp + lane < B)
+      l2_prefetch_bulk(a.y + (size_t)(tp - 1) * a.ys_t + (size_t)(bp + lane) * a.ys_b, (uint32_t)(H * sizeof(float)));
+  };
+  prefetch_blk(blk_begin); prefetch_blk(blk_begin + 1); prefetch_blk(blk_begin + 2);
+  for (long long blk = blk_begin; blk < blk_end; ++blk) {
+    prefetch_blk(blk + 3);
+    const int t = (int)(blk / ntiles), b0 = (int)(blk % ntiles) * 16;
+    const int nvalid = (B - b0) < 16 ? (B - b0) : 16;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      const int rr0 = 8 * ks + q, rr1 = rr0 + 4;
+      const bool v0 = rr0 < nvalid, v1 = rr1 < nvalid;
+      const size_t r0 = (size_t)t * B + b0 + rr0, r1 = r0 + 4;
+      float2 h0v = make_float2(0.f, 0.f), h1v = h0v, x0v = h0v, x1v = h0v;
+      if (uin) {
+        if (t > 0) {
+          if (v0) h0v = __ldg(reinterpret_cast<const float2*>(a.y + (size_t)(t - 1) * a.ys_t + (size_t)(b0 + rr0) * a.ys_b + ju));
+          if (v1) h1v = __ldg(reinterpret_cast<const float2*>(a.y + (size_t)(t - 1) * a.ys_t + (size_t)(b0 + rr1) * a.ys_b + ju));
+        } else if (a.h0) {
+          if (v0) h0v = __ldg(reinterpret_cast<const float2*>(a.h0 + (size_t)(b0 + rr0) * H + ju));
+          if (v1) h1v = __ldg(reinterpret_cast<const float2*>(a.h0 + (size_t)(b0 + rr1) * H + ju));
+        }
+      }
+      if (xcols) {
+        const float* xp0 = a.x + (size_t)t * a.xs_t + (size_t)(b0 + rr0) * a.xs_b + ju;
+        const float* xp1 = a.x + (size_t)t * a.xs_t + (size_t)(b0 + rr1) * a.xs_b + ju;
+        if (ju < I) { if (v0) x0v.x = __ldg(xp0); if (v1) x1v.x = __ldg(xp1); }
+        if (ju + 1 < I) { if (v0) x0v.y = __ldg(xp0 + 1); if (v1) x1v.y = __ldg(xp1 + 1); }
+      }
+      const float hv[4] = {h0v.x, h0v.y, h1v.x, h1v.y};
+      float hh[4], hl[4], xh[4], xl[4];
+      split4(hv, hh, hl);
+      if (xcols) {
+        const float xv[4] = {x0v.x, x0v.y, x1v.x, x1v.y};
+        split4(xv, xh, xl);
+      }
+#pragma unroll
+      for (int s = 0; s < KS; ++s) {
+        const float d0 = v0 ? __ldg(a.dzc + r0 * (8 * KS) + 8 * s + g) : 0.f;
+        const float d1 = v1 ? __ldg(a.dzc + r1 * (8 * KS) + 8 * s + g) : 0.f;
+        const float b0h = tf32_rna(d0), b1h = tf32_rna(d1);
+        mma_3x(accG[s], hh, hl, b0h, b1h, d0 - b0h, d1 - b1h);
+        if (xcols) mma_3x(accU[s], xh, xl, b0h, b1h, d0 - b0h, d1 - b1h);
+      }
+    }
+  }
+  const GradLayout L(I, H, RX, RH);
+  float* P = a.partial + (size_t)blockIdx.x * L.total;
+#pragma unroll
+  for (int s = 0; s < KS; ++s)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int j = ju + (i >> 1), slot = 8 * s + 2 * q + (i & 1);
+      if (j < H && slot < RH) P[L.oA + (size_t)j * RH + slot] = accG[s][i];
+      if (j < I && slot >= RH && slot < RH + RX) P[L.oUx + (size_t)j * RX + (slot - RH)] = accU[s][i];
+    }
+}
+
+int launch_bwd_fused(const SeqBwdFusedArgs& a, const GradOut& out, void* workspace, cudaStream_t st);
+long long bwd_fused_workspace_floats(int T, int B, int I, int H, int RX, int RH);
+bool bwd_fused_fits(int I, int H, int RX, int RH);
+
+}  // namespace vmlmf

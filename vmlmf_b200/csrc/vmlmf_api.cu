@@ -6,6 +6,7 @@
 #include <stdlib.h>
 
 #include "generic.cuh"
+#include "seq_bwd_fused.cuh"
 #include "seq_bwd_mma.cuh"
 #include "seq_mma.cuh"
 #include "seq_r1_launch.cuh"
@@ -40,6 +41,11 @@ bool simt_only() {
   return e && e[0] == '1';
 }
 // VMLMF_MMA_MIN_BATCH overrides the batch size from which the warp-MMA path is planned (tests force it to 1)
+// VMLMF_BWD_SPLIT=1 selects the two-kernel R1M backward (dPre through HBM) instead of the fused one
+bool use_fused_bwd(int I, int H, int RX, int RH) {
+  const char* e = getenv("VMLMF_BWD_SPLIT");
+  return !(e && e[0] == '1') && bwd_fused_fits(I, H, RX, RH);
+}
 int mma_min_batch() {
   const char* e = getenv("VMLMF_MMA_MIN_BATCH");
   return e ? atoi(e) : kMmaMinBatch;
@@ -88,6 +94,8 @@ int vmlmf_seq_plan(int T, int B, int I, int H, int RX, int RH, vmlmf_plan* plan)
     plan->gates_bytes = (long long)frag_floats(T, B, H, 4) * (long long)sizeof(float);
     plan->cs_bytes = (long long)frag_floats(T, B, H, 1) * (long long)sizeof(float);
     plan->bwd_workspace_bytes = bwd_mma_workspace_floats(T, B, I, H, RX, RH) * (long long)sizeof(float);
+    if (use_fused_bwd(I, H, RX, RH))        // fused backward: no dPre buffer, only the reduced dzc rows and the partials
+      plan->bwd_workspace_bytes = bwd_fused_workspace_floats(T, B, I, H, RX, RH) * (long long)sizeof(float);
     return VMLMF_OK;
   }
   const R1Choice c = choose_r1(I, H, RX, RH);
@@ -223,6 +231,13 @@ int vmlmf_seq_bwd(const vmlmf_plan* plan, const float* x, long long xs_t, long l
     if (!bwd_mma_fits(I, H, RX, RH) || plan->z_pitch != 8 * ceil_div(RH, 8) || plan->zx_pitch != round_up(RX, 4))
       return VMLMF_EPLAN;
     if ((ys_t & 1) || (ys_b & 1) || (reinterpret_cast<uintptr_t>(y) & 7)) return VMLMF_EINVAL;
+    GradOut o2{dUx, dVx, dDx, dA, dBm, dDh, dbias};
+    if (use_fused_bwd(I, H, RX, RH)) {
+      // fused: recurrence + weight-gradient accumulation (accumulators in tensor memory) + dX; then dA / dUx
+      SeqBwdFusedArgs fa{gates, cs, c0, dy, dys_t, dys_b, dhT, dcT, Ux, Vx, Dx, A, Bm, Dh, x, xs_t, xs_b, y, ys_t, ys_b, h0,
+                         z, zx, plan->z_pitch, plan->zx_pitch, nullptr, dx, dxs_t, dxs_b, dh0, dc0, nullptr, T, B, I, H, RX, RH};
+      return launch_bwd_fused(fa, o2, workspace, st);
+    }
     // reverse-time recurrence (K3a) + time-parallel gradient accumulation (K3b)
     SeqBwdMmaArgs ba{gates, cs, c0, dy, dys_t, dys_b, dhT, dcT, Vx, A, Bm, Dh, nullptr, nullptr, dh0, dc0, T, B, H, RX, RH};
     GradRowsArgs gr{nullptr, nullptr, z, zx, plan->z_pitch, plan->zx_pitch, y, ys_t, ys_b, h0, x, xs_t, xs_b, Ux, Dx,
