@@ -378,9 +378,10 @@ def run_ours(args):
 
     r_bwd, r_fwd = roof("seq_bwd", q_bwd), roof("seq_fwd", q_fwd)
     roofline = dict(r_bwd or {})
-    roofline["note"] = ("seq_bwd = one C-ABI call = reverse-time recurrence kernel + time-parallel gradient kernel + "
-                        "partial reduce; achieved = SURVEY 8(d) algorithmic bytes / event time of the whole call. "
-                        "The dPre round trip between the two kernels is traffic above the algorithmic bytes.")
+    roofline["note"] = ("seq_bwd = one C-ABI call = fused reverse-time recurrence + weight-gradient accumulation kernel "
+                        "(accumulators in tensor memory) + partial reduce; achieved = SURVEY 8(d) algorithmic bytes / "
+                        "CUDA-event time of the whole call, measured on eager steps; the timed region replays the same "
+                        "step as a CUDA graph.")
     roofline["other_kernels"] = [r_fwd, {"kernel": "xproj_fwd", "ms_per_launch": kernel_ms.get("xproj_fwd")}]
     roofline["step_share"] = {k: v / ms_step for k, v in kernel_ms.items()}
 
@@ -397,12 +398,12 @@ def run_ours(args):
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": B * world, "seq_len": T_STEPS,
-                   "parallelism": f"dp{world}", "cuda_graph": bool(use_graph), "l2_policy": "inputs larger than L2 (x 70 MB + 1.4 GB saved state + 0.9 GB dPre per step, 4 rotating batches)"},
+                   "parallelism": f"dp{world}", "cuda_graph": bool(use_graph), "l2_policy": "inputs larger than L2 (x 70 MB + 1.4 GB saved state per step, 4 rotating batches)"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "sequences/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": e2e_s * 1e3 / K},
-        # per step: xproj_small, seq_fwd_mma, seq_bwd_mma (K3a), grad_rows (K3b), reduce_partials
-        "gpu_launches": 5 * K,
+        # per step: 2 x diag_fwd, xproj_small, seq_fwd_mma, seq_bwd_fused, reduce_partials, 2 x diag_bwd
+        "gpu_launches": 8 * K,
         "roofline": roofline,
         "cpu_baseline": cpu,
         "inference": {"value": inf_value, "unit": "sequences/s", "ms_per_step": inf_ms / K},
