@@ -34,9 +34,8 @@ def test_plan_and_error_codes():
     assert p.path == _lib.PATH_R1M and p.zx_pitch == 8 and p.z_pitch == 8
     assert p.gates_bytes == 24 * 513 * 4 * 12 * 256 * 4 and p.cs_bytes * 4 == p.gates_bytes
     assert 0 < p.bwd_workspace_bytes < p.gates_bytes                       # fused backward: per-CTA partials only, no dPre
-    p = _lib.plan(24, 8200, 77, 180, 16, 16)                               # RH+RX+1 > 32 contraction rows: split backward
-    if p.path == _lib.PATH_R1M:
-        assert p.bwd_workspace_bytes >= p.gates_bytes
+    p = _lib.plan(24, 8200, 77, 180, 8, 16)                                # more than 16 contraction rows: split backward
+    assert p.path == _lib.PATH_R1M and p.bwd_workspace_bytes >= p.gates_bytes
     assert _lib.plan(24, 8200, 77, 181, 8, 6).path == _lib.PATH_R1          # H % 4 != 0 stays on the SIMT kernels
     assert _lib.plan(35, 4096, 650, 650, 300, 300).path == _lib.PATH_G
     with pytest.raises(TypeError):                       # H < I: the reference raises TypeError too
