@@ -92,7 +92,9 @@ int vmlmf_xproj_fwd(const float* x, long long xs_t, long long xs_b, const float*
  * (V/models/vmlmf.py:308-310 with the cell body :78-125; vmlmf_group.py:85-155;
  * vmlmf_lm.py:272-280 with lstm_step :222-269).
  *   h0,c0      [B,H] or NULL (= zeros, MyLSTM.forward :302-303)
- *   y          h_t for every t, strides (ys_t, ys_b)
+ *   y          h_t for every t, strides (ys_t, ys_b); may be NULL when nothing is saved and the plan
+ *              is PATH_R1 / PATH_R1M: a caller that consumes only the last step (Net.forward,
+ *              V/models/vmlmf.py:354-355) skips the [T,B,H] write and reads hT instead
  *   hT,cT      [B,H] final state
  *   gates,cs,z saved for backward: plan.gates_bytes / plan.cs_bytes / T*B*z_pitch floats, written by
  *              this call and read back only by vmlmf_seq_bwd (layout is private to the path);

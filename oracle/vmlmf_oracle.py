@@ -73,6 +73,21 @@ def plain_cell_step(p, x, h, c):
 
 
 # --------------------------------------------------------------------------- #
+# f4: uncompressed / plain low-rank baseline cell  (V/models/vmlmf.py:127-238)
+# --------------------------------------------------------------------------- #
+
+
+def lstm_cell_step(p, x, h, c):
+    """One step of MyLSTMCell.  p: [w,] w1..w4, [u,] u1..u4, bias_f, bias_i, bias_c, bias_o.
+    `w` / `u` present = low-rank factorisation of that side (:193-220); gate k uses (w_k, u_k) in the order
+    i, f, o, c~ (:222-231)."""
+    xs = x @ p["w"] if "w" in p else x
+    hs = h @ p["u"] if "u" in p else h
+    pre = [xs @ p[f"w{k}"] + hs @ p[f"u{k}"] for k in (1, 2, 3, 4)]
+    return _finish(pre[0] + p["bias_i"], pre[1] + p["bias_f"], pre[2] + p["bias_o"], pre[3] + p["bias_c"], c)
+
+
+# --------------------------------------------------------------------------- #
 # a6 / a7: group cells  (V/models/vmlmf_group.py:85-155, :203-251)
 # --------------------------------------------------------------------------- #
 
@@ -219,7 +234,7 @@ def lm_group_cell_step(p, x, h, c, g=2):
 # a3 / a4: layer stack and classifier net  (V/models/vmlmf.py:294-316, :352-355)
 # --------------------------------------------------------------------------- #
 
-_STEP = {"plain": plain_cell_step, "group": group_cell_step, "group_novm": group_ablation_step}
+_STEP = {"plain": plain_cell_step, "group": group_cell_step, "group_novm": group_ablation_step, "lstm": lstm_cell_step}
 
 
 def layer_stack(cells, x, kind="plain", batch_first=True, **kw):
@@ -230,7 +245,8 @@ def layer_stack(cells, x, kind="plain", batch_first=True, **kw):
     step = _STEP[kind]
     last = []
     for p in cells:
-        hidden = (p["dia_h"].shape[1] if "dia_h" in p else p["bias_h"].shape[1] // 4)
+        hidden = (p["dia_h"].shape[1] if "dia_h" in p else p["bias_f"].shape[1] if "bias_f" in p
+                  else p["bias_h"].shape[1] // 4)
         h = x.new_zeros(x.size(b_dim), hidden)
         c = x.new_zeros(x.size(b_dim), hidden)
         outs = []

@@ -20,7 +20,7 @@ import torch
 
 REF = "/root/reference/rnn_compression_factorization_vmlmf/src"
 sys.path.insert(0, REF)
-from models.vmlmf import MyLSTM, MyVMLMFCell, Net  # noqa: E402
+from models.vmlmf import MyLSTM, MyLSTMCell, MyVMLMFCell, Net  # noqa: E402
 from models.vmlmf_group import MyVMLMFCellg2, MyVMLMFgCellg2  # noqa: E402
 from models.vmlmf_lm import Model, MyVMLSTM, MyVMLSTMGroup  # noqa: E402
 
@@ -111,6 +111,16 @@ def case_mylstm_2layer():
     return _stack_case(lambda: MyLSTM(9, [16, 24], w_rank=4, u_ranks=[3], cell=MyVMLMFCell), (3, 7, 9), [16, 24], 51)
 
 
+def case_lstm_lowrank():
+    # the reference's plain low-rank baseline cell (V/models/vmlmf.py:127-238), two layers
+    return _stack_case(lambda: MyLSTM(9, [16, 24], w_rank=4, u_ranks=[3], cell=MyLSTMCell), (3, 7, 9), [16, 24], 53)
+
+
+def case_lstm_dense():
+    # ... and the uncompressed one (w_rank = u_ranks = None)
+    return _stack_case(lambda: MyLSTM(9, [16], cell=MyLSTMCell), (3, 6, 9), [16], 55)
+
+
 def case_group_ablation():
     return _stack_case(lambda: MyLSTM(9, [16], w_rank=4, u_ranks=[2, 3], cell=MyVMLMFgCellg2), (3, 5, 9), [16], 61)
 
@@ -171,6 +181,8 @@ CASES = {k[5:]: v for k, v in list(globals().items()) if k.startswith("case_")}
 
 if __name__ == "__main__":
     for name, fn in CASES.items():
+        if len(sys.argv) > 1 and name not in sys.argv[1:]:      # optional: regenerate only the named cases
+            continue
         rec = fn()
         path = os.path.join(HERE, name + ".npz")
         np.savez_compressed(path, **rec)

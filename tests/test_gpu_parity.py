@@ -97,6 +97,9 @@ def test_golden_net(case, build):
     ("mylstm_2layer", lambda: vb.MyLSTM(9, [16, 24], w_rank=4, u_ranks=[3], cell=vb.MyVMLMFCell)),
     ("group_ablation", lambda: vb.MyLSTM(9, [16], w_rank=4, u_ranks=[2, 3], cell=vb.MyVMLMFgCellg2)),
     ("group_g4", lambda: vb.MyLSTM(6, [16], w_rank=3, u_ranks=[2, 1, 3, 2], cell=vb.MyVMLMFCellg2, g=4)),
+    # the uncompressed / plain low-rank baseline cell runs through the same kernels (Dx = Dh = 0)
+    ("lstm_lowrank", lambda: vb.MyLSTM(9, [16, 24], w_rank=4, u_ranks=[3], cell=vb.MyLSTMCell)),
+    ("lstm_dense", lambda: vb.MyLSTM(9, [16], cell=vb.MyLSTMCell)),
 ])
 def test_golden_layer_stack(case, build):
     g = load_golden(case)
@@ -363,3 +366,24 @@ def test_full_size_properties_cfg2(r1_path):
         assert torch.equal(a, b)                           # fixed-order reductions: bitwise reproducible
     for a, b in zip(g1, g3):
         assert_close(b.cpu().numpy(), 3.0 * a.cpu().numpy(), 5e-6, "linearity")     # x3 is not exact in fp32: rounding only
+
+
+# ----------------------------- last-step-only output ----------------------------- #
+
+@pytest.mark.parametrize("B,T,I,H,RX,RH", [(37, 5, 9, 32, 4, 3), (70, 6, 77, 180, 8, 6), (1600, 3, 9, 128, 8, 6)])
+def test_last_step_only_skips_sequence_output(B, T, I, H, RX, RH):
+    """need_y=False: inference on the persistent kernels returns no [B,T,H] tensor and the same (hT, cT), bit for bit;
+    as soon as backward will run the sequence is kept (it holds h_{t-1})."""
+    torch.manual_seed(5)
+    net = vb.Net(I, [H], w_rank=RX, u_rank=[RH], cell=vb.MyVMLMFCell).to(DEV)
+    x = torch.randn(B, T, I, device=DEV)
+    canon = net.rnn.rnncells[0].canonical()
+    with torch.no_grad():
+        y_full, h_full, c_full = vmlmf_sequence(x, None, None, canon)
+        y_none, h_last, c_last = vmlmf_sequence(x, None, None, canon, need_y=False)
+        logits = net(x)
+    assert y_none is None and torch.equal(h_full, h_last) and torch.equal(c_full, c_last)
+    assert torch.equal(y_full[:, -1], h_last)
+    y_grad, h_grad, _ = vmlmf_sequence(x, None, None, canon, need_y=False)      # training: sequence kept for backward
+    assert y_grad is not None and torch.equal(h_grad, h_last)
+    assert torch.equal(net(x).detach(), logits)

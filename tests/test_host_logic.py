@@ -69,6 +69,8 @@ def test_state_dict_layout_and_init_match_reference():
     _same_seed_module("net_plain", lambda: vb.Net(9, [32], w_rank=8, u_rank=[6], cell=vb.MyVMLMFCell), 21)
     _same_seed_module("net_group", lambda: vb.Net(9, [16], w_rank=4, u_rank=[2, 3], cell=vb.MyVMLMFCellg2), 41)
     _same_seed_module("mylstm_2layer", lambda: vb.MyLSTM(9, [16, 24], w_rank=4, u_ranks=[3], cell=vb.MyVMLMFCell), 51)
+    _same_seed_module("lstm_lowrank", lambda: vb.MyLSTM(9, [16, 24], w_rank=4, u_ranks=[3], cell=vb.MyLSTMCell), 53)
+    _same_seed_module("lstm_dense", lambda: vb.MyLSTM(9, [16], cell=vb.MyLSTMCell), 55)
     _same_seed_module("group_ablation", lambda: vb.MyLSTM(9, [16], w_rank=4, u_ranks=[2, 3], cell=vb.MyVMLMFgCellg2), 61)
     _same_seed_module("group_g4", lambda: vb.MyLSTM(6, [16], w_rank=3, u_ranks=[2, 1, 3, 2], cell=vb.MyVMLMFCellg2, g=4), 63)
     _same_seed_module("lm_model", lambda: vb.Model(50, 16, 2, 0.0, 0.25, w_rank=4, u_ranks=[5], lstm_type="vmlmf"), 81)

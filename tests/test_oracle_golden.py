@@ -86,10 +86,11 @@ def test_net(case, kind, prefix, dt):
 @pytest.mark.parametrize("dt", [torch.float32, torch.float64])
 @pytest.mark.parametrize("case,kind,nl,kw", [("mylstm_2layer", "plain", 2, {}),
                                              ("group_ablation", "group_novm", 1, {}),
-                                             ("group_g4", "group", 1, {"g": 4})])
+                                             ("group_g4", "group", 1, {"g": 4}),
+                                             ("lstm_lowrank", "lstm", 2, {}), ("lstm_dense", "lstm", 1, {})])
 def test_layer_stack(case, kind, nl, kw, dt):
     g = load_golden(case)
-    sub = "" if kind == "plain" else "layers."
+    sub = "" if kind in ("plain", "lstm") else "layers."
     cells = [_params(g, f"rnncells.{l}.{sub}", dt) for l in range(nl)]
     x = _t(g["in/x"], dt, True)
     seq, hcat = vo.layer_stack(cells, x, kind=kind, **kw)

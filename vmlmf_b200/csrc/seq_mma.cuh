@@ -158,6 +158,7 @@ __global__ void __launch_bounds__(512, 1) seq_fwd_mma_kernel(const SeqFwdMmaArgs
   const int ntiles = ceil_div(B, 16);
   const int j0 = ubase + 2 * q;                          // this lane's units: j0 + 8P + e
   const int nthreads = blockDim.x;
+  const bool wy = aa.s.y != nullptr;                    // y == nullptr: the caller consumes only (hT, cT)
 
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int b0 = tile * 16;
@@ -359,8 +360,8 @@ __global__ void __launch_bounds__(512, 1) seq_fwd_mma_kernel(const SeqFwdMmaArgs
           }
         // ---- stores: y in the caller's layout (8 rows x 32 B per instruction); saved gates / c in the
         //      fragment-major layout (each warp instruction writes 256 contiguous bytes) ----
-        if (ok[0] && (j0 + 8 * P) < H) *reinterpret_cast<float2*>(yrow[0] + 8 * P) = make_float2(hnew[0][0], hnew[1][0]);
-        if (ok[1] && (j0 + 8 * P) < H) *reinterpret_cast<float2*>(yrow[1] + 8 * P) = make_float2(hnew[0][1], hnew[1][1]);
+        if (wy && ok[0] && (j0 + 8 * P) < H) *reinterpret_cast<float2*>(yrow[0] + 8 * P) = make_float2(hnew[0][0], hnew[1][0]);
+        if (wy && ok[1] && (j0 + 8 * P) < H) *reinterpret_cast<float2*>(yrow[1] + 8 * P) = make_float2(hnew[0][1], hnew[1][1]);
         if (SAVE) {
 #pragma unroll
           for (int hf = 0; hf < 2; ++hf) {

@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(NT_MAX, MIN_CTAS) seq_fwd_r1_kernel(const SeqF
         c[b] = fmaf(gf, c[b], gi * gn);
         h[b] = go * tanhf_acc(c[b]);
         if (ok[b] && live) {
-          a.y[(size_t)t * a.ys_t + (size_t)(b0 + b) * a.ys_b + j] = h[b];
+          if (a.y) a.y[(size_t)t * a.ys_t + (size_t)(b0 + b) * a.ys_b + j] = h[b];      // y == nullptr: last-step-only caller
           if (SAVE) {
             float* g = a.gates + ((size_t)t * B + b0 + b) * 4 * H + j;
             g[0] = gi; g[H] = gf; g[2 * H] = go; g[3 * H] = gn;

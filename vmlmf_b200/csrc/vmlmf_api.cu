@@ -168,11 +168,14 @@ int vmlmf_seq_fwd(const vmlmf_plan* plan, const float* x, long long xs_t, long l
                   const float* Dh, const float* bias, const float* h0, const float* c0, float* y,
                   long long ys_t, long long ys_b, float* hT, float* cT, float* gates, float* cs, float* z,
                   void* workspace, int T, int B, int I, int H, int RX, int RH, void* stream) {
-  if (!plan || !x || !zx || !Ux || !Vx || !Dx || !A || !Bm || !Dh || !bias || !y || !hT || !cT) return VMLMF_EINVAL;
+  if (!plan || !x || !zx || !Ux || !Vx || !Dx || !A || !Bm || !Dh || !bias || !hT || !cT) return VMLMF_EINVAL;
   const int rc = check_dims(T, B, I, H, RX, RH);
   if (rc) return rc;
   const bool save = gates || cs || z;
   if (save && !(gates && cs && z)) return VMLMF_EINVAL;
+  // y may be null for a last-step-only caller (V/models/vmlmf.py:354-355 reads y[:, -1] alone): inference on the
+  // persistent kernels only -- backward and the generic regime read h_{t-1} back from y
+  if (!y && (save || plan->path == VMLMF_PATH_G)) return VMLMF_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
   if (plan->path == VMLMF_PATH_R1) {
     const R1Choice c = choose_r1(I, H, RX, RH);

@@ -61,7 +61,7 @@ def _require_cuda(*ts):
 
 class VmlmfSeqFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, h0, c0, Ux, Vx, Dx, A, Bm, Dh, bias, batch_first, save=True):
+    def forward(ctx, x, h0, c0, Ux, Vx, Dx, A, Bm, Dh, bias, batch_first, save=True, need_y=True):
         _require_cuda(x, h0, c0, Ux, Vx, Dx, A, Bm, Dh, bias)
         x = _row_contig(x)
         params = [p.contiguous() for p in (Ux, Vx, Dx, A, Bm, Dh, bias)]
@@ -77,19 +77,24 @@ class VmlmfSeqFunction(torch.autograd.Function):
         plan = _lib.plan(T, B, I, H, RX, RH)
         lib = _lib.lib()
         new = x.new_empty
-        y = new((B, T, H)) if batch_first else new((T, B, H))
-        hT, cT = new((B, H)), new((B, H))
-        zx = new((T * B, plan.zx_pitch))
         # grad mode is always off inside Function.forward and needs_input_grad ignores torch.no_grad():
         # the caller (vmlmf_sequence) decides whether anything has to be kept for backward
         need_grad = save and any(ctx.needs_input_grad)
+        # last-step-only callers (Net.forward) skip the [T,B,H] output when nothing reads it back: backward and the
+        # generic regime take h_{t-1} from y
+        if need_y or need_grad or plan.path == _lib.PATH_G:
+            y = new((B, T, H)) if batch_first else new((T, B, H))
+        else:
+            y = None
+        hT, cT = new((B, H)), new((B, H))
+        zx = new((T * B, plan.zx_pitch))
         if need_grad:
             gates, cs, z = new((plan.gates_bytes // 4,)), new((plan.cs_bytes // 4,)), new((T * B, plan.z_pitch))
         else:
             gates = cs = z = None
         ws = new((plan.fwd_workspace_bytes + 3) // 4) if plan.fwd_workspace_bytes else None
         xs_t, xs_b = _tb_strides(x, batch_first)
-        ys_t, ys_b = _tb_strides(y, batch_first)
+        ys_t, ys_b = _tb_strides(y, batch_first) if y is not None else (0, 0)
         with torch.cuda.device_of(x):
             st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
             with _timed("xproj_fwd"):
@@ -137,7 +142,7 @@ class VmlmfSeqFunction(torch.autograd.Function):
                                          _ptr(dcT), _ptr(dx), dxs[0], dxs[1], _ptr(dh0), _ptr(dc0), _ptr(dUx),
                                          _ptr(dVx), _ptr(dDx), _ptr(dA), _ptr(dBm), _ptr(dDh), _ptr(dbias), _ptr(ws),
                                          T, B, I, H, RX, RH, st))
-        return dx, dh0, dc0, dUx, dVx, dDx, dA, dBm, dDh, dbias, None, None
+        return dx, dh0, dc0, dUx, dVx, dDx, dA, dBm, dDh, dbias, None, None, None
 
 
 class DiagCorrFunction(torch.autograd.Function):
@@ -226,7 +231,8 @@ def linear_tc(x, w, b):
     return LinearTCFunction.apply(x, w, b)
 
 
-def vmlmf_sequence(x, h0, c0, canon, batch_first=True):
-    """Run one VMLMF layer over a whole sequence.  canon = (Ux,Vx,Dx,A,Bm,Dh,bias)."""
+def vmlmf_sequence(x, h0, c0, canon, batch_first=True, need_y=True):
+    """Run one VMLMF layer over a whole sequence.  canon = (Ux,Vx,Dx,A,Bm,Dh,bias).  Returns (y, hT, cT); with
+    need_y=False the caller declares it reads only (hT, cT) and y may come back as None (inference)."""
     save = torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (x, h0, c0, *canon))
-    return VmlmfSeqFunction.apply(x, h0, c0, *canon, batch_first, save)
+    return VmlmfSeqFunction.apply(x, h0, c0, *canon, batch_first, save, need_y)

@@ -63,7 +63,11 @@ class MyVMLMFCell(nn.Module):
 
 class MyLSTMCell(nn.Module):
     """Vanilla (w_rank/u_ranks None) or plain low-rank LSTM cell -- the reference's uncompressed
-    baseline (V/models/vmlmf.py:127-238).  Eager PyTorch; not part of the accelerated path."""
+    baseline (V/models/vmlmf.py:127-238).  It is the canonical recurrence with no diagonal terms
+    (Dx = Dh = 0): low-rank sides map to (Ux, Vx) / (A, Bm) directly, dense sides use an identity
+    first factor, so the baseline runs through the same kernels as the compressed cells and the
+    compressed-vs-vanilla comparison is like for like.  `hidden_size < input_size`,
+    which the canonical form cannot express, is stepped in eager PyTorch."""
 
     def __init__(self, input_size, hidden_size, w_rank=None, u_ranks=None, recurrent_init=None, hidden_init=None):
         super().__init__()
@@ -86,8 +90,25 @@ class MyLSTMCell(nn.Module):
         for n in ("bias_f", "bias_i", "bias_c", "bias_o"):
             setattr(self, n, nn.Parameter(torch.ones([1, hidden_size])))
 
+    def canonical(self):
+        """(Ux, Vx, Dx, A, Bm, Dh, bias) in gate order (i, f, o, c~) = (w1..w4, u1..u4) (:222-231); None if H < I."""
+        n_in, hidden = self.input_size, self.hidden_size
+        if hidden < n_in:
+            return None
+        ref = self.w1
+        ux = self.w if self.w_rank is not None else torch.eye(n_in, dtype=ref.dtype, device=ref.device)
+        a = self.u if self.u_ranks is not None else torch.eye(hidden, dtype=ref.dtype, device=ref.device)
+        vx = torch.cat([self.w1, self.w2, self.w3, self.w4], 1).t()          # [4H, RX]
+        bm = torch.cat([self.u1, self.u2, self.u3, self.u4], 1).t()          # [4H, RH]
+        bias = torch.cat([self.bias_i, self.bias_f, self.bias_o, self.bias_c], 1).reshape(-1)
+        return ux, vx, ref.new_zeros(4, n_in), a, bm, ref.new_zeros(4, hidden), bias
+
     def forward(self, x, hidden_states):
         h, c = hidden_states
+        canon = self.canonical() if x.is_cuda else None
+        if canon is not None:
+            _, h1, c1 = vmlmf_sequence(x.unsqueeze(1), h, c, canon, batch_first=True)
+            return h1, c1
         xs = x if self.w_rank is None else x @ self.w
         hs = h if self.u_ranks is None else h @ self.u
         pre = [xs @ getattr(self, f"w{k}") + hs @ getattr(self, f"u{k}") for k in (1, 2, 3, 4)]   # i, f, o, c~
@@ -129,11 +150,15 @@ class MyLSTM(nn.Module):
             in_size = hidden_size
         self.rnncells = nn.ModuleList(cells)
 
-    def forward(self, x):
+    def forward(self, x, need_sequence=True):
+        """need_sequence=False (used by Net, which reads the last step only, V/models/vmlmf.py:354-355) lets the last
+        layer skip writing its [B,T,H] output; the first return value may then be None."""
         last = []
         for i, cell in enumerate(self.rnncells):
-            if hasattr(cell, "canonical"):
-                x, h, _ = vmlmf_sequence(x, None, None, cell.canonical(), batch_first=self.batch_first)
+            canon = cell.canonical() if hasattr(cell, "canonical") else None
+            if canon is not None:
+                need_y = need_sequence or i + 1 < len(self.rnncells)
+                x, h, _ = vmlmf_sequence(x, None, None, canon, batch_first=self.batch_first, need_y=need_y)
             else:
                 nb = x.size(self.batch_index)
                 h = x.new_zeros(nb, self.hidden_layer_sizes[i])
@@ -170,6 +195,6 @@ class Net(nn.Module):
         """x[B,T,I] -> logits[B,18].  The reference feeds y[:, -1] to the head (:354-355); the last
         layer's final hidden state is that same tensor, and using it lets backward skip reading a
         [B,T,H] upstream gradient that is zero everywhere but the last step."""
-        _, h_last = self.rnn(x)
+        _, h_last = self.rnn(x, need_sequence=False) if isinstance(self.rnn, MyLSTM) else self.rnn(x)
         top = self.rnn.hidden_layer_sizes[-1]
         return self.lin(h_last[:, -top:]).squeeze(1)
