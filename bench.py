@@ -181,9 +181,11 @@ def run_ours(args):
     torch.manual_seed(3)
     net = vb.Net(N_IN, [HIDDEN], w_rank=W_RANK, u_rank=[U_RANK], cell=vb.MyVMLMFCell).to(dev)
     broadcast_parameters(net)
-    opt = torch.optim.Adam(net.parameters(), lr=0.002, fused=True, capturable=True)
+    # the reference's step (V/train_test/train.py:58-65): zero_grad, forward, F.cross_entropy, backward, Adam(lr) --
+    # loss and optimizer are the library's own kernels (vmlmf_softmax_nll_*, vmlmf_adam_step over the flat bucket)
     bucket = GradBucket(net, average=True)
-    ce = torch.nn.functional.cross_entropy
+    opt = vb.FlatAdam(bucket, lr=0.002)
+    ce = vb.cross_entropy
     use_graph = not args.no_graph        # N > 1: forward+backward replay as a graph, the NCCL all-reduce and Adam stay eager
 
     POOL = 4                                   # distinct resident batches, rotated (each step's set >> L2)
@@ -402,8 +404,9 @@ def run_ours(args):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "sequences/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": e2e_s * 1e3 / K},
-        # per step: 2 x diag_fwd, xproj_small, seq_fwd_mma, seq_bwd_fused, reduce_partials, 2 x diag_bwd
-        "gpu_launches": 8 * K,
+        # this library's kernels per step: pack_plain_fwd, xproj_small, seq_fwd_mma, head_fwd, softmax_nll_fwd + sum_scale,
+        # softmax_nll_bwd, head_bwd + head_reduce, seq_bwd_fused, reduce_partials, pack_plain_bwd, adam
+        "gpu_launches": 13 * K,
         "roofline": roofline,
         "cpu_baseline": cpu,
         "inference": {"value": inf_value, "unit": "sequences/s", "ms_per_step": inf_ms / K},

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define VMLMF_ABI_VERSION 2
+#define VMLMF_ABI_VERSION 3
 
 enum {
   VMLMF_OK = 0,
@@ -81,6 +81,18 @@ int vmlmf_diag_fwd(const float* u, const float* v, const float* dia, float* D, i
                    void* stream);
 int vmlmf_diag_bwd(const float* u, const float* v, const float* dD, float* du, float* dv, float* ddia,
                    int n, int H, int R, void* stream);
+
+/* K0 / K5 for a whole plain cell (MyVMLMFCell, MyVMLSTM) in ONE launch each way.
+ * forward : Dx[4,I], Dh[4,H] as vmlmf_diag_fwd, and bias[4H] = b_x + b_h   (V/models/vmlmf.py:102-110).
+ * backward: turns the canonical gradients that vmlmf_seq_bwd wrote into the reference parameters' gradients IN PLACE
+ *           (dUx -> du_x, dVx -> dv_x, dA -> du_h, dBm -> dv_h get the diagonal-correction chain rule subtracted),
+ *           writes ddia_x[I], ddia_h[H] and db_h[4H] (a copy of dbias: b_x and b_h must not share a gradient buffer). */
+int vmlmf_pack_plain_fwd(const float* u_x, const float* v_x, const float* dia_x, const float* u_h, const float* v_h,
+                         const float* dia_h, const float* b_x, const float* b_h, float* Dx, float* Dh, float* bias,
+                         int I, int H, int RX, int RH, void* stream);
+int vmlmf_pack_plain_bwd(const float* u_x, const float* v_x, const float* u_h, const float* v_h, const float* dDx,
+                         const float* dDh, float* dUx, float* dVx, float* dA, float* dBm, float* ddia_x,
+                         float* ddia_h, const float* dbias, float* db_h, int I, int H, int RX, int RH, void* stream);
 
 /* K1: zx[t,b,:] = x[t,b,:] Ux for every timestep at once (time-parallel half of
  * `torch.matmul(x, self.u_x)`, V/models/vmlmf.py:98, vmlmf_group.py:98, vmlmf_lm.py:246).
@@ -134,6 +146,47 @@ int vmlmf_seq_bwd(const vmlmf_plan* plan, const float* x, long long xs_t, long l
 int vmlmf_gemm_nt(const float* A, long long lda, const float* B, long long ldb, float* C, long long ldc,
                   const float* bias, int M, int N, int K, int accumulate, void* workspace,
                   long long workspace_bytes, void* stream);
+
+/* ---- callers either side of the recurrence (SURVEY.md 8 rows f1 / f2 and the Net head, a4) ---------------- */
+
+/* Softmax-NLL over rows of scores[rows, C] (row pitch ld floats), labels int64 in [0, C):
+ *   lse[r]  = log sum_c exp(scores[r,c])            (kept for backward)
+ *   *loss   = scale * sum_r (lse[r] - scores[r, labels[r]])      summed in a fixed order
+ * scale = 1/rows is F.cross_entropy's mean (V/train_test/train.py:63); scale = batch/rows is the LM loss
+ * `torch.mean(-log(p[y]) * batch_size)` (V/train_test/lm_test.py:140-153) without its exp() overflow.
+ * workspace: vmlmf_softmax_nll_workspace_bytes(rows, C).                                                       */
+long long vmlmf_softmax_nll_workspace_bytes(long long rows, int C);
+int vmlmf_softmax_nll_fwd(const float* scores, long long ld, const long long* labels, float* lse, float* loss,
+                          float scale, void* workspace, long long rows, int C, void* stream);
+/* dscores[r,c] = (softmax(scores[r,:])[c] - [c == labels[r]]) * scale * (dloss ? *dloss : 1).  dloss is a device
+ * scalar (the upstream gradient) or NULL; dscores (row pitch ldd) may alias scores.                           */
+int vmlmf_softmax_nll_bwd(const float* scores, long long ld, const long long* labels, const float* lse,
+                          const float* dloss, float scale, float* dscores, long long ldd, long long rows, int C,
+                          void* stream);
+
+/* The classifier head of Net, `self.lin(y[:, -1])` with lin = nn.Linear(H_last, 18) (V/models/vmlmf.py:345-347,
+ * :354-355): out[B,N] = h[B,K] W[N,K]^T + bias[N] for N <= 32, K <= 1024 (h row pitch ldh, out dense).
+ * Backward: dh[B,K] (pitch lddh, may be NULL), dW[N,K], db[N] (may be NULL) from dout[B,N]; per-block partial sums
+ * are reduced in block order.  workspace: vmlmf_head_bwd_workspace_bytes(B, K, N).                             */
+int vmlmf_head_fwd(const float* h, long long ldh, const float* W, const float* bias, float* out, int B, int K, int N,
+                   void* stream);
+long long vmlmf_head_bwd_workspace_bytes(int B, int K, int N);
+int vmlmf_head_bwd(const float* h, long long ldh, const float* W, const float* dout, float* dh, long long lddh,
+                   float* dW, float* db, void* workspace, int B, int K, int N, void* stream);
+
+/* Optimizer steps on flat buffers of n floats (parameters, gradients and moments each one contiguous bucket --
+ * the gradient bucket is the one the data-parallel all-reduce already uses).
+ * Adam exactly as torch.optim.Adam(lr) (V/train_test/train.py:47,65): the step count t (>= 1, already incremented)
+ * is read from the device scalar step_dev (float; lets a CUDA graph replay advance it) or, if NULL, from `step`. */
+int vmlmf_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                    float eps, const float* step_dev, int step, void* stream);
+/* clip_grad_norm_(max_norm) then `param -= lr * param.grad` (V/train_test/lm_test.py:203-209) in two launches:
+ * coef = min(1, max_norm / (||g||_2 + 1e-6)) (max_norm <= 0: no clipping); scale_grads != 0 also writes g *= coef
+ * back like clip_grad_norm_ does.  norm_out (device scalar, may be NULL) receives ||g||_2.
+ * workspace: vmlmf_sgd_clip_workspace_bytes(n).                                                                */
+long long vmlmf_sgd_clip_workspace_bytes(long long n);
+int vmlmf_sgd_clip_step(float* p, float* g, long long n, float lr, float max_norm, int scale_grads,
+                        float* norm_out, void* workspace, void* stream);
 
 #ifdef __cplusplus
 }

@@ -150,6 +150,8 @@ def _rand_canon(rng, I, H, RX, RH, scale=0.3):
     (24, 81, 77, 180, 8, 6, True, False),   # reference unit-test shape
     (9, 3, 30, 256, 16, 8, False, True),    # widest compiled ranks at H=256
     (6, 7, 4, 64, 4, 16, True, True),
+    (2, 4800, 9, 128, 8, 6, True, True),    # H=128: two fused-backward CTAs per SM, some CTAs own two 16-sequence tiles
+    (2, 9500, 5, 64, 4, 3, False, False),   # H=64: four CTAs per SM (tensor-memory columns 4 x 128), 594 tiles
 ])
 def test_canonical_kernels_vs_numpy_spec(T, B, I, H, RX, RH, bf, state, scale=0.3):
     rng = np.random.default_rng(T * 1000 + B)

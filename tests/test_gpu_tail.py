@@ -1,0 +1,145 @@
+"""GPU: the callers either side of the recurrence (SURVEY 8 rows f1, f2 and the Net head) against their PyTorch
+definitions -- F.cross_entropy (V/train_test/train.py:63), the LM nll_loss (lm_test.py:140-153, via the oracle),
+nn.Linear, torch.optim.Adam (train.py:47) and clip_grad_norm_ + SGD (lm_test.py:203-209).  fp32, tolerance 1e-5
+relative unless a test says otherwise; everything goes through the C ABI."""
+import pytest
+import torch
+
+from conftest import rel_err
+from oracle import vmlmf_oracle as vo
+
+import vmlmf_b200 as vb
+from vmlmf_b200.graphs import GraphedTrainStep
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TOL = 1e-5
+
+
+def _close(a, b, tol=TOL, what=""):
+    e = max(rel_err(a.detach().cpu().numpy(), b.detach().cpu().numpy()))
+    assert e <= tol, f"{what}: rel err {e:.3e} > {tol}"
+
+
+@pytest.mark.parametrize("rows,C,pitch", [(37, 18, 18), (9472, 18, 18), (5, 3, 7), (1000, 2049, 2052), (70, 10000, 10000),
+                                          (3, 10001, 10001)])
+def test_softmax_nll_matches_cross_entropy(rows, C, pitch):
+    torch.manual_seed(rows + C)
+    buf = (torch.randn(rows, pitch, device=DEV) * 3.0)
+    y = torch.randint(0, C, (rows,), device=DEV)
+    up = torch.tensor(0.37, device=DEV)
+    a = buf[:, :C].detach().requires_grad_(True)
+    b = buf[:, :C].detach().clone().requires_grad_(True)
+    la = vb.cross_entropy(a, y)
+    lb = torch.nn.functional.cross_entropy(b.double(), y)
+    (la * up).backward()
+    (lb * up.double()).backward()
+    _close(la, lb.float(), 2e-6, "loss")
+    _close(a.grad, b.grad, TOL, "dlogits")
+    again = vb.cross_entropy(a.detach(), y)
+    assert torch.equal(again, la.detach()), "fixed-order sums must reproduce bit for bit"
+
+
+def test_lm_nll_loss_matches_reference_definition():
+    torch.manual_seed(9)
+    T, B, V = 7, 5, 50
+    s = torch.randn(T * B, V, device=DEV, requires_grad=True)
+    y = torch.randint(0, V, (T, B), device=DEV)
+    s_ref = s.detach().cpu().double().requires_grad_(True)
+    la, lb = vb.nll_loss(s, y), vo.lm_nll_loss(s_ref, y.cpu())
+    la.backward()
+    lb.backward()
+    _close(la, lb.float(), 2e-6, "loss")
+    _close(s.grad, s_ref.grad.float(), TOL, "dscores")
+    big = torch.full((4, 8), 200.0, device=DEV)          # exp(200) overflows fp32: the reference returns nan/inf here
+    assert torch.isfinite(vb.nll_loss(big, torch.zeros(2, 2, dtype=torch.long, device=DEV)))
+
+
+@pytest.mark.parametrize("B,K,N", [(37, 32, 18), (9472, 256, 18), (5, 180, 6), (300, 650, 32), (2, 16, 1), (1025, 1024, 9)])
+def test_head_linear_matches_nn_linear(B, K, N):
+    torch.manual_seed(B + K)
+    wide = torch.randn(B, K + 8, device=DEV)
+    h1 = wide[:, 8:].detach().requires_grad_(True)                  # strided rows, like h_last[:, -top:]
+    h2 = wide[:, 8:].detach().clone().requires_grad_(True)
+    lin = torch.nn.Linear(K, N).to(DEV)
+    w2, b2 = lin.weight.detach().clone().requires_grad_(True), lin.bias.detach().clone().requires_grad_(True)
+    up = torch.randn(B, N, device=DEV)
+    o1 = vb.head_linear(h1, lin.weight, lin.bias)
+    o2 = torch.nn.functional.linear(h2.double(), w2.double(), b2.double())
+    (o1 * up).sum().backward()
+    (o2 * up.double()).sum().backward()
+    _close(o1, o2.float(), TOL, "out")
+    _close(h1.grad, h2.grad, TOL, "dh")
+    _close(lin.weight.grad, w2.grad, TOL, "dW")
+    _close(lin.bias.grad, b2.grad, TOL, "db")
+
+
+def _har(seed=3):
+    torch.manual_seed(seed)
+    net = vb.Net(9, [32], w_rank=4, u_rank=[3], cell=vb.MyVMLMFCell).to(DEV)
+    x = torch.randn(48, 6, 9, device=DEV)
+    y = torch.randint(0, 6, (48,), device=DEV)
+    return net, x, y
+
+
+def test_flat_adam_matches_torch_adam():
+    net1, x, y = _har()
+    net2, _, _ = _har()
+    o1 = vb.FlatAdam(net1, lr=0.002)
+    o2 = torch.optim.Adam(net2.parameters(), lr=0.002)
+    for _ in range(6):
+        o1.zero_grad()
+        vb.cross_entropy(net1(x), y).backward()
+        o1.step()
+        o2.zero_grad()
+        torch.nn.functional.cross_entropy(net2(x), y).backward()
+        o2.step()
+    for (k, p1), (_, p2) in zip(net1.named_parameters(), net2.named_parameters()):
+        _close(p1, p2, 2e-5, k)            # six Adam steps amplify 1e-7 gradient differences where v is tiny
+    assert not any(p.grad is not None for k, p in net1.named_parameters() if k.startswith("cell."))
+    # parameters are views of one flat buffer; state_dict still has the reference's keys and shapes
+    assert list(net1.state_dict().keys()) == list(net2.state_dict().keys())
+
+
+def test_flat_adam_inside_cuda_graph():
+    net1, x, y = _har()
+    net2, _, _ = _har()
+    o1 = vb.FlatAdam(net1, lr=0.002)
+    o2 = vb.FlatAdam(net2, lr=0.002)
+    step = GraphedTrainStep(net1, o1, vb.cross_entropy, x, y, warmup=2, zero_fn=o1.zero_grad)      # 2 eager + capture
+    for _ in range(3):
+        step(x, y)
+    for _ in range(2 + 3):                  # capture itself does not execute the step
+        o2.zero_grad()
+        vb.cross_entropy(net2(x), y).backward()
+        o2.step()
+    assert float(o1.t) == float(o2.t) == 5.0
+    for (k, p1), (_, p2) in zip(net1.named_parameters(), net2.named_parameters()):
+        _close(p1, p2, 2e-5, k)
+
+
+def test_flat_clip_sgd_matches_clip_grad_norm_and_sgd():
+    def build():
+        torch.manual_seed(5)
+        return vb.Model(50, 16, 2, 0.0, 0.25, w_rank=4, u_ranks=[5], lstm_type="vmlmf").to(DEV)
+    m1, m2 = build(), build()
+    tok = torch.randint(0, 50, (6, 4), device=DEV)
+    y = torch.randint(0, 50, (6, 4), device=DEV)
+    opt = vb.FlatClipSGD(m1, lr=1.0, max_norm=0.25)
+    for it in range(3):
+        opt.zero_grad()
+        s1, _ = m1(tok, m1.state_init(4))
+        vb.nll_loss(s1, y).backward()
+        norm1 = opt.step()
+        m2.zero_grad()
+        s2, _ = m2(tok, m2.state_init(4))
+        vb.nll_loss(s2, y).backward()
+        with torch.no_grad():
+            norm2 = torch.nn.utils.clip_grad_norm_(m2.parameters(), 0.25)
+            for p in m2.parameters():
+                p -= 1.0 * p.grad
+        _close(norm1, norm2, TOL, f"norm step {it}")
+        assert float(norm2) > 0.25, "the clip must be active for this test to mean anything"
+    for (k, p1), (_, p2) in zip(m1.named_parameters(), m2.named_parameters()):
+        _close(p1, p2, TOL, k)
+        _close(p1.grad, p2.grad, TOL, k + ".grad")          # gradients rescaled in place like clip_grad_norm_

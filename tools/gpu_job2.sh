@@ -1,8 +1,6 @@
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 100 --warmup 10 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err; python -c "
-import json
-d=json.loads([l for l in open('gpurun_out/bench_n2.json') if l.startswith('{')][0])
-print('n',d['n_gpus'],'value',d['value'],'ms',d['ms_per_step'],'e2e',d['e2e']['value'],'graph',d['config']['cuda_graph'])
-"; wc -l gpurun_out/bench_n2.json; tail -3 gpurun_out/bench_n2.err
-python bench.py --steps 100 --warmup 10 --no-cpu-baseline 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read()); print('n',d['n_gpus'],'value',d['value'],'ms',d['ms_per_step'],'e2e',d['e2e']['value'])"
+set -x
+python -m pytest tests -q -m gpu -x 2>&1 | tail -6
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+python bench.py --no-cpu-baseline > gpurun_out/bench_tail.json 2> gpurun_out/bench_tail.err; tail -c 300 gpurun_out/bench_tail.json; tail -3 gpurun_out/bench_tail.err
+ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/tail_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph > gpurun_out/ncu_launch.log 2>&1; tail -2 gpurun_out/ncu_launch.log
+python tools/config_sweep.py gpurun_out/configs_tail.json > /dev/null 2> gpurun_out/configs_tail.err; tail -3 gpurun_out/configs_tail.err

@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvmlmf_b200.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 PATH_R1, PATH_G, PATH_R1M = 1, 2, 3
 
@@ -22,7 +22,7 @@ class Plan(C.Structure):
                 ("gates_bytes", C.c_longlong), ("cs_bytes", C.c_longlong), ("reserved", C.c_int * 8)]
 
 
-_P, _LL, _I = C.c_void_p, C.c_longlong, C.c_int
+_P, _LL, _I, _F = C.c_void_p, C.c_longlong, C.c_int, C.c_float
 
 # name -> argtypes; every function returns int except where noted
 SIGNATURES = {
@@ -31,11 +31,22 @@ SIGNATURES = {
     "vmlmf_seq_plan": [_I] * 6 + [C.POINTER(Plan)],
     "vmlmf_diag_fwd": [_P, _P, _P, _P, _I, _I, _I, _P],
     "vmlmf_diag_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
+    "vmlmf_pack_plain_fwd": [_P] * 11 + [_I] * 4 + [_P],
+    "vmlmf_pack_plain_bwd": [_P] * 14 + [_I] * 4 + [_P],
     "vmlmf_gemm_nt": [_P, _LL, _P, _LL, _P, _LL, _P, _I, _I, _I, _I, _P, _LL, _P],
     "vmlmf_xproj_fwd": [_P, _LL, _LL, _P, _P, _I, _I, _I, _I, _I, _P],
     "vmlmf_seq_fwd": [C.POINTER(Plan), _P, _LL, _LL] + [_P] * 10 + [_P, _LL, _LL] + [_P] * 6 + [_I] * 6 + [_P],
     "vmlmf_seq_bwd": [C.POINTER(Plan), _P, _LL, _LL] + [_P] * 9 + [_P, _LL, _LL] + [_P] * 3 + [_P, _LL, _LL]
                      + [_P] * 2 + [_P, _LL, _LL] + [_P] * 10 + [_I] * 6 + [_P],
+    "vmlmf_softmax_nll_workspace_bytes": [_LL, _I],                          # returns long long
+    "vmlmf_softmax_nll_fwd": [_P, _LL, _P, _P, _P, _F, _P, _LL, _I, _P],
+    "vmlmf_softmax_nll_bwd": [_P, _LL, _P, _P, _P, _F, _P, _LL, _LL, _I, _P],
+    "vmlmf_head_fwd": [_P, _LL, _P, _P, _P, _I, _I, _I, _P],
+    "vmlmf_head_bwd_workspace_bytes": [_I, _I, _I],                          # returns long long
+    "vmlmf_head_bwd": [_P, _LL, _P, _P, _P, _LL, _P, _P, _P, _I, _I, _I, _P],
+    "vmlmf_adam_step": [_P, _P, _P, _P, _LL, _F, _F, _F, _F, _P, _I, _P],
+    "vmlmf_sgd_clip_workspace_bytes": [_LL],                                 # returns long long
+    "vmlmf_sgd_clip_step": [_P, _P, _LL, _F, _F, _I, _P, _P, _P],
 }
 
 _lib = None
@@ -54,7 +65,8 @@ def lib():
         for name, args in SIGNATURES.items():
             fn = getattr(handle, name)
             fn.argtypes = args
-            fn.restype = C.c_char_p if name == "vmlmf_strerror" else C.c_int
+            fn.restype = (C.c_char_p if name == "vmlmf_strerror" else
+                          C.c_longlong if name.endswith("_workspace_bytes") else C.c_int)
         if handle.vmlmf_abi_version() != ABI_VERSION:
             raise RuntimeError("vmlmf_b200: libvmlmf_b200.so ABI version mismatch; rebuild")
         _lib = handle

@@ -7,11 +7,24 @@ namespace vmlmf {
 namespace {
 int ks_of(int RX, int RH) { return ceil_div(RH + RX + 1, 8); }
 int nz_of(int RH) { return ceil_div(RH, 8); }
-int grid_of(int B) { const int nt = ceil_div(B, 16); return nt < kNumSMs ? nt : kNumSMs; }
 int tmem_cols_of(int NW) {
   int c = kFusedCols * ceil_div(NW, 4), p = 32;
   while (p < c) p <<= 1;
   return p;
+}
+// CTAs that can share an SM: shared memory (227 KB, 1 KB reserved per CTA), tensor memory (512 columns), the register
+// file (128 registers per thread by __launch_bounds__) and 2048 threads.  Analytic so that vmlmf_seq_plan (no device
+// calls) and the launch agree on the number of per-CTA gradient partials.
+int occ_of(int NW, int KS, int I, int RX) {
+  const size_t smem = seq_bwd_fused_smem_bytes(NW, KS, I, RX) + 1024;
+  int occ = (int)((size_t)227 * 1024 / smem);
+  occ = occ < 512 / tmem_cols_of(NW) ? occ : 512 / tmem_cols_of(NW);
+  occ = occ < 65536 / (NW * 32 * 128) ? occ : 65536 / (NW * 32 * 128);
+  return occ < 1 ? 1 : occ;
+}
+int grid_of(int B, int NW, int KS, int I, int RX) {
+  const int nt = ceil_div(B, 16), cap = kNumSMs * occ_of(NW, KS, I, RX);
+  return nt < cap ? nt : cap;
 }
 }  // namespace
 
@@ -26,7 +39,7 @@ long long bwd_fused_workspace_floats(int T, int B, int I, int H, int RX, int RH)
   if (!bwd_fused_fits(I, H, RX, RH)) return 0;
   const GradLayout L(I, H, RX, RH);
   (void)T;
-  return (long long)grid_of(B) * L.total + 8;
+  return (long long)grid_of(B, ceil_div(H, 16), ks_of(RX, RH), I, RX) * L.total + 8;
 }
 
 template <int KS, int NZ>
@@ -45,7 +58,7 @@ static int launch_t(const SeqBwdFusedArgs& a, int NW, int G, cudaStream_t st) {
 
 int launch_bwd_fused(const SeqBwdFusedArgs& a0, const GradOut& out, void* workspace, cudaStream_t st) {
   const int KS = ks_of(a0.RX, a0.RH), NZ = nz_of(a0.RH), NW = ceil_div(a0.H, 16);
-  const int G = grid_of(a0.B);
+  const int G = grid_of(a0.B, NW, KS, a0.I, a0.RX);
   const GradLayout L(a0.I, a0.H, a0.RX, a0.RH);
   SeqBwdFusedArgs a = a0;
   a.dzc = nullptr;
@@ -55,7 +68,7 @@ int launch_bwd_fused(const SeqBwdFusedArgs& a0, const GradOut& out, void* worksp
   else if (KS == 2 && NZ == 1) rc = launch_t<2, 1>(a, NW, G, st);
   else if (KS == 2 && NZ == 2) rc = launch_t<2, 2>(a, NW, G, st);
   if (rc) return rc;
-  reduce_partials_kernel<<<ceil_div(L.total, 256), 256, 0, st>>>(a.partial, G, L, out);
+  reduce_partials_kernel<<<ceil_div(L.total, kReduceElems), 256, 0, st>>>(a.partial, G, L, out);
   return (int)cudaGetLastError();
 }
 

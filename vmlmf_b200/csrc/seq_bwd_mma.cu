@@ -99,7 +99,7 @@ int launch_bwd_mma(const SeqBwdMmaArgs& a0, const GradRowsArgs& g0, const GradOu
     case 4: rc = launch_b<4>(g, s.NW, G, st); break;
   }
   if (rc) return rc;
-  reduce_partials_kernel<<<ceil_div(L.total, 256), 256, 0, st>>>(g.partial, G, L, out);
+  reduce_partials_kernel<<<ceil_div(L.total, kReduceElems), 256, 0, st>>>(g.partial, G, L, out);
   return (int)cudaGetLastError();
 }
 

@@ -487,19 +487,32 @@ __global__ void __launch_bounds__(NT_MAX, MIN_CTAS) seq_bwd_r1_kernel(const SeqB
 // Fixed-order sum of the per-CTA partials -> the seven canonical gradient tensors.
 struct GradOut { float *dUx, *dVx, *dDx, *dA, *dBm, *dDh, *dbias; };
 
-static __global__ void reduce_partials_kernel(const float* __restrict__ partial, int nparts, GradLayout L, GradOut o) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= L.total) return;
+// Launch with kReduceElems outputs per 256-thread block: every output is summed by 8 threads over interleaved
+// slices of the partial list (enough independent loads in flight to cover DRAM/L2 latency), then across the slices
+// in slice order -- the association is fixed, so results reproduce bit for bit.
+constexpr int kReduceElems = 32;
+static __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partial, int nparts,
+                                                                     GradLayout L, GradOut o) {
+  __shared__ float sl[8][kReduceElems + 1];
+  const int e = threadIdx.x & (kReduceElems - 1), slice = threadIdx.x / kReduceElems;
+  const int p = blockIdx.x * kReduceElems + e;
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  int c = 0;
-  for (; c + 3 < nparts; c += 4) {
-    s0 += partial[(size_t)c * L.total + p];
-    s1 += partial[(size_t)(c + 1) * L.total + p];
-    s2 += partial[(size_t)(c + 2) * L.total + p];
-    s3 += partial[(size_t)(c + 3) * L.total + p];
+  if (p < L.total) {
+    int c = slice;
+    for (; c + 24 < nparts; c += 32) {
+      s0 += partial[(size_t)c * L.total + p];
+      s1 += partial[(size_t)(c + 8) * L.total + p];
+      s2 += partial[(size_t)(c + 16) * L.total + p];
+      s3 += partial[(size_t)(c + 24) * L.total + p];
+    }
+    for (; c < nparts; c += 8) s0 += partial[(size_t)c * L.total + p];
   }
-  for (; c < nparts; ++c) s0 += partial[(size_t)c * L.total + p];
-  const float s = (s0 + s1) + (s2 + s3);
+  sl[slice][e] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (slice != 0 || p >= L.total) return;
+  float s = 0.f;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) s += sl[q][e];
   if (p < L.oVx) o.dUx[p - L.oUx] = s;
   else if (p < L.oDx) o.dVx[p - L.oVx] = s;
   else if (p < L.oA) o.dDx[p - L.oDx] = s;

@@ -63,7 +63,7 @@ int launch_bwd_r1(const SeqBwdArgs& a, const GradOut& out, cudaStream_t st) {
   e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
   const GradLayout L(a.I, a.H, a.RX, a.RH);
-  reduce_partials_kernel<<<ceil_div(L.total, 256), 256, 0, st>>>(a.partial, grid, L, out);
+  reduce_partials_kernel<<<ceil_div(L.total, kReduceElems), 256, 0, st>>>(a.partial, grid, L, out);
   return (int)cudaGetLastError();
 }
 

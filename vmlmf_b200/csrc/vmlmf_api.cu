@@ -10,6 +10,7 @@
 #include "seq_bwd_mma.cuh"
 #include "seq_mma.cuh"
 #include "seq_r1_launch.cuh"
+#include "tail.cuh"
 #include "xproj.cuh"
 
 using namespace vmlmf;
@@ -130,6 +131,31 @@ int vmlmf_diag_bwd(const float* u, const float* v, const float* dD, float* du, f
   if (n > H) return VMLMF_ESHAPE;
   const long long threads = 4LL * H * R;
   diag_bwd_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(u, v, dD, du, dv, ddia, n, H, R);
+  return (int)cudaGetLastError();
+}
+
+int vmlmf_pack_plain_fwd(const float* u_x, const float* v_x, const float* dia_x, const float* u_h, const float* v_h,
+                         const float* dia_h, const float* b_x, const float* b_h, float* Dx, float* Dh, float* bias,
+                         int I, int H, int RX, int RH, void* stream) {
+  if (!u_x || !v_x || !dia_x || !u_h || !v_h || !dia_h || !b_x || !b_h || !Dx || !Dh || !bias) return VMLMF_EINVAL;
+  if (I <= 0 || H <= 0 || RX <= 0 || RH <= 0) return VMLMF_EINVAL;
+  if (I > H) return VMLMF_ESHAPE;
+  const long long threads = (4LL * I + 4LL * H + ceil_div(4 * H, 32)) * 32;
+  pack_plain_fwd_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      u_x, v_x, dia_x, u_h, v_h, dia_h, b_x, b_h, Dx, Dh, bias, I, H, RX, RH);
+  return (int)cudaGetLastError();
+}
+
+int vmlmf_pack_plain_bwd(const float* u_x, const float* v_x, const float* u_h, const float* v_h, const float* dDx,
+                         const float* dDh, float* dUx, float* dVx, float* dA, float* dBm, float* ddia_x,
+                         float* ddia_h, const float* dbias, float* db_h, int I, int H, int RX, int RH, void* stream) {
+  if (!u_x || !v_x || !u_h || !v_h || !dDx || !dDh || !dUx || !dVx || !dA || !dBm || !ddia_x || !ddia_h || !dbias || !db_h)
+    return VMLMF_EINVAL;
+  if (I <= 0 || H <= 0 || RX <= 0 || RH <= 0) return VMLMF_EINVAL;
+  if (I > H) return VMLMF_ESHAPE;
+  const long long threads = 4LL * H * RX + 4LL * H * RH + 4LL * H;
+  pack_plain_bwd_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      u_x, v_x, u_h, v_h, dDx, dDh, dUx, dVx, dA, dBm, ddia_x, ddia_h, dbias, db_h, I, H, RX, RH);
   return (int)cudaGetLastError();
 }
 
@@ -254,6 +280,127 @@ int vmlmf_seq_bwd(const vmlmf_plan* plan, const float* x, long long xs_t, long l
                            dy, dys_t, dys_b, dhT, dcT, dx, dxs_t, dxs_b, dh0, dc0, dUx, dVx, dDx, dA, dBm, dDh,
                            dbias, workspace, T, B, I, H, RX, RH, st);
   return VMLMF_EPLAN;
+}
+
+// ---------------- callers either side of the recurrence (tail.cuh) ----------------
+
+long long vmlmf_softmax_nll_workspace_bytes(long long rows, int C) {
+  if (rows <= 0 || C <= 0) return 0;
+  return (C <= 2048 ? (rows + 7) / 8 : rows) * (long long)sizeof(float);
+}
+
+int vmlmf_softmax_nll_fwd(const float* scores, long long ld, const long long* labels, float* lse, float* loss,
+                          float scale, void* workspace, long long rows, int C, void* stream) {
+  if (!scores || !labels || !lse || !loss || !workspace || rows <= 0 || C <= 0 || ld < C) return VMLMF_EINVAL;
+  if (rows > 0x7fffffffLL) return VMLMF_EUNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* partials = (float*)workspace;
+  long long nparts;
+  if (C <= 2048) {
+    nparts = (rows + 7) / 8;
+    softmax_nll_fwd_kernel<true><<<(unsigned)nparts, kTailThreads, 0, st>>>(scores, ld, labels, lse, partials, rows, C);
+  } else {
+    nparts = rows;
+    softmax_nll_fwd_kernel<false><<<(unsigned)nparts, kTailThreads, 0, st>>>(scores, ld, labels, lse, partials, rows, C);
+  }
+  sum_scale_kernel<<<1, kTailThreads, 0, st>>>(partials, nparts, scale, loss);
+  return (int)cudaGetLastError();
+}
+
+int vmlmf_softmax_nll_bwd(const float* scores, long long ld, const long long* labels, const float* lse,
+                          const float* dloss, float scale, float* dscores, long long ldd, long long rows, int C,
+                          void* stream) {
+  if (!scores || !labels || !lse || !dscores || rows <= 0 || C <= 0 || ld < C || ldd < C) return VMLMF_EINVAL;
+  if (rows > 0x7fffffffLL) return VMLMF_EUNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (C <= 2048)
+    softmax_nll_bwd_kernel<true><<<(unsigned)((rows + 7) / 8), kTailThreads, 0, st>>>(scores, ld, labels, lse, dloss, scale,
+                                                                                     dscores, ldd, rows, C);
+  else
+    softmax_nll_bwd_kernel<false><<<(unsigned)rows, kTailThreads, 0, st>>>(scores, ld, labels, lse, dloss, scale, dscores,
+                                                                          ldd, rows, C);
+  return (int)cudaGetLastError();
+}
+
+namespace {
+inline int head_np(int N) { return N <= 8 ? 8 : (N <= 16 ? 16 : 32); }
+inline int head_rows_per_block(int B) {
+  const int r = ceil_div(B, 2 * kNumSMs);
+  return r < 8 ? 8 : (r > 256 ? 256 : r);
+}
+}  // namespace
+
+int vmlmf_head_fwd(const float* h, long long ldh, const float* W, const float* bias, float* out, int B, int K, int N,
+                   void* stream) {
+  if (!h || !W || !out || B <= 0 || K <= 0 || N <= 0 || ldh < K) return VMLMF_EINVAL;
+  if (N > 32 || K > 1024) return VMLMF_EUNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int NP = head_np(N);
+  const size_t smem = (size_t)NP * K * sizeof(float);
+  int grid = ceil_div(ceil_div(B, 2), kTailThreads / 32);
+  if (grid > 2 * kNumSMs) grid = 2 * kNumSMs;
+#define VMLMF_HEAD_FWD(NP_)                                                                                          \
+  {                                                                                                                  \
+    if (smem > 48 * 1024) {                                                                                          \
+      cudaError_t e = cudaFuncSetAttribute(head_fwd_kernel<NP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      if (e != cudaSuccess) return (int)e;                                                                           \
+    }                                                                                                                \
+    head_fwd_kernel<NP_><<<grid, kTailThreads, smem, st>>>(h, ldh, W, bias, out, B, K, N);                           \
+  }
+  if (NP == 8) VMLMF_HEAD_FWD(8) else if (NP == 16) VMLMF_HEAD_FWD(16) else VMLMF_HEAD_FWD(32)
+#undef VMLMF_HEAD_FWD
+  return (int)cudaGetLastError();
+}
+
+long long vmlmf_head_bwd_workspace_bytes(int B, int K, int N) {
+  if (B <= 0 || K <= 0 || N <= 0 || N > 32) return 0;
+  const int NP = head_np(N);
+  return (long long)ceil_div(B, head_rows_per_block(B)) * (NP * K + NP) * (long long)sizeof(float);
+}
+
+int vmlmf_head_bwd(const float* h, long long ldh, const float* W, const float* dout, float* dh, long long lddh,
+                   float* dW, float* db, void* workspace, int B, int K, int N, void* stream) {
+  if (!h || !W || !dout || !dW || !workspace || B <= 0 || K <= 0 || N <= 0 || ldh < K || (dh && lddh < K))
+    return VMLMF_EINVAL;
+  if (N > 32 || K > 1024) return VMLMF_EUNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int NP = head_np(N), rpb = head_rows_per_block(B), grid = ceil_div(B, rpb);
+  const size_t smem = (size_t)rpb * NP * sizeof(float);
+  const int KJ = ceil_div(K, kTailThreads);
+  float* partials = (float*)workspace;
+#define VMLMF_HEAD_BWD(NP_, KJ_) \
+  head_bwd_kernel<NP_, KJ_><<<grid, kTailThreads, smem, st>>>(h, ldh, W, dout, dh, lddh, partials, B, K, N, rpb)
+#define VMLMF_HEAD_BWD_NP(NP_)                                    \
+  {                                                               \
+    if (KJ == 1) VMLMF_HEAD_BWD(NP_, 1);                          \
+    else if (KJ == 2) VMLMF_HEAD_BWD(NP_, 2);                     \
+    else VMLMF_HEAD_BWD(NP_, 4);                                  \
+  }
+  if (NP == 8) VMLMF_HEAD_BWD_NP(8) else if (NP == 16) VMLMF_HEAD_BWD_NP(16) else VMLMF_HEAD_BWD_NP(32)
+#undef VMLMF_HEAD_BWD_NP
+#undef VMLMF_HEAD_BWD
+  head_reduce_kernel<<<ceil_div(N * K + N, 16), kTailThreads, 0, st>>>(partials, grid, NP, K, N, dW, db);
+  return (int)cudaGetLastError();
+}
+
+int vmlmf_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                    float eps, const float* step_dev, int step, void* stream) {
+  if (!p || !g || !m || !v || n <= 0 || (!step_dev && step < 1)) return VMLMF_EINVAL;
+  adam_kernel<<<tail_grid(n), kTailThreads, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, step_dev, step);
+  return (int)cudaGetLastError();
+}
+
+long long vmlmf_sgd_clip_workspace_bytes(long long n) { return n <= 0 ? 0 : (long long)tail_grid(n) * (long long)sizeof(float); }
+
+int vmlmf_sgd_clip_step(float* p, float* g, long long n, float lr, float max_norm, int scale_grads, float* norm_out,
+                        void* workspace, void* stream) {
+  if (!p || !g || !workspace || n <= 0) return VMLMF_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = tail_grid(n);
+  float* partials = (float*)workspace;
+  sumsq_kernel<<<grid, kTailThreads, 0, st>>>(g, n, partials);
+  sgd_clip_kernel<<<grid, kTailThreads, 0, st>>>(p, g, n, lr, max_norm, partials, grid, scale_grads, norm_out);
+  return (int)cudaGetLastError();
 }
 
 }  // extern "C"

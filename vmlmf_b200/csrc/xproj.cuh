@@ -86,4 +86,72 @@ static __global__ void diag_bwd_kernel(const float* __restrict__ u, const float*
   if (i < n) ddia[i] = __ldg(dD + i) + __ldg(dD + n + i) + __ldg(dD + 2 * n + i) + __ldg(dD + 3 * n + i);
 }
 
+
+// ---- K0 / K5 for a whole plain cell in one launch each way (vmlmf_pack_plain_fwd / _bwd) ----
+// forward: warps [0,4I) -> Dx, warps [4I, 4I+4H) -> Dh, the remaining warps -> bias = b_x + b_h (32 elements each)
+static __global__ void pack_plain_fwd_kernel(const float* __restrict__ u_x, const float* __restrict__ v_x,
+                                             const float* __restrict__ dia_x, const float* __restrict__ u_h,
+                                             const float* __restrict__ v_h, const float* __restrict__ dia_h,
+                                             const float* __restrict__ b_x, const float* __restrict__ b_h,
+                                             float* __restrict__ Dx, float* __restrict__ Dh, float* __restrict__ bias,
+                                             int I, int H, int RX, int RH) {
+  int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= 4 * I + 4 * H) {
+    const int i = (w - 4 * I - 4 * H) * 32 + lane;
+    if (i < 4 * H) bias[i] = __ldg(b_x + i) + __ldg(b_h + i);
+    return;
+  }
+  const bool xside = w < 4 * I;
+  if (!xside) w -= 4 * I;
+  const int n = xside ? I : H, R = xside ? RX : RH;
+  const float* u = xside ? u_x : u_h;
+  const float* v = xside ? v_x : v_h;
+  const int k = w / n, j = w - k * n;
+  const float* ur = u + (size_t)j * R;
+  const float* vr = v + ((size_t)k * H + j) * R;
+  float s = 0.f;
+  for (int r = lane; r < R; r += 32) s = fmaf(__ldg(ur + r), __ldg(vr + r), s);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) (xside ? Dx : Dh)[w] = __ldg((xside ? dia_x : dia_h) + j) - s;
+}
+
+// backward, in place on the canonical gradients: one thread per element of dVx [4H,RX], then of dBm [4H,RH], then of
+// db_h [4H].   dv[kH+j,r] -= dD[k,j] u[j,r] (j < n);  du[j,r] -= sum_k dD[k,j] v[kH+j,r];  ddia[j] = sum_k dD[k,j]
+static __global__ void pack_plain_bwd_kernel(const float* __restrict__ u_x, const float* __restrict__ v_x,
+                                             const float* __restrict__ u_h, const float* __restrict__ v_h,
+                                             const float* __restrict__ dDx, const float* __restrict__ dDh,
+                                             float* __restrict__ dUx, float* __restrict__ dVx, float* __restrict__ dA,
+                                             float* __restrict__ dBm, float* __restrict__ ddia_x,
+                                             float* __restrict__ ddia_h, const float* __restrict__ dbias,
+                                             float* __restrict__ db_h, int I, int H, int RX, int RH) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long nx = (long long)4 * H * RX, nh = (long long)4 * H * RH;
+  if (i >= nx + nh) {
+    i -= nx + nh;
+    if (i < 4 * H) db_h[i] = __ldg(dbias + i);
+    return;
+  }
+  const bool xside = i < nx;
+  if (!xside) i -= nx;
+  const int n = xside ? I : H, R = xside ? RX : RH;
+  const float* u = xside ? u_x : u_h;
+  const float* v = xside ? v_x : v_h;
+  const float* dD = xside ? dDx : dDh;
+  float* du = xside ? dUx : dA;
+  float* dv = xside ? dVx : dBm;
+  float* ddia = xside ? ddia_x : ddia_h;
+  const int row = (int)(i / R), r = (int)(i - (long long)row * R);
+  const int k = row / H, j = row - k * H;
+  if (j < n) dv[i] -= __ldg(dD + k * n + j) * __ldg(u + (size_t)j * R + r);
+  if (i < (long long)n * R) {                 // here row = j < n <= H (k == 0), column r
+    float s = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) s = fmaf(__ldg(dD + kk * n + row), __ldg(v + ((size_t)kk * H + row) * R + r), s);
+    du[i] -= s;
+  }
+  if (i < n) ddia[i] = __ldg(dD + i) + __ldg(dD + n + i) + __ldg(dD + 2 * n + i) + __ldg(dD + 3 * n + i);
+}
+
 }  // namespace vmlmf

@@ -59,90 +59,160 @@ def _require_cuda(*ts):
             raise RuntimeError("vmlmf_b200: fp32 only (the reference computes in fp32)")
 
 
-class VmlmfSeqFunction(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, x, h0, c0, Ux, Vx, Dx, A, Bm, Dh, bias, batch_first, save=True, need_y=True):
-        _require_cuda(x, h0, c0, Ux, Vx, Dx, A, Bm, Dh, bias)
-        x = _row_contig(x)
-        params = [p.contiguous() for p in (Ux, Vx, Dx, A, Bm, Dh, bias)]
-        Ux, Vx, Dx, A, Bm, Dh, bias = params
-        if batch_first:
-            B, T, I = x.shape
-        else:
-            T, B, I = x.shape
-        H, RH = A.shape
-        RX = Ux.shape[1]
-        h0 = None if h0 is None else h0.contiguous()
-        c0 = None if c0 is None else c0.contiguous()
-        plan = _lib.plan(T, B, I, H, RX, RH)
-        lib = _lib.lib()
-        new = x.new_empty
-        # grad mode is always off inside Function.forward and needs_input_grad ignores torch.no_grad():
-        # the caller (vmlmf_sequence) decides whether anything has to be kept for backward
-        need_grad = save and any(ctx.needs_input_grad)
-        # last-step-only callers (Net.forward) skip the [T,B,H] output when nothing reads it back: backward and the
-        # generic regime take h_{t-1} from y
-        if need_y or need_grad or plan.path == _lib.PATH_G:
-            y = new((B, T, H)) if batch_first else new((T, B, H))
-        else:
-            y = None
-        hT, cT = new((B, H)), new((B, H))
-        zx = new((T * B, plan.zx_pitch))
-        if need_grad:
-            gates, cs, z = new((plan.gates_bytes // 4,)), new((plan.cs_bytes // 4,)), new((T * B, plan.z_pitch))
-        else:
-            gates = cs = z = None
-        ws = new((plan.fwd_workspace_bytes + 3) // 4) if plan.fwd_workspace_bytes else None
-        xs_t, xs_b = _tb_strides(x, batch_first)
-        ys_t, ys_b = _tb_strides(y, batch_first) if y is not None else (0, 0)
-        with torch.cuda.device_of(x):
-            st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-            with _timed("xproj_fwd"):
-                _lib.check(lib.vmlmf_xproj_fwd(_ptr(x), xs_t, xs_b, _ptr(Ux), _ptr(zx), T, B, I, RX, plan.zx_pitch, st))
-            with _timed("seq_fwd"):
-              _lib.check(lib.vmlmf_seq_fwd(C.byref(plan), _ptr(x), xs_t, xs_b, _ptr(zx), _ptr(Ux), _ptr(Vx), _ptr(Dx),
+def _seq_forward(x, h0, c0, canon, batch_first, need_grad, need_y):
+    """xproj + the whole time loop of one layer through the C ABI.  Returns (y, hT, cT, saved) where `saved` is what
+    _seq_backward needs (None when nothing is kept)."""
+    _require_cuda(x, h0, c0, *canon)
+    x = _row_contig(x)
+    Ux, Vx, Dx, A, Bm, Dh, bias = [p.contiguous() for p in canon]
+    if batch_first:
+        B, T, I = x.shape
+    else:
+        T, B, I = x.shape
+    H, RH = A.shape
+    RX = Ux.shape[1]
+    h0 = None if h0 is None else h0.contiguous()
+    c0 = None if c0 is None else c0.contiguous()
+    plan = _lib.plan(T, B, I, H, RX, RH)
+    lib = _lib.lib()
+    new = x.new_empty
+    # last-step-only callers (Net.forward) skip the [T,B,H] output when nothing reads it back: backward and the
+    # generic regime take h_{t-1} from y
+    if need_y or need_grad or plan.path == _lib.PATH_G:
+        y = new((B, T, H)) if batch_first else new((T, B, H))
+    else:
+        y = None
+    hT, cT = new((B, H)), new((B, H))
+    zx = new((T * B, plan.zx_pitch))
+    if need_grad:
+        gates, cs, z = new((plan.gates_bytes // 4,)), new((plan.cs_bytes // 4,)), new((T * B, plan.z_pitch))
+    else:
+        gates = cs = z = None
+    ws = new((plan.fwd_workspace_bytes + 3) // 4) if plan.fwd_workspace_bytes else None
+    xs_t, xs_b = _tb_strides(x, batch_first)
+    ys_t, ys_b = _tb_strides(y, batch_first) if y is not None else (0, 0)
+    with torch.cuda.device_of(x):
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        with _timed("xproj_fwd"):
+            _lib.check(lib.vmlmf_xproj_fwd(_ptr(x), xs_t, xs_b, _ptr(Ux), _ptr(zx), T, B, I, RX, plan.zx_pitch, st))
+        with _timed("seq_fwd"):
+            _lib.check(lib.vmlmf_seq_fwd(C.byref(plan), _ptr(x), xs_t, xs_b, _ptr(zx), _ptr(Ux), _ptr(Vx), _ptr(Dx),
                                          _ptr(A), _ptr(Bm), _ptr(Dh), _ptr(bias), _ptr(h0), _ptr(c0), _ptr(y), ys_t,
                                          ys_b, _ptr(hT), _ptr(cT), _ptr(gates), _ptr(cs), _ptr(z), _ptr(ws),
                                          T, B, I, H, RX, RH, st))
-        if need_grad:
-            ctx.save_for_backward(x, zx, Ux, Vx, Dx, A, Bm, Dh, h0, c0, y, gates, cs, z)
-            ctx.plan = plan
-            ctx.batch_first = batch_first
-            ctx.dims = (T, B, I, H, RX, RH)
-            ctx.set_materialize_grads(False)
-        return y, hT, cT
+    saved = None
+    if need_grad:
+        saved = dict(tensors=(x, zx, Ux, Vx, Dx, A, Bm, Dh, h0, c0, y, gates, cs, z), plan=plan, batch_first=batch_first,
+                     dims=(T, B, I, H, RX, RH))
+    return y, hT, cT, saved
 
-    @staticmethod
-    def backward(ctx, dy, dhT, dcT):
-        x, zx, Ux, Vx, Dx, A, Bm, Dh, h0, c0, y, gates, cs, z = ctx.saved_tensors
-        T, B, I, H, RX, RH = ctx.dims
-        plan, bf = ctx.plan, ctx.batch_first
-        lib = _lib.lib()
-        new = x.new_empty
-        dy = None if dy is None else _row_contig(dy)
-        dhT = None if dhT is None else dhT.contiguous()
-        dcT = None if dcT is None else dcT.contiguous()
-        need = ctx.needs_input_grad
-        dx = torch.empty_like(x, memory_format=torch.contiguous_format) if need[0] else None
-        dh0 = new((B, H)) if (h0 is not None and need[1]) else None
-        dc0 = new((B, H)) if (c0 is not None and need[2]) else None
-        dUx, dVx, dDx, dA, dBm, dDh = (torch.empty_like(p) for p in (Ux, Vx, Dx, A, Bm, Dh))
-        dbias = new((4 * H,))
-        ws = new((plan.bwd_workspace_bytes + 3) // 4) if plan.bwd_workspace_bytes else None
-        xs = _tb_strides(x, bf)
-        ys = _tb_strides(y, bf)
-        dys = _tb_strides(dy, bf) if dy is not None else (0, 0)
-        dxs = _tb_strides(dx, bf) if dx is not None else (0, 0)
-        with torch.cuda.device_of(x):
-            st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-            with _timed("seq_bwd"):
-              _lib.check(lib.vmlmf_seq_bwd(C.byref(plan), _ptr(x), xs[0], xs[1], _ptr(zx), _ptr(Ux), _ptr(Vx), _ptr(Dx),
+
+def _seq_backward(tensors, plan, batch_first, dims, dy, dhT, dcT, need_dx, need_dh0, need_dc0):
+    """BPTT of one layer through the C ABI -> (dx, dh0, dc0, dUx, dVx, dDx, dA, dBm, dDh, dbias)."""
+    x, zx, Ux, Vx, Dx, A, Bm, Dh, h0, c0, y, gates, cs, z = tensors
+    T, B, I, H, RX, RH = dims
+    bf = batch_first
+    lib = _lib.lib()
+    new = x.new_empty
+    dy = None if dy is None else _row_contig(dy)
+    dhT = None if dhT is None else dhT.contiguous()
+    dcT = None if dcT is None else dcT.contiguous()
+    dx = torch.empty_like(x, memory_format=torch.contiguous_format) if need_dx else None
+    dh0 = new((B, H)) if (h0 is not None and need_dh0) else None
+    dc0 = new((B, H)) if (c0 is not None and need_dc0) else None
+    dUx, dVx, dDx, dA, dBm, dDh = (torch.empty_like(p) for p in (Ux, Vx, Dx, A, Bm, Dh))
+    dbias = new((4 * H,))
+    ws = new((plan.bwd_workspace_bytes + 3) // 4) if plan.bwd_workspace_bytes else None
+    xs = _tb_strides(x, bf)
+    ys = _tb_strides(y, bf)
+    dys = _tb_strides(dy, bf) if dy is not None else (0, 0)
+    dxs = _tb_strides(dx, bf) if dx is not None else (0, 0)
+    with torch.cuda.device_of(x):
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        with _timed("seq_bwd"):
+            _lib.check(lib.vmlmf_seq_bwd(C.byref(plan), _ptr(x), xs[0], xs[1], _ptr(zx), _ptr(Ux), _ptr(Vx), _ptr(Dx),
                                          _ptr(A), _ptr(Bm), _ptr(Dh), _ptr(h0), _ptr(c0), _ptr(y), ys[0], ys[1],
                                          _ptr(gates), _ptr(cs), _ptr(z), _ptr(dy), dys[0], dys[1], _ptr(dhT),
                                          _ptr(dcT), _ptr(dx), dxs[0], dxs[1], _ptr(dh0), _ptr(dc0), _ptr(dUx),
                                          _ptr(dVx), _ptr(dDx), _ptr(dA), _ptr(dBm), _ptr(dDh), _ptr(dbias), _ptr(ws),
                                          T, B, I, H, RX, RH, st))
-        return dx, dh0, dc0, dUx, dVx, dDx, dA, dBm, dDh, dbias, None, None, None
+    return dx, dh0, dc0, dUx, dVx, dDx, dA, dBm, dDh, dbias
+
+
+def _stash(ctx, saved):
+    ctx.save_for_backward(*saved["tensors"])
+    ctx.plan, ctx.batch_first, ctx.dims = saved["plan"], saved["batch_first"], saved["dims"]
+    ctx.set_materialize_grads(False)
+
+
+class VmlmfSeqFunction(torch.autograd.Function):
+    """One layer over a whole sequence in canonical parameters (Ux, Vx, Dx, A, Bm, Dh, bias)."""
+
+    @staticmethod
+    def forward(ctx, x, h0, c0, Ux, Vx, Dx, A, Bm, Dh, bias, batch_first, save=True, need_y=True):
+        # grad mode is always off inside Function.forward and needs_input_grad ignores torch.no_grad():
+        # the caller (vmlmf_sequence) decides whether anything has to be kept for backward
+        need_grad = save and any(ctx.needs_input_grad)
+        y, hT, cT, saved = _seq_forward(x, h0, c0, (Ux, Vx, Dx, A, Bm, Dh, bias), batch_first, need_grad, need_y)
+        if saved is not None:
+            _stash(ctx, saved)
+        return y, hT, cT
+
+    @staticmethod
+    def backward(ctx, dy, dhT, dcT):
+        need = ctx.needs_input_grad
+        out = _seq_backward(ctx.saved_tensors, ctx.plan, ctx.batch_first, ctx.dims, dy, dhT, dcT, need[0], need[1], need[2])
+        return (*out, None, None, None)
+
+
+class PlainCellSeqFunction(torch.autograd.Function):
+    """One MyVMLMFCell / MyVMLSTM layer over a whole sequence in the REFERENCE's parameters (u_x, u_h, v_x, v_h, b_x,
+    b_h, dia_x, dia_h; V/models/vmlmf.py:56-69, vmlmf_lm.py:200-213).  Same kernels as VmlmfSeqFunction, with the map
+    to canonical parameters and its chain rule as one launch each way (vmlmf_pack_plain_fwd / _bwd), so a train
+    step has no per-parameter elementwise launches besides autograd's own accumulation into .grad."""
+
+    @staticmethod
+    def forward(ctx, x, h0, c0, u_x, u_h, v_x, v_h, b_x, b_h, dia_x, dia_h, batch_first, save=True, need_y=True):
+        _require_cuda(x, u_x, u_h, v_x, v_h, b_x, b_h, dia_x, dia_h)
+        u_x, u_h, v_x, v_h = u_x.contiguous(), u_h.contiguous(), v_x.contiguous(), v_h.contiguous()
+        n_in, rx = u_x.shape
+        hidden, rh = u_h.shape
+        if hidden < n_in:                                   # same exception type as the reference (V/models/vmlmf.py:92-94,117)
+            raise TypeError(_lib.lib().vmlmf_strerror(-2).decode())
+        new = u_x.new_empty
+        Dx, Dh, bias = new((4, n_in)), new((4, hidden)), new((4 * hidden,))
+        with torch.cuda.device_of(u_x):
+            st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            _lib.check(_lib.lib().vmlmf_pack_plain_fwd(_ptr(u_x), _ptr(v_x), _ptr(dia_x.contiguous()), _ptr(u_h), _ptr(v_h),
+                                                       _ptr(dia_h.contiguous()), _ptr(b_x.contiguous()),
+                                                       _ptr(b_h.contiguous()), _ptr(Dx), _ptr(Dh), _ptr(bias), n_in,
+                                                       hidden, rx, rh, st))
+        need_grad = save and any(ctx.needs_input_grad)
+        y, hT, cT, saved = _seq_forward(x, h0, c0, (u_x, v_x, Dx, u_h, v_h, Dh, bias), batch_first, need_grad, need_y)
+        if saved is not None:
+            _stash(ctx, saved)
+            ctx.shapes = (b_x.shape, b_h.shape, dia_x.shape, dia_h.shape)
+        return y, hT, cT
+
+    @staticmethod
+    def backward(ctx, dy, dhT, dcT):
+        need = ctx.needs_input_grad
+        tensors = ctx.saved_tensors
+        dx, dh0, dc0, dUx, dVx, dDx, dA, dBm, dDh, dbias = _seq_backward(tensors, ctx.plan, ctx.batch_first, ctx.dims,
+                                                                         dy, dhT, dcT, need[0], need[1], need[2])
+        u_x, v_x, u_h, v_h = tensors[2], tensors[3], tensors[5], tensors[6]
+        _, _, n_in, hidden, rx, rh = ctx.dims
+        new = u_x.new_empty
+        ddia_x, ddia_h, db_h = new((n_in,)), new((hidden,)), new((4 * hidden,))
+        with torch.cuda.device_of(u_x):
+            st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            _lib.check(_lib.lib().vmlmf_pack_plain_bwd(_ptr(u_x), _ptr(v_x), _ptr(u_h), _ptr(v_h), _ptr(dDx), _ptr(dDh),
+                                                       _ptr(dUx), _ptr(dVx), _ptr(dA), _ptr(dBm), _ptr(ddia_x),
+                                                       _ptr(ddia_h), _ptr(dbias), _ptr(db_h), n_in, hidden, rx, rh, st))
+        sb_x, sb_h, sd_x, sd_h = ctx.shapes
+        # b_x and b_h get two different tensors: sharing one would alias their .grad (see packing.pack_plain)
+        return (dx, dh0, dc0, dUx, dA, dVx, dBm, dbias.view(sb_x), db_h.view(sb_h), ddia_x.view(sd_x), ddia_h.view(sd_h),
+                None, None, None)
 
 
 class DiagCorrFunction(torch.autograd.Function):
@@ -229,6 +299,107 @@ class LinearTCFunction(torch.autograd.Function):
 
 def linear_tc(x, w, b):
     return LinearTCFunction.apply(x, w, b)
+
+
+class SoftmaxNLLFunction(torch.autograd.Function):
+    """loss = scale * sum_r (logsumexp(scores[r]) - scores[r, labels[r]]): one read of the scores forward (online
+    max/sum), one read + one write backward, sums in a fixed order (vmlmf_softmax_nll_fwd/_bwd)."""
+
+    @staticmethod
+    def forward(ctx, scores, labels, scale):
+        _require_cuda(scores)
+        if not labels.is_cuda:
+            raise RuntimeError("vmlmf_b200: tensors must live on a CUDA device (no CPU fallback exists)")
+        if scores.stride(1) != 1:
+            scores = scores.contiguous()
+        labels = labels.reshape(-1).to(torch.int64).contiguous()
+        rows, ncls = scores.shape
+        lib = _lib.lib()
+        lse = scores.new_empty((rows,))
+        loss = scores.new_empty(())
+        ws = scores.new_empty(((lib.vmlmf_softmax_nll_workspace_bytes(rows, ncls) + 3) // 4,))
+        with torch.cuda.device_of(scores):
+            st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            _lib.check(lib.vmlmf_softmax_nll_fwd(_ptr(scores), scores.stride(0), _ptr(labels), _ptr(lse), _ptr(loss),
+                                                 float(scale), _ptr(ws), rows, ncls, st))
+        ctx.save_for_backward(scores, labels, lse)
+        ctx.scale = float(scale)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        scores, labels, lse = ctx.saved_tensors
+        rows, ncls = scores.shape
+        dscores = torch.empty_like(scores, memory_format=torch.contiguous_format)
+        dloss = dloss.contiguous()
+        with torch.cuda.device_of(scores):
+            st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            _lib.check(_lib.lib().vmlmf_softmax_nll_bwd(_ptr(scores), scores.stride(0), _ptr(labels), _ptr(lse),
+                                                        _ptr(dloss), ctx.scale, _ptr(dscores), dscores.stride(0),
+                                                        rows, ncls, st))
+        return dscores, None, None
+
+
+def cross_entropy(logits, target):
+    """F.cross_entropy(logits[N,C], target[N]) with mean reduction -- the HAR training loss (V/train_test/train.py:63)."""
+    return SoftmaxNLLFunction.apply(logits, target, 1.0 / logits.shape[0])
+
+
+def nll_loss(scores, y):
+    """The LM loss of V/train_test/lm_test.py:140-153: mean over tokens of -log softmax(scores)[y], times the batch
+    size y.size(1); computed through log-sum-exp, so large scores do not overflow the way the reference's exp() does."""
+    return SoftmaxNLLFunction.apply(scores, y, float(y.size(1)) / scores.shape[0])
+
+
+class HeadLinearFunction(torch.autograd.Function):
+    """out = h W^T + b for the small classifier head of Net (nn.Linear(H_last, 18), V/models/vmlmf.py:345-347):
+    one kernel forward, two backward (per-block partial dW / db, then a fixed-order reduce)."""
+
+    @staticmethod
+    def forward(ctx, h, w, b):
+        _require_cuda(h, w, b)
+        if h.stride(1) != 1:
+            h = h.contiguous()
+        w = w.contiguous()
+        B, K = h.shape
+        N = w.shape[0]
+        out = h.new_empty((B, N))
+        with torch.cuda.device_of(h):
+            st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            _lib.check(_lib.lib().vmlmf_head_fwd(_ptr(h), h.stride(0), _ptr(w), _ptr(b), _ptr(out), B, K, N, st))
+        ctx.save_for_backward(h, w)
+        ctx.has_bias = b is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        h, w = ctx.saved_tensors
+        B, K = h.shape
+        N = w.shape[0]
+        lib = _lib.lib()
+        dout = dout.contiguous()
+        dh = h.new_empty((B, K)) if ctx.needs_input_grad[0] else None
+        dw = torch.empty_like(w)
+        db = h.new_empty((N,)) if ctx.has_bias else None
+        ws = h.new_empty(((lib.vmlmf_head_bwd_workspace_bytes(B, K, N) + 3) // 4,))
+        with torch.cuda.device_of(h):
+            st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            _lib.check(lib.vmlmf_head_bwd(_ptr(h), h.stride(0), _ptr(w), _ptr(dout), _ptr(dh), K, _ptr(dw), _ptr(db),
+                                          _ptr(ws), B, K, N, st))
+        return dh, dw, db
+
+
+def head_linear(h, w, b):
+    """nn.Linear for a narrow head (out_features <= 32, in_features <= 1024) on CUDA fp32; other shapes -> F.linear."""
+    if h.is_cuda and h.dim() == 2 and w.shape[0] <= 32 and w.shape[1] <= 1024 and h.dtype == torch.float32:
+        return HeadLinearFunction.apply(h, w, b)
+    return torch.nn.functional.linear(h, w, b)
+
+
+def vmlmf_plain_sequence(x, h0, c0, params, batch_first=True, need_y=True):
+    """Run one plain VMLMF layer given the reference's eight parameters (u_x, u_h, v_x, v_h, b_x, b_h, dia_x, dia_h)."""
+    save = torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (x, h0, c0, *params))
+    return PlainCellSeqFunction.apply(x, h0, c0, *params, batch_first, save, need_y)
 
 
 def vmlmf_sequence(x, h0, c0, canon, batch_first=True, need_y=True):

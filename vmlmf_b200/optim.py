@@ -1,0 +1,107 @@
+"""Flat-bucket optimizer steps: the reference's two update rules as single kernels over one
+contiguous parameter / gradient buffer.
+
+  FlatAdam     torch.optim.Adam(model.parameters(), lr)              V/train_test/train.py:47,65
+  FlatClipSGD  clip_grad_norm_(params, max_norm); p -= lr * p.grad   V/train_test/lm_test.py:203-209
+
+Both re-point every live parameter's `.data` and `.grad` at slices of two flat buffers (the gradient one is
+`parallel.GradBucket`'s, i.e. the buffer the data-parallel all-reduce already sums), so a step is one launch
+(two for the clipped SGD: the norm needs a grid-wide reduction) whatever the number of parameter tensors, and
+zeroing the gradients is one fill.  Parameters that never receive a gradient (the reference's dead `Net.cell`,
+V/models/vmlmf.py:348-350) are left alone, exactly as torch's optimizers skip `grad is None`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .parallel import GradBucket
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class _FlatOptimizer:
+    def __init__(self, module_or_bucket, average=True):
+        self.bucket = module_or_bucket if isinstance(module_or_bucket, GradBucket) else GradBucket(module_or_bucket, average)
+        self.pflat = None
+
+    def _build(self):
+        """first step: the bucket learns which parameters are live from their .grad; parameters move into one buffer"""
+        b = self.bucket
+        if b.flat is None:
+            b._build()
+        ref = b.params[0]
+        if not ref.is_cuda:
+            raise RuntimeError("vmlmf_b200.optim: parameters must live on a CUDA device (no CPU fallback)")
+        self.pflat = torch.empty_like(b.flat)
+        off = 0
+        for p in b.params:
+            view = self.pflat[off:off + p.numel()].view_as(p)
+            view.copy_(p.data)
+            p.data = view
+            off += p.numel()
+
+    def zero_grad(self):
+        self.bucket.zero()
+
+    def all_reduce(self):
+        return self.bucket.all_reduce()
+
+
+class FlatAdam(_FlatOptimizer):
+    """Adam with torch.optim.Adam's defaults and arithmetic (no amsgrad, no weight decay).  The step counter lives on
+    the device so that a captured CUDA graph advances it on replay."""
+
+    def __init__(self, module_or_bucket, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, average=True):
+        super().__init__(module_or_bucket, average)
+        self.lr, self.betas, self.eps = lr, betas, eps
+        self.m = self.v = self.t = None
+
+    def _build(self):
+        super()._build()
+        self.m = torch.zeros_like(self.pflat)
+        self.v = torch.zeros_like(self.pflat)
+        self.t = torch.zeros((), dtype=torch.float32, device=self.pflat.device)
+
+    @torch.no_grad()
+    def step(self):
+        if self.pflat is None:
+            self._build()
+        self.t += 1
+        g = self.bucket.flat
+        with torch.cuda.device_of(g):
+            st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            _lib.check(_lib.lib().vmlmf_adam_step(_ptr(self.pflat), _ptr(g), _ptr(self.m), _ptr(self.v), g.numel(),
+                                                  self.lr, self.betas[0], self.betas[1], self.eps, _ptr(self.t), 0, st))
+
+
+class FlatClipSGD(_FlatOptimizer):
+    """Global-norm clipping followed by plain SGD.  `step(lr)` returns the pre-clip gradient norm as a device scalar
+    (what clip_grad_norm_ returns); gradients are rescaled in place like clip_grad_norm_ does."""
+
+    def __init__(self, module_or_bucket, lr=1.0, max_norm=5.0, average=True):
+        super().__init__(module_or_bucket, average)
+        self.lr, self.max_norm = lr, max_norm
+        self.ws = self.norm = None
+
+    def _build(self):
+        super()._build()
+        n = self.pflat.numel()
+        self.ws = self.pflat.new_empty(((_lib.lib().vmlmf_sgd_clip_workspace_bytes(n) + 3) // 4,))
+        self.norm = self.pflat.new_zeros(())
+
+    @torch.no_grad()
+    def step(self, lr=None):
+        if self.pflat is None:
+            self._build()
+        g = self.bucket.flat
+        with torch.cuda.device_of(g):
+            st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            _lib.check(_lib.lib().vmlmf_sgd_clip_step(_ptr(self.pflat), _ptr(g), g.numel(),
+                                                      self.lr if lr is None else lr, self.max_norm, 1, _ptr(self.norm),
+                                                      _ptr(self.ws), st))
+        return self.norm

@@ -12,7 +12,7 @@ import torch
 from torch import nn
 
 from . import packing
-from .functional import vmlmf_sequence
+from .functional import head_linear, vmlmf_plain_sequence, vmlmf_sequence
 
 TIME_STEPS = 128
 RECURRENT_MAX = pow(2, 1 / TIME_STEPS)
@@ -54,10 +54,14 @@ class MyVMLMFCell(nn.Module):
         """(Ux,Vx,Dx,A,Bm,Dh,bias) for the fused kernels."""
         return packing.pack_plain(self.u_x, self.u_h, self.v_x, self.v_h, self.b_x, self.b_h, self.dia_x, self.dia_h)
 
+    def plain_params(self):
+        """the reference's eight parameters in PlainCellSeqFunction's order"""
+        return (self.u_x, self.u_h, self.v_x, self.v_h, self.b_x, self.b_h, self.dia_x, self.dia_h)
+
     def forward(self, x, hidden_states):
         """One step: x[B,I], (h[B,H], c[B,H]) -> (h', c').  Runs the fused kernel with T=1."""
         h, c = hidden_states
-        _, h1, c1 = vmlmf_sequence(x.unsqueeze(1), h, c, self.canonical(), batch_first=True)
+        _, h1, c1 = vmlmf_plain_sequence(x.unsqueeze(1), h, c, self.plain_params(), batch_first=True)
         return h1, c1
 
 
@@ -155,9 +159,16 @@ class MyLSTM(nn.Module):
         layer skip writing its [B,T,H] output; the first return value may then be None."""
         last = []
         for i, cell in enumerate(self.rnncells):
-            canon = cell.canonical() if hasattr(cell, "canonical") else None
+            need_y = need_sequence or i + 1 < len(self.rnncells)
+            canon = None
+            if hasattr(cell, "plain_params"):            # plain VMLMF cell: parameter map fused into the call
+                x, h, _ = vmlmf_plain_sequence(x, None, None, cell.plain_params(), batch_first=self.batch_first,
+                                               need_y=need_y)
+                last.append(h)
+                continue
+            if hasattr(cell, "canonical"):
+                canon = cell.canonical()
             if canon is not None:
-                need_y = need_sequence or i + 1 < len(self.rnncells)
                 x, h, _ = vmlmf_sequence(x, None, None, canon, batch_first=self.batch_first, need_y=need_y)
             else:
                 nb = x.size(self.batch_index)
@@ -197,4 +208,4 @@ class Net(nn.Module):
         [B,T,H] upstream gradient that is zero everywhere but the last step."""
         _, h_last = self.rnn(x, need_sequence=False) if isinstance(self.rnn, MyLSTM) else self.rnn(x)
         top = self.rnn.hidden_layer_sizes[-1]
-        return self.lin(h_last[:, -top:]).squeeze(1)
+        return head_linear(h_last[:, -top:], self.lin.weight, self.lin.bias).squeeze(1)

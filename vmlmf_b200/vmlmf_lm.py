@@ -9,7 +9,7 @@ import torch
 from torch import nn
 
 from . import packing
-from .functional import vmlmf_sequence
+from .functional import vmlmf_plain_sequence, vmlmf_sequence  # noqa: F401
 
 
 class Embed(nn.Module):
@@ -56,14 +56,19 @@ class MyVMLSTM(nn.Module):
             raise RuntimeError("MyVMLSTM requires input_size == hidden_size (as the reference does)")
         return packing.pack_plain(self.u_x, self.u_h, self.w_x, self.w_h, self.b_x, self.b_h, self.dia_x, self.dia_h)
 
+    def plain_params(self):
+        if self.input_size != self.hidden_size:
+            raise RuntimeError("MyVMLSTM requires input_size == hidden_size (as the reference does)")
+        return (self.u_x, self.u_h, self.w_x, self.w_h, self.b_x, self.b_h, self.dia_x, self.dia_h)
+
     def lstm_step(self, x, h, c):
-        _, h1, c1 = vmlmf_sequence(x.unsqueeze(0), h, c, self.canonical(), batch_first=False)
+        _, h1, c1 = vmlmf_plain_sequence(x.unsqueeze(0), h, c, self.plain_params(), batch_first=False)
         return h1, c1
 
     def forward(self, x, states):
         """x[T,B,X], (h,c) -> (out[T,B,H], (h_T, c_T))"""
         h, c = states
-        out, h1, c1 = vmlmf_sequence(x, h, c, self.canonical(), batch_first=False)
+        out, h1, c1 = vmlmf_plain_sequence(x, h, c, self.plain_params(), batch_first=False)
         return out, (h1, c1)
 
 
