@@ -241,6 +241,7 @@ def run_ours(args):
             bucket.zero()
             loss = ce(net(sx), sy)
             loss.backward()
+            bucket.pack()                        # gather into the flat bucket inside the graph
             return loss.detach()
 
         fb = GraphedCallable(fwd_bwd)
@@ -405,7 +406,8 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": "sequences/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": e2e_s * 1e3 / K},
         # this library's kernels per step: pack_plain_fwd, xproj_small, seq_fwd_mma, head_fwd, softmax_nll_fwd + sum_scale,
-        # softmax_nll_bwd, head_bwd + head_reduce, seq_bwd_fused, reduce_partials, pack_plain_bwd, adam
+        # softmax_nll_bwd, head_bwd + head_reduce, seq_bwd_fused, reduce_partials, pack_plain_bwd, adam (13); PyTorch adds
+        # three more (ones for d loss, the multi-tensor gradient gather, the Adam step counter)
         "gpu_launches": 13 * K,
         "roofline": roofline,
         "cpu_baseline": cpu,

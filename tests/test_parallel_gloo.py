@@ -48,13 +48,13 @@ def _worker(rank, world, port, out):
         x = torch.randn(8, 6, 9, generator=g)
         y = torch.randint(0, 18, (8,), generator=g)
         bucket = GradBucket(net, average=True)
-        for _ in range(2):                     # second pass exercises the aliased-.grad path and zero()
+        for _ in range(2):                     # second pass exercises zero() and re-packing
             bucket.zero()
             torch.nn.functional.cross_entropy(net(shard_batch(x)), shard_batch(y)).backward()
             flat = bucket.all_reduce()
         assert net.dead.grad is None and all(p.grad is not None for p in (net.u, net.v))
         assert flat.numel() == net.u.numel() + net.v.numel()          # dead parameter left out of the bucket
-        assert net.u.grad.data_ptr() == flat.data_ptr()               # .grad aliases the bucket: no packing copies
+        assert net.u.grad.data_ptr() == flat.data_ptr()               # after the all-reduce .grad is the bucket slice
         if rank == 0:
             torch.save({"u": net.u.grad.clone(), "v": net.v.grad.clone(), "w_u": net.u.detach().clone()}, out)
     finally:

@@ -32,8 +32,7 @@ class _FlatOptimizer:
     def _build(self):
         """first step: the bucket learns which parameters are live from their .grad; parameters move into one buffer"""
         b = self.bucket
-        if b.flat is None:
-            b._build()
+        b.pack()
         ref = b.params[0]
         if not ref.is_cuda:
             raise RuntimeError("vmlmf_b200.optim: parameters must live on a CUDA device (no CPU fallback)")
@@ -71,8 +70,8 @@ class FlatAdam(_FlatOptimizer):
     def step(self):
         if self.pflat is None:
             self._build()
+        g = self.bucket.pack()
         self.t += 1
-        g = self.bucket.flat
         with torch.cuda.device_of(g):
             st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
             _lib.check(_lib.lib().vmlmf_adam_step(_ptr(self.pflat), _ptr(g), _ptr(self.m), _ptr(self.v), g.numel(),
@@ -98,7 +97,7 @@ class FlatClipSGD(_FlatOptimizer):
     def step(self, lr=None):
         if self.pflat is None:
             self._build()
-        g = self.bucket.flat
+        g = self.bucket.pack()
         with torch.cuda.device_of(g):
             st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
             _lib.check(_lib.lib().vmlmf_sgd_clip_step(_ptr(self.pflat), _ptr(g), g.numel(),

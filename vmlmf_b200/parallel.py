@@ -14,15 +14,21 @@ import torch.distributed as dist
 
 
 class GradBucket:
-    """Flat view of every live parameter gradient; `.grad` tensors alias slices of one buffer so the
-    all-reduce needs no packing copies.  Parameters that never receive a gradient (the reference's
-    dead `Net.cell`, V/models/vmlmf.py:348-350) are left out -- found from the first backward."""
+    """One flat buffer holding every live parameter gradient, so the all-reduce (and the flat optimizer steps of
+    vmlmf_b200.optim) touch a single tensor.  Parameters that never receive a gradient (the reference's dead
+    `Net.cell`, V/models/vmlmf.py:348-350) are left out -- found from the first backward.
+
+    `zero()` drops the `.grad` tensors, so the next backward hands each parameter its freshly computed gradient
+    without an accumulation kernel; `pack()` (called by `all_reduce()` and by the optimizers) copies them into the
+    bucket with one multi-tensor launch and re-points `.grad` at the bucket slices, which is what callers see
+    afterwards (reduced / clipped values)."""
 
     def __init__(self, module, average=True):
         self.module = module
         self.average = average
         self.flat = None
         self.params = []
+        self.views = []
 
     def _build(self):
         self.params = [p for p in self.module.parameters() if p.grad is not None]
@@ -30,23 +36,39 @@ class GradBucket:
         ref = self.params[0]
         self.flat = torch.zeros(n, dtype=ref.dtype, device=ref.device)
         off = 0
+        self.views = []
         for p in self.params:
-            view = self.flat[off:off + p.numel()].view_as(p)
-            view.copy_(p.grad)
-            p.grad = view
+            self.views.append(self.flat[off:off + p.numel()].view_as(p))
             off += p.numel()
 
+    @torch.no_grad()
+    def pack(self):
+        """gather the current .grad tensors into the bucket (no-op for those that already live there)"""
+        if self.flat is None:
+            self._build()
+        dst, src = [], []
+        for p, v in zip(self.params, self.views):
+            if p.grad is None:
+                v.zero_()
+            elif p.grad.data_ptr() != v.data_ptr():
+                dst.append(v)
+                src.append(p.grad)
+            p.grad = v
+        if dst:
+            torch._foreach_copy_(dst, src)
+        return self.flat
+
     def zero(self):
-        """call instead of module.zero_grad(): keeps the aliasing alive"""
+        """call instead of module.zero_grad()"""
         if self.flat is not None:
-            self.flat.zero_()
+            for p in self.params:
+                p.grad = None
         else:
             self.module.zero_grad(set_to_none=True)
 
     def all_reduce(self):
-        """sum (or mean) the bucket over all ranks; no-op for a single process"""
-        if self.flat is None:
-            self._build()
+        """sum (or mean) the bucket over all ranks; packs first; no collective for a single process"""
+        self.pack()
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
             if self.average:

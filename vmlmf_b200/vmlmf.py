@@ -180,7 +180,7 @@ class MyLSTM(nn.Module):
                     outs.append(h)
                 x = torch.stack(outs, self.time_index)
             last.append(h)
-        return x, torch.cat(last, -1)
+        return x, (last[0] if len(last) == 1 else torch.cat(last, -1))
 
 
 class Net(nn.Module):
@@ -208,4 +208,6 @@ class Net(nn.Module):
         [B,T,H] upstream gradient that is zero everywhere but the last step."""
         _, h_last = self.rnn(x, need_sequence=False) if isinstance(self.rnn, MyLSTM) else self.rnn(x)
         top = self.rnn.hidden_layer_sizes[-1]
-        return head_linear(h_last[:, -top:], self.lin.weight, self.lin.bias).squeeze(1)
+        if h_last.size(-1) != top:                      # several layers: the head reads the last layer's slice of the cat
+            h_last = h_last[:, -top:]
+        return head_linear(h_last, self.lin.weight, self.lin.bias).squeeze(1)
