@@ -312,6 +312,16 @@ def run_ours(args):
     e2e_value = world * B * K / e2e_s
     h2d = host_x[0].numel() * 4 + host_y[0].numel() * 8
 
+    # data-parallel sanity: every rank applied the same averaged gradients, so the replicas must still be bit-identical
+    in_sync = None
+    if world > 1:
+        mine = opt.pflat.detach().clone()
+        ref0 = mine.clone()
+        dist.broadcast(ref0, 0)
+        diff = (mine != ref0).sum().to(torch.float64)
+        dist.all_reduce(diff)
+        in_sync = bool(diff.item() == 0)
+
     # ---------------- inference (no_grad) throughput, resident inputs ----------------
     net.eval()
     with torch.no_grad():
@@ -414,6 +424,7 @@ def run_ours(args):
         "inference": {"value": inf_value, "unit": "sequences/s", "ms_per_step": inf_ms / K},
         "recurrence_latency": latency,
         "grad_allreduce_bytes": bucket.nbytes,
+        "replicas_in_sync": in_sync,
     }
     sys.stdout.flush()
     os.write(json_fd, (json.dumps(out) + "\n").encode())

@@ -182,8 +182,19 @@ int vmlmf_xproj_fwd(const float* x, long long xs_t, long long xs_b, const float*
     }
     const long long nrows = (long long)T * B;
     long long grid = (nrows + rows - 1) / rows;
-    if (grid > kNumSMs * 16) grid = kNumSMs * 16;
-    xproj_small_kernel<<<(int)grid, 128, smem, st>>>(x, xs_t, xs_b, Ux, zx, T, B, I, RX, zx_pitch);
+    // resident blocks per SM: one wave, every block walks its share.  The query is a driver call: cached per
+    // shared-memory size (256-byte buckets; a benign race, every writer stores the same value)
+    static int occ_cache[257] = {0};
+    int& occ_slot = occ_cache[smem / 256 < 256 ? smem / 256 : 256];
+    if (occ_slot == 0) {
+      int q = 1;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, xproj_small_kernel, 128, smem) != cudaSuccess || q < 1) q = 1;
+      occ_slot = q;
+    }
+    const int occ = occ_slot;
+    if (grid > (long long)kNumSMs * occ) grid = (long long)kNumSMs * occ;
+    const int order = (xs_t == I && xs_b == (long long)T * I) ? 1 : ((xs_b == I && xs_t == (long long)B * I) ? 2 : 0);
+    xproj_small_kernel<<<(int)grid, 128, smem, st>>>(x, xs_t, xs_b, Ux, zx, T, B, I, RX, zx_pitch, order);
     return (int)cudaGetLastError();
   }
   return generic_xproj(x, xs_t, xs_b, Ux, zx, T, B, I, RX, zx_pitch, st);

@@ -11,13 +11,16 @@ namespace vmlmf {
 
 // block = 128 threads; each thread produces 4 consecutive outputs of one row.
 // smem: Us[I][pitch] | xs[ROWS][I+1]
+// `order`: 0 = arbitrary (time, batch) strides, rows walked as t*B + b;  1 = x is one contiguous [B,T,I] block,
+// 2 = one contiguous [T,B,I] block.  In the contiguous cases rows are walked in MEMORY order, so a block's ROWS rows
+// are a single contiguous span streamed with independent 16-byte loads (the 32-byte zx rows go wherever t*B + b says).
 static __global__ void __launch_bounds__(128) xproj_small_kernel(const float* __restrict__ x, long long xs_t,
                                                           long long xs_b, const float* __restrict__ Ux,
                                                           float* __restrict__ zx, int T, int B, int I,
-                                                          int RX, int pitch) {
+                                                          int RX, int pitch, int order) {
   extern __shared__ __align__(16) float smem[];
   const int G = pitch >> 2;                 // threads per row
-  const int ROWS = blockDim.x / G;          // rows per block
+  const int ROWS = blockDim.x / G;          // rows per block (a multiple of 4)
   float* Us = smem;                         // [I][pitch], zero padded
   float* xs = smem + I * pitch;             // [ROWS][I+1]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = blockDim.x >> 5;
@@ -26,20 +29,61 @@ static __global__ void __launch_bounds__(128) xproj_small_kernel(const float* __
     Us[i] = r < RX ? __ldg(Ux + (size_t)jj * RX + r) : 0.f;
   }
   const long long nrows = (long long)T * B;
+  const bool vec = order != 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
   for (long long row0 = (long long)blockIdx.x * ROWS; row0 < nrows; row0 += (long long)gridDim.x * ROWS) {
     __syncthreads();
-    for (int rr = warp; rr < ROWS; rr += NW) {
-      const long long row = row0 + rr;
-      if (row < nrows) {
-        const long long t = row / B, b = row % B;
-        const float* src = x + t * xs_t + b * xs_b;
-        for (int jj = lane; jj < I; jj += 32) xs[rr * (I + 1) + jj] = __ldg(src + jj);
+    if (order != 0) {
+      const float* src = x + row0 * I;
+      const long long left = nrows - row0;
+      const int n = (int)(left < ROWS ? left : ROWS) * I;          // floats in this block's span
+      int e = tid * 4;
+      if (vec) {
+        const int n4 = n & ~3;
+        for (; e + 3 * 512 < n4; e += 4 * 512) {                    // four independent 16-byte loads per thread
+          float4 v[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(src + e + u * 512));
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int e0 = e + u * 512;
+            int rr = e0 / I, jj = e0 - rr * I;
+            const float w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              xs[rr * (I + 1) + jj] = w[c];
+              if (++jj == I) { jj = 0; ++rr; }
+            }
+          }
+        }
+        for (; e < n4; e += 512) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(src + e));
+          int rr = e / I, jj = e - rr * I;
+          const float w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            xs[rr * (I + 1) + jj] = w[c];
+            if (++jj == I) { jj = 0; ++rr; }
+          }
+        }
+        for (int t1 = n4 + tid; t1 < n; t1 += blockDim.x) xs[(t1 / I) * (I + 1) + t1 % I] = __ldg(src + t1);
+      } else {
+        for (int t1 = tid; t1 < n; t1 += blockDim.x) xs[(t1 / I) * (I + 1) + t1 % I] = __ldg(src + t1);
+      }
+    } else {
+      for (int rr = warp; rr < ROWS; rr += NW) {
+        const long long row = row0 + rr;
+        if (row < nrows) {
+          const long long t = row / B, b = row % B;
+          const float* src = x + t * xs_t + b * xs_b;
+          for (int jj = lane; jj < I; jj += 32) xs[rr * (I + 1) + jj] = __ldg(src + jj);
+        }
       }
     }
     __syncthreads();
     const int rr = tid / G, rg = tid % G;
-    const long long row = row0 + rr;
+    long long row = row0 + rr;
     if (rr < ROWS && row < nrows) {
+      if (order == 1) row = (row % T) * B + row / T;      // memory order is (b, t): zx row is t*B + b
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
       const float* xr = xs + rr * (I + 1);
       for (int jj = 0; jj < I; ++jj) {
