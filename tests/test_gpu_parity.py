@@ -121,6 +121,21 @@ def test_golden_lm_layer_carried_state():
     _check(g, m, outs, ins)
 
 
+def test_golden_lm_group_layer_batch40():
+    """MyVMLSTMGroup at the only batch size the reference layer accepts (V/models/vmlmf_lm.py:112-113)."""
+    g = load_golden("lm_group_b40")
+    m = _load(vb.MyVMLSTMGroup(16, 16, w_rank=4, u_ranks=[2, 3]), g)
+    ins = {k: _inp(g, k) for k in ("x", "h0", "c0")}
+    out, (h, c) = m(ins["x"], (ins["h0"], ins["c0"]))
+    outs = {"out": out, "hT": h, "cT": c}
+    _weighted(outs, g).backward()
+    _check(g, m, outs, ins)
+    with pytest.raises(RuntimeError, match="40"):
+        m(ins["x"][:, :7].detach(), (ins["h0"][:7].detach(), ins["c0"][:7].detach()))
+    one, (h1, _) = m(ins["x"][:, :1].detach(), (ins["h0"][:1].detach(), ins["c0"][:1].detach()))
+    assert one.shape == (3, 40, 16) and torch.equal(one[:, 0], one[:, 39])      # a single sequence broadcasts to 40 rows
+
+
 def test_golden_lm_model():
     g = load_golden("lm_model")
     m = _load(vb.Model(50, 16, 2, 0.0, 0.25, w_rank=4, u_ranks=[5], lstm_type="vmlmf"), g)

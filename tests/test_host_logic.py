@@ -136,3 +136,36 @@ def test_pack_group_matches_numpy_spec_and_chain_rule(case, gsz, vm):
     back = cn.unpack_grads_group(pd, gc, g=gsz, with_vm=vm)
     for k, v in back.items():
         assert_close(p[k].grad.numpy().reshape(v.shape), v, 1e-12, k)
+
+
+def test_pack_lm_group_reproduces_reference_layer_fp64():
+    """MyVMLSTMGroup (V/models/vmlmf_lm.py:97-160, arithmetic as shipped) == the canonical recurrence with
+    packing.pack_lm_group's parameters: outputs against the live reference's fp64 run, and the parameter gradients
+    through the packing's autograd chain rule + the numpy BPTT against the reference's fp64 autograd."""
+    g = load_golden("lm_group_b40")
+    p = {k[len("param/"):]: torch.from_numpy(v.astype(np.float64)).requires_grad_(True)
+         for k, v in g.items() if k.startswith("param/")}
+    canon = packing.pack_lm_group(p["u_x"], p["w_x"], [p["u_h.0"], p["u_h.1"]], [p["v_h.0"], p["v_h.1"]], p["b_x"],
+                                  p["b_h"], p["dia_x"], p["dia_h"], 2)
+    cp = {n: t.detach().numpy() for n, t in zip(NAMES, canon)}
+    x, h0, c0 = (g[f"in/{k}"].astype(np.float64) for k in ("x", "h0", "c0"))
+    y, hT, cT, saved = cn.forward(cp, x, h0, c0)
+    assert_close(y, g["out64/out"], 1e-11, "out")
+    assert_close(hT, g["out64/hT"], 1e-11, "hT")
+    assert_close(cT, g["out64/cT"], 1e-11, "cT")
+    gr = cn.backward(cp, x, y, saved, g["in/w.out"].astype(np.float64), g["in/w.hT"].astype(np.float64),
+                     g["in/w.cT"].astype(np.float64), h0, c0)
+    sum((t * torch.from_numpy(gr[n])).sum() for n, t in zip(NAMES, canon)).backward()
+    for k, t in p.items():
+        assert_close(t.grad.numpy(), g[f"grad64/{k}"], 1e-10, k)
+    assert_close(gr["dx"], g["grad64/in.x"], 1e-10, "dx")
+
+
+def test_lm_group_layer_constructor_and_dispatch():
+    torch.manual_seed(91)
+    m = vb.MyVMLSTMGroup(16, 16, w_rank=4, u_ranks=[2, 3])
+    g = load_golden("lm_group_b40")
+    ref = {k[len("param/"):]: v.shape for k, v in g.items() if k.startswith("param/")}
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == ref
+    assert isinstance(vb.Model(50, 16, 1, 0.0, 0.1, w_rank=4, u_ranks=[2, 3], lstm_type="vmgroup").rnns[0], vb.MyVMLSTMGroup)
+    assert isinstance(vb.Model(50, 16, 1, 0.0, 0.1, w_rank=4, u_ranks=[2, 3], lstm_type="vm_group").rnns[0], torch.nn.LSTM)

@@ -53,56 +53,36 @@ def har(name, I, H, wr, ur, cell, B, T, classes, n=20, graph=False):
 
 
 def lm(B, n=10, graph=False):
+    """cfg4 train step as V/train_test/lm_test.py:196-209 runs it: carried + detached state, nll_loss, clip 5, SGD lr 1 --
+    loss and update on the library's kernels (vb.nll_loss, vb.FlatClipSGD)."""
     torch.manual_seed(3)
     model = vb.Model(10000, 650, 2, 0.5, 0.05, 300, [300], "vmlmf").to(dev)
     x = torch.randint(0, 10000, (35, B), device=dev)
-    y = torch.randint(0, 10000, (35 * B,), device=dev)
-    st = [model.state_init(B)]
+    y = torch.randint(0, 10000, (35, B), device=dev)
+    sgd = vb.FlatClipSGD(model, lr=1.0, max_norm=5.0)
+    static = model.state_init(B)
 
-    def train():
-        model.zero_grad()
-        st[0] = model.detach(st[0])
-        scores, st[0] = model(x, st[0])
-        ce(scores, y).backward()
-        torch.nn.utils.clip_grad_norm_(model.parameters(), 5)
+    def step():
+        sgd.zero_grad()
+        cur = [(h.detach(), c.detach()) for h, c in static]
+        scores, new = model(x, cur)
+        loss = vb.nll_loss(scores, y)
+        loss.backward()
+        sgd.step()
         with torch.no_grad():
-            for p in model.parameters():
-                p -= 1.0 * p.grad
+            for (h, c), (h1, c1) in zip(static, new):
+                h.copy_(h1)
+                c.copy_(c1)
+        return loss.detach()
 
     out = {"config": "cfg4 LM Model(10000,650,2,0.5,0.05,300,[300],'vmlmf') bptt 35", "batch": B, "seq_len": 35}
-    if graph:
-        # the same step as one CUDA graph: carried (h, c) live in static buffers that the graph updates in place;
-        # gradient clipping and the manual SGD update (V/train_test/lm_test.py:203-209) are captured too
-        from vmlmf_b200.graphs import GraphedCallable
-        static = model.state_init(B)
-        model.zero_grad(set_to_none=True)      # .grad buffers must be created during the side-stream warm-up
-
-        def gstep():
-            for p in model.parameters():
-                if p.grad is not None:
-                    p.grad.zero_()
-            cur = [(h.detach(), c.detach()) for h, c in static]
-            scores, new = model(x, cur)
-            loss = ce(scores, y)
-            loss.backward()
-            with torch.no_grad():
-                grads = [p.grad for p in model.parameters()]
-                total = torch.linalg.vector_norm(torch.stack(torch._foreach_norm(grads)))      # no host sync: capture-safe
-                coef = torch.clamp(5.0 / (total + 1e-6), max=1.0)
-                for gr in grads:
-                    gr.mul_(coef)
-                torch._foreach_add_(list(model.parameters()), grads, alpha=-1.0)
-                for (h, c), (h1, c1) in zip(static, new):
-                    h.copy_(h1)
-                    c.copy_(c1)
-            return loss.detach()
-
-        g = GraphedCallable(gstep)
-        trg = timeit(g, n)
-        out.update({"train_graph_ms": trg, "train_graph_seq_per_s": B / trg * 1e3, "train_graph_tokens_per_s": 35 * B / trg * 1e3})
-        model.zero_grad(set_to_none=True)
-    tr = timeit(train, n)
+    tr = timeit(step, n)
     out.update({"train_ms": tr, "train_seq_per_s": B / tr * 1e3, "train_tokens_per_s": 35 * B / tr * 1e3})
+    if graph:                                  # the same step as one CUDA graph (state lives in static buffers)
+        from vmlmf_b200.graphs import GraphedCallable
+        gstep = GraphedCallable(step)
+        trg = timeit(gstep, n)
+        out.update({"train_graph_ms": trg, "train_graph_seq_per_s": B / trg * 1e3, "train_graph_tokens_per_s": 35 * B / trg * 1e3})
     return out
 
 

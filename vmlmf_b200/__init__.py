@@ -4,6 +4,6 @@ from .functional import VmlmfSeqFunction, cross_entropy, head_linear, nll_loss, 
 from .optim import FlatAdam, FlatClipSGD  # noqa: F401
 from .vmlmf import MyLSTM, MyLSTMCell, MyVMLMFCell, Net  # noqa: F401
 from .vmlmf_group import MyVMLMFCellg2, MyVMLMFgCellg2  # noqa: F401
-from .vmlmf_lm import LSTM, Embed, Linear, Model, MyVMLSTM  # noqa: F401
+from .vmlmf_lm import LSTM, Embed, Linear, Model, MyVMLSTM, MyVMLSTMGroup  # noqa: F401
 
 __version__ = "0.1.0"

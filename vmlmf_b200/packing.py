@@ -77,3 +77,34 @@ def pack_group(layers, g, with_vm=True):
     zx = u_x.new_zeros(4, n_in)
     zh = u_x.new_zeros(4, hidden)
     return u_x, v_x[perm], zx, a, bm, zh, bx[perm] + bh[perm]
+
+
+def pack_lm_group(u_x, w_x, u_h, v_h, b_x, b_h, dia_x, dia_h, g):
+    """MyVMLSTMGroup.lstm_step (V/models/vmlmf_lm.py:97-160), arithmetic kept as shipped.
+
+    u_h[off]: [g, Hg, r_off], v_h[off]: [g, r_off, 4Hg].  The bmm result [B, g, 4Hg] is flattened GROUP-major to
+    [B, 4H] (:135) before chunk(4) (:155), so canonical row kH+p of Bm is flat column c = kH+p = j*4Hg + m: group j's
+    output m -- with g = 2, gates i,f read group 0 and o,n group 1.  The "diagonal" that is subtracted (:141-148)
+    pairs re_uh[p] = u_h[0] viewed [H, r0] with re_vh[kH+p] = v_h[0] transposed and viewed [4H, r0]; it multiplies
+    h[p] element-wise, which is exactly a Dh coefficient, whether or not it is the true diagonal (SURVEY B-5)."""
+    n_in, hidden = u_x.shape[0], w_x.shape[0] // 4
+    hg = hidden // g
+    a_cols, b_cols = [], []
+    for off in range(g):
+        u, v = u_h[off], v_h[off]
+        r = u.shape[2]
+        blk = u.new_zeros(g, hg, g, r)                             # [source group s, m', position j, r]
+        for j in range(g):
+            blk[(j + off) % g, :, j, :] = u[j]
+        a_cols.append(blk.reshape(hidden, g * r))
+        bb = u.new_zeros(g, 4 * hg, g, r)                          # [j, m, j', r], flat row j*4Hg + m
+        for j in range(g):
+            bb[j, :, j, :] = v[j].t()
+        b_cols.append(bb.reshape(4 * hidden, g * r))
+    a, bm = torch.cat(a_cols, 1), torch.cat(b_cols, 1)
+    r0 = u_h[0].shape[2]
+    re_u = u_h[0].reshape(hidden, r0)
+    re_v = v_h[0].transpose(1, 2).reshape(4 * hidden, r0)
+    dh = dia_h.reshape(1, hidden) - (re_u.unsqueeze(0) * re_v.view(4, hidden, r0)).sum(-1)
+    dx = dia_x.reshape(1, n_in) - _diag_corr(u_x, w_x, n_in)
+    return u_x, w_x, dx, a, bm, dh, b_x.reshape(-1) + b_h.reshape(-1) * 1.0

@@ -72,6 +72,62 @@ class MyVMLSTM(nn.Module):
         return out, (h1, c1)
 
 
+class MyVMLSTMGroup(nn.Module):
+    """Group VMLMF layer for the LM (V/models/vmlmf_lm.py:53-174), arithmetic as shipped (SURVEY B-5).
+
+    The reference hard-codes 40-row scratch tensors (:112-113): it runs at batch 40, and a batch of 1 broadcasts
+    to 40 identical rows; both behaviours are kept, any other batch raises like the reference's shape error.
+    Needs input_size == hidden_size (:116-119 add a [B,4I] tensor to a [B,4H] one)."""
+
+    BATCH = 40
+
+    def __init__(self, input_size, hidden_size, dropout=0, w_rank=None, u_ranks=None, g=2):
+        super().__init__()
+        self.input_size, self.hidden_size, self.dropout, self.g = input_size, hidden_size, dropout, g
+        self.w_rank, self.u_ranks = w_rank, u_ranks
+        hg = int(hidden_size / g)
+        self.u_x = nn.Parameter(torch.Tensor(input_size, w_rank))
+        self.w_x = nn.Parameter(torch.Tensor(4 * hidden_size, w_rank))
+        self.u_h = nn.ParameterList([nn.Parameter(torch.Tensor(g, hg, u_ranks[i])) for i in range(g)])
+        self.v_h = nn.ParameterList([nn.Parameter(torch.Tensor(g, u_ranks[i], 4 * hg)) for i in range(g)])
+        self.b_x = nn.Parameter(torch.Tensor(4 * hidden_size))
+        self.b_h = nn.Parameter(torch.Tensor(4 * hidden_size))
+        self.dia_x = nn.Parameter(torch.Tensor(1, input_size))
+        self.dia_h = nn.Parameter(torch.Tensor(1, hidden_size))
+        self.cnt = 0
+
+    def __repr__(self):
+        return f"LSTM(input: {self.input_size}, hidden: {self.hidden_size})"
+
+    def canonical(self):
+        if self.input_size != self.hidden_size:
+            raise RuntimeError("MyVMLSTMGroup requires input_size == hidden_size (as the reference does)")
+        return packing.pack_lm_group(self.u_x, self.w_x, list(self.u_h), list(self.v_h), self.b_x, self.b_h,
+                                     self.dia_x, self.dia_h, self.g)
+
+    def _batch40(self, x, h, c, bdim):
+        nb = x.size(bdim)
+        if nb == 1:                                   # the 40-row scratch broadcasts a single sequence to 40 rows
+            x = x.expand(*x.shape[:bdim], self.BATCH, *x.shape[bdim + 1:])
+            h, c = h.expand(self.BATCH, -1), c.expand(self.BATCH, -1)
+        elif nb != self.BATCH:
+            raise RuntimeError(f"The expanded size of the tensor ({self.BATCH}) must match the existing size ({nb}) at "
+                               "non-singleton dimension 0 (MyVMLSTMGroup is hard-wired to batch 40, vmlmf_lm.py:112)")
+        return x, h, c
+
+    def lstm_step(self, x, h, c):
+        x, h, c = self._batch40(x, h, c, 0)
+        _, h1, c1 = vmlmf_sequence(x.unsqueeze(0), h, c, self.canonical(), batch_first=False)
+        return h1, c1
+
+    def forward(self, x, states):
+        """x[T,40,X], (h,c) -> (out[T,40,H], (h_T, c_T))"""
+        h, c = states
+        x, h, c = self._batch40(x, h, c, 1)
+        out, h1, c1 = vmlmf_sequence(x, h, c, self.canonical(), batch_first=False)
+        return out, (h1, c1)
+
+
 class LSTM(nn.Module):
     """Plain dense LSTM layer, the reference's "custom" baseline (V/models/vmlmf_lm.py:283-339).
     Eager PyTorch; not part of the accelerated path."""
@@ -123,9 +179,8 @@ class Linear(nn.Module):
 class Model(nn.Module):
     """Embed -> dropout -> L x LSTM layers -> dropout -> FC (V/models/vmlmf_lm.py:363-441).
 
-    lstm_type "vmlmf" selects the fused VMLMF layers.  "custom" / "pytorch" build the reference's
-    dense baselines.  The reference's "vmgroup"/"vm_group" branch is unreachable as shipped
-     and is rejected here with an explicit error."""
+    lstm_type "vmlmf" selects the fused VMLMF layers, "vmgroup" the group layers (batch 40 only, like the
+    reference's layer); "custom" / "pytorch" (and the reference's misspelt "vm_group") build the dense baselines."""
 
     def __init__(self, vocab_size, hidden_size, layer_num, dropout, winit, w_rank=None, u_ranks=None,
                  lstm_type="pytorch"):
@@ -133,12 +188,15 @@ class Model(nn.Module):
         self.vocab_size, self.hidden_size, self.layer_num = vocab_size, hidden_size, layer_num
         self.winit, self.lstm_type = winit, lstm_type
         self.embed = Embed(vocab_size, hidden_size)
-        if lstm_type in ("vmgroup", "vm_group"):
-            raise NotImplementedError("the reference's group LM layer is unreachable through Model "
-                                      "(vmlmf_lm.py:387-393); use lstm_type='vmlmf'")
-        if u_ranks is not None:
-            u_ranks = u_ranks[-1]
-        if lstm_type == "vmlmf":
+        # The reference reduces u_ranks to its last entry unless lstm_type is "vm_group" (:387-388) and builds the group
+        # layers when it is "vmgroup" (:390): as shipped "vmgroup" dies on `u_ranks[g_idx]` of an int and "vm_group"
+        # falls through to nn.LSTM (SURVEY B-4).  Here "vmgroup" keeps the rank list and builds what was meant;
+        # "vm_group" still gets the reference's nn.LSTM.
+        if u_ranks is not None and lstm_type != "vmgroup":
+            u_ranks = u_ranks[-1] if lstm_type != "vm_group" else u_ranks
+        if lstm_type == "vmgroup":
+            rnns = [MyVMLSTMGroup(hidden_size, hidden_size, w_rank=w_rank, u_ranks=u_ranks) for _ in range(layer_num)]
+        elif lstm_type == "vmlmf":
             rnns = [MyVMLSTM(hidden_size, hidden_size, w_rank=w_rank, u_ranks=u_ranks) for _ in range(layer_num)]
         elif lstm_type == "custom":
             rnns = [LSTM(hidden_size, hidden_size) for _ in range(layer_num)]
