@@ -54,8 +54,16 @@ __device__ __forceinline__ void mma_3x(float (&d)[4], const float (&ahi)[4], con
 __device__ __forceinline__ void split4(const float (&v)[4], float (&hi)[4], float (&lo)[4]) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
+#ifdef VMLMF_SPLIT_ROUND
     hi[i] = tf32_rna(v[i]);
     lo[i] = v[i] - hi[i];            // exact; the tensor core drops its low 13 bits (|error| <= 2^-21 |v|)
+#else
+    // The tensor core ignores the low 13 mantissa bits of a tf32 operand, so the raw value IS its own truncated hi
+    // part: only the remainder costs instructions (one LOP, one FADD; exact).  |lo| < 2^-10 |v| instead of 2^-11 with
+    // round-to-nearest, so the dropped lo*lo term is <= 2^-20 of a product (measured end to end in the parity tests).
+    hi[i] = v[i];
+    lo[i] = v[i] - __uint_as_float(__float_as_uint(v[i]) & 0xffffe000u);
+#endif
   }
 }
 
