@@ -63,6 +63,23 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(taddr) : "memory");
   v[0] = __uint_as_float(r0); v[1] = __uint_as_float(r1); v[2] = __uint_as_float(r2); v[3] = __uint_as_float(r3);
 }
+// 8 consecutive columns (two accumulator fragments) in one instruction
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[2][4]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i >> 2][i & 3] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[2][4]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr),
+               "r"(__float_as_uint(v[0][0])), "r"(__float_as_uint(v[0][1])), "r"(__float_as_uint(v[0][2])),
+               "r"(__float_as_uint(v[0][3])), "r"(__float_as_uint(v[1][0])), "r"(__float_as_uint(v[1][1])),
+               "r"(__float_as_uint(v[1][2])), "r"(__float_as_uint(v[1][3]))
+               : "memory");
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cp_async4(float* dst_smem, const float* src) {
@@ -360,17 +377,26 @@ __global__ void __launch_bounds__(512, 1) seq_bwd_fused_kernel(const SeqBwdFused
         // ---- [z|zx|1]^T dPre of this half: B = dPre tile read back transposed (k = sequence, n = unit 8P+g of gate k) ----
         __syncwarp();
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          float acc[4];
-          tmem_ld4(tbase + 4 * (P * 4 + k), acc);
-          const float* tc0 = myT + k * 8 + g;
-          const float b[4] = {tc0[q * TP], tc0[(q + 4) * TP], tc0[(q + 8) * TP], tc0[(q + 12) * TP]};
-          float bh[4], bl[4];
-          split4(b, bh, bl);
+        for (int kk = 0; kk < 4; kk += 2) {              // two gates per TMEM round trip: two independent MMA chains
+          float acc[2][4], bh[2][4], bl[2][4];
+          tmem_ld8(tbase + 4 * (P * 4 + kk), acc);
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const float* tc0 = myT + (kk + u) * 8 + g;
+            const float b[4] = {tc0[q * TP], tc0[(q + 4) * TP], tc0[(q + 8) * TP], tc0[(q + 12) * TP]};
+            split4(b, bh[u], bl[u]);
+          }
           tmem_wait_ld();
-          mma_3x(acc, wah[0], wal[0], bh[0], bh[1], bl[0], bl[1]);
-          mma_3x(acc, wah[1], wal[1], bh[2], bh[3], bl[2], bl[3]);
-          tmem_st4(tbase + 4 * (P * 4 + k), acc);
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u) mma_tf32(acc[u], wal[ks], bh[u][2 * ks], bh[u][2 * ks + 1]);
+#pragma unroll
+            for (int u = 0; u < 2; ++u) mma_tf32(acc[u], wah[ks], bl[u][2 * ks], bl[u][2 * ks + 1]);
+#pragma unroll
+            for (int u = 0; u < 2; ++u) mma_tf32(acc[u], wah[ks], bh[u][2 * ks], bh[u][2 * ks + 1]);
+          }
+          tmem_st8(tbase + 4 * (P * 4 + kk), acc);
         }
         __syncwarp();                                    // tile reads done before the next half overwrites it
       }
