@@ -5,16 +5,17 @@
 // units 16w+8P+2q+{0,1} of sequences g, g+8.  The split design wrote dPre[T*B,4H] to HBM for a second kernel
 // (0.8 GB out + 0.8 GB in at the bench workload: traffic twice the algorithmic bytes).  Here the gradient
 // accumulators do not fit the register file next to the recurrence state (the kernel already runs at the
-// 128-register cap of a 512-thread CTA), so they live in TENSOR MEMORY: every warp owns 64 TMEM columns x 32 lanes
+// 128-register cap of a 512-thread CTA), so they live in TENSOR MEMORY: every warp owns 80 TMEM columns x 32 lanes
 // and moves accumulator fragments with tcgen05.ld / tcgen05.st around its mma.sync products:
 //   columns  0..31  [z|zx|1]^T dPre   (dBm | dVx | dbias)   8 n-tiles (gate k, half P) x 4 registers
 //   columns 32..47  dDh partial sums of the lane's 8 (unit, gate) pairs... per half P: 8 registers
 //   columns 48..63  dDx partial sums (x-side warps)
+//   columns 64..71  dA  = Hprev^T dz     columns 72..79  dUx = X^T dzx
 // Per step and half P: dPre fragments -> per-warp shared tile (accumulator layout) -> read back transposed as the
 // B operand (K = the 16 sequences) of the [z|zx|1]^T dPre product; A = the step's [z|zx|1] rows, brought in one
-// step ahead with cp.async.  dX = dzx Ux^T + sum_k dPre_k Dx_k is finished in the same kernel (x-side warps).
-// What remains for a second pass are the two products that need h_{t-1} and x TRANSPOSED against the reduced dzc
-// (dA = Hprev^T dz, dUx = X^T dzx): grad_hx_kernel streams y, x and dzc only (0.3 GB).
+// step ahead with cp.async.  dX = dzx Ux^T + sum_k dPre_k Dx_k is finished in the same kernel (x-side warps), and so
+// are the two products that need h_{t-1} and x TRANSPOSED against the reduced dzc (dA = Hprev^T dz, dUx = X^T dzx):
+// their operands are the rows this warp just read (L1/L2 hits).  One partial per CTA; reduce_partials_kernel sums.
 #pragma once
 #include "gemm_tc.cuh"
 #include "seq_bwd_mma.cuh"
@@ -30,7 +31,7 @@ struct SeqBwdFusedArgs {
   const float* y; long long ys_t, ys_b;
   const float* h0;
   const float *z, *zx; int zp, zxp;
-  float* dzc;                              // [T*B, 8*KS] reduced [dz | dzx] rows (for grad_hx_kernel)
+  float* dzc;                              // unused (kept so the argument block matches the split backward's)
   float* dx; long long dxs_t, dxs_b;       // may be null
   float *dh0, *dc0;
   float* partial;                          // [gridDim.x, GradLayout.total]; this kernel writes dVx, dDx, dBm, dDh, dbias
@@ -416,7 +417,7 @@ __global__ void __launch_bounds__(512, 1) seq_bwd_fused_kernel(const SeqBwdFused
       }
       cp_async_commit_wait_all();                        // this thread's staged element of step t-1 has landed
       __syncthreads();
-      // ---- fixed-order sum over warps -> Dz rows (and the global dzc rows grad_hx_kernel reads) ----
+      // ---- fixed-order sum over warps -> Dz rows ----
       for (int idx = tid; idx < 16 * 8 * KS * 4; idx += nthreads) {
         const int el = idx >> 2, part = idx & 3, seq = el / (8 * KS), slot = el - seq * (8 * KS);
         float s = 0.f;
@@ -608,99 +609,6 @@ __global__ void __launch_bounds__(512, 1) seq_bwd_fused_kernel(const SeqBwdFused
     tc::tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tslot), "r"(tmem_cols));
   }
-}
-
-// ------------------------------------------------------------------------------------------------- //
-// dA = Hprev^T dz and dUx = X^T dzx over all rows (the two products that need h_{t-1} / x transposed)
-// ------------------------------------------------------------------------------------------------- //
-struct GradHxArgs {
-  const float* dzc;                        // [T*B, 8*KS]
-  const float* y; long long ys_t, ys_b;
-  const float* h0;
-  const float* x; long long xs_t, xs_b;
-  float* partial;                          // [gridDim.x, GradLayout.total]; this kernel writes dUx and dA
-  int T, B, I, H, RX, RH;
-  int blocks_per_cta;
-};
-
-// blockDim = 32 * ceil(H/16): warp w owns units [16w,16w+16); lane (g,q) = unit pair 16w + 8(g>>2) + 2(g&3) + {0,1},
-// rows q, q+4 (+8, +12) of each 16-sequence block -- the mapping of grad_rows_kernel without its dPre part.
-template <int KS>
-__global__ void __launch_bounds__(512, 1) grad_hx_kernel(const GradHxArgs a) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int g = lane >> 2, q = lane & 3;
-  const int H = a.H, I = a.I, B = a.B, RH = a.RH, RX = a.RX;
-  const int ntiles = ceil_div(B, 16);
-  const long long nblocks = (long long)a.T * ntiles;
-  const int ju = warp * 16 + 8 * (g >> 2) + 2 * (g & 3);
-  const bool uin = ju < H, xcols = warp * 16 < I;
-  float accG[KS][4], accU[KS][4];
-#pragma unroll
-  for (int s = 0; s < KS; ++s)
-#pragma unroll
-    for (int i = 0; i < 4; ++i) accG[s][i] = accU[s][i] = 0.f;
-  const long long blk_begin = (long long)blockIdx.x * a.blocks_per_cta;
-  long long blk_end = blk_begin + a.blocks_per_cta;
-  if (blk_end > nblocks) blk_end = nblocks;
-  auto prefetch_blk = [&](long long pb) {                // h_{t-1} rows of a block into L2 (16 lanes of warp 0)
-    if (pb >= blk_end || warp != 0 || lane >= 16) return;
-    const int tp = (int)(pb / ntiles), bp = (int)(pb % ntiles) * 16;
-    if (tp > 0 && bp + lane < B)
-      l2_prefetch_bulk(a.y + (size_t)(tp - 1) * a.ys_t + (size_t)(bp + lane) * a.ys_b, (uint32_t)(H * sizeof(float)));
-  };
-  prefetch_blk(blk_begin); prefetch_blk(blk_begin + 1); prefetch_blk(blk_begin + 2);
-  for (long long blk = blk_begin; blk < blk_end; ++blk) {
-    prefetch_blk(blk + 3);
-    const int t = (int)(blk / ntiles), b0 = (int)(blk % ntiles) * 16;
-    const int nvalid = (B - b0) < 16 ? (B - b0) : 16;
-#pragma unroll
-    for (int ks = 0; ks < 2; ++ks) {
-      const int rr0 = 8 * ks + q, rr1 = rr0 + 4;
-      const bool v0 = rr0 < nvalid, v1 = rr1 < nvalid;
-      const size_t r0 = (size_t)t * B + b0 + rr0, r1 = r0 + 4;
-      float2 h0v = make_float2(0.f, 0.f), h1v = h0v, x0v = h0v, x1v = h0v;
-      if (uin) {
-        if (t > 0) {
-          if (v0) h0v = __ldg(reinterpret_cast<const float2*>(a.y + (size_t)(t - 1) * a.ys_t + (size_t)(b0 + rr0) * a.ys_b + ju));
-          if (v1) h1v = __ldg(reinterpret_cast<const float2*>(a.y + (size_t)(t - 1) * a.ys_t + (size_t)(b0 + rr1) * a.ys_b + ju));
-        } else if (a.h0) {
-          if (v0) h0v = __ldg(reinterpret_cast<const float2*>(a.h0 + (size_t)(b0 + rr0) * H + ju));
-          if (v1) h1v = __ldg(reinterpret_cast<const float2*>(a.h0 + (size_t)(b0 + rr1) * H + ju));
-        }
-      }
-      if (xcols) {
-        const float* xp0 = a.x + (size_t)t * a.xs_t + (size_t)(b0 + rr0) * a.xs_b + ju;
-        const float* xp1 = a.x + (size_t)t * a.xs_t + (size_t)(b0 + rr1) * a.xs_b + ju;
-        if (ju < I) { if (v0) x0v.x = __ldg(xp0); if (v1) x1v.x = __ldg(xp1); }
-        if (ju + 1 < I) { if (v0) x0v.y = __ldg(xp0 + 1); if (v1) x1v.y = __ldg(xp1 + 1); }
-      }
-      const float hv[4] = {h0v.x, h0v.y, h1v.x, h1v.y};
-      float hh[4], hl[4], xh[4], xl[4];
-      split4(hv, hh, hl);
-      if (xcols) {
-        const float xv[4] = {x0v.x, x0v.y, x1v.x, x1v.y};
-        split4(xv, xh, xl);
-      }
-#pragma unroll
-      for (int s = 0; s < KS; ++s) {
-        const float d0 = v0 ? __ldg(a.dzc + r0 * (8 * KS) + 8 * s + g) : 0.f;
-        const float d1 = v1 ? __ldg(a.dzc + r1 * (8 * KS) + 8 * s + g) : 0.f;
-        const float b0h = tf32_rna(d0), b1h = tf32_rna(d1);
-        mma_3x(accG[s], hh, hl, b0h, b1h, d0 - b0h, d1 - b1h);
-        if (xcols) mma_3x(accU[s], xh, xl, b0h, b1h, d0 - b0h, d1 - b1h);
-      }
-    }
-  }
-  const GradLayout L(I, H, RX, RH);
-  float* P = a.partial + (size_t)blockIdx.x * L.total;
-#pragma unroll
-  for (int s = 0; s < KS; ++s)
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int j = ju + (i >> 1), slot = 8 * s + 2 * q + (i & 1);
-      if (j < H && slot < RH) P[L.oA + (size_t)j * RH + slot] = accG[s][i];
-      if (j < I && slot >= RH && slot < RH + RX) P[L.oUx + (size_t)j * RX + (slot - RH)] = accU[s][i];
-    }
 }
 
 int launch_bwd_fused(const SeqBwdFusedArgs& a, const GradOut& out, void* workspace, cudaStream_t st);

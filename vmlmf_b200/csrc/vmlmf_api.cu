@@ -172,10 +172,9 @@ int vmlmf_xproj_fwd(const float* x, long long xs_t, long long xs_b, const float*
   if (!x || !Ux || !zx || T <= 0 || B <= 0 || I <= 0 || RX <= 0) return VMLMF_EINVAL;
   if (zx_pitch < RX || (zx_pitch & 3)) return VMLMF_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
-  const int G = zx_pitch / 4;
-  if (G <= 128 && (size_t)I * zx_pitch * 4 <= 64 * 1024 && I <= 512) {
-    const int rows = 128 / G;
-    const size_t smem = ((size_t)I * zx_pitch + (size_t)rows * (I + 1)) * sizeof(float);
+  const size_t smem = ((size_t)ceil_div(I, 8) * ceil_div(zx_pitch, 8) * 32 * 4 + (size_t)kXprojRows * I) * sizeof(float);
+  if (zx_pitch <= 128 && I <= 512 && smem <= 200 * 1024) {
+    const int rows = kXprojRows;
     if (smem > 48 * 1024) {
       cudaError_t e = cudaFuncSetAttribute(xproj_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return (int)e;
@@ -184,8 +183,8 @@ int vmlmf_xproj_fwd(const float* x, long long xs_t, long long xs_b, const float*
     long long grid = (nrows + rows - 1) / rows;
     // resident blocks per SM: one wave, every block walks its share.  The query is a driver call: cached per
     // shared-memory size (256-byte buckets; a benign race, every writer stores the same value)
-    static int occ_cache[257] = {0};
-    int& occ_slot = occ_cache[smem / 256 < 256 ? smem / 256 : 256];
+    static int occ_cache[1024] = {0};
+    int& occ_slot = occ_cache[smem / 256 < 1023 ? smem / 256 : 1023];
     if (occ_slot == 0) {
       int q = 1;
       if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, xproj_small_kernel, 128, smem) != cudaSuccess || q < 1) q = 1;

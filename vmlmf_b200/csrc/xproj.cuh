@@ -1,98 +1,108 @@
-// xproj.cuh -- K1 (small-shape variant): zx[t,b,:] = x[t,b,:] Ux for all T*B rows at once.
-// Time-parallel half of `torch.matmul(x, self.u_x)` (V/models/vmlmf.py:98, vmlmf_group.py:98,
-// vmlmf_lm.py:246).  In regime R1 the contraction is [T*B, I<=256] x [I, RX<=16]: K and N are
-// far below one tcgen05 tile, the op is bound by reading x once (I floats/row) and SIMT FMAs,
-// so it is a shared-memory tiled SIMT kernel; the large-shape x projection (regime G) goes
-// through the GEMM path instead.
+// xproj.cuh -- K1 (small-shape variant): zx[t,b,:] = x[t,b,:] Ux for all T*B rows at once, and the parameter
+// packing kernels K0 / K5.  Time-parallel half of `torch.matmul(x, self.u_x)` (V/models/vmlmf.py:98,
+// vmlmf_group.py:98, vmlmf_lm.py:246).  In regime R1 the contraction is [T*B, I<=512] x [I, RX<=128]: K and N are
+// far below one tcgen05 tile and the op is bound by reading x once (I floats per row), so it is a shared-memory
+// staged warp-MMA kernel (mma.sync m16n8k8, 3xTF32); the large-shape x projection (regime G) goes through the
+// tcgen05 GEMM path instead.
 #pragma once
 #include "common.cuh"
+#include "seq_mma.cuh"
 
 namespace vmlmf {
 
 // block = 128 threads; each thread produces 4 consecutive outputs of one row.
 // smem: Us[I][pitch] | xs[ROWS][I+1]
 // `order`: 0 = arbitrary (time, batch) strides, rows walked as t*B + b;  1 = x is one contiguous [B,T,I] block,
-// 2 = one contiguous [T,B,I] block.  In the contiguous cases rows are walked in MEMORY order, so a block's ROWS rows
-// are a single contiguous span streamed with independent 16-byte loads (the 32-byte zx rows go wherever t*B + b says).
+// 2 = one contiguous [T,B,I] block.  In the contiguous cases rows are walked in MEMORY order, so a block's 64 rows
+// are a single contiguous span copied to shared memory with independent 16-byte loads (the 32-byte zx rows go wherever
+// t*B + b says).  The product itself runs on mma.sync m16n8k8 with the 3xTF32 split (fp32-accurate): a warp owns 16
+// rows, A fragments come from the staged rows, B fragments (Ux, split once per block) from shared memory -- a fifth of
+// the instructions of the SIMT inner product, which leaves the kernel bound by reading x once.
+// block = 128 threads = 4 warps x 16 rows.  smem: Uf[nk][NT][32] float4 {b0hi, b1hi, b0lo, b1lo} | xs[64][I]
+constexpr int kXprojRows = 64;
 static __global__ void __launch_bounds__(128) xproj_small_kernel(const float* __restrict__ x, long long xs_t,
                                                           long long xs_b, const float* __restrict__ Ux,
                                                           float* __restrict__ zx, int T, int B, int I,
                                                           int RX, int pitch, int order) {
   extern __shared__ __align__(16) float smem[];
-  const int G = pitch >> 2;                 // threads per row
-  const int ROWS = blockDim.x / G;          // rows per block (a multiple of 4)
-  float* Us = smem;                         // [I][pitch], zero padded
-  float* xs = smem + I * pitch;             // [ROWS][I+1]
+  const int nk = (I + 7) >> 3, NT = (pitch + 7) >> 3;
+  float4* Uf = reinterpret_cast<float4*>(smem);
+  float* xs = smem + (size_t)nk * NT * 32 * 4;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = blockDim.x >> 5;
-  for (int i = tid; i < I * pitch; i += blockDim.x) {
-    const int jj = i / pitch, r = i % pitch;
-    Us[i] = r < RX ? __ldg(Ux + (size_t)jj * RX + r) : 0.f;
+  const int g = lane >> 2, q = lane & 3;
+  for (int i = tid; i < nk * NT * 32; i += blockDim.x) {
+    const int ln = i & 31, f = i >> 5, nt = f % NT, ks = f / NT;
+    const int k0 = 8 * ks + (ln & 3), k1 = k0 + 4, n = 8 * nt + (ln >> 2);
+    const float b0 = (k0 < I && n < RX) ? __ldg(Ux + (size_t)k0 * RX + n) : 0.f;
+    const float b1 = (k1 < I && n < RX) ? __ldg(Ux + (size_t)k1 * RX + n) : 0.f;
+    const float b0h = tf32_rna(b0), b1h = tf32_rna(b1);
+    Uf[i] = make_float4(b0h, b1h, b0 - b0h, b1 - b1h);
   }
   const long long nrows = (long long)T * B;
   const bool vec = order != 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
-  for (long long row0 = (long long)blockIdx.x * ROWS; row0 < nrows; row0 += (long long)gridDim.x * ROWS) {
+  for (long long row0 = (long long)blockIdx.x * kXprojRows; row0 < nrows; row0 += (long long)gridDim.x * kXprojRows) {
     __syncthreads();
+    const long long left = nrows - row0;
+    const int nr = (int)(left < kXprojRows ? left : kXprojRows);
     if (order != 0) {
       const float* src = x + row0 * I;
-      const long long left = nrows - row0;
-      const int n = (int)(left < ROWS ? left : ROWS) * I;          // floats in this block's span
+      const int n = nr * I, n4 = vec ? (n & ~3) : 0;                // floats in this block's span
       int e = tid * 4;
-      if (vec) {
-        const int n4 = n & ~3;
-        for (; e + 3 * 512 < n4; e += 4 * 512) {                    // four independent 16-byte loads per thread
-          float4 v[4];
+      for (; e + 3 * 512 < n4; e += 4 * 512) {                       // four independent 16-byte loads per thread
+        float4 v[4];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(src + e + u * 512));
+        for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(src + e + u * 512));
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int e0 = e + u * 512;
-            int rr = e0 / I, jj = e0 - rr * I;
-            const float w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              xs[rr * (I + 1) + jj] = w[c];
-              if (++jj == I) { jj = 0; ++rr; }
-            }
-          }
-        }
-        for (; e < n4; e += 512) {
-          const float4 v = __ldg(reinterpret_cast<const float4*>(src + e));
-          int rr = e / I, jj = e - rr * I;
-          const float w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            xs[rr * (I + 1) + jj] = w[c];
-            if (++jj == I) { jj = 0; ++rr; }
-          }
-        }
-        for (int t1 = n4 + tid; t1 < n; t1 += blockDim.x) xs[(t1 / I) * (I + 1) + t1 % I] = __ldg(src + t1);
-      } else {
-        for (int t1 = tid; t1 < n; t1 += blockDim.x) xs[(t1 / I) * (I + 1) + t1 % I] = __ldg(src + t1);
+        for (int u = 0; u < 4; ++u) *reinterpret_cast<float4*>(xs + e + u * 512) = v[u];
       }
+      for (; e < n4; e += 512) *reinterpret_cast<float4*>(xs + e) = __ldg(reinterpret_cast<const float4*>(src + e));
+      for (int t1 = n4 + tid; t1 < n; t1 += blockDim.x) xs[t1] = __ldg(src + t1);
     } else {
-      for (int rr = warp; rr < ROWS; rr += NW) {
+      for (int rr = warp; rr < nr; rr += NW) {
         const long long row = row0 + rr;
-        if (row < nrows) {
-          const long long t = row / B, b = row % B;
-          const float* src = x + t * xs_t + b * xs_b;
-          for (int jj = lane; jj < I; jj += 32) xs[rr * (I + 1) + jj] = __ldg(src + jj);
-        }
+        long long t, b;
+        if (nrows <= 0xffffffffLL) { const unsigned tq = (unsigned)row / (unsigned)B; t = tq; b = (unsigned)row - tq * (unsigned)B; }
+        else { t = row / B; b = row % B; }
+        const float* src = x + t * xs_t + b * xs_b;
+        for (int jj = lane; jj < I; jj += 32) xs[rr * I + jj] = __ldg(src + jj);
       }
     }
     __syncthreads();
-    const int rr = tid / G, rg = tid % G;
-    long long row = row0 + rr;
-    if (rr < ROWS && row < nrows) {
-      if (order == 1) row = (row % T) * B + row / T;      // memory order is (b, t): zx row is t*B + b
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      const float* xr = xs + rr * (I + 1);
-      for (int jj = 0; jj < I; ++jj) {
-        const float xv = xr[jj];
-        const float4 u = *reinterpret_cast<const float4*>(Us + jj * pitch + 4 * rg);
-        acc.x = fmaf(xv, u.x, acc.x); acc.y = fmaf(xv, u.y, acc.y);
-        acc.z = fmaf(xv, u.z, acc.z); acc.w = fmaf(xv, u.w, acc.w);
+    // ---- this warp's 16 rows: C[16 x 8 NT] = A[16 x 8 nk] B ----
+    const int r0 = 16 * warp + g, r1 = r0 + 8;
+    const bool v0 = r0 < nr, v1 = r1 < nr;
+    const float* x0 = xs + r0 * I;
+    const float* x1 = xs + r1 * I;
+    for (int nt = 0; nt < NT; ++nt) {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      const float4* uf = Uf + (size_t)nt * 32 + lane;
+#pragma unroll 2
+      for (int ks = 0; ks < nk; ++ks) {
+        const int k0 = 8 * ks + q, k1 = k0 + 4;
+        const float av[4] = {(v0 && k0 < I) ? x0[k0] : 0.f, (v1 && k0 < I) ? x1[k0] : 0.f,
+                             (v0 && k1 < I) ? x0[k1] : 0.f, (v1 && k1 < I) ? x1[k1] : 0.f};
+        float ah[4], al[4];
+        split4(av, ah, al);
+        const float4 b = uf[(size_t)ks * NT * 32];
+        mma_3x(acc, ah, al, b.x, b.y, b.z, b.w);
       }
-      *reinterpret_cast<float4*>(zx + row * pitch + 4 * rg) = acc;
+      // accumulator fragment: (row g, cols 2q, 2q+1), (row g+8, same cols) of n-tile nt
+      const int c = 8 * nt + 2 * q;
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        if (!(hf ? v1 : v0) || c >= pitch) continue;
+        long long row = row0 + (hf ? r1 : r0);
+        if (order == 1) {                                   // memory order is (b, t): zx row is t*B + b
+          if (nrows <= 0xffffffffLL) {                      // 32-bit division: a 64-bit one costs ~100 instructions
+            const unsigned r32 = (unsigned)row, bq = r32 / (unsigned)T;
+            row = (long long)(r32 - bq * (unsigned)T) * B + bq;
+          } else {
+            row = (row % T) * B + row / T;
+          }
+        }
+        float* o = zx + row * pitch + c;                    // pitch % 4 == 0 and c even: 8-byte aligned
+        *reinterpret_cast<float2*>(o) = make_float2(acc[2 * hf], acc[2 * hf + 1]);
+      }
     }
   }
 }
