@@ -1,8 +1,8 @@
 // seq_bwd_fused.cuh -- regime R1M backward with the weight-gradient accumulation fused into the reverse-time
 // recurrence: dPre never leaves the SM.
 //
-// Same tiling as seq_bwd_mma_kernel (K3a): CTA = 16 sequences, warp w = hidden units [16w,16w+16), lane (g,q) =
-// units 16w+8P+2q+{0,1} of sequences g, g+8.  The split design wrote dPre[T*B,4H] to HBM for a second kernel
+// Same tiling as the forward (seq_mma.cuh): CTA = 16 sequences, warp w = the 8-unit halves [8w, 8w+8) (P = 0) and
+// [8NW+8w, 8NW+8w+8) (P = 1), lane (g,q) = units half(P)+2q+{0,1} of sequences g, g+8.  The split design wrote dPre[T*B,4H] to HBM for a second kernel
 // (0.8 GB out + 0.8 GB in at the bench workload: traffic twice the algorithmic bytes).  Here the gradient
 // accumulators do not fit the register file next to the recurrence state (the kernel already runs at the
 // 128-register cap of a 512-thread CTA), so they live in TENSOR MEMORY: every warp owns 80 TMEM columns x 32 lanes
@@ -98,9 +98,11 @@ __global__ void __launch_bounds__(512, 1) seq_bwd_fused_kernel(const SeqBwdFused
   const int g = lane >> 2, q = lane & 3;
   const int H = a.H, I = a.I, B = a.B, T = a.T, RH = a.RH, RX = a.RX;
   const int HP = NW * 16;
-  const int ubase = warp * 16;
-  const int j0 = ubase + 2 * q;                          // this lane's units: j0 + 8P + e
-  const bool xwarp = ubase < I;
+  const int ubase = warp * 8;                            // first unit of this warp's half P = 0
+  const int PS = 8 * (blockDim.x >> 5);                  // half P = 1 holds units PS + 8 warp .. (mapping of seq_mma.cuh)
+  const int j0 = ubase + 2 * q;                          // this lane's units: j0 + PS*P + e
+  const bool xwarp = ubase < I;                          // some unit of this warp has an input-side term ...
+  const bool xhalf[2] = {ubase < I, ubase + PS < I};     // ... per half
 
   extern __shared__ __align__(16) float smem[];
   float4* Bf = reinterpret_cast<float4*>(smem);          // [NW][2 P][4 k][KS][32]
@@ -132,7 +134,7 @@ __global__ void __launch_bounds__(512, 1) seq_bwd_fused_kernel(const SeqBwdFused
     const int P = pk >> 2, k = pk & 3;
 #pragma unroll
     for (int s = 0; s < KS; ++s) {
-      const float b0 = wc(k, j0 + 8 * P, 8 * s + g), b1 = wc(k, j0 + 8 * P + 1, 8 * s + g);
+      const float b0 = wc(k, j0 + PS * P, 8 * s + g), b1 = wc(k, j0 + PS * P + 1, 8 * s + g);
       const float b0h = tf32_rna(b0), b1h = tf32_rna(b1);
       myB[(pk * KS + s) * 32] = make_float4(b0h, b1h, tf32_rna(b0 - b0h), tf32_rna(b1 - b1h));
     }
@@ -151,7 +153,7 @@ __global__ void __launch_bounds__(512, 1) seq_bwd_fused_kernel(const SeqBwdFused
     for (int s = 0; s < NZ; ++s)
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        const int j = ubase + 8 * P + g, r = 8 * s + q + 4 * e;
+        const int j = ubase + PS * P + g, r = 8 * s + q + 4 * e;
         const float v = (j < H && r < RH) ? __ldg(a.A + (size_t)j * RH + r) : 0.f;
         Ath[P][s][e] = tf32_rna(v);
         Atl[P][s][e] = tf32_rna(v - Ath[P][s][e]);
@@ -190,15 +192,15 @@ __global__ void __launch_bounds__(512, 1) seq_bwd_fused_kernel(const SeqBwdFused
 #pragma unroll
     for (int hf = 0; hf < 2; ++hf)
 #pragma unroll
-      for (int P = 0; P < 2; ++P) ok[hf][P] = sq[hf] < B && (j0 + 8 * P) < H;
+      for (int P = 0; P < 2; ++P) ok[hf][P] = sq[hf] < B && (j0 + PS * P) < H;
     float dhn[2][2][2], dcn[2][2][2];                    // [P][e][hf]
 #pragma unroll
     for (int P = 0; P < 2; ++P)
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
         float2 v = make_float2(0.f, 0.f), w = v;
-        if (ok[hf][P] && a.dhT) v = __ldg(reinterpret_cast<const float2*>(a.dhT + (size_t)sq[hf] * H + j0 + 8 * P));
-        if (ok[hf][P] && a.dcT) w = __ldg(reinterpret_cast<const float2*>(a.dcT + (size_t)sq[hf] * H + j0 + 8 * P));
+        if (ok[hf][P] && a.dhT) v = __ldg(reinterpret_cast<const float2*>(a.dhT + (size_t)sq[hf] * H + j0 + PS * P));
+        if (ok[hf][P] && a.dcT) w = __ldg(reinterpret_cast<const float2*>(a.dcT + (size_t)sq[hf] * H + j0 + PS * P));
         dhn[P][0][hf] = v.x; dhn[P][1][hf] = v.y;
         dcn[P][0][hf] = w.x; dcn[P][1][hf] = w.y;
       }
@@ -287,20 +289,20 @@ __global__ void __launch_bounds__(512, 1) seq_bwd_fused_kernel(const SeqBwdFused
           float2 cp2 = make_float2(0.f, 0.f), dy2 = cp2;
           hp2[hf] = cp2; xv2[hf] = cp2;
           if (t > 0) cp2 = __ldg(reinterpret_cast<const float2*>(cfrag - cstep + o));
-          else if (ok[hf][P] && a.c0) cp2 = __ldg(reinterpret_cast<const float2*>(a.c0 + (size_t)sq[hf] * H + j0 + 8 * P));
+          else if (ok[hf][P] && a.c0) cp2 = __ldg(reinterpret_cast<const float2*>(a.c0 + (size_t)sq[hf] * H + j0 + PS * P));
           if (ok[hf][P]) {
             if (a.dy) {
-              const float* dp = dyrow[hf] + 8 * P;
+              const float* dp = dyrow[hf] + PS * P;
               if (dy_vec) dy2 = __ldg(reinterpret_cast<const float2*>(dp));
               else { dy2.x = __ldg(dp); dy2.y = __ldg(dp + 1); }
             }
-            if (t > 0) hp2[hf] = __ldg(reinterpret_cast<const float2*>(yrow[hf] + 8 * P));
-            else if (a.h0) hp2[hf] = __ldg(reinterpret_cast<const float2*>(a.h0 + (size_t)sq[hf] * H + j0 + 8 * P));
+            if (t > 0) hp2[hf] = __ldg(reinterpret_cast<const float2*>(yrow[hf] + PS * P));
+            else if (a.h0) hp2[hf] = __ldg(reinterpret_cast<const float2*>(a.h0 + (size_t)sq[hf] * H + j0 + PS * P));
           }
-          if (xwarp && sq[hf] < B) {
-            const float* xp = xrow[hf] + 8 * P;
-            if (j0 + 8 * P < I) xv2[hf].x = __ldg(xp);
-            if (j0 + 8 * P + 1 < I) xv2[hf].y = __ldg(xp + 1);
+          if (xhalf[P] && sq[hf] < B) {
+            const float* xp = xrow[hf] + PS * P;
+            if (j0 + PS * P < I) xv2[hf].x = __ldg(xp);
+            if (j0 + PS * P + 1 < I) xv2[hf].y = __ldg(xp + 1);
           }
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
@@ -332,7 +334,7 @@ __global__ void __launch_bounds__(512, 1) seq_bwd_fused_kernel(const SeqBwdFused
           tmem_wait_ld();
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const float2 d2 = *reinterpret_cast<const float2*>(DhS + k * HP + j0 + 8 * P);
+            const float2 d2 = *reinterpret_cast<const float2*>(DhS + k * HP + j0 + PS * P);
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {
               sd[P][0][hf] = fmaf(dpre[k][0][hf], d2.x, sd[P][0][hf]);
@@ -343,14 +345,14 @@ __global__ void __launch_bounds__(512, 1) seq_bwd_fused_kernel(const SeqBwdFused
           }
           tmem_st4(tbase + 32 + 8 * P, gd[0]);
           tmem_st4(tbase + 36 + 8 * P, gd[1]);
-          if (xwarp) {
+          if (xhalf[P]) {
             float gx[2][4];
             tmem_ld4(tbase + 48 + 8 * P, gx[0]);
             tmem_ld4(tbase + 52 + 8 * P, gx[1]);
             tmem_wait_ld();
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              const float2 d2 = *reinterpret_cast<const float2*>(DxS + k * HP + j0 + 8 * P);
+              const float2 d2 = *reinterpret_cast<const float2*>(DxS + k * HP + j0 + PS * P);
 #pragma unroll
               for (int hf = 0; hf < 2; ++hf) {
                 sx[P][0][hf] = fmaf(dpre[k][0][hf], d2.x, sx[P][0][hf]);
@@ -462,7 +464,7 @@ __global__ void __launch_bounds__(512, 1) seq_bwd_fused_kernel(const SeqBwdFused
           split4(av, ah, al);
 #pragma unroll
           for (int P = 0; P < 2; ++P) {                  // B = Ux^T restricted to the zx slots: (k = slot, n = g <-> unit 8P+g)
-            const int j = ubase + 8 * P + g;
+            const int j = ubase + PS * P + g;
             const float b0 = (j < I && s0 >= RH && s0 < RH + RX) ? UxS[j * RX + (s0 - RH)] : 0.f;
             const float b1 = (j < I && s1 >= RH && s1 < RH + RX) ? UxS[j * RX + (s1 - RH)] : 0.f;
             const float b0h = tf32_rna(b0), b1h = tf32_rna(b1);
@@ -473,9 +475,9 @@ __global__ void __launch_bounds__(512, 1) seq_bwd_fused_kernel(const SeqBwdFused
         for (int P = 0; P < 2; ++P)
 #pragma unroll
           for (int hf = 0; hf < 2; ++hf) {
-            const int j = j0 + 8 * P;
+            const int j = j0 + PS * P;
             if (sq[hf] < B) {
-              float* o = dxrow[hf] + 8 * P;
+              float* o = dxrow[hf] + PS * P;
               if (j < I) o[0] = ax[P][2 * hf];
               if (j + 1 < I) o[1] = ax[P][2 * hf + 1];
             }
@@ -485,7 +487,7 @@ __global__ void __launch_bounds__(512, 1) seq_bwd_fused_kernel(const SeqBwdFused
       // ---- dA += Hprev^T dz, dUx += X^T dzx: A = (m = g: unit ju, m = g+8: unit ju+1; k = sequence q / q+4) read transposed
       //      from the rows this warp touched in phase 1 (L1/L2 hits), B = the reduced dzc rows (k = sequence, n = slot) ----
       {
-        const int ju = ubase + 8 * (g >> 2) + 2 * (g & 3);
+        const int ju = ubase + PS * (g >> 2) + 2 * (g & 3);
         const bool uin = ju < H;
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) {
@@ -537,8 +539,8 @@ __global__ void __launch_bounds__(512, 1) seq_bwd_fused_kernel(const SeqBwdFused
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf)
         if (ok[hf][P]) {
-          if (a.dh0) *reinterpret_cast<float2*>(a.dh0 + (size_t)sq[hf] * H + j0 + 8 * P) = make_float2(dhn[P][0][hf], dhn[P][1][hf]);
-          if (a.dc0) *reinterpret_cast<float2*>(a.dc0 + (size_t)sq[hf] * H + j0 + 8 * P) = make_float2(dcn[P][0][hf], dcn[P][1][hf]);
+          if (a.dh0) *reinterpret_cast<float2*>(a.dh0 + (size_t)sq[hf] * H + j0 + PS * P) = make_float2(dhn[P][0][hf], dhn[P][1][hf]);
+          if (a.dc0) *reinterpret_cast<float2*>(a.dc0 + (size_t)sq[hf] * H + j0 + PS * P) = make_float2(dcn[P][0][hf], dcn[P][1][hf]);
         }
   }
 
@@ -556,7 +558,7 @@ __global__ void __launch_bounds__(512, 1) seq_bwd_fused_kernel(const SeqBwdFused
       tmem_wait_ld();
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int slot = g + 8 * (i >> 1), j = j0 + 8 * P + (i & 1);
+        const int slot = g + 8 * (i >> 1), j = j0 + PS * P + (i & 1);
         if (j >= H) continue;
         const size_t row = (size_t)k * H + j;
         if (slot < RH) Pout[L.oBm + row * RH + slot] = acc[i];
@@ -564,7 +566,7 @@ __global__ void __launch_bounds__(512, 1) seq_bwd_fused_kernel(const SeqBwdFused
         else if (slot == RH + RX) Pout[L.oBias + row] = acc[i];
       }
     }
-  // dDh / dDx: sum over the eight g lanes (sequences), lanes g == 0 store units j0 + 8P + e
+  // dDh / dDx: sum over the eight g lanes (sequences), lanes g == 0 store units j0 + PS*P + e
 #pragma unroll
   for (int P = 0; P < 2; ++P)
 #pragma unroll
@@ -573,7 +575,7 @@ __global__ void __launch_bounds__(512, 1) seq_bwd_fused_kernel(const SeqBwdFused
       tmem_ld4(tbase + 32 + 8 * P + 4 * e, gd);
       tmem_ld4(tbase + 48 + 8 * P + 4 * e, gx);
       tmem_wait_ld();
-      const int j = j0 + 8 * P + e;
+      const int j = j0 + PS * P + e;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         float v = gd[k], w = gx[k];
@@ -588,7 +590,7 @@ __global__ void __launch_bounds__(512, 1) seq_bwd_fused_kernel(const SeqBwdFused
     }
   // dA / dUx: C fragment (m = g [+8] <-> unit ju [+1], n = slot 8s + 2q [+1])
   {
-    const int ju = ubase + 8 * (g >> 2) + 2 * (g & 3);
+    const int ju = ubase + PS * (g >> 2) + 2 * (g & 3);
 #pragma unroll
     for (int s = 0; s < KS; ++s) {
       float ag[4], au[4];

@@ -51,8 +51,9 @@ __global__ void __launch_bounds__(512, 1) seq_bwd_mma_kernel(const SeqBwdMmaArgs
   const int g = lane >> 2, q = lane & 3;
   const int H = a.H, B = a.B, T = a.T, RH = a.RH, RX = a.RX;
   const int HP = NW * 16;
-  const int ubase = warp * 16;
-  const int j0 = ubase + 2 * q;                          // this lane's units: j0 + 8P + e  (same as the forward)
+  const int ubase = warp * 8;                            // half P = 0: units 8w..; half P = 1: units PS + 8w.. (as the forward)
+  const int PS = 8 * NW;
+  const int j0 = ubase + 2 * q;                          // this lane's units: j0 + PS*P + e  (same as the forward)
 
   extern __shared__ __align__(16) float smem[];
   float4* Bf = reinterpret_cast<float4*>(smem);          // [NW][2 P][4 k][KS][32]
@@ -74,7 +75,7 @@ __global__ void __launch_bounds__(512, 1) seq_bwd_mma_kernel(const SeqBwdMmaArgs
     const int P = pk >> 2, k = pk & 3;
 #pragma unroll
     for (int s = 0; s < KS; ++s) {                       // k-slot q <-> unit 8P+2q, q+4 <-> 8P+2q+1; n = g <-> slot 8s+g
-      const float b0 = wc(k, j0 + 8 * P, 8 * s + g), b1 = wc(k, j0 + 8 * P + 1, 8 * s + g);
+      const float b0 = wc(k, j0 + PS * P, 8 * s + g), b1 = wc(k, j0 + PS * P + 1, 8 * s + g);
       const float b0h = tf32_rna(b0), b1h = tf32_rna(b1);
       myB[(pk * KS + s) * 32] = make_float4(b0h, b1h, tf32_rna(b0 - b0h), tf32_rna(b1 - b1h));
     }
@@ -91,7 +92,7 @@ __global__ void __launch_bounds__(512, 1) seq_bwd_mma_kernel(const SeqBwdMmaArgs
     for (int s = 0; s < NZ; ++s)
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        const int j = ubase + 8 * P + g, r = 8 * s + q + 4 * e;
+        const int j = ubase + PS * P + g, r = 8 * s + q + 4 * e;
         const float v = (j < H && r < RH) ? __ldg(a.A + (size_t)j * RH + r) : 0.f;
         Ath[P][s][e] = tf32_rna(v);
         Atl[P][s][e] = tf32_rna(v - Ath[P][s][e]);
@@ -109,15 +110,15 @@ __global__ void __launch_bounds__(512, 1) seq_bwd_mma_kernel(const SeqBwdMmaArgs
 #pragma unroll
     for (int hf = 0; hf < 2; ++hf)
 #pragma unroll
-      for (int P = 0; P < 2; ++P) ok[hf][P] = sq[hf] < B && (j0 + 8 * P) < H;
+      for (int P = 0; P < 2; ++P) ok[hf][P] = sq[hf] < B && (j0 + PS * P) < H;
     float dhn[2][2][2], dcn[2][2][2];                    // [P][e][hf]
 #pragma unroll
     for (int P = 0; P < 2; ++P)
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
         float2 v = make_float2(0.f, 0.f), w = v;
-        if (ok[hf][P] && a.dhT) v = __ldg(reinterpret_cast<const float2*>(a.dhT + (size_t)sq[hf] * H + j0 + 8 * P));
-        if (ok[hf][P] && a.dcT) w = __ldg(reinterpret_cast<const float2*>(a.dcT + (size_t)sq[hf] * H + j0 + 8 * P));
+        if (ok[hf][P] && a.dhT) v = __ldg(reinterpret_cast<const float2*>(a.dhT + (size_t)sq[hf] * H + j0 + PS * P));
+        if (ok[hf][P] && a.dcT) w = __ldg(reinterpret_cast<const float2*>(a.dcT + (size_t)sq[hf] * H + j0 + PS * P));
         dhn[P][0][hf] = v.x; dhn[P][1][hf] = v.y;
         dcn[P][0][hf] = w.x; dcn[P][1][hf] = w.y;
       }
@@ -156,9 +157,9 @@ __global__ void __launch_bounds__(512, 1) seq_bwd_mma_kernel(const SeqBwdMmaArgs
           const float2 ct2 = __ldg(reinterpret_cast<const float2*>(cfrag + o));
           float2 cp2 = make_float2(0.f, 0.f), dy2 = cp2;
           if (t > 0) cp2 = __ldg(reinterpret_cast<const float2*>(cfrag - cstep + o));
-          else if (ok[hf][P] && a.c0) cp2 = __ldg(reinterpret_cast<const float2*>(a.c0 + (size_t)sq[hf] * H + j0 + 8 * P));
+          else if (ok[hf][P] && a.c0) cp2 = __ldg(reinterpret_cast<const float2*>(a.c0 + (size_t)sq[hf] * H + j0 + PS * P));
           if (ok[hf][P] && a.dy) {
-            const float* dp = a.dy + (size_t)t * a.dys_t + (size_t)sq[hf] * a.dys_b + j0 + 8 * P;
+            const float* dp = a.dy + (size_t)t * a.dys_t + (size_t)sq[hf] * a.dys_b + j0 + PS * P;
             if (dy_vec) dy2 = __ldg(reinterpret_cast<const float2*>(dp));
             else { dy2.x = __ldg(dp); dy2.y = __ldg(dp + 1); }
           }
@@ -186,7 +187,7 @@ __global__ void __launch_bounds__(512, 1) seq_bwd_mma_kernel(const SeqBwdMmaArgs
           for (int hf = 0; hf < 2; ++hf) sd[P][e][hf] = 0.f;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const float2 d2 = *reinterpret_cast<const float2*>(DhS + k * HP + j0 + 8 * P);
+          const float2 d2 = *reinterpret_cast<const float2*>(DhS + k * HP + j0 + PS * P);
 #pragma unroll
           for (int hf = 0; hf < 2; ++hf) {
             sd[P][0][hf] = fmaf(dpre[k][0][hf], d2.x, sd[P][0][hf]);
@@ -250,8 +251,8 @@ __global__ void __launch_bounds__(512, 1) seq_bwd_mma_kernel(const SeqBwdMmaArgs
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf)
         if (ok[hf][P]) {
-          if (a.dh0) *reinterpret_cast<float2*>(a.dh0 + (size_t)sq[hf] * H + j0 + 8 * P) = make_float2(dhn[P][0][hf], dhn[P][1][hf]);
-          if (a.dc0) *reinterpret_cast<float2*>(a.dc0 + (size_t)sq[hf] * H + j0 + 8 * P) = make_float2(dcn[P][0][hf], dcn[P][1][hf]);
+          if (a.dh0) *reinterpret_cast<float2*>(a.dh0 + (size_t)sq[hf] * H + j0 + PS * P) = make_float2(dhn[P][0][hf], dhn[P][1][hf]);
+          if (a.dc0) *reinterpret_cast<float2*>(a.dc0 + (size_t)sq[hf] * H + j0 + PS * P) = make_float2(dcn[P][0][hf], dcn[P][1][hf]);
         }
   }
 }
@@ -292,9 +293,10 @@ __global__ void __launch_bounds__(NT_MAX, 1) grad_rows_kernel(const GradRowsArgs
   const int ntiles = ceil_div(B, 16);
   const long long nblocks = (long long)a.T * ntiles;
   const int Pg = g >> 2, qq = g & 3;
-  const int ju = warp * 16 + 8 * Pg + 2 * qq;            // this lane's unit pair ju, ju+1 (of every gate)
+  const int PS = 8 * NW;                                 // unit offset of half P = 1 (same mapping as the recurrence kernels)
+  const int ju = warp * 8 + PS * Pg + 2 * qq;            // this lane's unit pair ju, ju+1 (of every gate)
   const bool uin = ju < H;                               // H % 4 == 0
-  const bool xcols = warp * 16 < I;                      // this warp's units overlap the input width
+  const bool xcols = warp * 8 < I;                      // this warp's units overlap the input width
 
   extern __shared__ __align__(16) float smem[];
   float* UxS = smem;                                     // [I][RX]
@@ -448,7 +450,7 @@ __global__ void __launch_bounds__(NT_MAX, 1) grad_rows_kernel(const GradRowsArgs
       if (rr < nvalid) {
         const size_t r = (size_t)t * B + b0 + rr;
         const int hf = rr >> 3, gs = rr & 7, Pu = lane & 1;
-        const int jb = warp * 16 + 8 * Pu;
+        const int jb = warp * 8 + PS * Pu;
         float sx[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) sx[i] = 0.f;
@@ -486,7 +488,7 @@ __global__ void __launch_bounds__(NT_MAX, 1) grad_rows_kernel(const GradRowsArgs
         for (int i = 0; i < 4; ++i) {
           const int slot = 16 * m + g + 8 * (i >> 1);
           const int n = 2 * q + (i & 1);
-          const int j = warp * 16 + 8 * (n >> 2) + 2 * (n & 3) + X;
+          const int j = warp * 8 + PS * (n >> 2) + 2 * (n & 3) + X;
           if (j >= H) continue;
           const size_t row = (size_t)k * H + j;
           const float v = accW[m][2 * k + X][i];

@@ -11,9 +11,11 @@
 // fragment of the gate GEMM *is* the A fragment of the next step's z GEMM (same lane, same registers),
 // so h never leaves the register file.  The time-parallel GEMMs (regime G) are the tcgen05 kernels.
 //
-// Tiling: one CTA owns 16 sequences for all T steps (persistent over batch tiles); warp w owns hidden
-// units [32w, 32w+32).  Lane (g = lane/4, q = lane%4) owns, for P = 0..3, the two units 32w+8P+2q+{0,1}
-// of sequences g and g+8: 16 (sequence, unit) pairs whose c and h_{t-1} live in registers.
+// Tiling: one CTA owns 16 sequences for all T steps (persistent over batch tiles); warp w owns two 8-unit halves,
+// P = 0: units [8w, 8w+8) and P = 1: units [8NW + 8w, 8NW + 8w + 8) -- halves of one warp are NOT adjacent, so
+// the units with an input-side term (j < I, the low indices) are spread over as many warps as possible instead of
+// loading the first I/16 warps with all of the x-side work.  Lane (g = lane/4, q = lane%4) owns the two units
+// half(P) + 2q + {0,1} of sequences g and g+8: 8 (sequence, unit) pairs whose c and h_{t-1} live in registers.
 // Per step:
 //   A fragments   rows [z | zx | 1 | 0] of the 16 sequences: z = sum over warps of last step's partial
 //                 products (smem), zx from the time-parallel x projection, "1" carries the bias.
@@ -107,7 +109,8 @@ __global__ void __launch_bounds__(512, 1) seq_fwd_mma_kernel(const SeqFwdMmaArgs
   const int g = lane >> 2, q = lane & 3;
   const int H = aa.s.H, I = aa.s.I, B = aa.s.B, T = aa.s.T, RH = aa.s.RH, RX = aa.s.RX;
   const int HP = NW * 16;
-  const int ubase = warp * 16;                           // first unit of this warp
+  const int ubase = warp * 8;                            // first unit of this warp's half P = 0
+  const int PS = 8 * NW;                                 // half P = 1 holds units PS + 8 warp .. (see the tiling note above)
   const int zp = aa.zp, zxp = aa.zxp;
 
   extern __shared__ __align__(16) float smem[];
@@ -135,7 +138,7 @@ __global__ void __launch_bounds__(512, 1) seq_fwd_mma_kernel(const SeqFwdMmaArgs
     const int P = pk >> 2, k = pk & 3;
 #pragma unroll
     for (int s = 0; s < KS; ++s) {
-      const float b0 = wcat(k, ubase + 8 * P + g, 8 * s + q), b1 = wcat(k, ubase + 8 * P + g, 8 * s + q + 4);
+      const float b0 = wcat(k, ubase + PS * P + g, 8 * s + q), b1 = wcat(k, ubase + PS * P + g, 8 * s + q + 4);
       const float b0h = tf32_rna(b0), b1h = tf32_rna(b1);
       const_cast<float4*>(myB)[(pk * KS + s) * 32] = make_float4(b0h, b1h, tf32_rna(b0 - b0h), tf32_rna(b1 - b1h));
     }
@@ -154,7 +157,7 @@ __global__ void __launch_bounds__(512, 1) seq_fwd_mma_kernel(const SeqFwdMmaArgs
     for (int nz = 0; nz < NZ; ++nz)
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        const int j = ubase + 8 * P + 2 * q + e, r = 8 * nz + g;
+        const int j = ubase + PS * P + 2 * q + e, r = 8 * nz + g;
         const float v = (j < H && r < RH) ? __ldg(aa.s.A + (size_t)j * RH + r) : 0.f;
         Azh[P][nz][e] = tf32_rna(v);
         Azl[P][nz][e] = tf32_rna(v - Azh[P][nz][e]);
@@ -164,7 +167,7 @@ __global__ void __launch_bounds__(512, 1) seq_fwd_mma_kernel(const SeqFwdMmaArgs
 
   const bool xwarp = ubase < I;                          // this warp has units with an x term
   const int ntiles = ceil_div(B, 16);
-  const int j0 = ubase + 2 * q;                          // this lane's units: j0 + 8P + e
+  const int j0 = ubase + 2 * q;                          // this lane's units: j0 + PS*P + e
   const int nthreads = blockDim.x;
   const bool wy = aa.s.y != nullptr;                    // y == nullptr: the caller consumes only (hT, cT)
 
@@ -190,11 +193,11 @@ __global__ void __launch_bounds__(512, 1) seq_fwd_mma_kernel(const SeqFwdMmaArgs
       for (int e = 0; e < 2; ++e)
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
-          const int j = j0 + 8 * P + e;
+          const int j = j0 + PS * P + e;
           const bool ld = ok[hf] && j < H;
           hp[P][e][hf] = (ld && aa.s.h0) ? aa.s.h0[(size_t)sq[hf] * H + j] : 0.f;
           c[P][e][hf] = (ld && aa.s.c0) ? aa.s.c0[(size_t)sq[hf] * H + j] : 0.f;
-          xn[P][e][hf] = (ok[hf] && j < I) ? xrow[hf][8 * P + e] : 0.f;                 // t = 0
+          xn[P][e][hf] = (ok[hf] && j < I) ? xrow[hf][PS * P + e] : 0.f;                 // t = 0
         }
     // zx staging (warp NW-1): lane -> (sequence lane/2, half of each 8-column group)
     const int zsb = lane >> 1, zhh = lane & 1;
@@ -302,7 +305,7 @@ __global__ void __launch_bounds__(512, 1) seq_fwd_mma_kernel(const SeqFwdMmaArgs
             for (int P = 0; P < 2; ++P)
 #pragma unroll
               for (int e = 0; e < 2; ++e)
-                xn[P][e][hf] = (ok[hf] && (j0 + 8 * P + e) < I) ? xrow[hf][8 * P + e] : 0.f;
+                xn[P][e][hf] = (ok[hf] && (j0 + PS * P + e) < I) ? xrow[hf][PS * P + e] : 0.f;
           }
         }
       }
@@ -315,7 +318,7 @@ __global__ void __launch_bounds__(512, 1) seq_fwd_mma_kernel(const SeqFwdMmaArgs
 
 #pragma unroll
       for (int P = 0; P < 2; ++P) {
-        // ---- gate GEMM for units ubase+8P .. +7: acc[k][i], i = 2*hf + e ----
+        // ---- gate GEMM for units ubase+PS*P .. +7: acc[k][i], i = 2*hf + e ----
         float acc[4][4];
 #pragma unroll
         for (int k = 0; k < 4; ++k)
@@ -337,8 +340,8 @@ __global__ void __launch_bounds__(512, 1) seq_fwd_mma_kernel(const SeqFwdMmaArgs
         float2 dh[4], dx[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          dh[k] = *reinterpret_cast<const float2*>(DhS + k * HP + j0 + 8 * P);
-          dx[k] = *reinterpret_cast<const float2*>(DxS + k * HP + j0 + 8 * P);
+          dh[k] = *reinterpret_cast<const float2*>(DhS + k * HP + j0 + PS * P);
+          dx[k] = *reinterpret_cast<const float2*>(DxS + k * HP + j0 + PS * P);
         }
         float hnew[2][2];                                // [e][hf]
         float gsave[4][2][2];
@@ -368,8 +371,8 @@ __global__ void __launch_bounds__(512, 1) seq_fwd_mma_kernel(const SeqFwdMmaArgs
           }
         // ---- stores: y in the caller's layout (8 rows x 32 B per instruction); saved gates / c in the
         //      fragment-major layout (each warp instruction writes 256 contiguous bytes) ----
-        if (wy && ok[0] && (j0 + 8 * P) < H) *reinterpret_cast<float2*>(yrow[0] + 8 * P) = make_float2(hnew[0][0], hnew[1][0]);
-        if (wy && ok[1] && (j0 + 8 * P) < H) *reinterpret_cast<float2*>(yrow[1] + 8 * P) = make_float2(hnew[0][1], hnew[1][1]);
+        if (wy && ok[0] && (j0 + PS * P) < H) *reinterpret_cast<float2*>(yrow[0] + PS * P) = make_float2(hnew[0][0], hnew[1][0]);
+        if (wy && ok[1] && (j0 + PS * P) < H) *reinterpret_cast<float2*>(yrow[1] + PS * P) = make_float2(hnew[0][1], hnew[1][1]);
         if (SAVE) {
 #pragma unroll
           for (int hf = 0; hf < 2; ++hf) {
@@ -406,7 +409,7 @@ __global__ void __launch_bounds__(512, 1) seq_fwd_mma_kernel(const SeqFwdMmaArgs
       for (int e = 0; e < 2; ++e)
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
-          const int j = j0 + 8 * P + e;
+          const int j = j0 + PS * P + e;
           if (ok[hf] && j < H) {
             aa.s.hT[(size_t)sq[hf] * H + j] = hp[P][e][hf];
             aa.s.cT[(size_t)sq[hf] * H + j] = c[P][e][hf];
