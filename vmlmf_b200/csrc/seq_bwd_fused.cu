@@ -35,11 +35,19 @@ bool bwd_fused_fits(int I, int H, int RX, int RH) {
   return seq_bwd_fused_smem_bytes(ceil_div(H, 16), KS, I, RX) <= 227 * 1024;
 }
 
+// blocks of dux_rows_kernel: one resident wave at most (its shared memory allows >= 2 blocks per SM for every fitting shape)
+int dux_grid(int T, int B) {
+  const long long tiles = ((long long)T * B + kDuxRows - 1) / kDuxRows;
+  return (int)(tiles < 6LL * kNumSMs ? tiles : 6LL * kNumSMs);
+}
+
+// workspace: [per-CTA gradient partials | dzx rows | per-block dUx partials], each part a multiple of 4 floats
 long long bwd_fused_workspace_floats(int T, int B, int I, int H, int RX, int RH) {
   if (!bwd_fused_fits(I, H, RX, RH)) return 0;
   const GradLayout L(I, H, RX, RH);
-  (void)T;
-  return (long long)grid_of(B, ceil_div(H, 16), ks_of(RX, RH), I, RX) * L.total + 8;
+  const long long zxp = round_up(RX, 4);
+  const long long part = round_up((int)((long long)grid_of(B, ceil_div(H, 16), ks_of(RX, RH), I, RX) * L.total + 8), 4);
+  return part + (long long)T * B * zxp + (long long)dux_grid(T, B) * I * zxp;
 }
 
 template <int KS, int NZ>
@@ -61,14 +69,30 @@ int launch_bwd_fused(const SeqBwdFusedArgs& a0, const GradOut& out, void* worksp
   const int G = grid_of(a0.B, NW, KS, a0.I, a0.RX);
   const GradLayout L(a0.I, a0.H, a0.RX, a0.RH);
   SeqBwdFusedArgs a = a0;
-  a.dzc = nullptr;
+  const int zxp = a0.zxp;
+  const long long part = round_up((int)((long long)G * L.total + 8), 4);
   a.partial = (float*)workspace;
+  a.dzc = a.partial + part;                             // dzx rows, in the row order of x when x is one contiguous block
+  float* pbuf = a.dzc + (size_t)a0.T * a0.B * zxp;
+  const bool x_bt = a0.xs_t == a0.I && a0.xs_b == (long long)a0.T * a0.I;
+  const bool x_tb = a0.xs_b == a0.I && a0.xs_t == (long long)a0.B * a0.I;
+  a.dz_bt = x_bt ? 1 : 0;
   int rc = kMmaNoFit;
   if (KS == 1) rc = launch_t<1, 1>(a, NW, G, st);
   else if (KS == 2 && NZ == 1) rc = launch_t<2, 1>(a, NW, G, st);
   else if (KS == 2 && NZ == 2) rc = launch_t<2, 2>(a, NW, G, st);
   if (rc) return rc;
   reduce_partials_kernel<<<ceil_div(L.total, kReduceElems), 256, 0, st>>>(a.partial, G, L, out);
+  // dUx = X^T dZX (overwrites the unwritten dUx slice the reduce just summed)
+  const int GX = dux_grid(a0.T, a0.B);
+  DuxArgs d{a0.x, a0.xs_t, a0.xs_b, a.dzc, pbuf, a0.T, a0.B, a0.I, zxp, (x_bt || x_tb) ? 1 : 0};
+  const size_t dsm = (size_t)kDuxRows * (a0.I + zxp) * sizeof(float);
+  if (dsm > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(dux_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm);
+    if (e != cudaSuccess) return (int)e;
+  }
+  dux_rows_kernel<<<GX, kDuxThreads, dsm, st>>>(d);
+  dux_reduce_kernel<<<ceil_div(a0.I * a0.RX, 16), 256, 0, st>>>(pbuf, GX, a0.I, a0.RX, zxp, out.dUx);
   return (int)cudaGetLastError();
 }
 

@@ -31,7 +31,8 @@ struct SeqBwdFusedArgs {
   const float* y; long long ys_t, ys_b;
   const float* h0;
   const float *z, *zx; int zp, zxp;
-  float* dzc;                              // unused (kept so the argument block matches the split backward's)
+  float* dzc;                              // out: [T*B, zxp] rows of dzx = (reduced dzc)[RH .. RH+RX), for dux_rows_kernel
+  int dz_bt;                               // row order of dzc: 1 = b*T + t (x is a contiguous [B,T,I] block), 0 = t*B + b
   float* dx; long long dxs_t, dxs_b;       // may be null
   float *dh0, *dc0;
   float* partial;                          // [gridDim.x, GradLayout.total]; this kernel writes dVx, dDx, dBm, dDh, dbias
@@ -431,6 +432,14 @@ __global__ void __launch_bounds__(512, 1) seq_bwd_fused_kernel(const SeqBwdFused
         }
       }
       __syncthreads();
+      // ---- dzx rows of this step -> HBM, in the row order of x (a.dz_bt: [B,T] else [T,B]), pad columns zero ----
+      for (int idx = tid; idx < 16 * a.zxp; idx += nthreads) {
+        const int seq = idx / a.zxp, r = idx - seq * a.zxp;
+        if (b0 + seq < B) {
+          const size_t row = a.dz_bt ? (size_t)(b0 + seq) * T + t : (size_t)t * B + b0 + seq;
+          a.dzc[row * a.zxp + r] = r < RX ? Dz[seq * PP + RH + r] : 0.f;
+        }
+      }
       // ---- dh_{t-1} = dz A^T + sum_k dPre_k Dh_k ; dx_t = dzx Ux^T + sum_k dPre_k Dx_k ----
       float acc[2][4];
 #pragma unroll
@@ -484,8 +493,10 @@ __global__ void __launch_bounds__(512, 1) seq_bwd_fused_kernel(const SeqBwdFused
           }
       }
       if (a.dx) { dxrow[0] -= a.dxs_t; dxrow[1] -= a.dxs_t; }
-      // ---- dA += Hprev^T dz, dUx += X^T dzx: A = (m = g: unit ju, m = g+8: unit ju+1; k = sequence q / q+4) read transposed
-      //      from the rows this warp touched in phase 1 (L1/L2 hits), B = the reduced dzc rows (k = sequence, n = slot) ----
+      // ---- dA += Hprev^T dz: A = (m = g: unit ju, m = g+8: unit ju+1; k = sequence q / q+4) read transposed from the rows
+      //      this warp touched in phase 1 (L1/L2 hits), B = the reduced dz rows (k = sequence, n = slot).  dUx = X^T dzx
+      //      is NOT formed here: only the warps that own input-side units could do it, and they are the critical path of
+      //      every barrier; the dzx rows go to HBM (32 B per sequence-step) for dux_rows_kernel ----
       {
         const int ju = ubase + PS * (g >> 2) + 2 * (g & 3);
         const bool uin = ju < H;
@@ -493,7 +504,7 @@ __global__ void __launch_bounds__(512, 1) seq_bwd_fused_kernel(const SeqBwdFused
         for (int ks = 0; ks < 2; ++ks) {
           const int rr0 = 8 * ks + q, rr1 = rr0 + 4;
           const bool v0 = (b0 + rr0) < B, v1 = (b0 + rr1) < B;
-          float2 h0v = make_float2(0.f, 0.f), h1v = h0v, x0v = h0v, x1v = h0v;
+          float2 h0v = make_float2(0.f, 0.f), h1v = h0v;
           if (uin) {
             if (t > 0) {
               const float* yb = a.y + (size_t)(t - 1) * a.ys_t + (size_t)b0 * a.ys_b + ju;
@@ -504,32 +515,18 @@ __global__ void __launch_bounds__(512, 1) seq_bwd_fused_kernel(const SeqBwdFused
               if (v1) h1v = __ldg(reinterpret_cast<const float2*>(a.h0 + (size_t)(b0 + rr1) * H + ju));
             }
           }
-          if (xwarp) {
-            const float* xb = a.x + (size_t)t * a.xs_t + (size_t)b0 * a.xs_b + ju;
-            if (ju < I) { if (v0) x0v.x = __ldg(xb + (size_t)rr0 * a.xs_b); if (v1) x1v.x = __ldg(xb + (size_t)rr1 * a.xs_b); }
-            if (ju + 1 < I) { if (v0) x0v.y = __ldg(xb + (size_t)rr0 * a.xs_b + 1); if (v1) x1v.y = __ldg(xb + (size_t)rr1 * a.xs_b + 1); }
-          }
           const float hv[4] = {h0v.x, h0v.y, h1v.x, h1v.y};
-          float hh[4], hl[4], xh[4], xl[4];
+          float hh[4], hl[4];
           split4(hv, hh, hl);
-          if (xwarp) {
-            const float xv[4] = {x0v.x, x0v.y, x1v.x, x1v.y};
-            split4(xv, xh, xl);
-          }
 #pragma unroll
-          for (int s = 0; s < KS; ++s) {
-            float ag[4], au[4];
+          for (int s = 0; s < NZ; ++s) {                 // only the dz slots (n-tiles below NZ) feed dA
+            float ag[4];
             tmem_ld4(tbase + 64 + 4 * s, ag);
-            if (xwarp) tmem_ld4(tbase + 72 + 4 * s, au);
             const float d0 = Dz[rr0 * PP + 8 * s + g], d1 = Dz[rr1 * PP + 8 * s + g];
             const float b0h = tf32_rna(d0), b1h = tf32_rna(d1);
             tmem_wait_ld();
             mma_3x(ag, hh, hl, b0h, b1h, d0 - b0h, d1 - b1h);
             tmem_st4(tbase + 64 + 4 * s, ag);
-            if (xwarp) {
-              mma_3x(au, xh, xl, b0h, b1h, d0 - b0h, d1 - b1h);
-              tmem_st4(tbase + 72 + 4 * s, au);
-            }
           }
         }
       }
@@ -588,20 +585,19 @@ __global__ void __launch_bounds__(512, 1) seq_bwd_fused_kernel(const SeqBwdFused
         if (g == 0 && j < I) Pout[L.oDx + k * I + j] = w;
       }
     }
-  // dA / dUx: C fragment (m = g [+8] <-> unit ju [+1], n = slot 8s + 2q [+1])
+  // dA: C fragment (m = g [+8] <-> unit ju [+1], n = slot 8s + 2q [+1]); the dUx slice of the partial stays unwritten
+  // (launch_bwd_fused overwrites dUx with dux_rows_kernel's result after the reduce)
   {
     const int ju = ubase + PS * (g >> 2) + 2 * (g & 3);
 #pragma unroll
-    for (int s = 0; s < KS; ++s) {
-      float ag[4], au[4];
+    for (int s = 0; s < NZ; ++s) {
+      float ag[4];
       tmem_ld4(tbase + 64 + 4 * s, ag);
-      tmem_ld4(tbase + 72 + 4 * s, au);
       tmem_wait_ld();
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int j = ju + (i >> 1), slot = 8 * s + 2 * q + (i & 1);
         if (j < H && slot < RH) Pout[L.oA + (size_t)j * RH + slot] = ag[i];
-        if (j < I && slot >= RH && slot < RH + RX) Pout[L.oUx + (size_t)j * RX + (slot - RH)] = au[i];
       }
     }
   }
@@ -610,6 +606,108 @@ __global__ void __launch_bounds__(512, 1) seq_bwd_fused_kernel(const SeqBwdFused
   if (warp == 0) {
     tc::tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tslot), "r"(tmem_cols));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------- //
+// dUx = X^T dZX over all T*B rows: a streaming pass over x (read once, I floats per row) and the dzx rows the fused
+// kernel wrote (zxp floats per row), both in x's row order.  Same staging as xproj_small_kernel (64-row tiles,
+// contiguous spans copied with 16-byte loads); thread = (input unit j, 4 slots), accumulators in registers, one
+// partial per block, summed by dux_reduce_kernel in block order.
+// ------------------------------------------------------------------------------------------------- //
+constexpr int kDuxRows = 64, kDuxThreads = 128, kDuxItems = 8;      // I * zxp / 4 <= 1024 work items
+struct DuxArgs {
+  const float* x; long long xs_t, xs_b;
+  const float* dzx;                        // [T*B, zxp]
+  float* pbuf;                             // [gridDim.x, I * zxp]
+  int T, B, I, zxp, contiguous;            // contiguous: rows are one span in memory (either order); else (t, b) strides
+};
+
+static __global__ void __launch_bounds__(kDuxThreads) dux_rows_kernel(const DuxArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const int I = a.I, zxp = a.zxp, NQ = zxp >> 2, nitems = I * NQ;
+  float* xs = smem;                                    // [64][I]
+  float* ds = smem + (size_t)kDuxRows * I;             // [64][zxp]   (64 * I * 4 bytes is a multiple of 16)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float4 acc[kDuxItems];
+#pragma unroll
+  for (int it = 0; it < kDuxItems; ++it) acc[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const long long nrows = (long long)a.T * a.B;
+  const bool vec = a.contiguous && (reinterpret_cast<uintptr_t>(a.x) & 15) == 0;
+  for (long long row0 = (long long)blockIdx.x * kDuxRows; row0 < nrows; row0 += (long long)gridDim.x * kDuxRows) {
+    __syncthreads();
+    const long long left = nrows - row0;
+    const int nr = (int)(left < kDuxRows ? left : kDuxRows);
+    if (a.contiguous) {
+      const float* src = a.x + row0 * I;
+      const int n = nr * I, n4 = vec ? (n & ~3) : 0;
+      int e = tid * 4;
+      for (; e + 3 * 4 * kDuxThreads < n4; e += 4 * 4 * kDuxThreads) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(src + e + u * 4 * kDuxThreads));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) *reinterpret_cast<float4*>(xs + e + u * 4 * kDuxThreads) = v[u];
+      }
+      for (; e < n4; e += 4 * kDuxThreads) *reinterpret_cast<float4*>(xs + e) = __ldg(reinterpret_cast<const float4*>(src + e));
+      for (int t1 = n4 + tid; t1 < n; t1 += kDuxThreads) xs[t1] = __ldg(src + t1);
+    } else {
+      for (int rr = warp; rr < nr; rr += kDuxThreads / 32) {
+        const long long row = row0 + rr, t = row / a.B, b = row % a.B;
+        const float* src = a.x + t * a.xs_t + b * a.xs_b;
+        for (int jj = lane; jj < I; jj += 32) xs[rr * I + jj] = __ldg(src + jj);
+      }
+    }
+    {                                                  // dzx rows: contiguous, zxp % 4 == 0
+      const float4* src = reinterpret_cast<const float4*>(a.dzx + row0 * zxp);
+      for (int e = tid; e < nr * NQ; e += kDuxThreads) reinterpret_cast<float4*>(ds)[e] = __ldg(src + e);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < kDuxItems; ++it) {
+      const int item = tid + it * kDuxThreads;
+      if (item >= nitems) break;
+      const int j = item / NQ, nq = item - j * NQ;
+      float4 s = acc[it];
+#pragma unroll 4
+      for (int r = 0; r < nr; ++r) {
+        const float xv = xs[r * I + j];
+        const float4 d = *reinterpret_cast<const float4*>(ds + r * zxp + 4 * nq);
+        s.x = fmaf(xv, d.x, s.x); s.y = fmaf(xv, d.y, s.y); s.z = fmaf(xv, d.z, s.z); s.w = fmaf(xv, d.w, s.w);
+      }
+      acc[it] = s;
+    }
+  }
+  float* out = a.pbuf + (size_t)blockIdx.x * I * zxp;
+#pragma unroll
+  for (int it = 0; it < kDuxItems; ++it) {
+    const int item = tid + it * kDuxThreads;
+    if (item >= nitems) break;
+    *reinterpret_cast<float4*>(out + (size_t)item * 4) = acc[it];            // item = j * NQ + nq  ->  offset j * zxp + 4 nq
+  }
+}
+
+// dUx[j, r] = sum over blocks of pbuf[block][j * zxp + r]: 16 outputs per block x 16 slices of the block list, fixed order
+static __global__ void __launch_bounds__(256) dux_reduce_kernel(const float* __restrict__ pbuf, int nblocks, int I, int RX,
+                                                                int zxp, float* __restrict__ dUx) {
+  __shared__ float sl[16][17];
+  const int e = threadIdx.x & 15, slice = threadIdx.x >> 4;
+  const int i = blockIdx.x * 16 + e;                   // output index j * RX + r
+  const bool live = i < I * RX;
+  const int j = live ? i / RX : 0, r = live ? i - j * RX : 0;
+  const size_t stride = (size_t)I * zxp, off = (size_t)j * zxp + r;
+  float s = 0.f;
+  if (live) {
+#pragma unroll 4
+    for (int b = slice; b < nblocks; b += 16) s += pbuf[(size_t)b * stride + off];
+  }
+  sl[slice][e] = s;
+  __syncthreads();
+  if (slice == 0 && live) {
+    float t = 0.f;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) t += sl[q][e];
+    dUx[i] = t;
   }
 }
 

@@ -274,7 +274,7 @@ int vmlmf_seq_bwd(const vmlmf_plan* plan, const float* x, long long xs_t, long l
     if (use_fused_bwd(I, H, RX, RH)) {
       // fused: recurrence + weight-gradient accumulation (accumulators in tensor memory) + dX; then dA / dUx
       SeqBwdFusedArgs fa{gates, cs, c0, dy, dys_t, dys_b, dhT, dcT, Ux, Vx, Dx, A, Bm, Dh, x, xs_t, xs_b, y, ys_t, ys_b, h0,
-                         z, zx, plan->z_pitch, plan->zx_pitch, nullptr, dx, dxs_t, dxs_b, dh0, dc0, nullptr, T, B, I, H, RX, RH};
+                         z, zx, plan->z_pitch, plan->zx_pitch, nullptr, 0, dx, dxs_t, dxs_b, dh0, dc0, nullptr, T, B, I, H, RX, RH};
       return launch_bwd_fused(fa, o2, workspace, st);
     }
     // reverse-time recurrence (K3a) + time-parallel gradient accumulation (K3b)
