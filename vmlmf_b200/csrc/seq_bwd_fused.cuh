@@ -326,8 +326,13 @@ __global__ void __launch_bounds__(512, 1) seq_bwd_fused_kernel(const SeqBwdFused
         // ---- vector-multiplication terms: dh seed, dx seed, and the dDh / dDx sums (accumulators in tensor memory) ----
         {
           float gd[2][4];                                // [e][k] running sums of dPre_k * h_{t-1} over this lane's sequences
+          float gx[2][4];                                // ... and of dPre_k * x_t (halves that hold input-side units)
           tmem_ld4(tbase + 32 + 8 * P, gd[0]);
           tmem_ld4(tbase + 36 + 8 * P, gd[1]);
+          if (xhalf[P]) {                                // one wait covers both accumulator sets
+            tmem_ld4(tbase + 48 + 8 * P, gx[0]);
+            tmem_ld4(tbase + 52 + 8 * P, gx[1]);
+          }
 #pragma unroll
           for (int e = 0; e < 2; ++e)
 #pragma unroll
@@ -347,23 +352,26 @@ __global__ void __launch_bounds__(512, 1) seq_bwd_fused_kernel(const SeqBwdFused
           tmem_st4(tbase + 32 + 8 * P, gd[0]);
           tmem_st4(tbase + 36 + 8 * P, gd[1]);
           if (xhalf[P]) {
-            float gx[2][4];
-            tmem_ld4(tbase + 48 + 8 * P, gx[0]);
-            tmem_ld4(tbase + 52 + 8 * P, gx[1]);
-            tmem_wait_ld();
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const float2 d2 = *reinterpret_cast<const float2*>(DxS + k * HP + j0 + PS * P);
+            for (int k = 0; k < 4; ++k)
 #pragma unroll
               for (int hf = 0; hf < 2; ++hf) {
-                sx[P][0][hf] = fmaf(dpre[k][0][hf], d2.x, sx[P][0][hf]);
-                sx[P][1][hf] = fmaf(dpre[k][1][hf], d2.y, sx[P][1][hf]);
                 gx[0][k] = fmaf(dpre[k][0][hf], xv2[hf].x, gx[0][k]);
                 gx[1][k] = fmaf(dpre[k][1][hf], xv2[hf].y, gx[1][k]);
               }
-            }
             tmem_st4(tbase + 48 + 8 * P, gx[0]);
             tmem_st4(tbase + 52 + 8 * P, gx[1]);
+            if (a.dx) {                                  // dx seed, only when the caller wants dX
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float2 d2 = *reinterpret_cast<const float2*>(DxS + k * HP + j0 + PS * P);
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                  sx[P][0][hf] = fmaf(dpre[k][0][hf], d2.x, sx[P][0][hf]);
+                  sx[P][1][hf] = fmaf(dpre[k][1][hf], d2.y, sx[P][1][hf]);
+                }
+              }
+            }
           }
         }
         // ---- partial dzc GEMM of this half (dPre registers are the A fragments) ----
