@@ -92,7 +92,7 @@ int launch_bwd_fused(const SeqBwdFusedArgs& a0, const GradOut& out, void* worksp
     if (e != cudaSuccess) return (int)e;
   }
   dux_rows_kernel<<<GX, kDuxThreads, dsm, st>>>(d);
-  dux_reduce_kernel<<<ceil_div(a0.I * a0.RX, 16), 256, 0, st>>>(pbuf, GX, a0.I, a0.RX, zxp, out.dUx);
+  dux_reduce_kernel<<<ceil_div(a0.I * a0.RX, 4), 256, 0, st>>>(pbuf, GX, a0.I, a0.RX, zxp, out.dUx);
   return (int)cudaGetLastError();
 }
 

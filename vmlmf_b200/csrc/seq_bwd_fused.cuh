@@ -695,26 +695,33 @@ static __global__ void __launch_bounds__(kDuxThreads) dux_rows_kernel(const DuxA
   }
 }
 
-// dUx[j, r] = sum over blocks of pbuf[block][j * zxp + r]: 16 outputs per block x 16 slices of the block list, fixed order
+// dUx[j, r] = sum over blocks of pbuf[block][j * zxp + r]: 4 outputs per 256-thread block, each summed by 64 threads over
+// interleaved slices of the block list (independent loads in flight), then across the slices in slice order (fixed order)
 static __global__ void __launch_bounds__(256) dux_reduce_kernel(const float* __restrict__ pbuf, int nblocks, int I, int RX,
                                                                 int zxp, float* __restrict__ dUx) {
-  __shared__ float sl[16][17];
-  const int e = threadIdx.x & 15, slice = threadIdx.x >> 4;
-  const int i = blockIdx.x * 16 + e;                   // output index j * RX + r
+  __shared__ float sl[64][5];
+  const int e = threadIdx.x & 3, slice = threadIdx.x >> 2;
+  const int i = blockIdx.x * 4 + e;                    // output index j * RX + r
   const bool live = i < I * RX;
   const int j = live ? i / RX : 0, r = live ? i - j * RX : 0;
   const size_t stride = (size_t)I * zxp, off = (size_t)j * zxp + r;
-  float s = 0.f;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
   if (live) {
-#pragma unroll 4
-    for (int b = slice; b < nblocks; b += 16) s += pbuf[(size_t)b * stride + off];
+    int b = slice;
+    for (; b + 192 < nblocks; b += 256) {
+      s0 += pbuf[(size_t)b * stride + off];
+      s1 += pbuf[(size_t)(b + 64) * stride + off];
+      s2 += pbuf[(size_t)(b + 128) * stride + off];
+      s3 += pbuf[(size_t)(b + 192) * stride + off];
+    }
+    for (; b < nblocks; b += 64) s0 += pbuf[(size_t)b * stride + off];
   }
-  sl[slice][e] = s;
+  sl[slice][e] = (s0 + s1) + (s2 + s3);
   __syncthreads();
   if (slice == 0 && live) {
     float t = 0.f;
-#pragma unroll
-    for (int q = 0; q < 16; ++q) t += sl[q][e];
+#pragma unroll 8
+    for (int q = 0; q < 64; ++q) t += sl[q][e];
     dUx[i] = t;
   }
 }
