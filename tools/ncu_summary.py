@@ -69,6 +69,7 @@ def main():
           "(serialised, cold cache: compare shares and ratios, not absolute times).", ""]
     table = []
     traffic = {}
+    per_name = {}
     for r in body:
         name = r[col["Kernel Name"]]
         md += [f"## `{name}`", "", "| metric | value | unit |", "|---|---|---|"]
@@ -94,9 +95,10 @@ def main():
             wr = to_bytes(r[col["dram__bytes_write.sum"]], units[col["dram__bytes_write.sum"]])
             rec["dram_bytes_total"] = rd + wr
             md += ["", f"DRAM traffic per launch: {rd + wr:.4g} B (read {rd:.4g} + write {wr:.4g})"]
-            for k, rx in tkeys.items():
+            for k, rx in tkeys.items():           # a key may cover several kernels of one call: sum over distinct names
                 if rx.search(name):
-                    traffic[k] = rd + wr
+                    per_name.setdefault(k, {})[name] = rd + wr
+                    traffic[k] = sum(per_name[k].values())
         md.append("")
         table.append(rec)
     with open(out + ".md", "w") as f:
