@@ -172,15 +172,21 @@ int vmlmf_xproj_fwd(const float* x, long long xs_t, long long xs_b, const float*
   if (!x || !Ux || !zx || T <= 0 || B <= 0 || I <= 0 || RX <= 0) return VMLMF_EINVAL;
   if (zx_pitch < RX || (zx_pitch & 3)) return VMLMF_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t smem = ((size_t)ceil_div(I, 8) * ceil_div(zx_pitch, 8) * 32 * 4 + (size_t)kXprojRows * I) * sizeof(float);
-  if (zx_pitch <= 128 && I <= 512 && smem <= 200 * 1024) {
-    const int rows = kXprojRows;
-    if (smem > 48 * 1024) {
-      cudaError_t e = cudaFuncSetAttribute(xproj_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const size_t uf_bytes = (size_t)ceil_div(I, 8) * ceil_div(zx_pitch, 8) * 32 * 4 * sizeof(float);
+  const size_t tile_bytes = (size_t)kXprojRows * I * sizeof(float);
+  if (zx_pitch <= 128 && I <= 512 && uf_bytes + tile_bytes <= 200 * 1024) {
+    const int order = (xs_t == I && xs_b == (long long)T * I) ? 1 : ((xs_b == I && xs_t == (long long)B * I) ? 2 : 0);
+    // three tiles in flight per block when the input is one contiguous block and three blocks still fit an SM
+    const int stages = (order != 0 && 3 * (uf_bytes + 3 * tile_bytes + 1024) <= 227 * 1024) ? 3 : 1;
+    const size_t smem = uf_bytes + stages * tile_bytes;
+    static bool attr_done = false;                        // benign race
+    if (!attr_done) {
+      cudaError_t e = cudaFuncSetAttribute(xproj_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       if (e != cudaSuccess) return (int)e;
+      attr_done = true;
     }
     const long long nrows = (long long)T * B;
-    long long grid = (nrows + rows - 1) / rows;
+    long long grid = (nrows + kXprojRows - 1) / kXprojRows;
     // resident blocks per SM: one wave, every block walks its share.  The query is a driver call: cached per
     // shared-memory size (256-byte buckets; a benign race, every writer stores the same value)
     static int occ_cache[1024] = {0};
@@ -192,8 +198,7 @@ int vmlmf_xproj_fwd(const float* x, long long xs_t, long long xs_b, const float*
     }
     const int occ = occ_slot;
     if (grid > (long long)kNumSMs * occ) grid = (long long)kNumSMs * occ;
-    const int order = (xs_t == I && xs_b == (long long)T * I) ? 1 : ((xs_b == I && xs_t == (long long)B * I) ? 2 : 0);
-    xproj_small_kernel<<<(int)grid, 128, smem, st>>>(x, xs_t, xs_b, Ux, zx, T, B, I, RX, zx_pitch, order);
+    xproj_small_kernel<<<(int)grid, 128, smem, st>>>(x, xs_t, xs_b, Ux, zx, T, B, I, RX, zx_pitch, order, stages);
     return (int)cudaGetLastError();
   }
   return generic_xproj(x, xs_t, xs_b, Ux, zx, T, B, I, RX, zx_pitch, st);

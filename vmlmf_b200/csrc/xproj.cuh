@@ -18,12 +18,13 @@ namespace vmlmf {
 // t*B + b says).  The product itself runs on mma.sync m16n8k8 with the 3xTF32 split (fp32-accurate): a warp owns 16
 // rows, A fragments come from the staged rows, B fragments (Ux, split once per block) from shared memory -- a fifth of
 // the instructions of the SIMT inner product, which leaves the kernel bound by reading x once.
-// block = 128 threads = 4 warps x 16 rows.  smem: Uf[nk][NT][32] float4 {b0hi, b1hi, b0lo, b1lo} | xs[64][I]
+// block = 128 threads = 4 warps x 16 rows.  smem: Uf[nk][NT][32] float4 {b0hi, b1hi, b0lo, b1lo} | xs[stages][64][I]
+// (stages = 3 when the pipelined path fits, else 1)
 constexpr int kXprojRows = 64;
 static __global__ void __launch_bounds__(128) xproj_small_kernel(const float* __restrict__ x, long long xs_t,
                                                           long long xs_b, const float* __restrict__ Ux,
                                                           float* __restrict__ zx, int T, int B, int I,
-                                                          int RX, int pitch, int order) {
+                                                          int RX, int pitch, int order, int stages) {
   extern __shared__ __align__(16) float smem[];
   const int nk = (I + 7) >> 3, NT = (pitch + 7) >> 3;
   float4* Uf = reinterpret_cast<float4*>(smem);
@@ -40,39 +41,14 @@ static __global__ void __launch_bounds__(128) xproj_small_kernel(const float* __
   }
   const long long nrows = (long long)T * B;
   const bool vec = order != 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
-  for (long long row0 = (long long)blockIdx.x * kXprojRows; row0 < nrows; row0 += (long long)gridDim.x * kXprojRows) {
-    __syncthreads();
-    const long long left = nrows - row0;
-    const int nr = (int)(left < kXprojRows ? left : kXprojRows);
-    if (order != 0) {
-      const float* src = x + row0 * I;
-      const int n = nr * I, n4 = vec ? (n & ~3) : 0;                // floats in this block's span
-      int e = tid * 4;
-      for (; e + 3 * 512 < n4; e += 4 * 512) {                       // four independent 16-byte loads per thread
-        float4 v[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(src + e + u * 512));
-#pragma unroll
-        for (int u = 0; u < 4; ++u) *reinterpret_cast<float4*>(xs + e + u * 512) = v[u];
-      }
-      for (; e < n4; e += 512) *reinterpret_cast<float4*>(xs + e) = __ldg(reinterpret_cast<const float4*>(src + e));
-      for (int t1 = n4 + tid; t1 < n; t1 += blockDim.x) xs[t1] = __ldg(src + t1);
-    } else {
-      for (int rr = warp; rr < nr; rr += NW) {
-        const long long row = row0 + rr;
-        long long t, b;
-        if (nrows <= 0xffffffffLL) { const unsigned tq = (unsigned)row / (unsigned)B; t = tq; b = (unsigned)row - tq * (unsigned)B; }
-        else { t = row / B; b = row % B; }
-        const float* src = x + t * xs_t + b * xs_b;
-        for (int jj = lane; jj < I; jj += 32) xs[rr * I + jj] = __ldg(src + jj);
-      }
-    }
-    __syncthreads();
-    // ---- this warp's 16 rows: C[16 x 8 NT] = A[16 x 8 nk] B ----
+  const size_t stage_floats = (size_t)kXprojRows * I;
+
+  // C[16 x 8 NT] = A[16 x 8 nk] B for this warp's 16 rows of the tile staged at xt
+  auto compute = [&](const float* xt, long long row0, int nr) {
     const int r0 = 16 * warp + g, r1 = r0 + 8;
     const bool v0 = r0 < nr, v1 = r1 < nr;
-    const float* x0 = xs + r0 * I;
-    const float* x1 = xs + r1 * I;
+    const float* x0 = xt + r0 * I;
+    const float* x1 = xt + r1 * I;
     for (int nt = 0; nt < NT; ++nt) {
       float acc[4] = {0.f, 0.f, 0.f, 0.f};
       const float4* uf = Uf + (size_t)nt * 32 + lane;
@@ -104,6 +80,55 @@ static __global__ void __launch_bounds__(128) xproj_small_kernel(const float* __
         *reinterpret_cast<float2*>(o) = make_float2(acc[2 * hf], acc[2 * hf + 1]);
       }
     }
+  };
+
+  const long long step = (long long)gridDim.x * kXprojRows;
+  if (vec && stages >= 3) {
+    // contiguous, 16-byte aligned input: three tiles in flight per block (cp.async.cg 16 B), loads overlap the MMAs
+    auto issue = [&](long long row0, int stage) {
+      if (row0 < nrows) {
+        const long long left = nrows - row0;
+        const int n = (int)(left < kXprojRows ? left : kXprojRows) * I, n4 = n & ~3;
+        const float* src = x + row0 * I;
+        float* dst = xs + (size_t)stage * stage_floats;
+        for (int e = tid * 4; e < n4; e += 4 * 128)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst + e)), "l"(src + e) : "memory");
+        for (int t1 = n4 + tid; t1 < n; t1 += 128) dst[t1] = __ldg(src + t1);
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");   // always: keeps the group count uniform
+    };
+    long long row0 = (long long)blockIdx.x * kXprojRows;
+    issue(row0, 0);
+    issue(row0 + step, 1);
+    for (int i = 0; row0 < nrows; ++i, row0 += step) {
+      issue(row0 + 2 * step, (i + 2) % 3);              // that buffer was consumed in iteration i-1 (barrier below)
+      asm volatile("cp.async.wait_group 2;" ::: "memory");
+      __syncthreads();
+      const long long left = nrows - row0;
+      compute(xs + (size_t)(i % 3) * stage_floats, row0, (int)(left < kXprojRows ? left : kXprojRows));
+      __syncthreads();
+    }
+    return;
+  }
+  for (long long row0 = (long long)blockIdx.x * kXprojRows; row0 < nrows; row0 += step) {
+    __syncthreads();
+    const long long left = nrows - row0;
+    const int nr = (int)(left < kXprojRows ? left : kXprojRows);
+    if (order != 0) {
+      const float* src = x + row0 * I;
+      for (int t1 = tid; t1 < nr * I; t1 += blockDim.x) xs[t1] = __ldg(src + t1);
+    } else {
+      for (int rr = warp; rr < nr; rr += NW) {
+        const long long row = row0 + rr;
+        long long t, b;
+        if (nrows <= 0xffffffffLL) { const unsigned tq = (unsigned)row / (unsigned)B; t = tq; b = (unsigned)row - tq * (unsigned)B; }
+        else { t = row / B; b = row % B; }
+        const float* src = x + t * xs_t + b * xs_b;
+        for (int jj = lane; jj < I; jj += 32) xs[rr * I + jj] = __ldg(src + jj);
+      }
+    }
+    __syncthreads();
+    compute(xs, row0, nr);
   }
 }
 
