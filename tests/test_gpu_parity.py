@@ -207,6 +207,9 @@ def test_canonical_kernels_vs_numpy_spec(T, B, I, H, RX, RH, bf, state, scale=0.
     (3, 96, 650, 650, 300, 300, False, True),    # the LM layer (V/models/vmlmf_lm.py, hidden 650, ranks 300), carried state
     (3, 150, 12, 40, 20, 24, True, False),       # ranks beyond R1, ragged 128-row tile, H < one 128-column tile
     (2, 9, 8, 300, 8, 8, False, True),           # H > 256 with small ranks: K = 8 (one tf32 k-step)
+    (4, 20, 650, 650, 300, 300, False, True),    # the LM layer at the reference's batch of 20
+    (3, 32, 10, 42, 17, 23, True, False),        # small batch, nothing aligned to 4 (operands that miss the TMA constraints)
+    (2, 1, 24, 24, 20, 20, False, True),         # a single sequence
 ])
 def test_generic_regime_vs_numpy_spec(T, B, I, H, RX, RH, bf, state, gemm, monkeypatch, r1_path):
     """Regime G (time-parallel XP GEMM + per-step GEMMs): with the tcgen05/TMA 3xTF32 GEMM and with the SIMT GEMM."""
