@@ -143,3 +143,26 @@ def test_flat_clip_sgd_matches_clip_grad_norm_and_sgd():
     for (k, p1), (_, p2) in zip(m1.named_parameters(), m2.named_parameters()):
         _close(p1, p2, TOL, k)
         _close(p1.grad, p2.grad, TOL, k + ".grad")          # gradients rescaled in place like clip_grad_norm_
+
+
+def test_graphed_step_with_static_inputs_reads_the_callers_buffers():
+    """static_inputs=True: the tensors passed at construction are the graph's input buffers, so new data written into
+    them (e.g. by the host-to-device copy of a double-buffered pipeline) is what the next replay trains on."""
+    net1, x, y = _har()
+    net2, _, _ = _har()
+    xa, ya = x.clone(), y.clone()
+    o1 = vb.FlatAdam(net1, lr=0.002)
+    step = GraphedTrainStep(net1, o1, vb.cross_entropy, xa, ya, warmup=1, zero_fn=o1.zero_grad, static_inputs=True)
+    assert step.static_x.data_ptr() == xa.data_ptr()
+    x2 = torch.randn_like(x)
+    xa.copy_(x2)                                   # new batch lands in the graph's own input buffer
+    l1 = float(step(xa, ya))
+    o2 = vb.FlatAdam(net2, lr=0.002)
+    for data in (x, x2):                           # 1 eager warm-up step on x, then the replayed step on x2
+        o2.zero_grad()
+        l2 = vb.cross_entropy(net2(data), y)
+        l2.backward()
+        o2.step()
+    assert abs(l1 - float(l2)) <= 1e-5 * max(1.0, abs(float(l2)))
+    for (k, p1), (_, p2) in zip(net1.named_parameters(), net2.named_parameters()):
+        _close(p1, p2, 2e-5, k)

@@ -36,14 +36,16 @@ class GraphedTrainStep:
     """step = GraphedTrainStep(net, opt, loss_fn, x_example, y_example);  loss = step(x, y)
 
     `opt` must be capturable (e.g. torch.optim.Adam(..., capturable=True) or fused=True with capturable=True).
-    `zero_fn` replaces `opt.zero_grad(set_to_none=False)` (e.g. GradBucket.zero, which keeps .grad aliased to the
-    flat all-reduce buffer); `after_backward` is called between backward and the optimizer step INSIDE the capture
+    `zero_fn` replaces `opt.zero_grad(set_to_none=False)` (e.g. GradBucket.zero / FlatAdam.zero_grad); `after_backward` is called between backward and the optimizer step INSIDE the capture
     (leave None when it would issue a collective)."""
 
-    def __init__(self, module, opt, loss_fn, x_example, y_example, warmup=3, zero_fn=None, after_backward=None):
+    def __init__(self, module, opt, loss_fn, x_example, y_example, warmup=3, zero_fn=None, after_backward=None,
+                 static_inputs=False):
         self.module, self.opt, self.loss_fn = module, opt, loss_fn
-        self.static_x = x_example.clone()
-        self.static_y = y_example.clone()
+        # static_inputs=True: the caller's tensors ARE the graph's input buffers (e.g. the two halves of a double-buffered
+        # host->device pipeline, one graph each): calling with them replays without the device-to-device input copy
+        self.static_x = x_example if static_inputs else x_example.clone()
+        self.static_y = y_example if static_inputs else y_example.clone()
         if zero_fn is None:
             # .grad buffers created earlier on another stream would make autograd synchronise with that stream
             # during capture (cudaErrorStreamCaptureImplicit): let the side-stream warm-up create them
