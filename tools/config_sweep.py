@@ -2,7 +2,7 @@
 """Train-step and inference throughput of the five BASELINE.json configurations on one GPU (synthetic data, random
 init, fp32) -- secondary numbers next to bench.py's headline line.  Prints one JSON object.
 usage: python tools/config_sweep.py [out.json]"""
-import json, os, sys, time
+import json, os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import vmlmf_b200 as vb

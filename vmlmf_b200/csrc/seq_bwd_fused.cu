@@ -35,10 +35,10 @@ bool bwd_fused_fits(int I, int H, int RX, int RH) {
   return seq_bwd_fused_smem_bytes(ceil_div(H, 16), KS, I, RX) <= 227 * 1024;
 }
 
-// blocks of dux_rows_kernel: one resident wave at most (its shared memory allows >= 2 blocks per SM for every fitting shape)
+// blocks of dux_rows_kernel: at most three per SM (three pipeline stages of shared memory each); two partials per block
 int dux_grid(int T, int B) {
   const long long tiles = ((long long)T * B + kDuxRows - 1) / kDuxRows;
-  return (int)(tiles < 6LL * kNumSMs ? tiles : 6LL * kNumSMs);
+  return (int)(tiles < 3LL * kNumSMs ? tiles : 3LL * kNumSMs);
 }
 
 // workspace: [per-CTA gradient partials | dzx rows | per-block dUx partials], each part a multiple of 4 floats
@@ -47,7 +47,7 @@ long long bwd_fused_workspace_floats(int T, int B, int I, int H, int RX, int RH)
   const GradLayout L(I, H, RX, RH);
   const long long zxp = round_up(RX, 4);
   const long long part = round_up((int)((long long)grid_of(B, ceil_div(H, 16), ks_of(RX, RH), I, RX) * L.total + 8), 4);
-  return part + (long long)T * B * zxp + (long long)dux_grid(T, B) * I * zxp;
+  return part + (long long)T * B * zxp + 2LL * dux_grid(T, B) * I * zxp;
 }
 
 template <int KS, int NZ>
@@ -85,14 +85,19 @@ int launch_bwd_fused(const SeqBwdFusedArgs& a0, const GradOut& out, void* worksp
   reduce_partials_kernel<<<ceil_div(L.total, kReduceElems), 256, 0, st>>>(a.partial, G, L, out);
   // dUx = X^T dZX (overwrites the unwritten dUx slice the reduce just summed)
   const int GX = dux_grid(a0.T, a0.B);
-  DuxArgs d{a0.x, a0.xs_t, a0.xs_b, a.dzc, pbuf, a0.T, a0.B, a0.I, zxp, (x_bt || x_tb) ? 1 : 0};
-  const size_t dsm = (size_t)kDuxRows * (a0.I + zxp) * sizeof(float);
-  if (dsm > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(dux_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm);
+  const size_t stage_bytes = (size_t)kDuxRows * (a0.I + zxp) * sizeof(float);
+  const bool pipelined = (x_bt || x_tb) && (reinterpret_cast<uintptr_t>(a0.x) & 15) == 0 &&
+                         3 * (kDuxStages * stage_bytes + 1024) <= 227 * 1024;
+  const size_t dsm = (pipelined ? kDuxStages : 1) * stage_bytes;
+  DuxArgs d{a0.x, a0.xs_t, a0.xs_b, a.dzc, pbuf, a0.T, a0.B, a0.I, zxp, (x_bt || x_tb) ? 1 : 0, pipelined ? kDuxStages : 1};
+  static bool dux_attr = false;                         // benign race
+  if (!dux_attr) {
+    cudaError_t e = cudaFuncSetAttribute(dux_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return (int)e;
+    dux_attr = true;
   }
   dux_rows_kernel<<<GX, kDuxThreads, dsm, st>>>(d);
-  dux_reduce_kernel<<<ceil_div(a0.I * a0.RX, 4), 256, 0, st>>>(pbuf, GX, a0.I, a0.RX, zxp, out.dUx);
+  dux_reduce_kernel<<<ceil_div(a0.I * a0.RX, 4), 256, 0, st>>>(pbuf, 2 * GX, a0.I, a0.RX, zxp, out.dUx);
   return (int)cudaGetLastError();
 }
 

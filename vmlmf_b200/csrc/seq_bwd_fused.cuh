@@ -623,73 +623,106 @@ __global__ void __launch_bounds__(512, 1) seq_bwd_fused_kernel(const SeqBwdFused
 // contiguous spans copied with 16-byte loads); thread = (input unit j, 4 slots), accumulators in registers, one
 // partial per block, summed by dux_reduce_kernel in block order.
 // ------------------------------------------------------------------------------------------------- //
-constexpr int kDuxRows = 64, kDuxThreads = 128, kDuxItems = 8;      // I * zxp / 4 <= 1024 work items
+constexpr int kDuxRows = 64, kDuxThreads = 256, kDuxItems = 8;      // I * zxp / 4 <= 1024 work items
+constexpr int kDuxStages = 3;
 struct DuxArgs {
   const float* x; long long xs_t, xs_b;
   const float* dzx;                        // [T*B, zxp]
-  float* pbuf;                             // [gridDim.x, I * zxp]
+  float* pbuf;                             // [2 * gridDim.x, I * zxp]: two partials per block (row halves of its tiles)
   int T, B, I, zxp, contiguous;            // contiguous: rows are one span in memory (either order); else (t, b) strides
+  int stages;                              // 3: cp.async pipeline (contiguous, 16-byte aligned x), 1: plain staging
 };
 
+// block = 256 threads: thread = (work item (input unit j, 4 slots), half of the tile's rows).  smem per stage: xs[64][I] | ds[64][zxp]
 static __global__ void __launch_bounds__(kDuxThreads) dux_rows_kernel(const DuxArgs a) {
   extern __shared__ __align__(16) float smem[];
   const int I = a.I, zxp = a.zxp, NQ = zxp >> 2, nitems = I * NQ;
-  float* xs = smem;                                    // [64][I]
-  float* ds = smem + (size_t)kDuxRows * I;             // [64][zxp]   (64 * I * 4 bytes is a multiple of 16)
+  const size_t stage_floats = (size_t)kDuxRows * (I + zxp);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int half = tid >> 7, t7 = tid & 127;           // rows [32 half, 32 half + 32) of every tile
   float4 acc[kDuxItems];
 #pragma unroll
   for (int it = 0; it < kDuxItems; ++it) acc[it] = make_float4(0.f, 0.f, 0.f, 0.f);
   const long long nrows = (long long)a.T * a.B;
-  const bool vec = a.contiguous && (reinterpret_cast<uintptr_t>(a.x) & 15) == 0;
-  for (long long row0 = (long long)blockIdx.x * kDuxRows; row0 < nrows; row0 += (long long)gridDim.x * kDuxRows) {
-    __syncthreads();
-    const long long left = nrows - row0;
-    const int nr = (int)(left < kDuxRows ? left : kDuxRows);
-    if (a.contiguous) {
-      const float* src = a.x + row0 * I;
-      const int n = nr * I, n4 = vec ? (n & ~3) : 0;
-      int e = tid * 4;
-      for (; e + 3 * 4 * kDuxThreads < n4; e += 4 * 4 * kDuxThreads) {
-        float4 v[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(src + e + u * 4 * kDuxThreads));
-#pragma unroll
-        for (int u = 0; u < 4; ++u) *reinterpret_cast<float4*>(xs + e + u * 4 * kDuxThreads) = v[u];
-      }
-      for (; e < n4; e += 4 * kDuxThreads) *reinterpret_cast<float4*>(xs + e) = __ldg(reinterpret_cast<const float4*>(src + e));
-      for (int t1 = n4 + tid; t1 < n; t1 += kDuxThreads) xs[t1] = __ldg(src + t1);
-    } else {
-      for (int rr = warp; rr < nr; rr += kDuxThreads / 32) {
-        const long long row = row0 + rr, t = row / a.B, b = row % a.B;
-        const float* src = a.x + t * a.xs_t + b * a.xs_b;
-        for (int jj = lane; jj < I; jj += 32) xs[rr * I + jj] = __ldg(src + jj);
-      }
-    }
-    {                                                  // dzx rows: contiguous, zxp % 4 == 0
-      const float4* src = reinterpret_cast<const float4*>(a.dzx + row0 * zxp);
-      for (int e = tid; e < nr * NQ; e += kDuxThreads) reinterpret_cast<float4*>(ds)[e] = __ldg(src + e);
-    }
-    __syncthreads();
+  const long long step = (long long)gridDim.x * kDuxRows;
+
+  auto compute = [&](const float* xs, const float* ds, int nr) {
+    const int r0 = 32 * half, r1 = min(nr, r0 + 32);
 #pragma unroll
     for (int it = 0; it < kDuxItems; ++it) {
-      const int item = tid + it * kDuxThreads;
+      const int item = t7 + it * 128;
       if (item >= nitems) break;
       const int j = item / NQ, nq = item - j * NQ;
       float4 s = acc[it];
 #pragma unroll 4
-      for (int r = 0; r < nr; ++r) {
+      for (int r = r0; r < r1; ++r) {
         const float xv = xs[r * I + j];
         const float4 d = *reinterpret_cast<const float4*>(ds + r * zxp + 4 * nq);
         s.x = fmaf(xv, d.x, s.x); s.y = fmaf(xv, d.y, s.y); s.z = fmaf(xv, d.z, s.z); s.w = fmaf(xv, d.w, s.w);
       }
       acc[it] = s;
     }
+  };
+
+  if (a.stages >= 3) {
+    auto issue = [&](long long row0, int stage) {
+      if (row0 < nrows) {
+        const long long left = nrows - row0;
+        const int nr = (int)(left < kDuxRows ? left : kDuxRows);
+        float* xs = smem + (size_t)stage * stage_floats;
+        float* ds = xs + (size_t)kDuxRows * I;
+        const float* src = a.x + row0 * I;
+        const int n = nr * I, n4 = n & ~3;
+        for (int e = tid * 4; e < n4; e += 4 * kDuxThreads)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(xs + e)), "l"(src + e) : "memory");
+        for (int t1 = n4 + tid; t1 < n; t1 += kDuxThreads) xs[t1] = __ldg(src + t1);
+        const float* dsrc = a.dzx + row0 * zxp;
+        for (int e = tid * 4; e < nr * zxp; e += 4 * kDuxThreads)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(ds + e)), "l"(dsrc + e) : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    long long row0 = (long long)blockIdx.x * kDuxRows;
+    issue(row0, 0);
+    issue(row0 + step, 1);
+    for (int i = 0; row0 < nrows; ++i, row0 += step) {
+      issue(row0 + 2 * step, (i + 2) % 3);              // that stage was consumed in iteration i-1 (barrier below)
+      asm volatile("cp.async.wait_group 2;" ::: "memory");
+      __syncthreads();
+      const long long left = nrows - row0;
+      const float* xs = smem + (size_t)(i % 3) * stage_floats;
+      compute(xs, xs + (size_t)kDuxRows * I, (int)(left < kDuxRows ? left : kDuxRows));
+      __syncthreads();
+    }
+  } else {
+    float* xs = smem;
+    float* ds = smem + (size_t)kDuxRows * I;
+    for (long long row0 = (long long)blockIdx.x * kDuxRows; row0 < nrows; row0 += step) {
+      __syncthreads();
+      const long long left = nrows - row0;
+      const int nr = (int)(left < kDuxRows ? left : kDuxRows);
+      if (a.contiguous) {
+        const float* src = a.x + row0 * I;
+        for (int t1 = tid; t1 < nr * I; t1 += kDuxThreads) xs[t1] = __ldg(src + t1);
+      } else {
+        for (int rr = warp; rr < nr; rr += kDuxThreads / 32) {
+          const long long row = row0 + rr, t = row / a.B, b = row % a.B;
+          const float* src = a.x + t * a.xs_t + b * a.xs_b;
+          for (int jj = lane; jj < I; jj += 32) xs[rr * I + jj] = __ldg(src + jj);
+        }
+      }
+      {                                                  // dzx rows: contiguous, zxp % 4 == 0
+        const float4* src = reinterpret_cast<const float4*>(a.dzx + row0 * zxp);
+        for (int e = tid; e < nr * NQ; e += kDuxThreads) reinterpret_cast<float4*>(ds)[e] = __ldg(src + e);
+      }
+      __syncthreads();
+      compute(xs, ds, nr);
+    }
   }
-  float* out = a.pbuf + (size_t)blockIdx.x * I * zxp;
+  float* out = a.pbuf + ((size_t)blockIdx.x * 2 + half) * I * zxp;
 #pragma unroll
   for (int it = 0; it < kDuxItems; ++it) {
-    const int item = tid + it * kDuxThreads;
+    const int item = t7 + it * 128;
     if (item >= nitems) break;
     *reinterpret_cast<float4*>(out + (size_t)item * 4) = acc[it];            // item = j * NQ + nq  ->  offset j * zxp + 4 nq
   }
