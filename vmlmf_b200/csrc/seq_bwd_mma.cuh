@@ -423,7 +423,7 @@ __global__ void __launch_bounds__(NT_MAX, 1) grad_rows_kernel(const GradRowsArgs
           const float b0h = tf32_rna(b0), b1h = tf32_rna(b1);
           const float b0l = b0 - b0h, b1l = b1 - b1h;
 #pragma unroll
-          for (int m = 0; m < MT; ++m) mma_3x(accW[m][2 * k + X], ah[m], al[m], b0h, b1h, b0l, b1l);
+          for (int m = 0; m < MT; ++m) mma_3x_rn(accW[m][2 * k + X], ah[m], al[m], b0h, b1h, b0l, b1l);
         }
       // ---- Hprev^T dzc and X^T dzc: A = (m = g: pair element 0, m = g+8: element 1; k = row), B = dzc ----
       {
@@ -438,8 +438,8 @@ __global__ void __launch_bounds__(NT_MAX, 1) grad_rows_kernel(const GradRowsArgs
         for (int s = 0; s < KS; ++s) {
           const float b0h = tf32_rna(dzv[s][0]), b1h = tf32_rna(dzv[s][1]);
           const float b0l = dzv[s][0] - b0h, b1l = dzv[s][1] - b1h;
-          mma_3x(accG[s], hh, hl, b0h, b1h, b0l, b1l);
-          if (xcols) mma_3x(accU[s], xh, xl, b0h, b1h, b0l, b1l);
+          mma_3x_rn(accG[s], hh, hl, b0h, b1h, b0l, b1l);
+          if (xcols) mma_3x_rn(accU[s], xh, xl, b0h, b1h, b0l, b1l);
         }
       }
     }

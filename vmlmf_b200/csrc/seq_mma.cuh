@@ -53,6 +53,16 @@ __device__ __forceinline__ void mma_3x(float (&d)[4], const float (&ahi)[4], con
   mma_tf32(d, ahi, b0lo, b1lo);
   mma_tf32(d, ahi, b0hi, b1hi);
 }
+// For sums that run over many timesteps / tiles: the tensor core adds into its fp32 accumulator with truncation (~3e-8
+// relative per add, always toward zero), so a long-lived MMA accumulator drifts linearly with the number of adds.  Here the
+// three products go into a fresh accumulator and join the running sum with FADDs (round to nearest).
+__device__ __forceinline__ void mma_3x_rn(float (&sum)[4], const float (&ahi)[4], const float (&alo)[4], float b0hi,
+                                          float b1hi, float b0lo, float b1lo) {
+  float t[4] = {0.f, 0.f, 0.f, 0.f};
+  mma_3x(t, ahi, alo, b0hi, b1hi, b0lo, b1lo);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) sum[i] += t[i];
+}
 __device__ __forceinline__ void split4(const float (&v)[4], float (&hi)[4], float (&lo)[4]) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
