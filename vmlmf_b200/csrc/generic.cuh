@@ -328,6 +328,19 @@ inline int g_splits(int M, int N, long long K) {
   return (int)s;
 }
 constexpr int kColSplits = 64;
+// The tcgen05 accumulate truncates (~3e-8 relative per add): a K = T*B contraction kept in one accumulator set drifts
+// with its length (8e-6 at K = 196 608 with 32 splits, measured).  Splits for the time-parallel gradient GEMMs are
+// therefore also bounded below so that one split covers at most kTcMaxKPerSplit of K (<= 64 adds per accumulator),
+// within a 64 MB budget for the partials.
+constexpr long long kTcMaxKPerSplit = 1536;
+inline int tc_accuracy_splits(int M, int N, long long K) {
+  long long s = (K + kTcMaxKPerSplit - 1) / kTcMaxKPerSplit;
+  const long long cap = (64LL << 20) / ((long long)M * N * 4);
+  if (s > cap) s = cap;
+  if (s > 128) s = 128;
+  if (s < 1) s = 1;
+  return (int)s;
+}
 
 struct GenericSizes {
   int zxp, zp;
@@ -353,6 +366,10 @@ inline GenericSizes generic_sizes(int T, int B, int I, int H, int RX, int RH) {
   q = (long long)g_splits(4 * H, RX, rows) * 4 * H * RX; if (q > p) p = q;     // dVx
   q = (long long)g_splits(I, RX, rows) * I * RX; if (q > p) p = q;             // dUx
   q = (long long)kColSplits * (8 * H + 4 * I); if (q > p) p = q;               // column reductions
+  q = (long long)tc_accuracy_splits(4 * H, RH, rows) * 4 * H * RH; if (q > p) p = q;   // accuracy-driven splits (tensor-core path)
+  q = (long long)tc_accuracy_splits(4 * H, RX, rows) * 4 * H * RX; if (q > p) p = q;
+  q = (long long)tc_accuracy_splits(H, RH, rows) * H * RH; if (q > p) p = q;
+  q = (long long)tc_accuracy_splits(I, RX, rows) * I * RX; if (q > p) p = q;
   s.n_part = p;
   s.hp4 = round_up(H, 4);
   s.ip4 = round_up(I, 4);
@@ -478,6 +495,8 @@ inline int gemm_nt_public(const float* A, long long lda, const float* Bm, long l
                           cudaStream_t st) {
   if (!g_simt_only() && tc::encode_fn() && tc::tc_operand_ok(A, lda) && tc::tc_operand_ok(Bm, ldb)) {
     int splits = tc::tc_splits(M, N, K, 16);
+    const int acc_splits = tc_accuracy_splits(M, N, K);      // long contractions: bound the adds per accumulator
+    if (splits < acc_splits) splits = acc_splits;
     while (splits > 1 && (!part || (long long)splits * M * N > part_floats)) --splits;
     if (splits <= 1) return tc::gemm_tc(A, lda, Bm, ldb, M, N, K, tc::EpiBiasTC{C, ldc, bias, accumulate}, st);
     const int nkb = ceil_div(K, tc::BK), kbs = ceil_div(nkb, splits), nz = ceil_div(nkb, kbs);
@@ -654,6 +673,8 @@ inline int generic_seq_bwd(const vmlmf_plan* plan, const float* x, long long xs_
   // C[M,N] = At[M, rows] Bt[N, rows]^T, split over K with a fixed-order reduce into `out`
   auto tc_tn = [&](int M, int N, float* out) -> int {
     int splits = tc::tc_splits(M, N, (int)rows, 32);
+    const int acc_splits = tc_accuracy_splits(M, N, rows);
+    if (splits < acc_splits) splits = acc_splits;
     while (splits > 1 && (long long)splits * M * N > s.n_part) --splits;
     const int nkb = ceil_div((int)rows, tc::BK), kbs = ceil_div(nkb, splits), nz = ceil_div(nkb, kbs);
     int rc = tc::gemm_tc(tA, s.ldt, tB, s.ldt, M, N, (int)rows, tc::EpiPartialTC{part, M, N}, st, splits);

@@ -270,7 +270,11 @@ def gemm_nt(a, b, bias=None, out=None, accumulate=False):
     b2, ldb = _pad4(b)
     if out is None:
         out = a.new_empty((m, n))
-    ws = a.new_empty((min(16, max(1, -(-k // 128))) * m * n,)) if m * n <= (1 << 24) else None
+    # split-K partials: up to 16 splits to fill the SMs, more for long contractions (<= 1536 of K per split keeps the
+    # tensor core's truncating accumulate below 2e-6), within 64 MB
+    nsp = max(min(16, max(1, -(-k // 128))), min(128, -(-k // 1536)))
+    nsp = max(1, min(nsp, (1 << 24) // max(1, m * n)))
+    ws = a.new_empty((nsp * m * n,)) if m * n <= (1 << 24) else None
     with torch.cuda.device_of(a):
         st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         _lib.check(_lib.lib().vmlmf_gemm_nt(_ptr(a2), lda, _ptr(b2), ldb, _ptr(out), out.stride(0), _ptr(bias), m, n, k,
