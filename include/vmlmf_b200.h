@@ -125,7 +125,11 @@ int vmlmf_seq_fwd(const vmlmf_plan* plan, const float* x, long long xs_t, long l
  * gradient is formed.  dy (strides dys_t,dys_b), dhT, dcT may each be NULL (= zeros).
  * Outputs: dx (strides dxs_t,dxs_b; may be NULL), dh0,dc0 [B,H] (may be NULL) and the
  * canonical-parameter gradients dUx,dVx,dDx,dA,dBm,dDh,dbias (overwritten, not added).
- * The sum over CTAs is a fixed-order tree: results are bit-reproducible run to run.     */
+ * The sum over CTAs is a fixed-order tree: results are bit-reproducible run to run.
+ * workspace: plan.bwd_workspace_bytes (per-CTA gradient partials; on PATH_R1M also the
+ * dzx rows and the partials of the streaming dUx = X^T dZX pass that follows the
+ * recurrence kernel).  x is read twice on that path: keep it valid until the call's work
+ * on `stream` has finished, like every other argument.                                   */
 int vmlmf_seq_bwd(const vmlmf_plan* plan, const float* x, long long xs_t, long long xs_b,
                   const float* zx, const float* Ux, const float* Vx, const float* Dx,
                   const float* A, const float* Bm, const float* Dh,
