@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Error of the fused kernels against the fp64 numpy spec at a cfg2-shaped problem (warp-MMA regime forced).
-usage: python tools/precision_probe.py [B [RX RH]]   (ranks beyond 16 plan the generic regime)"""
+usage: python tools/precision_probe.py [B [RX RH [T I H]]]   (ranks beyond 16 or H > 256 plan the generic regime;
+       the LM layer is `512 300 300 35 650 650`)"""
 import os, sys
 import numpy as np
 import torch
@@ -10,11 +11,12 @@ from oracle import canonical_numpy as cn
 from vmlmf_b200.functional import vmlmf_sequence
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 512
-T, I, H = 24, 77, 256
+T, I, H = (int(sys.argv[4]), int(sys.argv[5]), int(sys.argv[6])) if len(sys.argv) > 6 else (24, 77, 256)
 RX = int(sys.argv[2]) if len(sys.argv) > 3 else 8
 RH = int(sys.argv[3]) if len(sys.argv) > 3 else 6
 rng = np.random.default_rng(0)
-f = lambda *s: (rng.standard_normal(s) * 0.1).astype(np.float32)
+scale = 0.03 if H > 256 else 0.1          # the LM initialises U(-0.05, 0.05)
+f = lambda *s: (rng.standard_normal(s) * scale).astype(np.float32)
 cp = dict(Ux=f(I, RX), Vx=f(4 * H, RX), Dx=f(4, I), A=f(H, RH), Bm=f(4 * H, RH), Dh=f(4, H), bias=f(4 * H))
 x = rng.standard_normal((T, B, I)).astype(np.float32)
 dy = rng.standard_normal((T, B, H)).astype(np.float32)
