@@ -169,3 +169,31 @@ def test_lm_group_layer_constructor_and_dispatch():
     assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == ref
     assert isinstance(vb.Model(50, 16, 1, 0.0, 0.1, w_rank=4, u_ranks=[2, 3], lstm_type="vmgroup").rnns[0], vb.MyVMLSTMGroup)
     assert isinstance(vb.Model(50, 16, 1, 0.0, 0.1, w_rank=4, u_ranks=[2, 3], lstm_type="vm_group").rnns[0], torch.nn.LSTM)
+
+
+def test_grad_bucket_pack_zero_semantics_single_process():
+    """GradBucket: live parameters found from the first backward, gradients gathered with one multi-tensor copy, `.grad`
+    re-pointed at the bucket slices, `zero()` drops them so the next backward needs no accumulation kernels."""
+    from vmlmf_b200.parallel import GradBucket
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(5, 3)
+    dead = torch.nn.Parameter(torch.randn(4))
+    mod = torch.nn.Module()
+    mod.lin, mod.dead = lin, dead
+    bucket = GradBucket(mod)
+    x = torch.randn(7, 5)
+    for it in range(3):
+        bucket.zero()
+        assert all(p.grad is None for p in mod.parameters())
+        lin(x).pow(2).sum().backward()
+        ref = [p.grad.clone() for p in lin.parameters()]
+        flat = bucket.all_reduce()                       # no process group: packs only
+        assert flat.numel() == 3 * 5 + 3 and dead.grad is None
+        off = 0
+        for p, r in zip(lin.parameters(), ref):
+            assert p.grad.data_ptr() == flat.data_ptr() + 4 * off          # .grad is the bucket slice
+            assert torch.equal(p.grad, r)
+            off += p.numel()
+    # accumulation across two backwards before a step still works (the second one adds into the slices)
+    lin(x).pow(2).sum().backward()
+    assert torch.allclose(bucket.pack()[:15].view(3, 5), 2 * ref[0])
