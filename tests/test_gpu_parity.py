@@ -148,6 +148,48 @@ def test_golden_lm_model():
     _check(g, m, outs, {})
 
 
+@pytest.mark.parametrize("B", [20, 64])
+def test_lm_model_cfg4_size_vs_cpu_oracle(B, monkeypatch, r1_path):
+    """BASELINE configs[3] at its real size: Model(10000, 650, 2, ., 0.05, 300, [300], "vmlmf"), bptt 35, carried non-zero
+    state, the LM loss (V/train_test/lm_test.py:140-153), every gradient against the CPU oracle
+    (V/models/vmlmf_lm.py:433-441).  Also asserts that the large-H recurrence path and the tensor-core head ran."""
+    if r1_path != "auto":
+        pytest.skip("the LM shapes do not depend on the R1 kernel choice")
+    from vmlmf_b200 import _lib, functional
+    T, V, H, R = 35, 10000, 650, 300
+    assert _lib.plan(T, B, H, H, R, R).path in _lib.LARGE_PATHS
+    calls = {"gemm": 0}
+    real_gemm = functional.gemm_nt
+
+    def counting_gemm(*a, **k):
+        calls["gemm"] += 1
+        return real_gemm(*a, **k)
+    monkeypatch.setattr(functional, "gemm_nt", counting_gemm)
+    torch.manual_seed(3)
+    m = vb.Model(V, H, 2, 0.0, 0.05, w_rank=R, u_ranks=[R], lstm_type="vmlmf")
+    g = torch.Generator().manual_seed(11)
+    tok = torch.randint(0, V, (T, B), generator=g)
+    y = torch.randint(0, V, (T, B), generator=g)
+    st = [(torch.randn(B, H, generator=g) * 0.3, torch.randn(B, H, generator=g) * 0.3) for _ in range(2)]
+    # CPU oracle
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    layers = [vo.split_state_dict(sd, f"rnns.{i}.") for i in range(2)]
+    so, new_o = vo.lm_model_forward(sd["embed.w"], layers, sd["fc.w"], sd["fc.b"], tok, [(h.clone(), c.clone()) for h, c in st])
+    vo.lm_nll_loss(so, y).backward()
+    # fused path
+    m = m.to(DEV)
+    sg, new_g = m(tok.to(DEV), [(h.to(DEV), c.to(DEV)) for h, c in st])
+    loss = vb.nll_loss(sg, y.to(DEV))
+    loss.backward()
+    assert calls["gemm"] >= 3, "the vocabulary projection must run on the tcgen05 GEMM (forward, dX, dW)"
+    assert_close(sg.detach().cpu().numpy(), so.detach().numpy(), TOL, "scores")
+    for l in range(2):
+        assert_close(new_g[l][0].detach().cpu().numpy(), new_o[l][0].detach().numpy(), TOL, f"hT{l}")
+        assert_close(new_g[l][1].detach().cpu().numpy(), new_o[l][1].detach().numpy(), TOL, f"cT{l}")
+    for k, p in m.named_parameters():
+        assert_close(p.grad.cpu().numpy(), sd[k].grad.numpy(), TOL, f"grad {k}")
+
+
 # ------------------ (b) canonical kernels vs the numpy spec, ragged shapes ------------------ #
 
 def _rand_canon(rng, I, H, RX, RH, scale=0.3):
@@ -210,6 +252,11 @@ def test_canonical_kernels_vs_numpy_spec(T, B, I, H, RX, RH, bf, state, scale=0.
     (4, 20, 650, 650, 300, 300, False, True),    # the LM layer at the reference's batch of 20
     (3, 32, 10, 42, 17, 23, True, False),        # small batch, nothing aligned to 4 (operands that miss the TMA constraints)
     (2, 1, 24, 24, 20, 20, False, True),         # a single sequence
+    # BASELINE configs[4] (scaling sweep: hidden 1024-4096, rank 16-256) at oracle-sized batches
+    (3, 130, 9, 1024, 64, 64, True, True),       # ragged 128-row batch tile
+    (2, 64, 9, 2048, 16, 16, True, False),
+    (2, 32, 9, 4096, 256, 256, True, True),
+    (3, 200, 77, 256, 32, 32, True, False),      # BASELINE configs[1] at ranks 32/32 (beyond the register-resident regime)
 ])
 def test_generic_regime_vs_numpy_spec(T, B, I, H, RX, RH, bf, state, gemm, monkeypatch, r1_path):
     """Regime G (time-parallel XP GEMM + per-step GEMMs): with the tcgen05/TMA 3xTF32 GEMM and with the SIMT GEMM."""
@@ -218,10 +265,11 @@ def test_generic_regime_vs_numpy_spec(T, B, I, H, RX, RH, bf, state, gemm, monke
         pytest.skip("regime G does not depend on the R1 kernel choice")
     if gemm == "simt":
         monkeypatch.setenv("VMLMF_G_SIMT", "1")
-    assert _lib.plan(T, B, I, H, RX, RH).path == _lib.PATH_G
+    assert _lib.plan(T, B, I, H, RX, RH).path in _lib.LARGE_PATHS
     # the LM initialises U(-0.05, 0.05) (V/train_test/lm_test.py:57); 0.3-scale factors at H = 650 would drive every
     # pre-activation to |40| and make the comparison a test of saturation, not of the kernels
-    test_canonical_kernels_vs_numpy_spec(T, B, I, H, RX, RH, bf, state, scale=0.05 if H >= 300 else 0.3)
+    # the reference initialises 0.1 * randn (V/models/vmlmf.py:56-69); 0.3 at I = 77, ranks 32 saturates the same way
+    test_canonical_kernels_vs_numpy_spec(T, B, I, H, RX, RH, bf, state, scale=0.05 if H >= 300 else (0.1 if I >= 64 else 0.3))
 
 
 def test_inference_mode_matches_training_forward_and_noncontiguous_upstream():
@@ -259,6 +307,8 @@ def _oracle_net(net_cpu_sd, x, label, kind="plain"):
     ("cfg1", lambda: vb.Net(9, [128], w_rank=8, u_rank=[6], cell=vb.MyVMLMFCell), (64, 128, 9), 6, "plain"),
     ("cfg2", lambda: vb.Net(77, [256], w_rank=8, u_rank=[6], cell=vb.MyVMLMFCell), (81, 24, 77), 18, "plain"),
     ("cfg3", lambda: vb.Net(9, [128], w_rank=8, u_rank=[2, 4], cell=vb.MyVMLMFCellg2), (96, 128, 9), 6, "group"),
+    # large enough for `auto` to plan the warp-MMA kernels: the backward cfg3 really takes at its bench batch of 8192
+    ("cfg3_b1600", lambda: vb.Net(9, [128], w_rank=8, u_rank=[2, 4], cell=vb.MyVMLMFCellg2), (1600, 128, 9), 6, "group"),
 ])
 def test_benchmark_configs_vs_cpu_oracle(name, build, shape, classes, kind):
     torch.manual_seed(3)                                   # demo.sh seed

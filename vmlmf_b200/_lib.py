@@ -12,7 +12,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvmlmf_b200.so")
 ABI_VERSION = 3
 
-PATH_R1, PATH_G, PATH_R1M = 1, 2, 3
+PATH_R1, PATH_G, PATH_R1M, PATH_R2 = 1, 2, 3, 4
+LARGE_PATHS = (PATH_G, PATH_R2)      # regimes for shapes beyond the register-resident kernels
 
 
 class Plan(C.Structure):

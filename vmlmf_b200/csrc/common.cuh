@@ -94,4 +94,31 @@ __device__ __forceinline__ int warp_multi_reduce_index(int lane) {
 
 __device__ __forceinline__ float ldg_f(const float* p) { return __ldg(p); }
 
+// ---- host side: per-DEVICE caches.  Function attributes (cudaFuncSetAttribute), occupancy and the SM count belong
+// to a device, not to the process: a process that uses several GPUs (torch.cuda.device_of) must set / query them once
+// per device.  Benign races throughout: every writer stores the same value.
+constexpr int kMaxDevices = 64;
+inline int device_slot() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess) { (void)cudaGetLastError(); return kMaxDevices; }   // no device: shared slot
+  return (d >= 0 && d < kMaxDevices) ? d : kMaxDevices;
+}
+struct PerDevice {
+  int v[kMaxDevices + 1] = {0};
+  int& cur() { return v[device_slot()]; }
+};
+inline int num_sms() {
+  static PerDevice cache;
+  int& n = cache.cur();
+  if (n == 0) {
+    int d = 0, q = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || cudaDeviceGetAttribute(&q, cudaDevAttrMultiProcessorCount, d) != cudaSuccess || q <= 0) {
+      (void)cudaGetLastError();
+      q = 148;                                         // B200; also what vmlmf_seq_plan assumes when no device is visible
+    }
+    n = q;
+  }
+  return n;
+}
+
 }  // namespace vmlmf

@@ -446,7 +446,7 @@ inline bool tc_operand_ok(const float* p, long long ld) {
 inline int tc_splits(int M, int N, int K, int max_splits) {
   const long long tiles = (long long)ceil_div(M, BM) * ceil_div(N, BN);
   const int nkb = ceil_div(K, BK);
-  long long s = (148 + tiles - 1) / tiles;
+  long long s = (num_sms() + tiles - 1) / tiles;
   if (s > nkb / 4) s = nkb / 4;                      // keep at least 4 k-blocks per split
   if (s > max_splits) s = max_splits;
   if (s < 1) s = 1;
@@ -464,11 +464,12 @@ inline int gemm_tc(const float* A, long long lda, const float* Bm, long long ldb
   rc = Epi::kGate ? make_map_gate3d(&mb, Bm, N / 4, K, ldb) : make_map_2d(&mb, Bm, N, K, ldb);
   if (rc) return rc;
   auto kern = gemm_tc_kernel<Epi>;
-  static bool attr = false;
+  static PerDevice attr_pd;                            // one flag per (epilogue instantiation, device)
+  int& attr = attr_pd.cur();
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e != cudaSuccess) return (int)e;
-    attr = true;
+    attr = 1;
   }
   const int ntn = Epi::kGate ? ceil_div(N / 4, 32) : ceil_div(N, BN);
   const int nkb = ceil_div(K, BK);

@@ -320,7 +320,7 @@ static __global__ void colreduce_final_kernel(const float* __restrict__ part, in
 // --------------------------------------------------------------------------------------------- //
 inline int g_splits(int M, int N, long long K) {
   const long long tiles = (long long)ceil_div(M, GBM) * ceil_div(N, GBN);
-  long long s = (2LL * 148 + tiles - 1) / tiles;
+  long long s = (2LL * num_sms() + tiles - 1) / tiles;
   const long long kmax = (K + 255) / 256;
   if (s > kmax) s = kmax;
   if (s > 128) s = 128;

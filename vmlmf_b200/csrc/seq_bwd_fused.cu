@@ -23,7 +23,7 @@ int occ_of(int NW, int KS, int I, int RX) {
   return occ < 1 ? 1 : occ;
 }
 int grid_of(int B, int NW, int KS, int I, int RX) {
-  const int nt = ceil_div(B, 16), cap = kNumSMs * occ_of(NW, KS, I, RX);
+  const int nt = ceil_div(B, 16), cap = num_sms() * occ_of(NW, KS, I, RX);
   return nt < cap ? nt : cap;
 }
 }  // namespace
@@ -38,7 +38,7 @@ bool bwd_fused_fits(int I, int H, int RX, int RH) {
 // blocks of dux_rows_kernel: at most three per SM (three pipeline stages of shared memory each); two partials per block
 int dux_grid(int T, int B) {
   const long long tiles = ((long long)T * B + kDuxRows - 1) / kDuxRows;
-  return (int)(tiles < 3LL * kNumSMs ? tiles : 3LL * kNumSMs);
+  return (int)(tiles < 3LL * num_sms() ? tiles : 3LL * num_sms());
 }
 
 // workspace: [per-CTA gradient partials | dzx rows | per-block dUx partials], each part a multiple of 4 floats
@@ -54,11 +54,12 @@ template <int KS, int NZ>
 static int launch_t(const SeqBwdFusedArgs& a, int NW, int G, cudaStream_t st) {
   auto kern = seq_bwd_fused_kernel<KS, NZ>;
   const size_t smem = seq_bwd_fused_smem_bytes(NW, KS, a.I, a.RX);
-  static bool attr_done = false;                        // benign race
+  static PerDevice attr;                                // the attribute is per device
+  int& attr_done = attr.cur();
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return (int)e;
-    attr_done = true;
+    attr_done = 1;
   }
   kern<<<G, NW * 32, smem, st>>>(a, tmem_cols_of(NW));
   return (int)cudaGetLastError();
@@ -90,11 +91,12 @@ int launch_bwd_fused(const SeqBwdFusedArgs& a0, const GradOut& out, void* worksp
                          3 * (kDuxStages * stage_bytes + 1024) <= 227 * 1024;
   const size_t dsm = (pipelined ? kDuxStages : 1) * stage_bytes;
   DuxArgs d{a0.x, a0.xs_t, a0.xs_b, a.dzc, pbuf, a0.T, a0.B, a0.I, zxp, (x_bt || x_tb) ? 1 : 0, pipelined ? kDuxStages : 1};
-  static bool dux_attr = false;                         // benign race
+  static PerDevice dux_attr_pd;
+  int& dux_attr = dux_attr_pd.cur();
   if (!dux_attr) {
     cudaError_t e = cudaFuncSetAttribute(dux_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return (int)e;
-    dux_attr = true;
+    dux_attr = 1;
   }
   dux_rows_kernel<<<GX, kDuxThreads, dsm, st>>>(d);
   dux_reduce_kernel<<<ceil_div(a0.I * a0.RX, 4), 256, 0, st>>>(pbuf, 2 * GX, a0.I, a0.RX, zxp, out.dUx);

@@ -8,7 +8,7 @@ namespace {
 struct Shape { int KS, NZ, NW; };
 Shape shape_of(int H, int RX, int RH) { return Shape{ceil_div(RH + RX + 1, 8), ceil_div(RH, 8), ceil_div(H, 16)}; }
 long long n_blocks(int T, int B) { return (long long)T * ceil_div(B, 16); }
-int grad_ctas(long long blocks) { return (int)(blocks < kNumSMs ? blocks : kNumSMs); }
+int grad_ctas(long long blocks) { return (int)(blocks < num_sms() ? blocks : num_sms()); }
 }  // namespace
 
 bool bwd_mma_fits(int I, int H, int RX, int RH) {
@@ -32,14 +32,15 @@ template <int KS, int NZ>
 static int launch_a(const SeqBwdMmaArgs& a, int NW, cudaStream_t st) {
   auto kern = seq_bwd_mma_kernel<KS, NZ>;
   const size_t smem = seq_bwd_mma_smem_bytes(NW, KS);
-  static bool attr_done = false;                        // benign race
+  static PerDevice attr;                                // the attribute is per device
+  int& attr_done = attr.cur();
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return (int)e;
-    attr_done = true;
+    attr_done = 1;
   }
   const int ntiles = ceil_div(a.B, 16);
-  const int grid = ntiles < kNumSMs ? ntiles : kNumSMs;
+  const int grid = ntiles < num_sms() ? ntiles : num_sms();
   kern<<<grid, NW * 32, smem, st>>>(a);
   return (int)cudaGetLastError();
 }
@@ -48,11 +49,12 @@ template <int KS, int NT_MAX>
 static int launch_b_t(const GradRowsArgs& g, int NW, int grid, cudaStream_t st) {
   auto kern = grad_rows_kernel<KS, NT_MAX>;
   const size_t smem = grad_rows_smem_bytes(KS, g.I, g.RX);
-  static bool attr_done = false;
+  static PerDevice attr;
+  int& attr_done = attr.cur();
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return (int)e;
-    attr_done = true;
+    attr_done = 1;
   }
   kern<<<grid, NW * 32, smem, st>>>(g);
   return (int)cudaGetLastError();

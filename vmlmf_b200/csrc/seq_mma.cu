@@ -12,18 +12,19 @@ static int launch_fwd_mma_t(const SeqFwdMmaArgs& a, bool save, cudaStream_t st) 
   auto go = [&](auto kern, int variant) -> int {
     // attribute + occupancy are per (instantiation, NW): cached so a launch costs one driver call
     // (benign race: every thread computes the same values)
-    static int occ_cache[2][17] = {{0}};             // [variant][NW]: the two variants share one pointer type
-    int occ = occ_cache[variant][NW];
+    static PerDevice occ_cache[2][17];               // [variant][NW], per device: the two variants share one pointer type
+    int& slot = occ_cache[variant][NW].cur();
+    int occ = slot;
     if (occ == 0) {
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       if (e != cudaSuccess) return (int)e;
       e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NW * 32, smem);
       if (e != cudaSuccess) return (int)e;
       if (occ < 1) occ = 1;
-      occ_cache[variant][NW] = occ;
+      slot = occ;
     }
     const int ntiles = ceil_div(a.s.B, 16);
-    const int grid = ntiles < kNumSMs * occ ? ntiles : kNumSMs * occ;
+    const int grid = ntiles < num_sms() * occ ? ntiles : num_sms() * occ;
     kern<<<grid, NW * 32, smem, st>>>(a);
     return (int)cudaGetLastError();
   };

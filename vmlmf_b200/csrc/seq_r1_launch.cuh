@@ -5,7 +5,6 @@
 
 namespace vmlmf {
 
-constexpr int kNumSMs = 148;          // B200
 constexpr int kFwdBT = 4;             // sequences per CTA tile, forward
 constexpr int kBwdBT = 2;             // sequences per CTA tile, backward
 constexpr int kMaxCtasPerSM = 4;      // cap used to size the backward partial workspace
@@ -26,15 +25,16 @@ int launch_fwd_r1(const SeqFwdArgs& a, bool save, cudaStream_t st) {
   const int smem = r1_fwd_smem_bytes(RH_T, RX_T, NT);
   const int ntiles = ceil_div(a.B, kFwdBT);
   auto go = [&](auto kern, int variant) -> int {
-    static int occ_cache[2][9] = {{0}};                 // [variant][NT/32]; benign race
-    int occ = occ_cache[variant][NT / 32];
+    static PerDevice occ_cache[2][9];                   // [variant][NT/32], per device
+    int& slot = occ_cache[variant][NT / 32].cur();
+    int occ = slot;
     if (occ == 0) {
       cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem);
       if (e != cudaSuccess) return (int)e;
       if (occ < 1) occ = 1;
-      occ_cache[variant][NT / 32] = occ;
+      slot = occ;
     }
-    const int grid = ntiles < kNumSMs * occ ? ntiles : kNumSMs * occ;
+    const int grid = ntiles < num_sms() * occ ? ntiles : num_sms() * occ;
     kern<<<grid, NT, smem, st>>>(a);
     return (int)cudaGetLastError();
   };
@@ -48,17 +48,18 @@ int launch_bwd_r1(const SeqBwdArgs& a, const GradOut& out, cudaStream_t st) {
   const int smem = r1_bwd_smem_bytes(RH_T, RX_T, NT);
   const int ntiles = ceil_div(a.B, kBwdBT);
   auto kern = seq_bwd_r1_kernel<RH_T, RX_T, kBwdBT, 256, 1>;
-  static int occ_cache[9] = {0};
-  int occ = occ_cache[NT / 32];
+  static PerDevice occ_cache[9];
+  int& slot = occ_cache[NT / 32].cur();
+  int occ = slot;
   cudaError_t e;
   if (occ == 0) {
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem);
     if (e != cudaSuccess) return (int)e;
     if (occ < 1) occ = 1;
     if (occ > kMaxCtasPerSM) occ = kMaxCtasPerSM;
-    occ_cache[NT / 32] = occ;
+    slot = occ;
   }
-  const int grid = ntiles < kNumSMs * occ ? ntiles : kNumSMs * occ;
+  const int grid = ntiles < num_sms() * occ ? ntiles : num_sms() * occ;
   kern<<<grid, NT, smem, st>>>(a);
   e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;

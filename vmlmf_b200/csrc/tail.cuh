@@ -72,7 +72,8 @@ softmax_nll_fwd_kernel(const float* __restrict__ scores, long long ld, const lon
       if (lane == 0) {
         const float l = a.m + logf(a.s);
         lse[r] = l;
-        my_loss = l - __ldg(row + labels[r]);
+        const long long y = labels[r];
+        my_loss = (y >= 0 && y < C) ? l - __ldg(row + y) : __int_as_float(0x7fc00000);   // out-of-range label: NaN loss, no stray read
       }
     }
     const float t = block_sum_256(lane == 0 ? my_loss : 0.f, red);
@@ -101,7 +102,8 @@ softmax_nll_fwd_kernel(const float* __restrict__ scores, long long ld, const lon
       for (int w = 1; w < 8; ++w) t = ms_merge(t, wms[w]);
       const float l = t.m + logf(t.s);
       lse[r] = l;
-      partials[r] = l - __ldg(row + labels[r]);
+      const long long y = labels[r];
+      partials[r] = (y >= 0 && y < C) ? l - __ldg(row + y) : __int_as_float(0x7fc00000);
     }
   }
 }

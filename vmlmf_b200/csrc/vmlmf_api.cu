@@ -52,6 +52,12 @@ int mma_min_batch() {
   return e ? atoi(e) : kMmaMinBatch;
 }
 
+// any of the (nullable) [B,H] state pointers not 8-byte aligned (the warp-MMA kernels move them as float2)
+bool misaligned8(const void* a, const void* b, const void* c, const void* d, const void* e, const void* f) {
+  return ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c) |
+           reinterpret_cast<uintptr_t>(d) | reinterpret_cast<uintptr_t>(e) | reinterpret_cast<uintptr_t>(f)) & 7) != 0;
+}
+
 int check_dims(int T, int B, int I, int H, int RX, int RH) {
   if (T <= 0 || B <= 0 || I <= 0 || H <= 0 || RX <= 0 || RH <= 0) return VMLMF_EINVAL;
   if (H < I) return VMLMF_ESHAPE;
@@ -95,8 +101,10 @@ int vmlmf_seq_plan(int T, int B, int I, int H, int RX, int RH, vmlmf_plan* plan)
     plan->gates_bytes = (long long)frag_floats(T, B, H, 4) * (long long)sizeof(float);
     plan->cs_bytes = (long long)frag_floats(T, B, H, 1) * (long long)sizeof(float);
     plan->bwd_workspace_bytes = bwd_mma_workspace_floats(T, B, I, H, RX, RH) * (long long)sizeof(float);
-    if (use_fused_bwd(I, H, RX, RH))        // fused backward: no dPre buffer, only the reduced dzc rows and the partials
+    if (use_fused_bwd(I, H, RX, RH)) {      // fused backward: no dPre buffer, only the reduced dzc rows and the partials
       plan->bwd_workspace_bytes = bwd_fused_workspace_floats(T, B, I, H, RX, RH) * (long long)sizeof(float);
+      plan->reserved[2] = 1;                // the backward variant is fixed here: the workspace was sized for it
+    }
     return VMLMF_OK;
   }
   const R1Choice c = choose_r1(I, H, RX, RH);
@@ -108,7 +116,7 @@ int vmlmf_seq_plan(int T, int B, int I, int H, int RX, int RH, vmlmf_plan* plan)
     plan->fwd_workspace_bytes = 0;
     const GradLayout L(I, H, RX, RH);
     const long long ntiles = ceil_div(B, kBwdBT);
-    const long long cap = (long long)kNumSMs * kMaxCtasPerSM;
+    const long long cap = (long long)num_sms() * kMaxCtasPerSM;
     plan->bwd_workspace_bytes = (ntiles < cap ? ntiles : cap) * L.total * (long long)sizeof(float);
     plan->reserved[0] = c.rh_t;
     plan->reserved[1] = c.rx_t;
@@ -179,25 +187,26 @@ int vmlmf_xproj_fwd(const float* x, long long xs_t, long long xs_b, const float*
     // three tiles in flight per block when the input is one contiguous block and three blocks still fit an SM
     const int stages = (order != 0 && 3 * (uf_bytes + 3 * tile_bytes + 1024) <= 227 * 1024) ? 3 : 1;
     const size_t smem = uf_bytes + stages * tile_bytes;
-    static bool attr_done = false;                        // benign race
+    static PerDevice attr;                                // the attribute is per device
+    int& attr_done = attr.cur();
     if (!attr_done) {
       cudaError_t e = cudaFuncSetAttribute(xproj_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       if (e != cudaSuccess) return (int)e;
-      attr_done = true;
+      attr_done = 1;
     }
     const long long nrows = (long long)T * B;
     long long grid = (nrows + kXprojRows - 1) / kXprojRows;
     // resident blocks per SM: one wave, every block walks its share.  The query is a driver call: cached per
     // shared-memory size (256-byte buckets; a benign race, every writer stores the same value)
-    static int occ_cache[1024] = {0};
-    int& occ_slot = occ_cache[smem / 256 < 1023 ? smem / 256 : 1023];
+    static PerDevice occ_cache[1024];
+    int& occ_slot = occ_cache[smem / 256 < 1023 ? smem / 256 : 1023].cur();
     if (occ_slot == 0) {
       int q = 1;
       if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, xproj_small_kernel, 128, smem) != cudaSuccess || q < 1) q = 1;
       occ_slot = q;
     }
     const int occ = occ_slot;
-    if (grid > (long long)kNumSMs * occ) grid = (long long)kNumSMs * occ;
+    if (grid > (long long)num_sms() * occ) grid = (long long)num_sms() * occ;
     xproj_small_kernel<<<(int)grid, 128, smem, st>>>(x, xs_t, xs_b, Ux, zx, T, B, I, RX, zx_pitch, order, stages);
     return (int)cudaGetLastError();
   }
@@ -234,6 +243,7 @@ int vmlmf_seq_fwd(const vmlmf_plan* plan, const float* x, long long xs_t, long l
     if (!fwd_mma_fits(I, H, RX, RH) || plan->z_pitch != 8 * ceil_div(RH, 8) || plan->zx_pitch != round_up(RX, 4))
       return VMLMF_EPLAN;
     if ((ys_t & 1) || (ys_b & 1) || (reinterpret_cast<uintptr_t>(y) & 7)) return VMLMF_EINVAL;
+    if (misaligned8(h0, c0, hT, cT, nullptr, nullptr)) return VMLMF_EINVAL;   // read / written as float2
     SeqFwdArgs a{x, xs_t, xs_b, zx, Vx, Dx, A, Bm, Dh, bias, h0, c0, y, ys_t, ys_b, hT, cT, gates, cs, z,
                  T, B, I, H, RX, RH};
     return launch_fwd_mma(SeqFwdMmaArgs{a, plan->z_pitch, plan->zx_pitch}, save, st);
@@ -276,7 +286,9 @@ int vmlmf_seq_bwd(const vmlmf_plan* plan, const float* x, long long xs_t, long l
       return VMLMF_EPLAN;
     if ((ys_t & 1) || (ys_b & 1) || (reinterpret_cast<uintptr_t>(y) & 7)) return VMLMF_EINVAL;
     GradOut o2{dUx, dVx, dDx, dA, dBm, dDh, dbias};
-    if (use_fused_bwd(I, H, RX, RH)) {
+    if (misaligned8(h0, c0, dhT, dcT, dh0, dc0)) return VMLMF_EINVAL;      // read / written as float2
+    if (plan->reserved[2] == 1) {
+      if (!bwd_fused_fits(I, H, RX, RH)) return VMLMF_EPLAN;
       // fused: recurrence + weight-gradient accumulation (accumulators in tensor memory) + dX; then dA / dUx
       SeqBwdFusedArgs fa{gates, cs, c0, dy, dys_t, dys_b, dhT, dcT, Ux, Vx, Dx, A, Bm, Dh, x, xs_t, xs_b, y, ys_t, ys_b, h0,
                          z, zx, plan->z_pitch, plan->zx_pitch, nullptr, 0, dx, dxs_t, dxs_b, dh0, dc0, nullptr, T, B, I, H, RX, RH};
@@ -340,7 +352,7 @@ int vmlmf_softmax_nll_bwd(const float* scores, long long ld, const long long* la
 namespace {
 inline int head_np(int N) { return N <= 8 ? 8 : (N <= 16 ? 16 : 32); }
 inline int head_rows_per_block(int B) {
-  const int r = ceil_div(B, 2 * kNumSMs);
+  const int r = ceil_div(B, 2 * num_sms());
   return r < 8 ? 8 : (r > 256 ? 256 : r);
 }
 }  // namespace
@@ -353,7 +365,7 @@ int vmlmf_head_fwd(const float* h, long long ldh, const float* W, const float* b
   const int NP = head_np(N);
   const size_t smem = (size_t)NP * K * sizeof(float);
   int grid = ceil_div(ceil_div(B, 2), kTailThreads / 32);
-  if (grid > 2 * kNumSMs) grid = 2 * kNumSMs;
+  if (grid > 2 * num_sms()) grid = 2 * num_sms();
 #define VMLMF_HEAD_FWD(NP_)                                                                                          \
   {                                                                                                                  \
     if (smem > 48 * 1024) {                                                                                          \

@@ -46,6 +46,15 @@ def _row_contig(t):
     return t if t.stride(-1) == 1 else t.contiguous()
 
 
+def _state(t):
+    """contiguous [B,H] state / state-gradient tensor whose base is 16-byte aligned (the kernels move float2 / float4);
+    a contiguous view that starts at an odd float offset is copied."""
+    if t is None:
+        return None
+    t = t.contiguous()
+    return t if t.data_ptr() % 16 == 0 else t.clone()
+
+
 def _tb_strides(t, batch_first):
     """(time stride, batch stride) in elements of a [B,T,F] / [T,B,F] tensor"""
     return (t.stride(1), t.stride(0)) if batch_first else (t.stride(0), t.stride(1))
@@ -71,8 +80,7 @@ def _seq_forward(x, h0, c0, canon, batch_first, need_grad, need_y):
         T, B, I = x.shape
     H, RH = A.shape
     RX = Ux.shape[1]
-    h0 = None if h0 is None else h0.contiguous()
-    c0 = None if c0 is None else c0.contiguous()
+    h0, c0 = _state(h0), _state(c0)
     plan = _lib.plan(T, B, I, H, RX, RH)
     lib = _lib.lib()
     new = x.new_empty
@@ -115,8 +123,7 @@ def _seq_backward(tensors, plan, batch_first, dims, dy, dhT, dcT, need_dx, need_
     lib = _lib.lib()
     new = x.new_empty
     dy = None if dy is None else _row_contig(dy)
-    dhT = None if dhT is None else dhT.contiguous()
-    dcT = None if dcT is None else dcT.contiguous()
+    dhT, dcT = _state(dhT), _state(dcT)
     dx = torch.empty_like(x, memory_format=torch.contiguous_format) if need_dx else None
     dh0 = new((B, H)) if (h0 is not None and need_dh0) else None
     dc0 = new((B, H)) if (c0 is not None and need_dc0) else None
