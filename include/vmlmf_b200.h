@@ -49,8 +49,11 @@ enum {
 enum {
   VMLMF_PATH_R1 = 1,  /* persistent SIMT, factors register-resident, thread = hidden unit      */
   VMLMF_PATH_G = 2,   /* generic: time-parallel XP GEMM + one fused launch per timestep        */
-  VMLMF_PATH_R1M = 3  /* persistent warp-MMA (mma.sync 3xTF32) recurrence, CTA = 16 sequences;
+  VMLMF_PATH_R1M = 3, /* persistent warp-MMA (mma.sync 3xTF32) recurrence, CTA = 16 sequences;
                          needs H % 4 == 0, H <= 256, RH <= 16, RH + RX + 1 <= 32               */
+  VMLMF_PATH_R2 = 4   /* persistent tcgen05 recurrence for every other shape (large H, high ranks):
+                         a thread-block cluster owns a 128-sequence tile for all T steps, the hidden
+                         units are split over the cluster's CTAs, operands arrive as TMA tiles     */
 };
 
 typedef struct vmlmf_plan {

@@ -37,7 +37,7 @@ def test_plan_and_error_codes():
     p = _lib.plan(24, 8200, 77, 180, 8, 16)                                # more than 16 contraction rows: split backward
     assert p.path == _lib.PATH_R1M and p.bwd_workspace_bytes >= p.gates_bytes
     assert _lib.plan(24, 8200, 77, 181, 8, 6).path == _lib.PATH_R1          # H % 4 != 0 stays on the SIMT kernels
-    assert _lib.plan(35, 4096, 650, 650, 300, 300).path == _lib.PATH_G
+    assert _lib.plan(35, 4096, 650, 650, 300, 300).path in _lib.LARGE_PATHS   # R2 on a GPU box, G without a driver
     with pytest.raises(TypeError):                       # H < I: the reference raises TypeError too
         _lib.plan(4, 2, 20, 10, 4, 4)
     with pytest.raises(RuntimeError):

@@ -1,0 +1,28 @@
+// seq_r2_host.cuh -- host interface of regime R2 (implemented in seq_r2.cu, device code in seq_r2.cuh).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace vmlmf {
+namespace r2 {
+
+// geometry of one call: cluster size, hidden slice per CTA, padded sizes, workspace offsets (in floats)
+struct Geom {
+  int ntiles, CS, HS, Hp, zp, zxp, RHr, KZP, KXP, KPp, ncl;
+  long long o_hop_hi, o_hop_lo, o_zop_hi, o_zop_lo, o_zpart, o_zx_hi, o_zx_lo, o_at_hi, o_at_lo, o_w2_hi, o_w2_lo, o_cbuf;
+  long long fwd_floats;
+};
+Geom geom(int T, int B, int I, int H, int RX, int RH);
+bool fits(int T, int B, int I, int H, int RX, int RH);
+
+struct FwdCall {
+  const float* x; long long xs_t, xs_b;
+  const float* zx;                                   // [T*B, zxp]
+  const float *Vx, *Dx, *A, *Bm, *Dh, *bias, *h0, *c0;
+  float* y; long long ys_t, ys_b;
+  float *hT, *cT, *gates, *cs, *z;
+  int T, B, I, H, RX, RH;
+};
+int launch_fwd(const FwdCall& c, void* workspace, cudaStream_t st);
+
+}  // namespace r2
+}  // namespace vmlmf

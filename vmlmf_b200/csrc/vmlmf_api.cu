@@ -10,6 +10,7 @@
 #include "seq_bwd_mma.cuh"
 #include "seq_mma.cuh"
 #include "seq_r1_launch.cuh"
+#include "seq_r2_host.cuh"
 #include "tail.cuh"
 #include "xproj.cuh"
 
@@ -122,7 +123,16 @@ int vmlmf_seq_plan(int T, int B, int I, int H, int RX, int RH, vmlmf_plan* plan)
     plan->reserved[1] = c.rx_t;
     return VMLMF_OK;
   }
-  return generic_plan(T, B, I, H, RX, RH, plan);
+  const int grc = generic_plan(T, B, I, H, RX, RH, plan);
+  if (grc) return grc;
+  // beyond the register-resident kernels: the persistent tcgen05 recurrence (one launch for all T steps) when TMA is
+  // available; the launch-per-timestep generic regime otherwise.  Pitches and the saved-state layouts are shared.
+  if (r2::fits(T, B, I, H, RX, RH)) {
+    plan->path = VMLMF_PATH_R2;
+    plan->xp_cols = 0;
+    plan->fwd_workspace_bytes = (r2::geom(T, B, I, H, RX, RH).fwd_floats + 64) * (long long)sizeof(float);
+  }
+  return VMLMF_OK;
 }
 
 int vmlmf_diag_fwd(const float* u, const float* v, const float* dia, float* D, int n, int H, int R, void* stream) {
@@ -225,7 +235,7 @@ int vmlmf_seq_fwd(const vmlmf_plan* plan, const float* x, long long xs_t, long l
   if (save && !(gates && cs && z)) return VMLMF_EINVAL;
   // y may be null for a last-step-only caller (V/models/vmlmf.py:354-355 reads y[:, -1] alone): inference on the
   // persistent kernels only -- backward and the generic regime read h_{t-1} back from y
-  if (!y && (save || plan->path == VMLMF_PATH_G)) return VMLMF_EINVAL;
+  if (!y && (save || plan->path == VMLMF_PATH_G || plan->path == VMLMF_PATH_R2)) return VMLMF_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
   if (plan->path == VMLMF_PATH_R1) {
     const R1Choice c = choose_r1(I, H, RX, RH);
@@ -247,6 +257,12 @@ int vmlmf_seq_fwd(const vmlmf_plan* plan, const float* x, long long xs_t, long l
     SeqFwdArgs a{x, xs_t, xs_b, zx, Vx, Dx, A, Bm, Dh, bias, h0, c0, y, ys_t, ys_b, hT, cT, gates, cs, z,
                  T, B, I, H, RX, RH};
     return launch_fwd_mma(SeqFwdMmaArgs{a, plan->z_pitch, plan->zx_pitch}, save, st);
+  }
+  if (plan->path == VMLMF_PATH_R2) {
+    if (!r2::fits(T, B, I, H, RX, RH) || plan->zx_pitch != round_up(RX, 4) || plan->z_pitch != round_up(RH, 4)) return VMLMF_EPLAN;
+    if (!workspace) return VMLMF_EWORKSPACE;
+    r2::FwdCall c{x, xs_t, xs_b, zx, Vx, Dx, A, Bm, Dh, bias, h0, c0, y, ys_t, ys_b, hT, cT, gates, cs, z, T, B, I, H, RX, RH};
+    return r2::launch_fwd(c, workspace, st);
   }
   if (plan->path == VMLMF_PATH_G)
     return generic_seq_fwd(plan, x, xs_t, xs_b, zx, Ux, Vx, Dx, A, Bm, Dh, bias, h0, c0, y, ys_t, ys_b, hT, cT,
@@ -302,7 +318,7 @@ int vmlmf_seq_bwd(const vmlmf_plan* plan, const float* x, long long xs_t, long l
     int nparts = 0;
     return launch_bwd_mma(ba, gr, o, workspace, &nparts, st);
   }
-  if (plan->path == VMLMF_PATH_G)
+  if (plan->path == VMLMF_PATH_G || plan->path == VMLMF_PATH_R2)
     return generic_seq_bwd(plan, x, xs_t, xs_b, zx, Ux, Vx, Dx, A, Bm, Dh, h0, c0, y, ys_t, ys_b, gates, cs, z,
                            dy, dys_t, dys_b, dhT, dcT, dx, dxs_t, dxs_b, dh0, dc0, dUx, dVx, dDx, dA, dBm, dDh,
                            dbias, workspace, T, B, I, H, RX, RH, st);

@@ -86,7 +86,7 @@ def _seq_forward(x, h0, c0, canon, batch_first, need_grad, need_y):
     new = x.new_empty
     # last-step-only callers (Net.forward) skip the [T,B,H] output when nothing reads it back: backward and the
     # generic regime take h_{t-1} from y
-    if need_y or need_grad or plan.path == _lib.PATH_G:
+    if need_y or need_grad or plan.path in _lib.LARGE_PATHS:
         y = new((B, T, H)) if batch_first else new((T, B, H))
     else:
         y = None
