@@ -102,7 +102,7 @@ struct EpiGate {            // columns are gate-interleaved: n = 4*j + k  (needs
     if (hT) { hT[(size_t)m * H + j] = h; cT[(size_t)m * H + j] = c; }
   }
 };
-struct EpiDX {              // dX[m,j] = acc + sum_k dPre[m,kH+j] Dx[k,j]
+struct EpiDX {              // dX[m,j] = acc + sum_k dPre[m,kG+j] Dx[k,j]   (G = gate stride of dPre, row pitch 4G)
   RowView dX; const float* dpre; const float* Dx; int H, I;
   __device__ void operator()(int m, int n, int N, const float (&v)[4]) const {
     float* o = dX.row(m);
@@ -121,7 +121,7 @@ struct EpiDX {              // dX[m,j] = acc + sum_k dPre[m,kH+j] Dx[k,j]
 };
 
 struct EpiDXTC {            // tensor-core epilogue of dX = dZX Ux^T + sum_k dPre_k Dx_k  (lane <-> column, see gemm_tc.cuh)
-  float* dx; long long dxs_t, dxs_b; int Bsz; const float* dpre; const float* Dx; int H, I;
+  float* dx; long long dxs_t, dxs_b; int Bsz; const float* dpre; const float* Dx; int H, I;   // H = gate stride of dPre
   static constexpr bool kGate = false;
   __device__ void operator()(int m, int n0, int N, int lane, const float (&v)[4]) const {
     float* o = dx + (long long)(m / Bsz) * dxs_t + (long long)(m % Bsz) * dxs_b;
@@ -281,23 +281,46 @@ struct ColRedArgs {
   RowView X;
   float* part;               // [nsplit][4H + 4H + 4I]
   int T, B, H, I; long long rows_per_split;
+  int G;                     // gate stride of dPre (row pitch 4G); G >= H
 };
 static __global__ void colreduce_kernel(const ColRedArgs a) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;          // column of dPre
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;          // column (gate k, unit j) of dPre
   if (n >= 4 * a.H) return;
   const int k = n / a.H, j = n - k * a.H;
   const long long rows = (long long)a.T * a.B;
   const long long r0 = (long long)blockIdx.y * a.rows_per_split;
   const long long r1 = r0 + a.rows_per_split < rows ? r0 + a.rows_per_split : rows;
+  const bool has_x = j < a.I;
   float sb = 0.f, sh = 0.f, sx = 0.f;
-  for (long long r = r0; r < r1; ++r) {
-    const float d = a.dpre[(size_t)r * 4 * a.H + n];
-    sb += d;
-    float hp = 0.f;
-    if (r >= a.B) hp = a.Y.row(r - a.B)[j];
-    else if (a.h0) hp = a.h0[(size_t)r * a.H + j];
-    sh = fmaf(d, hp, sh);
-    if (j < a.I) sx = fmaf(d, a.X.row(r)[j], sx);
+  // (t, b) walked incrementally: no division per row; four rows of loads in flight
+  int t = (int)(r0 / a.B), b = (int)(r0 - (long long)t * a.B);
+  const float* dp = a.dpre + (size_t)r0 * 4 * a.G + (size_t)k * a.G + j;
+  const size_t dstep = (size_t)4 * a.G;
+  long long r = r0;
+  while (r < r1) {
+    float d[4], hp[4], xv[4];
+    int nv = 0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      d[u] = hp[u] = xv[u] = 0.f;
+      if (r + u < r1) {
+        d[u] = dp[u * dstep];
+        const float* hrow = t > 0 ? a.Y.p + (long long)(t - 1) * a.Y.s_t + (long long)b * a.Y.s_b
+                                  : (a.h0 ? a.h0 + (size_t)b * a.H : nullptr);
+        if (hrow) hp[u] = hrow[j];
+        if (has_x) xv[u] = a.X.p[(long long)t * a.X.s_t + (long long)b * a.X.s_b + j];
+        if (++b == a.B) { b = 0; ++t; }
+        ++nv;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {           // fixed order; absent rows add zeros
+      sb += d[u];
+      sh = fmaf(d[u], hp[u], sh);
+      sx = fmaf(d[u], xv[u], sx);
+    }
+    r += nv;
+    dp += nv * dstep;
   }
   float* p = a.part + (size_t)blockIdx.y * (8 * a.H + 4 * a.I);
   p[n] = sb;
@@ -327,7 +350,7 @@ inline int g_splits(int M, int N, long long K) {
   if (s < 1) s = 1;
   return (int)s;
 }
-constexpr int kColSplits = 64;
+constexpr int kColSplits = 256;
 // The tcgen05 accumulate truncates (~3e-8 relative per add): a K = T*B contraction kept in one accumulator set drifts
 // with its length (8e-6 at K = 196 608 with 32 splits, measured).  Splits for the time-parallel gradient GEMMs are
 // therefore also bounded below so that one split covers at most kTcMaxKPerSplit of K (<= 64 adds per accumulator),
@@ -604,6 +627,181 @@ inline int generic_seq_fwd(const vmlmf_plan* plan, const float* x, long long xs_
   return VMLMF_OK;
 }
 
+// ---- time-parallel half of the backward: every contraction over the T*B rows, shared by regimes G and R2 ----
+//   dBm = dPre^T Z, dVx = dPre^T ZX, dA = Hprev^T dZ, dZX = dPre Vx (unless the caller already has it), dUx = X^T dZX,
+//   dX = dZX Ux^T + sum_k dPre_k (.) Dx_k, column sums dbias / dDh / dDx.  dPre is [T*B, 4, G] (G >= H: regime R2 pads the
+//   gate stride so that its TMA tiles never straddle a gate); pad columns must be zero.
+struct TpArgs {
+  const float* dpre; int G;
+  const float* z; int zp; const float* zx; int zxp;
+  float* dz; float* dzx; bool have_dzx;
+  const float* x; long long xs_t, xs_b; const float* y; long long ys_t, ys_b; const float* h0;
+  const float *Ux, *Vx, *Dx;
+  float* dx; long long dxs_t, dxs_b;
+  float *dUx, *dVx, *dDx, *dA, *dBm, *dDh, *dbias;
+  float* part; long long n_part;       // split-K partials
+  float* vxt;                          // Vx^T [RX, 4G] scratch (only when !have_dzx)
+  float* tA; float* tB; float* gtmp;   // transposed operands [4G, ldt], [max(RH,RX), ldt]; [4G, max(RH,RX)] when G != H
+  long long ldt; float* unused;
+  int T, B, I, H, RX, RH; bool use_tc;
+};
+// dst[k*H + j, :] = src[k*G + j, :]  (rows of R floats)
+static __global__ void compact_gate_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, int H, int G, int R) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 4LL * H * R) return;
+  const int c = (int)(i % R);
+  const long long row = i / R;
+  const int k = (int)(row / H), j = (int)(row % H);
+  dst[i] = src[((size_t)k * G + j) * R + c];
+}
+// scratch of generic_bwd_tp for a gate stride G (floats): partials, transposed operands, gate-compaction buffer
+struct TpScratch { long long n_part, ldt, n_tA, n_tB, n_gtmp, total; };
+inline TpScratch tp_scratch(int T, int B, int I, int H, int G, int RX, int RH) {
+  TpScratch s;
+  const long long rows = (long long)T * B;
+  long long p = (long long)(g_splits(4 * G, RH, rows) + 1) * 4 * G * RH;
+  long long q = (long long)(g_splits(H, RH, rows) + 1) * H * RH; if (q > p) p = q;
+  q = (long long)g_splits(4 * G, RX, rows) * 4 * G * RX; if (q > p) p = q;
+  q = (long long)g_splits(I, RX, rows) * I * RX; if (q > p) p = q;
+  q = (long long)kColSplits * (8 * H + 4 * I); if (q > p) p = q;
+  q = (long long)tc_accuracy_splits(4 * G, RH, rows) * 4 * G * RH; if (q > p) p = q;
+  q = (long long)tc_accuracy_splits(4 * G, RX, rows) * 4 * G * RX; if (q > p) p = q;
+  q = (long long)tc_accuracy_splits(H, RH, rows) * H * RH; if (q > p) p = q;
+  q = (long long)tc_accuracy_splits(I, RX, rows) * I * RX; if (q > p) p = q;
+  s.n_part = p;
+  s.ldt = (rows + 3) / 4 * 4;
+  s.n_tA = 4LL * G * s.ldt;
+  s.n_tB = (long long)(RH > RX ? RH : RX) * s.ldt;
+  s.n_gtmp = G != H ? 4LL * G * (RH > RX ? RH : RX) : 0;
+  s.total = s.n_part + s.n_tA + s.n_tB + s.n_gtmp + 64;
+  return s;
+}
+inline int generic_bwd_tp(TpArgs& a, cudaStream_t st) {
+  const int T = a.T, B = a.B, I = a.I, H = a.H, G = a.G, RX = a.RX, RH = a.RH;
+  const long long rows = (long long)T * B;
+  float* part = a.part;
+  const RowView Xv = tb_view(a.x, a.xs_t, a.xs_b, B), Yv = tb_view(a.y, a.ys_t, a.ys_b, B);
+  const RowView dPv = plain_view(a.dpre, 4 * G), Zv = plain_view(a.z, a.zp), ZXv = plain_view(a.zx, a.zxp);
+  auto reduce_to = [&](int nsplit, long long n, float* out) -> int {
+    splitk_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(part, nsplit, n, out);
+    return (int)cudaGetLastError();
+  };
+  // gate-padded [4G, R] result -> [4H, R]
+  auto finish_gate = [&](float* tmp, float* out, int R) -> int {
+    if (G == H) return 0;
+    const long long n = 4LL * H * R;
+    compact_gate_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(tmp, out, H, G, R);
+    return (int)cudaGetLastError();
+  };
+  float* tA = a.tA;
+  float* tB = a.tB;
+  const bool tc_tp = a.use_tc && rows >= 256 && tc::encode_fn() != nullptr;   // K = rows contractions on the tensor cores
+  // C[M,N] = At[M, rows] Bt[N, rows]^T, split over K with a fixed-order reduce into `out`
+  auto tc_tn = [&](int M, int N, float* out) -> int {
+    int splits = tc::tc_splits(M, N, (int)rows, 32);
+    const int acc_splits = tc_accuracy_splits(M, N, rows);
+    if (splits < acc_splits) splits = acc_splits;
+    while (splits > 1 && (long long)splits * M * N > a.n_part) --splits;
+    const int nkb = ceil_div((int)rows, tc::BK), kbs = ceil_div(nkb, splits), nz = ceil_div(nkb, kbs);
+    int rc = tc::gemm_tc(tA, a.ldt, tB, a.ldt, M, N, (int)rows, tc::EpiPartialTC{part, M, N}, st, splits);
+    if (rc) return rc;
+    return reduce_to(nz, (long long)M * N, out);
+  };
+  float* gBm = (G == H) ? a.dBm : a.gtmp;
+  float* gVx = (G == H) ? a.dVx : a.gtmp;
+  if (tc_tp) {
+    // dBm = dPre^T Z, dVx = dPre^T ZX share the transposed dPre
+    G_TRY(transpose_rows_launch(dPv, nullptr, 0, 0, rows, 4 * G, tA, a.ldt, st));
+    G_TRY(transpose_rows_launch(Zv, nullptr, 0, 0, rows, RH, tB, a.ldt, st));
+    G_TRY(tc_tn(4 * G, RH, gBm));
+    G_TRY(finish_gate(gBm, a.dBm, RH));
+    G_TRY(transpose_rows_launch(ZXv, nullptr, 0, 0, rows, RX, tB, a.ldt, st));
+    G_TRY(tc_tn(4 * G, RX, gVx));
+    G_TRY(finish_gate(gVx, a.dVx, RX));
+    // dA = Hprev^T dZ: row (t,b) of Hprev is y[t-1,b], or h0[b] / 0 at t = 0
+    G_TRY(transpose_rows_launch(Yv, a.h0, H, B, rows, H, tA, a.ldt, st));
+    G_TRY(transpose_rows_launch(plain_view(a.dz, a.zp), nullptr, 0, 0, rows, RH, tB, a.ldt, st));
+    G_TRY(tc_tn(H, RH, a.dA));
+  } else {
+    // dBm = dPre^T Z   [4G,RH]
+    {
+      const int sp = g_splits(4 * G, RH, rows);
+      G_TRY((gemm_launch<true, false>(dPv, Zv, 4 * G, RH, rows, sp, NIdent{}, EpiPartial{part, 4 * G, RH}, st)));
+      G_TRY(reduce_to(sp, (long long)4 * G * RH, gBm));
+      G_TRY(finish_gate(gBm, a.dBm, RH));
+    }
+    // dA = Hprev^T dZ  [H,RH]: rows t>=1 pair y[t-1] with dz[t]; rows of t=0 pair h0 with dz[0]
+    {
+      const long long r1 = rows - B;
+      int sp = 0;
+      if (r1 > 0) {
+        sp = g_splits(H, RH, r1);
+        G_TRY((gemm_launch<true, false>(Yv, plain_view(a.dz + (size_t)B * a.zp, a.zp), H, RH, r1, sp, NIdent{},
+                                        EpiPartial{part, H, RH}, st)));
+      }
+      if (a.h0) {
+        G_TRY((gemm_launch<true, false>(plain_view(a.h0, H), plain_view(a.dz, a.zp), H, RH, B, 1, NIdent{},
+                                        EpiPartial{part + (size_t)sp * H * RH, H, RH}, st)));
+        ++sp;
+      }
+      if (sp == 0) G_TRY((int)cudaMemsetAsync(a.dA, 0, (size_t)H * RH * sizeof(float), st));
+      else G_TRY(reduce_to(sp, (long long)H * RH, a.dA));
+    }
+    // dVx = dPre^T ZX  [4G,RX]
+    {
+      const int sp = g_splits(4 * G, RX, rows);
+      G_TRY((gemm_launch<true, false>(dPv, ZXv, 4 * G, RX, rows, sp, NIdent{}, EpiPartial{part, 4 * G, RX}, st)));
+      G_TRY(reduce_to(sp, (long long)4 * G * RX, gVx));
+      G_TRY(finish_gate(gVx, a.dVx, RX));
+    }
+  }
+  // dZX = dPre Vx    [T*B,RX]   (regime R2 forms it inside its recurrence kernel)
+  if (!a.have_dzx) {
+    if (a.zxp > RX) G_TRY((int)cudaMemsetAsync(a.dzx, 0, (size_t)rows * a.zxp * sizeof(float), st));
+    int rc = tc::kTcNoFit;
+    if (a.use_tc && tc::tc_operand_ok(a.dpre, 4 * G) && tc::tc_operand_ok(a.dzx, a.zxp)) {
+      G_TRY(transpose_launch(a.Vx, 4 * H, RX, a.vxt, 4 * H, st));
+      rc = tc::gemm_tc(a.dpre, 4 * G, a.vxt, 4 * H, (int)rows, RX, 4 * H, tc::EpiStoreTC{a.dzx, a.zxp, 0}, st);
+    }
+    if (rc == tc::kTcNoFit)
+      rc = gemm_launch<false, false>(dPv, plain_view(a.Vx, RX), (int)rows, RX, 4 * H, 1, NIdent{},
+                                     EpiStore{plain_view(a.dzx, a.zxp), 0}, st);
+    G_TRY(rc);
+  }
+  // dUx = X^T dZX    [I,RX]
+  if (tc_tp) {
+    G_TRY(transpose_rows_launch(Xv, nullptr, 0, 0, rows, I, tA, a.ldt, st));
+    G_TRY(transpose_rows_launch(plain_view(a.dzx, a.zxp), nullptr, 0, 0, rows, RX, tB, a.ldt, st));
+    G_TRY(tc_tn(I, RX, a.dUx));
+  } else {
+    const int sp = g_splits(I, RX, rows);
+    G_TRY((gemm_launch<true, false>(Xv, plain_view(a.dzx, a.zxp), I, RX, rows, sp, NIdent{}, EpiPartial{part, I, RX}, st)));
+    G_TRY(reduce_to(sp, (long long)I * RX, a.dUx));
+  }
+  // dX = dZX Ux^T + sum_k dPre[:, kG:kG+I] (.) Dx_k
+  if (a.dx) {
+    int rc = tc::kTcNoFit;
+    if (a.use_tc && tc::tc_operand_ok(a.dzx, a.zxp) && tc::tc_operand_ok(a.Ux, RX))
+      rc = tc::gemm_tc(a.dzx, a.zxp, a.Ux, RX, (int)rows, I, RX, EpiDXTC{a.dx, a.dxs_t, a.dxs_b, B, a.dpre, a.Dx, G, I}, st);
+    if (rc == tc::kTcNoFit)
+      rc = gemm_launch<false, true>(plain_view(a.dzx, a.zxp), plain_view(a.Ux, RX), (int)rows, I, RX, 1, NIdent{},
+                                    EpiDX{tb_view(a.dx, a.dxs_t, a.dxs_b, B), a.dpre, a.Dx, G, I}, st);
+    G_TRY(rc);
+  }
+  // dbias, dDh, dDx
+  {
+    long long rps = (rows + kColSplits - 1) / kColSplits;
+    if (rps < 1) rps = 1;
+    const int nsp = (int)((rows + rps - 1) / rps);
+    ColRedArgs ca{a.dpre, Yv, a.h0, Xv, part, T, B, H, I, rps, G};
+    colreduce_kernel<<<dim3(ceil_div(4 * H, 128), nsp), 128, 0, st>>>(ca);
+    G_TRY((int)cudaGetLastError());
+    colreduce_final_kernel<<<ceil_div(8 * H + 4 * I, 256), 256, 0, st>>>(part, nsp, H, I, a.dbias, a.dDh, a.dDx);
+    G_TRY((int)cudaGetLastError());
+  }
+  return VMLMF_OK;
+}
+
 inline int generic_seq_bwd(const vmlmf_plan* plan, const float* x, long long xs_t, long long xs_b, const float* zx,
                            const float* Ux, const float* Vx, const float* Dx, const float* A, const float* Bm,
                            const float* Dh, const float* h0, const float* c0, const float* y, long long ys_t,
@@ -661,113 +859,11 @@ inline int generic_seq_bwd(const vmlmf_plan* plan, const float* x, long long xs_
   if (dh0) G_TRY((int)cudaMemcpyAsync(dh0, dh, sb, cudaMemcpyDeviceToDevice, st));
   if (dc0) G_TRY((int)cudaMemcpyAsync(dc0, dc, sb, cudaMemcpyDeviceToDevice, st));
 
-  const RowView Xv = tb_view(x, xs_t, xs_b, B), Yv = tb_view(y, ys_t, ys_b, B);
-  const RowView dPv = plain_view(dpre, 4 * H), Zv = plain_view(z, s.zp), ZXv = plain_view(zx, s.zxp);
-  auto reduce_to = [&](int nsplit, long long n, float* out) -> int {
-    splitk_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(part, nsplit, n, out);
-    return (int)cudaGetLastError();
-  };
-  float* tA = align4(tcpart + s.n_tcpart);                       // transposed A-side operand [<=4H, ldt]
-  float* tB = align4(tA + s.n_tA);                               // transposed B-side operand [<=max(RH,RX), ldt]
-  const bool tc_tp = use_tc && rows >= 256;                      // K = rows contractions on the tensor cores
-  // C[M,N] = At[M, rows] Bt[N, rows]^T, split over K with a fixed-order reduce into `out`
-  auto tc_tn = [&](int M, int N, float* out) -> int {
-    int splits = tc::tc_splits(M, N, (int)rows, 32);
-    const int acc_splits = tc_accuracy_splits(M, N, rows);
-    if (splits < acc_splits) splits = acc_splits;
-    while (splits > 1 && (long long)splits * M * N > s.n_part) --splits;
-    const int nkb = ceil_div((int)rows, tc::BK), kbs = ceil_div(nkb, splits), nz = ceil_div(nkb, kbs);
-    int rc = tc::gemm_tc(tA, s.ldt, tB, s.ldt, M, N, (int)rows, tc::EpiPartialTC{part, M, N}, st, splits);
-    if (rc) return rc;
-    return reduce_to(nz, (long long)M * N, out);
-  };
-  if (tc_tp) {
-    // dBm = dPre^T Z, dVx = dPre^T ZX share the transposed dPre
-    G_TRY(transpose_rows_launch(dPv, nullptr, 0, 0, rows, 4 * H, tA, s.ldt, st));
-    G_TRY(transpose_rows_launch(Zv, nullptr, 0, 0, rows, RH, tB, s.ldt, st));
-    G_TRY(tc_tn(4 * H, RH, dBm));
-    G_TRY(transpose_rows_launch(ZXv, nullptr, 0, 0, rows, RX, tB, s.ldt, st));
-    G_TRY(tc_tn(4 * H, RX, dVx));
-    // dA = Hprev^T dZ: row (t,b) of Hprev is y[t-1,b], or h0[b] / 0 at t = 0
-    G_TRY(transpose_rows_launch(Yv, h0, H, B, rows, H, tA, s.ldt, st));
-    G_TRY(transpose_rows_launch(plain_view(dz, s.zp), nullptr, 0, 0, rows, RH, tB, s.ldt, st));
-    G_TRY(tc_tn(H, RH, dA));
-  } else {
-  // dBm = dPre^T Z   [4H,RH]
-    {
-      const int sp = g_splits(4 * H, RH, rows);
-      G_TRY((gemm_launch<true, false>(dPv, Zv, 4 * H, RH, rows, sp, NIdent{}, EpiPartial{part, 4 * H, RH}, st)));
-      G_TRY(reduce_to(sp, (long long)4 * H * RH, dBm));
-    }
-    // dA = Hprev^T dZ  [H,RH]: rows t>=1 pair y[t-1] with dz[t]; rows of t=0 pair h0 with dz[0]
-    {
-      const long long r1 = rows - B;
-      int sp = 0;
-      if (r1 > 0) {
-        sp = g_splits(H, RH, r1);
-        G_TRY((gemm_launch<true, false>(Yv, plain_view(dz + (size_t)B * s.zp, s.zp), H, RH, r1, sp, NIdent{},
-                                        EpiPartial{part, H, RH}, st)));
-      }
-      if (h0) {
-        G_TRY((gemm_launch<true, false>(plain_view(h0, H), plain_view(dz, s.zp), H, RH, B, 1, NIdent{},
-                                        EpiPartial{part + (size_t)sp * H * RH, H, RH}, st)));
-        ++sp;
-      }
-      if (sp == 0) G_TRY((int)cudaMemsetAsync(dA, 0, (size_t)H * RH * sizeof(float), st));
-      else G_TRY(reduce_to(sp, (long long)H * RH, dA));
-    }
-    // dVx = dPre^T ZX  [4H,RX]
-    {
-      const int sp = g_splits(4 * H, RX, rows);
-      G_TRY((gemm_launch<true, false>(dPv, ZXv, 4 * H, RX, rows, sp, NIdent{}, EpiPartial{part, 4 * H, RX}, st)));
-      G_TRY(reduce_to(sp, (long long)4 * H * RX, dVx));
-    }
-  }
-  // dZX = dPre Vx    [T*B,RX]
-  if (s.zxp > RX) G_TRY((int)cudaMemsetAsync(dzx, 0, (size_t)s.n_dzx * sizeof(float), st));
-  {
-    int rc = tc::kTcNoFit;
-    if (use_tc && tc::tc_operand_ok(dpre, 4 * H) && tc::tc_operand_ok(dzx, s.zxp)) {
-      G_TRY(transpose_launch(Vx, 4 * H, RX, vxt, 4 * H, st));
-      rc = tc::gemm_tc(dpre, 4 * H, vxt, 4 * H, (int)rows, RX, 4 * H, tc::EpiStoreTC{dzx, s.zxp, 0}, st);
-    }
-    if (rc == tc::kTcNoFit)
-      rc = gemm_launch<false, false>(dPv, plain_view(Vx, RX), (int)rows, RX, 4 * H, 1, NIdent{},
-                                     EpiStore{plain_view(dzx, s.zxp), 0}, st);
-    G_TRY(rc);
-  }
-  // dUx = X^T dZX    [I,RX]
-  if (tc_tp) {
-    G_TRY(transpose_rows_launch(Xv, nullptr, 0, 0, rows, I, tA, s.ldt, st));
-    G_TRY(transpose_rows_launch(plain_view(dzx, s.zxp), nullptr, 0, 0, rows, RX, tB, s.ldt, st));
-    G_TRY(tc_tn(I, RX, dUx));
-  } else
-  {
-    const int sp = g_splits(I, RX, rows);
-    G_TRY((gemm_launch<true, false>(Xv, plain_view(dzx, s.zxp), I, RX, rows, sp, NIdent{}, EpiPartial{part, I, RX}, st)));
-    G_TRY(reduce_to(sp, (long long)I * RX, dUx));
-  }
-  // dX = dZX Ux^T + sum_k dPre[:, kH:kH+I] (.) Dx_k
-  if (dx) {
-    int rc = tc::kTcNoFit;
-    if (use_tc && tc::tc_operand_ok(dzx, s.zxp) && tc::tc_operand_ok(Ux, RX))
-      rc = tc::gemm_tc(dzx, s.zxp, Ux, RX, (int)rows, I, RX, EpiDXTC{dx, dxs_t, dxs_b, B, dpre, Dx, H, I}, st);
-    if (rc == tc::kTcNoFit)
-      rc = gemm_launch<false, true>(plain_view(dzx, s.zxp), plain_view(Ux, RX), (int)rows, I, RX, 1, NIdent{},
-                                    EpiDX{tb_view(dx, dxs_t, dxs_b, B), dpre, Dx, H, I}, st);
-    G_TRY(rc);
-  }
-  // dbias, dDh, dDx
-  {
-    long long rps = (rows + kColSplits - 1) / kColSplits;
-    if (rps < 1) rps = 1;
-    const int nsp = (int)((rows + rps - 1) / rps);
-    ColRedArgs ca{dpre, Yv, h0, Xv, part, T, B, H, I, rps};
-    colreduce_kernel<<<dim3(ceil_div(4 * H, 128), nsp), 128, 0, st>>>(ca);
-    G_TRY((int)cudaGetLastError());
-    colreduce_final_kernel<<<ceil_div(8 * H + 4 * I, 256), 256, 0, st>>>(part, nsp, H, I, dbias, dDh, dDx);
-    G_TRY((int)cudaGetLastError());
-  }
+  TpArgs tp{dpre, H, z, s.zp, zx, s.zxp, dz, dzx, false, x, xs_t, xs_b, y, ys_t, ys_b, h0, Ux, Vx, Dx, dx, dxs_t, dxs_b,
+            dUx, dVx, dDx, dA, dBm, dDh, dbias, part, s.n_part, vxt, align4(tcpart + s.n_tcpart), nullptr, nullptr, s.ldt, nullptr,
+            T, B, I, H, RX, RH, use_tc};
+  tp.tB = align4(tp.tA + s.n_tA);
+  G_TRY(generic_bwd_tp(tp, st));
   return VMLMF_OK;
 }
 

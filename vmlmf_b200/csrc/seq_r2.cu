@@ -46,6 +46,36 @@ __global__ void pack_fwd_kernel(const float* __restrict__ A, const float* __rest
   }
 }
 
+// backward operands:
+// w2t[n, k, j] = Bm[kH+j, n]        n <  RH       [KPp, 4, Hp]  (B operand of phase 1: N = column n of [dz | dzx], K = (gate, unit))
+//              = Vx[kH+j, n-KZP]    KZP <= n < KZP+RX
+// ap[j, q]     = A[j, q]                          [Hp, KZP]     (B operand of phase 2: N = unit j, K = z column q)
+__global__ void pack_bwd_kernel(const float* __restrict__ A, const float* __restrict__ Bm, const float* __restrict__ Vx,
+                                float* __restrict__ w2t_hi, float* __restrict__ w2t_lo, float* __restrict__ ap_hi,
+                                float* __restrict__ ap_lo, int H, int RH, int RX, int Hp, int KZP, int KPp) {
+  const long long n_w = (long long)KPp * 4 * Hp, n_a = (long long)Hp * KZP;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_w + n_a; i += (long long)gridDim.x * blockDim.x) {
+    float v = 0.f;
+    if (i < n_w) {
+      const int j = (int)(i % Hp), k = (int)((i / Hp) & 3), n = (int)(i / (4LL * Hp));
+      if (j < H) {
+        if (n < RH) v = __ldg(Bm + ((size_t)k * H + j) * RH + n);
+        else if (n >= KZP && n < KZP + RX) v = __ldg(Vx + ((size_t)k * H + j) * RX + (n - KZP));
+      }
+      const float hi = split_hi(v);
+      w2t_hi[i] = hi;
+      w2t_lo[i] = split_lo(v, hi);
+    } else {
+      const long long e = i - n_w;
+      const int q = (int)(e % KZP), j = (int)(e / KZP);
+      if (j < H && q < RH) v = __ldg(A + (size_t)j * RH + q);
+      const float hi = split_hi(v);
+      ap_hi[e] = hi;
+      ap_lo[e] = split_lo(v, hi);
+    }
+  }
+}
+
 // hop[b, j] = h0[b, j] (0 when h0 is null or j >= H), as tf32 hi / lo
 __global__ void prep_state_kernel(const float* __restrict__ h0, float* __restrict__ hop_hi, float* __restrict__ hop_lo,
                                   int B, int H, int Hp) {
@@ -164,6 +194,25 @@ Geom geom(int T, int B, int I, int H, int RX, int RH) {
   g.o_w2_lo = o; o += al64(4LL * g.Hp * g.KPp);
   g.o_cbuf = o; o += al64(2LL * B * H);
   g.fwd_floats = o + 64;
+  // backward: phase 1 contracts over 4 * HS values per CTA; at most 16 K tiles (64 tf32 k-steps) per accumulator
+  g.KSPLIT = ceil_div(4 * (g.HS / 32), 16);
+  g.NP = g.CS * g.KSPLIT;
+  o = 0;
+  g.b_dpre = o; o += al64((long long)T * B * 4 * g.Hp);
+  g.b_dz = o; o += al64((long long)T * B * g.zp);
+  g.b_dzx = o; o += al64((long long)T * B * g.zxp);
+  g.b_dpo_hi = o; o += al64((long long)B * 4 * g.Hp);
+  g.b_dpo_lo = o; o += al64((long long)B * 4 * g.Hp);
+  g.b_dzo_hi = o; o += al64((long long)B * g.zp);
+  g.b_dzo_lo = o; o += al64((long long)B * g.zp);
+  g.b_dhrun = o; o += al64((long long)B * g.Hp);
+  g.b_dcrun = o; o += al64((long long)B * g.Hp);
+  g.b_part = o; o += al64(g.NP > 1 ? (long long)g.ncl * g.NP * BM * g.KPp : 0);
+  g.b_w2t_hi = o; o += al64((long long)g.KPp * 4 * g.Hp);
+  g.b_w2t_lo = o; o += al64((long long)g.KPp * 4 * g.Hp);
+  g.b_ap_hi = o; o += al64((long long)g.Hp * g.KZP);
+  g.b_ap_lo = o; o += al64((long long)g.Hp * g.KZP);
+  g.bwd_floats = o + 64;
   return g;
 }
 
@@ -213,6 +262,37 @@ int launch_fwd(const FwdCall& c, void* workspace, cudaStream_t st) {
                             m_zx_hi, m_zx_lo, m_w2_hi, m_w2_lo, a);
   return launch_clustered(r2_fwd_kernel<false>, grid, g.CS, st, m_hop_hi, m_hop_lo, m_at_hi, m_at_lo, m_zop_hi, m_zop_lo,
                           m_zx_hi, m_zx_lo, m_w2_hi, m_w2_lo, a);
+}
+
+int launch_bwd(const BwdCall& c, void* workspace, BwdOut* out, cudaStream_t st) {
+  const Geom g = geom(c.T, c.B, c.I, c.H, c.RX, c.RH);
+  float* ws = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+  float *dpo_hi = ws + g.b_dpo_hi, *dpo_lo = ws + g.b_dpo_lo, *dzo_hi = ws + g.b_dzo_hi, *dzo_lo = ws + g.b_dzo_lo;
+  float *w2t_hi = ws + g.b_w2t_hi, *w2t_lo = ws + g.b_w2t_lo, *ap_hi = ws + g.b_ap_hi, *ap_lo = ws + g.b_ap_lo;
+  // the operand copy of dPre keeps zeros in its pad units (never written by the kernel; dpo_hi and dpo_lo are adjacent)
+  cudaError_t e = cudaMemsetAsync(dpo_hi, 0, (size_t)(g.b_dzo_hi - g.b_dpo_hi) * sizeof(float), st);
+  if (e != cudaSuccess) return (int)e;
+  pack_bwd_kernel<<<ew_grid((long long)g.KPp * 4 * g.Hp + (long long)g.Hp * g.KZP), 256, 0, st>>>(
+      c.A, c.Bm, c.Vx, w2t_hi, w2t_lo, ap_hi, ap_lo, c.H, c.RH, c.RX, g.Hp, g.KZP, g.KPp);
+  int rc = (int)cudaGetLastError();
+  if (rc) return rc;
+  CUtensorMap m_dpo_hi, m_dpo_lo, m_w2t_hi, m_w2t_lo, m_dzo_hi, m_dzo_lo, m_ap_hi, m_ap_lo;
+  if (map_3d(&m_dpo_hi, dpo_hi, g.Hp, 4, c.B, g.Hp, 4LL * g.Hp, 1, BM) || map_3d(&m_dpo_lo, dpo_lo, g.Hp, 4, c.B, g.Hp, 4LL * g.Hp, 1, BM) ||
+      map_3d(&m_w2t_hi, w2t_hi, g.Hp, 4, g.KPp, g.Hp, 4LL * g.Hp, 1, 128) || map_3d(&m_w2t_lo, w2t_lo, g.Hp, 4, g.KPp, g.Hp, 4LL * g.Hp, 1, 128) ||
+      map_2d(&m_dzo_hi, dzo_hi, g.zp, c.B, g.zp) || map_2d(&m_dzo_lo, dzo_lo, g.zp, c.B, g.zp) ||
+      map_2d(&m_ap_hi, ap_hi, g.KZP, g.Hp, g.KZP) || map_2d(&m_ap_lo, ap_lo, g.KZP, g.Hp, g.KZP))
+    return VMLMF_EUNSUPPORTED;
+  BwdArgs a;
+  a.gates = c.gates; a.cs = c.cs; a.c0 = c.c0; a.dy = c.dy; a.dys_t = c.dys_t; a.dys_b = c.dys_b;
+  a.dhT = c.dhT; a.dcT = c.dcT; a.Dh = c.Dh; a.dh0 = c.dh0; a.dc0 = c.dc0;
+  a.dpre = ws + g.b_dpre; a.dz_all = ws + g.b_dz; a.dzx_all = ws + g.b_dzx;
+  a.dpo_hi = dpo_hi; a.dpo_lo = dpo_lo; a.dzo_hi = dzo_hi; a.dzo_lo = dzo_lo;
+  a.dhrun = ws + g.b_dhrun; a.dcrun = ws + g.b_dcrun; a.part = ws + g.b_part;
+  a.T = c.T; a.B = c.B; a.H = c.H; a.RX = c.RX; a.RH = c.RH;
+  a.Hp = g.Hp; a.HS = g.HS; a.CS = g.CS; a.zp = g.zp; a.zxp = g.zxp; a.KZP = g.KZP; a.KPp = g.KPp; a.KSPLIT = g.KSPLIT;
+  out->dpre = a.dpre; out->G = g.Hp; out->dz = a.dz_all; out->dzx = a.dzx_all; out->after = ws + g.bwd_floats;
+  return launch_clustered(r2_bwd_kernel, g.ncl * g.CS, g.CS, st, m_dpo_hi, m_dpo_lo, m_w2t_hi, m_w2t_lo, m_dzo_hi, m_dzo_lo,
+                          m_ap_hi, m_ap_lo, a);
 }
 
 }  // namespace r2

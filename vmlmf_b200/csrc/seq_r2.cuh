@@ -499,5 +499,374 @@ r2_fwd_kernel(const __grid_constant__ CUtensorMap m_hop_hi, const __grid_constan
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------- backward
+// Reverse-time recurrence of the same decomposition (autograd replay of V/models/vmlmf.py:95-125 / vmlmf_lm.py:222-269):
+//   phase 1   partial dzc_s[128, KP] = dPre_t[:, 4 gates x slice s] * [Bm | Vx][slice s rows, :]     K = 4*HS (K-split)
+//   exchange  dzc = sum of the partials -> dz_t (kept for dA = Hprev^T dZ), dzx_t (kept for dUx, dX), tf32 operand copy
+//   phase 2   dh_{t-1}[128, slice s] = dz_t * A[slice s, :]^T + sum_k dPre_t,k (.) Dh_k               K = RH
+//             epilogue = the gate-gradient algebra of step t-1 on the fresh dh_{t-1}: dPre_{t-1} (exact copy for the
+//             time-parallel weight-gradient GEMMs + tf32 hi / lo operand copy), dc_{t-2}, the Dh term of dh_{t-2}.
+// The weight gradients themselves (dBm, dVx, dA, dUx, dX, column sums) are contractions over all T*B rows: time-parallel
+// tcgen05 GEMMs after this kernel (generic_bwd_tp).
+struct BwdArgs {
+  const float* gates;         // [T,B,4,H]
+  const float* cs;            // [T,B,H]
+  const float* c0;            // [B,H] or null
+  const float* dy; long long dys_t, dys_b;      // or null
+  const float *dhT, *dcT;     // [B,H] or null
+  const float* Dh;
+  float *dh0, *dc0;           // [B,H] or null
+  float* dpre;                // [T*B, 4, Hp]
+  float* dz_all;              // [T*B, zp]
+  float* dzx_all;             // [T*B, zxp]
+  float *dpo_hi, *dpo_lo;     // [B, 4, Hp]   tf32 operand copy of dPre_t
+  float *dzo_hi, *dzo_lo;     // [B, zp]      tf32 operand copy of dz_t
+  float *dhrun, *dcrun;       // [B, Hp]
+  float* part;                // [nclusters, NP, 128, KPp]   NP = CS * KSPLIT partials
+  int T, B, H, RX, RH;
+  int Hp, HS, CS, zp, zxp, KZP, KPp, KSPLIT;
+};
+
+// gate-gradient algebra of one (row m, unit j) at step tq, in two halves so that a warp can have the loads of eight
+// cells in flight before the first store (the scratch buffers it writes may alias what it reads as far as the compiler
+// can tell, so loads are hoisted by hand).  Saved activations go through the read-only path.
+struct PwIn { float gi, gf, go, gn, ct, cp, dhs, dcin; };
+// dhs = dy_t + (dh seed, or the Dh term kept in dhrun); dcin = dc seed or dcrun
+__device__ __forceinline__ void pw_load(const BwdArgs& a, int tq, int m, int j, bool seed, PwIn& in) {
+  const size_t rowq = (size_t)tq * a.B + m;
+  const float* g = a.gates + rowq * 4 * a.H + j;
+  in.gi = __ldg(g); in.gf = __ldg(g + a.H); in.go = __ldg(g + 2 * a.H); in.gn = __ldg(g + 3 * a.H);
+  in.ct = __ldg(a.cs + rowq * a.H + j);
+  in.cp = tq > 0 ? __ldg(a.cs + (rowq - a.B) * a.H + j) : (a.c0 ? __ldg(a.c0 + (size_t)m * a.H + j) : 0.f);
+  const float dyv = a.dy ? __ldg(a.dy + (long long)tq * a.dys_t + (long long)m * a.dys_b + j) : 0.f;
+  if (seed) {
+    in.dhs = dyv + (a.dhT ? __ldg(a.dhT + (size_t)m * a.H + j) : 0.f);
+    in.dcin = a.dcT ? __ldg(a.dcT + (size_t)m * a.H + j) : 0.f;
+  } else {
+    in.dhs = dyv + a.dhrun[(size_t)m * a.Hp + j];
+    in.dcin = a.dcrun[(size_t)m * a.Hp + j];
+  }
+}
+__device__ __forceinline__ void pw_finish(const BwdArgs& a, int tq, int m, int j, const PwIn& in, float dh, const float (&dhc)[4]) {
+  const size_t rowq = (size_t)tq * a.B + m;
+  const float tcv = tanhf_acc(in.ct);
+  const float dc = fmaf(dh * in.go, 1.f - tcv * tcv, in.dcin);
+  float d[4];
+  d[0] = dc * in.gn * in.gi * (1.f - in.gi);
+  d[1] = dc * in.cp * in.gf * (1.f - in.gf);
+  d[2] = dh * tcv * in.go * (1.f - in.go);
+  d[3] = dc * in.gi * (1.f - in.gn * in.gn);
+  float* o = a.dpre + rowq * 4 * a.Hp + j;
+  float* oh = a.dpo_hi + (size_t)m * 4 * a.Hp + j;
+  float* ol = a.dpo_lo + (size_t)m * 4 * a.Hp + j;
+  float sdh = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    o[(size_t)k * a.Hp] = d[k];
+    const float hi = split_hi(d[k]);
+    oh[(size_t)k * a.Hp] = hi;
+    ol[(size_t)k * a.Hp] = split_lo(d[k], hi);
+    sdh = fmaf(d[k], dhc[k], sdh);
+  }
+  a.dcrun[(size_t)m * a.Hp + j] = dc * in.gf;
+  a.dhrun[(size_t)m * a.Hp + j] = sdh;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+r2_bwd_kernel(const __grid_constant__ CUtensorMap m_dpo_hi, const __grid_constant__ CUtensorMap m_dpo_lo,
+              const __grid_constant__ CUtensorMap m_w2t_hi, const __grid_constant__ CUtensorMap m_w2t_lo,
+              const __grid_constant__ CUtensorMap m_dzo_hi, const __grid_constant__ CUtensorMap m_dzo_lo,
+              const __grid_constant__ CUtensorMap m_ap_hi, const __grid_constant__ CUtensorMap m_ap_lo, const BwdArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const Smem sm = carve(smem_raw);
+  Bars* bars = sm.bars;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int CS = a.CS, KSPLIT = a.KSPLIT, NP = CS * KSPLIT;
+  const int s_rank = CS > 1 ? (int)cluster_ctarank() : 0;
+  const int cid = CS > 1 ? (int)cluster_id_x() : (int)blockIdx.x;
+  const int ncl = CS > 1 ? (int)ncluster_x() : (int)gridDim.x;
+  const int ntiles = (a.B + BM - 1) / BM;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&bars->accf[b], 1); mbar_init(&bars->acce[b], kEpiWarps); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_slot)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = bars->tmem_slot;
+
+  const int u0 = s_rank * a.HS;
+  const int uvalid = min(a.HS, a.H - u0);
+  const int nkh = (uvalid + BK - 1) / BK;                    // K tiles per gate in phase 1
+  const int KT = 4 * nkh;                                    // phase 1 K tiles (gate-major)
+  const int kseg = (KT + KSPLIT - 1) / KSPLIT;               // K tiles per accumulation segment
+  const int nch1 = (a.KPp + 127) / 128;                      // phase 1 chunks (128 columns of [dz | dzx])
+  const int nch2 = (uvalid + 127) / 128;                     // phase 2 chunks (128 units)
+  const int nkz = (a.RH + BK - 1) / BK;                      // phase 2 K tiles
+
+  const int eq = warp & 3, ehalf = (warp - 2) >> 2;
+  const int rl = lane & 3, c8 = lane >> 2;
+
+  uint32_t n_tile = 0, n_chunk = 0;
+
+  for (int tile = cid; tile < ntiles; tile += ncl) {
+    const int row0 = tile * BM;
+    // ---- seed: gate-gradient algebra of the last step with dh = dhT, dc = dcT ----
+    if (warp >= 2) {
+      const int tq = a.T - 1;
+      for (int ug = ehalf; ug * 8 < uvalid; ug += 2) {
+        const int j = u0 + ug * 8 + c8;
+        if (j < a.H) {
+          float dhc[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) dhc[k] = __ldg(a.Dh + k * a.H + j);
+          PwIn in[8];
+#pragma unroll
+          for (int rg = 0; rg < 8; ++rg) {
+            const int m = row0 + eq * 32 + rg * 4 + rl;
+            if (m < a.B) pw_load(a, tq, m, j, true, in[rg]);
+          }
+#pragma unroll
+          for (int rg = 0; rg < 8; ++rg) {
+            const int m = row0 + eq * 32 + rg * 4 + rl;
+            if (m < a.B) pw_finish(a, tq, m, j, in[rg], in[rg].dhs, dhc);
+          }
+        }
+      }
+      fence_proxy_async_all();
+    }
+    __syncthreads();
+    for (int t = a.T - 1; t >= 0; --t) {
+      // ======================================= phase 1 =======================================
+      if (warp == 0) {
+        if (lane == 0) {
+          fence_proxy_async_all();
+          for (int c = 0; c < nch1; ++c)
+            for (int ka = 0; ka < KT; ++ka, ++n_tile) {
+              const int k = ka / nkh, kt = ka - k * nkh;
+              const int s = n_tile % kStages, it = n_tile / kStages;
+              if (it > 0) mbar_wait(&bars->empty[s], (it - 1) & 1);
+              uint8_t* st = sm.stages + s * kStageBytes;
+              mbar_arrive_expect_tx(&bars->full[s], kStageBytes);
+              tma_load_3d(st, &m_dpo_hi, u0 + kt * BK, k, row0, &bars->full[s]);
+              tma_load_3d(st + kTile, &m_dpo_lo, u0 + kt * BK, k, row0, &bars->full[s]);
+              tma_load_3d(st + 2 * kTile, &m_w2t_hi, u0 + kt * BK, k, c * 128, &bars->full[s]);
+              tma_load_3d(st + 3 * kTile, &m_w2t_lo, u0 + kt * BK, k, c * 128, &bars->full[s]);
+            }
+        }
+        __syncwarp();
+      } else if (warp == 1) {
+        if (lane == 0) {
+          for (int c = 0; c < nch1; ++c) {
+            const int ncol = min(128, a.KPp - c * 128);
+            const uint32_t idesc = make_idesc(BM, ncol);
+            for (int ks = 0; ks < KSPLIT; ++ks, ++n_chunk) {
+              const int buf = n_chunk & 1, use = n_chunk >> 1;
+              if (use > 0) mbar_wait(&bars->acce[buf], (use - 1) & 1);
+              tc_fence_after();
+              const uint32_t acc_main = tmem_d + buf * 256, acc_cross = acc_main + 128;
+              const int ka0 = ks * kseg, ka1 = min(KT, ka0 + kseg);
+              for (int ka = ka0; ka < ka1; ++ka, ++n_tile) {
+                const int kt = ka % nkh;
+                const int s = n_tile % kStages, it = n_tile / kStages;
+                mbar_wait(&bars->full[s], it & 1);
+                tc_fence_after();
+                issue_tile(smem_u32(sm.stages + s * kStageBytes), acc_main, acc_cross, idesc, tile_ksteps(uvalid, kt), ka == ka0);
+                mma_commit(&bars->empty[s]);
+              }
+              mma_commit(&bars->accf[buf]);
+            }
+          }
+        }
+        __syncwarp();
+      } else {
+        for (int c = 0; c < nch1; ++c) {
+          const int ncol = min(128, a.KPp - c * 128);
+          for (int ks = 0; ks < KSPLIT; ++ks, ++n_chunk) {
+            const int buf = n_chunk & 1, use = n_chunk >> 1;
+            mbar_wait(&bars->accf[buf], use & 1);
+            tc_fence_after();
+            const uint32_t t_main = tmem_d + ((uint32_t)(eq * 32) << 16) + buf * 256;
+#pragma unroll 1
+            for (int pp = 0; pp < 2; ++pp) {
+              const int cb = (ehalf * 2 + pp) * 32;
+              if (cb >= ncol) break;
+              float v[32];
+              tmem_ld_groups(t_main, t_main + 128, cb, cb + 8, cb + 16, cb + 24, v);
+              xpose8(v, lane);
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const int n = c * 128 + cb + g * 8 + c8;            // column of [dz | pad | dzx | pad]
+#pragma unroll
+                for (int rg = 0; rg < 8; ++rg) {
+                  const int r = eq * 32 + rg * 4 + rl, m = row0 + r;
+                  if (m < a.B) {
+                    const float val = v[g * 8 + rg];
+                    if (NP > 1) {
+                      a.part[(((size_t)cid * NP + s_rank * KSPLIT + ks) * BM + r) * a.KPp + n] = val;
+                    } else if (n < a.zp) {
+                      a.dz_all[((size_t)t * a.B + m) * a.zp + n] = val;
+                      const float hi = split_hi(val);
+                      a.dzo_hi[(size_t)m * a.zp + n] = hi;
+                      a.dzo_lo[(size_t)m * a.zp + n] = split_lo(val, hi);
+                    } else if (n >= a.KZP && n < a.KZP + a.zxp) {
+                      a.dzx_all[((size_t)t * a.B + m) * a.zxp + (n - a.KZP)] = val;
+                    }
+                  }
+                }
+              }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->acce[buf]);
+          }
+        }
+        fence_proxy_async_all();
+      }
+      // ======================================= exchange =======================================
+      if (NP > 1) {
+        if (CS > 1) cluster_sync_all(); else __syncthreads();
+        if (warp >= 2) {
+          const int rows_valid = min(BM, a.B - row0);
+          const int rpc = (rows_valid + CS - 1) / CS;
+          const int r_lo = s_rank * rpc, r_hi = min(rows_valid, r_lo + rpc);
+          const int et = threadIdx.x - 64;
+          const int wcols = a.zp + a.zxp;
+          const int nel = (r_hi - r_lo) * wcols;
+          const float* pbase = a.part + (size_t)cid * NP * BM * a.KPp;
+          const size_t pstride = (size_t)BM * a.KPp;
+          for (int e = et; e < nel; e += 32 * kEpiWarps) {
+            const int r = r_lo + e / wcols, cc = e - (e / wcols) * wcols;
+            const int n = cc < a.zp ? cc : a.KZP + (cc - a.zp);
+            const float* src = pbase + (size_t)r * a.KPp + n;
+            float v = 0.f;
+            int p = 0;
+            for (; p + 4 <= NP; p += 4) {
+              const float p0 = __ldcg(src + (size_t)p * pstride), p1 = __ldcg(src + (size_t)(p + 1) * pstride);
+              const float p2 = __ldcg(src + (size_t)(p + 2) * pstride), p3 = __ldcg(src + (size_t)(p + 3) * pstride);
+              v += p0; v += p1; v += p2; v += p3;
+            }
+            for (; p < NP; ++p) v += __ldcg(src + (size_t)p * pstride);
+            const int m = row0 + r;
+            if (cc < a.zp) {
+              a.dz_all[((size_t)t * a.B + m) * a.zp + cc] = v;
+              const float hi = split_hi(v);
+              a.dzo_hi[(size_t)m * a.zp + cc] = hi;
+              a.dzo_lo[(size_t)m * a.zp + cc] = split_lo(v, hi);
+            } else {
+              a.dzx_all[((size_t)t * a.B + m) * a.zxp + (cc - a.zp)] = v;
+            }
+          }
+          fence_proxy_async_all();
+        }
+        if (CS > 1) cluster_sync_all(); else __syncthreads();
+      } else {
+        __syncthreads();
+      }
+      // ======================================= phase 2 =======================================
+      if (warp == 0) {
+        if (lane == 0) {
+          fence_proxy_async_all();
+          for (int c = 0; c < nch2; ++c)
+            for (int kt = 0; kt < nkz; ++kt, ++n_tile) {
+              const int s = n_tile % kStages, it = n_tile / kStages;
+              if (it > 0) mbar_wait(&bars->empty[s], (it - 1) & 1);
+              uint8_t* st = sm.stages + s * kStageBytes;
+              mbar_arrive_expect_tx(&bars->full[s], kStageBytes);
+              tma_load_2d(st, &m_dzo_hi, kt * BK, row0, &bars->full[s]);
+              tma_load_2d(st + kTile, &m_dzo_lo, kt * BK, row0, &bars->full[s]);
+              tma_load_2d(st + 2 * kTile, &m_ap_hi, kt * BK, u0 + c * 128, &bars->full[s]);
+              tma_load_2d(st + 3 * kTile, &m_ap_lo, kt * BK, u0 + c * 128, &bars->full[s]);
+            }
+        }
+        __syncwarp();
+      } else if (warp == 1) {
+        if (lane == 0) {
+          const uint32_t idesc = make_idesc(BM, 128);
+          for (int c = 0; c < nch2; ++c, ++n_chunk) {
+            const int buf = n_chunk & 1, use = n_chunk >> 1;
+            if (use > 0) mbar_wait(&bars->acce[buf], (use - 1) & 1);
+            tc_fence_after();
+            const uint32_t acc_main = tmem_d + buf * 256, acc_cross = acc_main + 128;
+            for (int kt = 0; kt < nkz; ++kt, ++n_tile) {
+              const int s = n_tile % kStages, it = n_tile / kStages;
+              mbar_wait(&bars->full[s], it & 1);
+              tc_fence_after();
+              issue_tile(smem_u32(sm.stages + s * kStageBytes), acc_main, acc_cross, idesc, tile_ksteps(a.RH, kt), kt == 0);
+              mma_commit(&bars->empty[s]);
+            }
+            mma_commit(&bars->accf[buf]);
+          }
+        }
+        __syncwarp();
+      } else {
+        for (int c = 0; c < nch2; ++c, ++n_chunk) {
+          const int buf = n_chunk & 1, use = n_chunk >> 1;
+          mbar_wait(&bars->accf[buf], use & 1);
+          tc_fence_after();
+          const uint32_t t_main = tmem_d + ((uint32_t)(eq * 32) << 16) + buf * 256;
+#pragma unroll 1
+          for (int pp = 0; pp < 2; ++pp) {
+            const int cb = (ehalf * 2 + pp) * 32;                  // 32 units of the chunk
+            if (c * 128 + cb >= uvalid) break;
+            float v[32];
+            tmem_ld_groups(t_main, t_main + 128, cb, cb + 8, cb + 16, cb + 24, v);
+            xpose8(v, lane);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int j = u0 + c * 128 + cb + g * 8 + c8;
+              if (j < a.H) {
+                if (t > 0) {
+                  float dhc[4];
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) dhc[k] = __ldg(a.Dh + k * a.H + j);
+                  PwIn in[8];
+#pragma unroll
+                  for (int rg = 0; rg < 8; ++rg) {
+                    const int m = row0 + eq * 32 + rg * 4 + rl;
+                    if (m < a.B) pw_load(a, t - 1, m, j, false, in[rg]);
+                  }
+#pragma unroll
+                  for (int rg = 0; rg < 8; ++rg) {
+                    const int m = row0 + eq * 32 + rg * 4 + rl;
+                    if (m < a.B) pw_finish(a, t - 1, m, j, in[rg], in[rg].dhs + v[g * 8 + rg], dhc);
+                  }
+                } else {
+#pragma unroll
+                  for (int rg = 0; rg < 8; ++rg) {
+                    const int m = row0 + eq * 32 + rg * 4 + rl;
+                    if (m < a.B) {
+                      if (a.dh0) a.dh0[(size_t)m * a.H + j] = a.dhrun[(size_t)m * a.Hp + j] + v[g * 8 + rg];
+                      if (a.dc0) a.dc0[(size_t)m * a.H + j] = a.dcrun[(size_t)m * a.Hp + j];
+                    }
+                  }
+                }
+              }
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars->acce[buf]);
+        }
+        fence_proxy_async_all();
+      }
+      __syncthreads();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(512));
+  }
+}
+
 }  // namespace r2
 }  // namespace vmlmf

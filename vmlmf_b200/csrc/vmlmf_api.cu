@@ -130,7 +130,9 @@ int vmlmf_seq_plan(int T, int B, int I, int H, int RX, int RH, vmlmf_plan* plan)
   if (r2::fits(T, B, I, H, RX, RH)) {
     plan->path = VMLMF_PATH_R2;
     plan->xp_cols = 0;
-    plan->fwd_workspace_bytes = (r2::geom(T, B, I, H, RX, RH).fwd_floats + 64) * (long long)sizeof(float);
+    const r2::Geom g = r2::geom(T, B, I, H, RX, RH);
+    plan->fwd_workspace_bytes = (g.fwd_floats + 64) * (long long)sizeof(float);
+    plan->bwd_workspace_bytes = (g.bwd_floats + tp_scratch(T, B, I, H, g.Hp, RX, RH).total + 128) * (long long)sizeof(float);
   }
   return VMLMF_OK;
 }
@@ -318,7 +320,24 @@ int vmlmf_seq_bwd(const vmlmf_plan* plan, const float* x, long long xs_t, long l
     int nparts = 0;
     return launch_bwd_mma(ba, gr, o, workspace, &nparts, st);
   }
-  if (plan->path == VMLMF_PATH_G || plan->path == VMLMF_PATH_R2)
+  if (plan->path == VMLMF_PATH_R2) {
+    if (!r2::fits(T, B, I, H, RX, RH) || plan->zx_pitch != round_up(RX, 4) || plan->z_pitch != round_up(RH, 4)) return VMLMF_EPLAN;
+    // persistent reverse-time recurrence, then the contractions over all T*B rows
+    r2::BwdCall bc{Vx, A, Bm, Dh, c0, gates, cs, dy, dys_t, dys_b, dhT, dcT, dh0, dc0, T, B, I, H, RX, RH};
+    r2::BwdOut bo;
+    int rc2 = r2::launch_bwd(bc, workspace, &bo, st);
+    if (rc2) return rc2;
+    const TpScratch ts = tp_scratch(T, B, I, H, bo.G, RX, RH);
+    float* part = align4(bo.after);
+    TpArgs tp{bo.dpre, bo.G, z, plan->z_pitch, zx, plan->zx_pitch, bo.dz, bo.dzx, true, x, xs_t, xs_b, y, ys_t, ys_b, h0, Ux, Vx, Dx,
+              dx, dxs_t, dxs_b, dUx, dVx, dDx, dA, dBm, dDh, dbias, part, ts.n_part, nullptr, nullptr, nullptr, nullptr, ts.ldt, nullptr,
+              T, B, I, H, RX, RH, true};
+    tp.tA = align4(part + ts.n_part);
+    tp.tB = align4(tp.tA + ts.n_tA);
+    tp.gtmp = align4(tp.tB + ts.n_tB);
+    return generic_bwd_tp(tp, st);
+  }
+  if (plan->path == VMLMF_PATH_G)
     return generic_seq_bwd(plan, x, xs_t, xs_b, zx, Ux, Vx, Dx, A, Bm, Dh, h0, c0, y, ys_t, ys_b, gates, cs, z,
                            dy, dys_t, dys_b, dhT, dcT, dx, dxs_t, dxs_b, dh0, dc0, dUx, dVx, dDx, dA, dBm, dDh,
                            dbias, workspace, T, B, I, H, RX, RH, st);
