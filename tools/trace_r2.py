@@ -21,8 +21,17 @@ sc = 0.05 if H >= 300 else 0.1
 r = lambda *s: torch.randn(*s, device=dev, generator=g) * sc
 canon = [r(I, RX), r(4 * H, RX), r(4, I), r(H, RH), r(4 * H, RH), r(4, H), r(4 * H)]
 x = torch.randn(T, B, I, device=dev, generator=g)
-with torch.no_grad():
-    vmlmf_sequence(x, None, None, canon, False)
+bwd = len(sys.argv) > 7 and sys.argv[7] == "bwd"
+tr_buf0 = (ctypes.c_longlong * 8192)()
+if bwd:
+    for p in canon:
+        p.requires_grad_(True)
+    y, hT, cT = vmlmf_sequence(x, None, None, canon, False)
+    ctypes.CDLL(out).vmlmf_r2_trace_read(tr_buf0, 4096)          # drop the forward's events
+    (y.sum() + hT.sum()).backward()
+else:
+    with torch.no_grad():
+        vmlmf_sequence(x, None, None, canon, False)
 torch.cuda.synchronize()
 tr_buf = (ctypes.c_longlong * 8192)()
 h = ctypes.CDLL(out)

@@ -123,25 +123,16 @@ int map_3d(CUtensorMap* m, const float* p, long long cols, long long d1, long lo
   return r == CUDA_SUCCESS ? 0 : tc::kTcNoFit;
 }
 
+// Cooperative launch: every CTA of the grid is resident at once (grid <= SMs, one CTA per SM by shared-memory size), which
+// the group barriers inside the kernels rely on.
 template <class Kern, class... Args>
-int launch_clustered(Kern kern, int grid, int cs, cudaStream_t st, Args... args) {
+int launch_coop(Kern kern, int grid, cudaStream_t st, Args... args) {
   // set on every launch: kernels that differ only in a template flag share this function's instantiation (same pointer
   // type), and the attribute is per device; the call is a few microseconds against a launch that runs T timesteps
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
   if (e != cudaSuccess) return (int)e;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = kSmemBytes;
-  cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = cs;
-  at[0].val.clusterDim.y = 1;
-  at[0].val.clusterDim.z = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = cs > 1 ? 1 : 0;
-  return (int)cudaLaunchKernelEx(&cfg, kern, args...);
+  void* argv[] = {(void*)&args...};
+  return (int)cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(kThreads), argv, kSmemBytes, st);
 }
 
 }  // namespace
@@ -156,16 +147,16 @@ Geom geom(int T, int B, int I, int H, int RX, int RH) {
   (void)I;
   Geom g;
   g.ntiles = ceil_div(B, BM);
-  // widest cluster that still has work for every CTA: enough CTAs to cover the SMs, at least 32 units per CTA
+  // widest group that still has work for every CTA: enough CTAs to cover the SMs, at least 32 units per CTA
   int cs = num_sms() / g.ntiles;
-  if (cs > kMaxCluster) cs = kMaxCluster;
+  if (cs > kMaxGroup) cs = kMaxGroup;
   if (cs < 1) cs = 1;
   if (cs > ceil_div(H, 32)) cs = ceil_div(H, 32);
+  const char* force = getenv("VMLMF_R2_CLUSTER");     // tests: force a group size
+  if (force && atoi(force) >= 1 && atoi(force) <= kMaxGroup && atoi(force) <= ceil_div(H, 32)) cs = atoi(force);
   // at most 512 units (64 tf32 k-steps) per CTA in the K-split z product: the tensor core's accumulate truncates, so
   // the rounding error of one accumulator grows with the number of k-steps (measured 3e-8 per step)
-  const char* force = getenv("VMLMF_R2_CLUSTER");     // tests: force a cluster size
-  if (force && atoi(force) >= 1 && atoi(force) <= kMaxCluster && atoi(force) <= ceil_div(H, 32)) cs = atoi(force);
-  if (cs < ceil_div(H, 512)) cs = ceil_div(H, 512) < kMaxCluster ? ceil_div(H, 512) : kMaxCluster;
+  if (cs < ceil_div(H, 512)) cs = ceil_div(H, 512);
   g.HS = 32 * ceil_div(H, 32 * cs);
   g.CS = ceil_div(H, g.HS);
   g.Hp = g.CS * g.HS;
@@ -193,6 +184,7 @@ Geom geom(int T, int B, int I, int H, int RX, int RH) {
   g.o_w2_hi = o; o += al64(4LL * g.Hp * g.KPp);
   g.o_w2_lo = o; o += al64(4LL * g.Hp * g.KPp);
   g.o_cbuf = o; o += al64(2LL * B * H);
+  g.o_sync = o; o += al64(32LL * g.ncl);
   g.fwd_floats = o + 64;
   // backward: phase 1 contracts over 4 * HS values per CTA; at most 16 K tiles (64 tf32 k-steps) per accumulator
   g.KSPLIT = ceil_div(4 * (g.HS / 32), 16);
@@ -212,6 +204,7 @@ Geom geom(int T, int B, int I, int H, int RX, int RH) {
   g.b_w2t_lo = o; o += al64((long long)g.KPp * 4 * g.Hp);
   g.b_ap_hi = o; o += al64((long long)g.Hp * g.KZP);
   g.b_ap_lo = o; o += al64((long long)g.Hp * g.KZP);
+  g.b_sync = o; o += al64(32LL * g.ncl);
   g.bwd_floats = o + 64;
   return g;
 }
@@ -256,12 +249,15 @@ int launch_fwd(const FwdCall& c, void* workspace, cudaStream_t st) {
   a.hop_hi = hop_hi; a.hop_lo = hop_lo; a.zop_hi = zop_hi; a.zop_lo = zop_lo; a.zpart = ws + g.o_zpart;
   a.T = c.T; a.B = c.B; a.I = c.I; a.H = c.H; a.RX = c.RX; a.RH = c.RH;
   a.Hp = g.Hp; a.HS = g.HS; a.CS = g.CS; a.zp = g.zp; a.KZP = g.KZP; a.save = save ? 1 : 0;
+  a.sync = reinterpret_cast<unsigned int*>(ws + g.o_sync);
+  cudaError_t me = cudaMemsetAsync(a.sync, 0, 32 * sizeof(unsigned int) * (size_t)g.ncl, st);
+  if (me != cudaSuccess) return (int)me;
   const int grid = g.ncl * g.CS;
   if (save)
-    return launch_clustered(r2_fwd_kernel<true>, grid, g.CS, st, m_hop_hi, m_hop_lo, m_at_hi, m_at_lo, m_zop_hi, m_zop_lo,
-                            m_zx_hi, m_zx_lo, m_w2_hi, m_w2_lo, a);
-  return launch_clustered(r2_fwd_kernel<false>, grid, g.CS, st, m_hop_hi, m_hop_lo, m_at_hi, m_at_lo, m_zop_hi, m_zop_lo,
-                          m_zx_hi, m_zx_lo, m_w2_hi, m_w2_lo, a);
+    return launch_coop(r2_fwd_kernel<true>, grid, st, m_hop_hi, m_hop_lo, m_at_hi, m_at_lo, m_zop_hi, m_zop_lo,
+                       m_zx_hi, m_zx_lo, m_w2_hi, m_w2_lo, a);
+  return launch_coop(r2_fwd_kernel<false>, grid, st, m_hop_hi, m_hop_lo, m_at_hi, m_at_lo, m_zop_hi, m_zop_lo,
+                     m_zx_hi, m_zx_lo, m_w2_hi, m_w2_lo, a);
 }
 
 int launch_bwd(const BwdCall& c, void* workspace, BwdOut* out, cudaStream_t st) {
@@ -291,8 +287,11 @@ int launch_bwd(const BwdCall& c, void* workspace, BwdOut* out, cudaStream_t st) 
   a.T = c.T; a.B = c.B; a.H = c.H; a.RX = c.RX; a.RH = c.RH;
   a.Hp = g.Hp; a.HS = g.HS; a.CS = g.CS; a.zp = g.zp; a.zxp = g.zxp; a.KZP = g.KZP; a.KPp = g.KPp; a.KSPLIT = g.KSPLIT;
   out->dpre = a.dpre; out->G = g.Hp; out->dz = a.dz_all; out->dzx = a.dzx_all; out->after = ws + g.bwd_floats;
-  return launch_clustered(r2_bwd_kernel, g.ncl * g.CS, g.CS, st, m_dpo_hi, m_dpo_lo, m_w2t_hi, m_w2t_lo, m_dzo_hi, m_dzo_lo,
-                          m_ap_hi, m_ap_lo, a);
+  a.sync = reinterpret_cast<unsigned int*>(ws + g.b_sync);
+  e = cudaMemsetAsync(a.sync, 0, 32 * sizeof(unsigned int) * (size_t)g.ncl, st);
+  if (e != cudaSuccess) return (int)e;
+  return launch_coop(r2_bwd_kernel, g.ncl * g.CS, st, m_dpo_hi, m_dpo_lo, m_w2t_hi, m_w2t_lo, m_dzo_hi, m_dzo_lo,
+                     m_ap_hi, m_ap_lo, a);
 }
 
 }  // namespace r2

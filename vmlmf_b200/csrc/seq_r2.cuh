@@ -4,11 +4,13 @@
 // H=650 r=300, V/models/vmlmf_lm.py:272-280 with lstm_step :222-269; ranks > 16; the H >= 1024 sweep,
 // V/models/vmlmf.py:308-310 with the cell body :78-125).  One launch runs all T timesteps.
 //
-// Decomposition.  A thread-block CLUSTER of CS CTAs owns one 128-row batch tile for all T steps; CTA s of the
-// cluster owns the hidden units [s*HS, (s+1)*HS) (HS % 32 == 0).  Clusters walk the batch tiles round-robin.
+// Decomposition.  A GROUP of CS co-resident CTAs (cooperative launch, one CTA per SM) owns one 128-row batch tile for
+// all T steps; CTA s of the group owns the hidden units [s*HS, (s+1)*HS) (HS % 32 == 0).  Groups walk the batch tiles
+// round-robin.  CS is chosen so that groups x CS covers the SMs: up to H/32 CTAs per tile (a thread-block cluster would
+// cap it at 8; the exchange goes through L2 either way, so the group barrier is a release/acquire counter in global memory).
 // Per timestep, per CTA (fp32-accurate 3xTF32 products, accumulators in tensor memory):
-//   phase Z   partial z_s[128, RH]   = h_{t-1}[:, slice s] * A[slice s, :]            K = HS   (K-split over the cluster)
-//   exchange  z = sum_s z_s  (partials through L2, fixed-order reduce, rows split over the cluster's CTAs)
+//   phase Z   partial z_s[128, RH]   = h_{t-1}[:, slice s] * A[slice s, :]            K = HS   (K-split over the group)
+//   exchange  z = sum_s z_s  (partials through L2, fixed-order reduce, rows split over the group's CTAs)
 //   phase G   pre[128, 4 x 32 units] = [z | zx_t] * [Bm | Vx]^T  per 32-unit chunk      K = RH + RX  (x side fused:
 //             XP[T*B,4H] is never materialised), epilogue = + x (.) Dx + h_{t-1} (.) Dh + bias, gates, c/h update,
 //             saved activations, and h_t written back as the next step's tensor-core operand (tf32 hi / lo parts).
@@ -54,14 +56,25 @@ constexpr int kStageBytes = 4 * kTile;       // A hi | A lo | B hi | B lo
 constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*alignment*/ + 256 /*barriers*/;
 constexpr int kEpiWarps = 8;                 // two per tensor-memory lane quarter
 constexpr int kThreads = 64 + 32 * kEpiWarps;
-constexpr int kMaxCluster = 8;
+constexpr int kMaxGroup = 64;                // CTAs per batch tile
 
 // ------------------------------------------------------------------------------------------------- PTX
-__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ uint32_t cluster_id_x() { uint32_t r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
-__device__ __forceinline__ uint32_t ncluster_x() { uint32_t r; asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r)); return r; }
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+// Barrier among the CS CTAs of one tile group (all co-resident: cooperative launch).  `ctr` is the group's monotonic
+// arrival counter (zeroed before the launch); the k-th barrier completes when it reaches (k+1) * CS.  Release / acquire at
+// GPU scope: everything the group's threads wrote before the barrier is visible to all of them after it.
+__device__ __forceinline__ void group_sync(unsigned int* ctr, unsigned int& epoch, int CS) {
+  __syncthreads();
+  ++epoch;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(ctr, 1u);
+    const unsigned int target = epoch * (unsigned int)CS;
+    unsigned int seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
+    } while (seen < target);
+  }
+  __syncthreads();
 }
 // generic-proxy writes (st.global / st.shared) -> visible to the async proxy (TMA reads) once a barrier follows
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
@@ -159,6 +172,30 @@ __device__ __forceinline__ void xpose8(float (&v)[32], int lane) {
     }
   }
 }
+// the same exchange on one 8-column group: v[i] (row lane, column i) -> lane (c8, rl) holds v[rg] = (row rg*4 + rl, column c8)
+__device__ __forceinline__ void xpose8_group(float (&v)[8], int lane) {
+#pragma unroll
+  for (int s = 0; s < 3; ++s) {
+    const int c = 1 << s, lb = 4 << s;
+    const bool up = (lane & lb) != 0;
+#pragma unroll
+    for (int r0 = 0; r0 < 8; ++r0) {
+      if (r0 & c) continue;
+      const int r1 = r0 | c;
+      const float send = up ? v[r0] : v[r1];
+      const float recv = __shfl_xor_sync(0xffffffffu, send, lb);
+      if (up) v[r0] = recv; else v[r1] = recv;
+    }
+  }
+}
+__device__ __forceinline__ void tmem_ld_group(uint32_t t_main, uint32_t t_cross, int c0, float (&v)[8]) {
+  float b[8];
+  tc::tmem_ld8_raw(t_main + c0, v);
+  tc::tmem_ld8_raw(t_cross + c0, b);
+  tc::tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] += b[i];
+}
 // v[g*8 + i] = main + cross of this thread's row at columns col(g) + i, g = 0..3 (four 8-column groups)
 __device__ __forceinline__ void tmem_ld_groups(uint32_t t_main, uint32_t t_cross, int c0, int c1, int c2, int c3, float (&v)[32]) {
   float a[4][8], b[4][8];
@@ -188,7 +225,8 @@ struct FwdArgs {
   // operand scratch
   float *hop_hi, *hop_lo;     // [B, Hp]
   float *zop_hi, *zop_lo;     // [B, zp]
-  float* zpart;               // [nclusters, CS, 128, zp] partial z (CS > 1)
+  float* zpart;               // [groups, CS, 128, zp] partial z (CS > 1)
+  unsigned int* sync;         // [groups, 32] group barrier counters, zeroed before the launch
   int T, B, I, H, RX, RH;
   int Hp, HS, CS, zp, KZP;    // KZP = round_up(RH, 32): K offset of the x side inside the packed gate factor
   int save;
@@ -206,10 +244,10 @@ r2_fwd_kernel(const __grid_constant__ CUtensorMap m_hop_hi, const __grid_constan
   Bars* bars = sm.bars;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int CS = a.CS;
-  const int s_rank = CS > 1 ? (int)cluster_ctarank() : 0;
-  const int cid = CS > 1 ? (int)cluster_id_x() : (int)blockIdx.x;
-  const int ncl = CS > 1 ? (int)ncluster_x() : (int)gridDim.x;
+  const int s_rank = (int)blockIdx.x % CS, cid = (int)blockIdx.x / CS, ncl = (int)gridDim.x / CS;
   const int ntiles = (a.B + BM - 1) / BM;
+  unsigned int* const sync_ctr = a.sync + cid * 32;          // one 128-byte line per group
+  unsigned int epoch = 0;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
@@ -330,10 +368,10 @@ r2_fwd_kernel(const __grid_constant__ CUtensorMap m_hop_hi, const __grid_constan
       }
       // ======================================= exchange =======================================
       if (CS > 1) {
-        cluster_sync_all();
+        group_sync(sync_ctr, epoch, CS);
         if (warp == 2) R2_TRACE(30);
         if (warp >= 2) {
-          // fixed-order sum of the CS partials; the tile's valid rows are split over the cluster's CTAs
+          // fixed-order sum of the CS partials; the tile's valid rows are split over the group's CTAs
           const int rows_valid = min(BM, a.B - row0);
           const int rpc = (rows_valid + CS - 1) / CS;
           const int r_lo = s_rank * rpc, r_hi = min(rows_valid, r_lo + rpc);
@@ -342,12 +380,14 @@ r2_fwd_kernel(const __grid_constant__ CUtensorMap m_hop_hi, const __grid_constan
           const float* pbase = a.zpart + ((size_t)cid * CS * BM + r_lo) * a.zp;
           const int pstride = BM * a.zp;
           for (int e = et; e < nel; e += 32 * kEpiWarps) {
-            float pv[kMaxCluster];
+            float v = 0.f;
+            for (int q0 = 0; q0 < CS; q0 += 8) {                              // eight loads in flight; fixed summation order
+              float pv[8];
 #pragma unroll
-            for (int q = 0; q < kMaxCluster; ++q) pv[q] = q < CS ? __ldcg(pbase + q * pstride + e) : 0.f;   // all loads in flight
-            float v = pv[0];
+              for (int q = 0; q < 8; ++q) pv[q] = q0 + q < CS ? __ldcg(pbase + (size_t)(q0 + q) * pstride + e) : 0.f;
 #pragma unroll
-            for (int q = 1; q < kMaxCluster; ++q) v += pv[q];                 // fixed order; absent ranks add +0
+              for (int q = 0; q < 8; ++q) v += pv[q];                         // absent ranks add +0
+            }
             const int r = r_lo + e / a.zp, c = e - (e / a.zp) * a.zp;
             const int m = row0 + r;
             if (SAVE) a.z[((size_t)t * a.B + m) * a.zp + c] = v;
@@ -358,7 +398,7 @@ r2_fwd_kernel(const __grid_constant__ CUtensorMap m_hop_hi, const __grid_constan
           fence_proxy_async_all();
           if (warp == 2) R2_TRACE(31);
         }
-        cluster_sync_all();
+        group_sync(sync_ctr, epoch, CS);
         if (warp == 2) R2_TRACE(32);
       } else {
         __syncthreads();
@@ -523,7 +563,8 @@ struct BwdArgs {
   float *dpo_hi, *dpo_lo;     // [B, 4, Hp]   tf32 operand copy of dPre_t
   float *dzo_hi, *dzo_lo;     // [B, zp]      tf32 operand copy of dz_t
   float *dhrun, *dcrun;       // [B, Hp]
-  float* part;                // [nclusters, NP, 128, KPp]   NP = CS * KSPLIT partials
+  float* part;                // [groups, NP, 128, KPp]   NP = CS * KSPLIT partials
+  unsigned int* sync;         // [groups, 32] group barrier counters, zeroed before the launch
   int T, B, H, RX, RH;
   int Hp, HS, CS, zp, zxp, KZP, KPp, KSPLIT;
 };
@@ -583,10 +624,10 @@ r2_bwd_kernel(const __grid_constant__ CUtensorMap m_dpo_hi, const __grid_constan
   Bars* bars = sm.bars;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int CS = a.CS, KSPLIT = a.KSPLIT, NP = CS * KSPLIT;
-  const int s_rank = CS > 1 ? (int)cluster_ctarank() : 0;
-  const int cid = CS > 1 ? (int)cluster_id_x() : (int)blockIdx.x;
-  const int ncl = CS > 1 ? (int)ncluster_x() : (int)gridDim.x;
+  const int s_rank = (int)blockIdx.x % CS, cid = (int)blockIdx.x / CS, ncl = (int)gridDim.x / CS;
   const int ntiles = (a.B + BM - 1) / BM;
+  unsigned int* const sync_ctr = a.sync + cid * 32;          // one 128-byte line per group
+  unsigned int epoch = 0;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
@@ -732,7 +773,7 @@ r2_bwd_kernel(const __grid_constant__ CUtensorMap m_dpo_hi, const __grid_constan
       }
       // ======================================= exchange =======================================
       if (NP > 1) {
-        if (CS > 1) cluster_sync_all(); else __syncthreads();
+        if (CS > 1) group_sync(sync_ctr, epoch, CS); else __syncthreads();
         if (warp >= 2) {
           const int rows_valid = min(BM, a.B - row0);
           const int rpc = (rows_valid + CS - 1) / CS;
@@ -766,7 +807,7 @@ r2_bwd_kernel(const __grid_constant__ CUtensorMap m_dpo_hi, const __grid_constan
           }
           fence_proxy_async_all();
         }
-        if (CS > 1) cluster_sync_all(); else __syncthreads();
+        if (CS > 1) group_sync(sync_ctr, epoch, CS); else __syncthreads();
       } else {
         __syncthreads();
       }
@@ -812,40 +853,39 @@ r2_bwd_kernel(const __grid_constant__ CUtensorMap m_dpo_hi, const __grid_constan
           mbar_wait(&bars->accf[buf], use & 1);
           tc_fence_after();
           const uint32_t t_main = tmem_d + ((uint32_t)(eq * 32) << 16) + buf * 256;
+          // this warp's eight 8-unit groups of the chunk, one per (deliberately not unrolled) iteration: the body holds the
+          // gate-gradient algebra of eight cells and must stay inside the instruction cache
 #pragma unroll 1
-          for (int pp = 0; pp < 2; ++pp) {
-            const int cb = (ehalf * 2 + pp) * 32;                  // 32 units of the chunk
+          for (int gg = 0; gg < 8; ++gg) {
+            const int cb = (ehalf * 8 + gg) * 8;
             if (c * 128 + cb >= uvalid) break;
-            float v[32];
-            tmem_ld_groups(t_main, t_main + 128, cb, cb + 8, cb + 16, cb + 24, v);
-            xpose8(v, lane);
+            float v[8];
+            tmem_ld_group(t_main, t_main + 128, cb, v);
+            xpose8_group(v, lane);
+            const int j = u0 + c * 128 + cb + c8;
+            if (j < a.H) {
+              if (t > 0) {
+                float dhc[4];
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const int j = u0 + c * 128 + cb + g * 8 + c8;
-              if (j < a.H) {
-                if (t > 0) {
-                  float dhc[4];
+                for (int k = 0; k < 4; ++k) dhc[k] = __ldg(a.Dh + k * a.H + j);
+                PwIn in[8];
 #pragma unroll
-                  for (int k = 0; k < 4; ++k) dhc[k] = __ldg(a.Dh + k * a.H + j);
-                  PwIn in[8];
+                for (int rg = 0; rg < 8; ++rg) {
+                  const int m = row0 + eq * 32 + rg * 4 + rl;
+                  if (m < a.B) pw_load(a, t - 1, m, j, false, in[rg]);
+                }
 #pragma unroll
-                  for (int rg = 0; rg < 8; ++rg) {
-                    const int m = row0 + eq * 32 + rg * 4 + rl;
-                    if (m < a.B) pw_load(a, t - 1, m, j, false, in[rg]);
-                  }
+                for (int rg = 0; rg < 8; ++rg) {
+                  const int m = row0 + eq * 32 + rg * 4 + rl;
+                  if (m < a.B) pw_finish(a, t - 1, m, j, in[rg], in[rg].dhs + v[rg], dhc);
+                }
+              } else {
 #pragma unroll
-                  for (int rg = 0; rg < 8; ++rg) {
-                    const int m = row0 + eq * 32 + rg * 4 + rl;
-                    if (m < a.B) pw_finish(a, t - 1, m, j, in[rg], in[rg].dhs + v[g * 8 + rg], dhc);
-                  }
-                } else {
-#pragma unroll
-                  for (int rg = 0; rg < 8; ++rg) {
-                    const int m = row0 + eq * 32 + rg * 4 + rl;
-                    if (m < a.B) {
-                      if (a.dh0) a.dh0[(size_t)m * a.H + j] = a.dhrun[(size_t)m * a.Hp + j] + v[g * 8 + rg];
-                      if (a.dc0) a.dc0[(size_t)m * a.H + j] = a.dcrun[(size_t)m * a.Hp + j];
-                    }
+                for (int rg = 0; rg < 8; ++rg) {
+                  const int m = row0 + eq * 32 + rg * 4 + rl;
+                  if (m < a.B) {
+                    if (a.dh0) a.dh0[(size_t)m * a.H + j] = a.dhrun[(size_t)m * a.Hp + j] + v[rg];
+                    if (a.dc0) a.dc0[(size_t)m * a.H + j] = a.dcrun[(size_t)m * a.Hp + j];
                   }
                 }
               }

@@ -8,12 +8,12 @@ namespace r2 {
 // geometry of one call: cluster size, hidden slice per CTA, padded sizes, workspace offsets (in floats)
 struct Geom {
   int ntiles, CS, HS, Hp, zp, zxp, RHr, KZP, KXP, KPp, ncl;
-  long long o_hop_hi, o_hop_lo, o_zop_hi, o_zop_lo, o_zpart, o_zx_hi, o_zx_lo, o_at_hi, o_at_lo, o_w2_hi, o_w2_lo, o_cbuf;
+  long long o_hop_hi, o_hop_lo, o_zop_hi, o_zop_lo, o_zpart, o_zx_hi, o_zx_lo, o_at_hi, o_at_lo, o_w2_hi, o_w2_lo, o_cbuf, o_sync;
   long long fwd_floats;
   // backward
   int KSPLIT, NP;            // K segments of phase 1 per CTA (<= 64 tf32 k-steps per accumulator), partials per tile
   long long b_dpre, b_dz, b_dzx, b_dpo_hi, b_dpo_lo, b_dzo_hi, b_dzo_lo, b_dhrun, b_dcrun, b_part, b_w2t_hi, b_w2t_lo,
-      b_ap_hi, b_ap_lo;
+      b_ap_hi, b_ap_lo, b_sync;
   long long bwd_floats;      // recurrence part only; the time-parallel GEMMs' scratch follows it in the caller's workspace
 };
 Geom geom(int T, int B, int I, int H, int RX, int RH);
