@@ -172,6 +172,24 @@ __device__ __forceinline__ void xpose8(float (&v)[32], int lane) {
     }
   }
 }
+// Variant for outputs whose 32 columns are contiguous in memory (z, dz, partials): exchange register bits 4..2 (column / 4)
+// with lane bits 4..2.  Afterwards lane (c4 = lane >> 2, rl = lane & 3) holds v[rg*4 + i] = (row rg*4 + rl, column c4*4 + i):
+// one float4 per row, and a warp instruction writes 4 rows x 128 contiguous bytes.
+__device__ __forceinline__ void xpose_vec4(float (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 0; s < 3; ++s) {
+    const int c = 4 << s, lb = 4 << s;
+    const bool up = (lane & lb) != 0;
+#pragma unroll
+    for (int r0 = 0; r0 < 32; ++r0) {
+      if (r0 & c) continue;
+      const int r1 = r0 | c;
+      const float send = up ? v[r0] : v[r1];
+      const float recv = __shfl_xor_sync(0xffffffffu, send, lb);
+      if (up) v[r0] = recv; else v[r1] = recv;
+    }
+  }
+}
 // the same exchange on one 8-column group: v[i] (row lane, column i) -> lane (c8, rl) holds v[rg] = (row rg*4 + rl, column c8)
 __device__ __forceinline__ void xpose8_group(float (&v)[8], int lane) {
 #pragma unroll
@@ -331,29 +349,31 @@ r2_fwd_kernel(const __grid_constant__ CUtensorMap m_hop_hi, const __grid_constan
           if (warp == 2) R2_TRACE(20);
           const int ncol = min(128, RHr - zc * 128);
           const uint32_t t_main = tmem_d + ((uint32_t)(eq * 32) << 16) + buf * 256;
-          // this warp's two 32-column passes of the chunk: partial z (CS > 1) or the final z (CS == 1)
+          // this warp's two 32-column passes of the chunk: partial z (CS > 1) or the final z (CS == 1); zp % 4 == 0, so a
+          // lane's four columns are all inside or all outside the row
 #pragma unroll 1
           for (int pp = 0; pp < 2; ++pp) {
             const int cb = (ehalf * 2 + pp) * 32;
             if (cb >= ncol) break;
             float v[32];
             tmem_ld_groups(t_main, t_main + 128, cb, cb + 8, cb + 16, cb + 24, v);
-            xpose8(v, lane);
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const int c = zc * 128 + cb + g * 8 + c8;
+            xpose_vec4(v, lane);
+            const int c = zc * 128 + cb + (lane >> 2) * 4;
+            if (c < a.zp) {
 #pragma unroll
               for (int rg = 0; rg < 8; ++rg) {
                 const int r = eq * 32 + rg * 4 + rl, m = row0 + r;
-                if (c < a.zp && m < a.B) {
-                  const float val = v[g * 8 + rg];
+                if (m < a.B) {
+                  const float4 val = make_float4(v[rg * 4], v[rg * 4 + 1], v[rg * 4 + 2], v[rg * 4 + 3]);
                   if (CS > 1) {
-                    a.zpart[(((size_t)cid * CS + s_rank) * BM + r) * a.zp + c] = val;
+                    *reinterpret_cast<float4*>(a.zpart + (((size_t)cid * CS + s_rank) * BM + r) * a.zp + c) = val;
                   } else {
-                    if (SAVE) a.z[((size_t)t * a.B + m) * a.zp + c] = val;
-                    const float hi = split_hi(val);
-                    a.zop_hi[(size_t)m * a.zp + c] = hi;
-                    a.zop_lo[(size_t)m * a.zp + c] = split_lo(val, hi);
+                    if (SAVE) *reinterpret_cast<float4*>(a.z + ((size_t)t * a.B + m) * a.zp + c) = val;
+                    float4 hi, lo;
+                    hi.x = split_hi(val.x); hi.y = split_hi(val.y); hi.z = split_hi(val.z); hi.w = split_hi(val.w);
+                    lo.x = split_lo(val.x, hi.x); lo.y = split_lo(val.y, hi.y); lo.z = split_lo(val.z, hi.z); lo.w = split_lo(val.w, hi.w);
+                    *reinterpret_cast<float4*>(a.zop_hi + (size_t)m * a.zp + c) = hi;
+                    *reinterpret_cast<float4*>(a.zop_lo + (size_t)m * a.zp + c) = lo;
                   }
                 }
               }
@@ -376,24 +396,27 @@ r2_fwd_kernel(const __grid_constant__ CUtensorMap m_hop_hi, const __grid_constan
           const int rpc = (rows_valid + CS - 1) / CS;
           const int r_lo = s_rank * rpc, r_hi = min(rows_valid, r_lo + rpc);
           const int et = threadIdx.x - 64;                                   // 0 .. 32 * kEpiWarps - 1
-          const int nel = (r_hi - r_lo) * a.zp;
-          const float* pbase = a.zpart + ((size_t)cid * CS * BM + r_lo) * a.zp;
-          const int pstride = BM * a.zp;
+          const int zp4 = a.zp >> 2;
+          const int nel = (r_hi - r_lo) * zp4;                               // float4 elements of this CTA's rows
+          const float4* pbase = reinterpret_cast<const float4*>(a.zpart + ((size_t)cid * CS * BM + r_lo) * a.zp);
+          const size_t pstride = (size_t)BM * zp4;
           for (int e = et; e < nel; e += 32 * kEpiWarps) {
-            float v = 0.f;
-            for (int q0 = 0; q0 < CS; q0 += 8) {                              // eight loads in flight; fixed summation order
-              float pv[8];
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int q0 = 0; q0 < CS; q0 += 8) {                              // eight 16-byte loads in flight; fixed summation order
+              float4 pv[8];
 #pragma unroll
-              for (int q = 0; q < 8; ++q) pv[q] = q0 + q < CS ? __ldcg(pbase + (size_t)(q0 + q) * pstride + e) : 0.f;
+              for (int q = 0; q < 8; ++q) pv[q] = q0 + q < CS ? __ldcg(pbase + (size_t)(q0 + q) * pstride + e) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-              for (int q = 0; q < 8; ++q) v += pv[q];                         // absent ranks add +0
+              for (int q = 0; q < 8; ++q) { v.x += pv[q].x; v.y += pv[q].y; v.z += pv[q].z; v.w += pv[q].w; }   // absent ranks add +0
             }
-            const int r = r_lo + e / a.zp, c = e - (e / a.zp) * a.zp;
+            const int r = r_lo + e / zp4, c = (e - (e / zp4) * zp4) * 4;
             const int m = row0 + r;
-            if (SAVE) a.z[((size_t)t * a.B + m) * a.zp + c] = v;
-            const float hi = split_hi(v);
-            a.zop_hi[(size_t)m * a.zp + c] = hi;
-            a.zop_lo[(size_t)m * a.zp + c] = split_lo(v, hi);
+            if (SAVE) *reinterpret_cast<float4*>(a.z + ((size_t)t * a.B + m) * a.zp + c) = v;
+            float4 hi, lo;
+            hi.x = split_hi(v.x); hi.y = split_hi(v.y); hi.z = split_hi(v.z); hi.w = split_hi(v.w);
+            lo.x = split_lo(v.x, hi.x); lo.y = split_lo(v.y, hi.y); lo.z = split_lo(v.z, hi.z); lo.w = split_lo(v.w, hi.w);
+            *reinterpret_cast<float4*>(a.zop_hi + (size_t)m * a.zp + c) = hi;
+            *reinterpret_cast<float4*>(a.zop_lo + (size_t)m * a.zp + c) = lo;
           }
           fence_proxy_async_all();
           if (warp == 2) R2_TRACE(31);
@@ -741,25 +764,24 @@ r2_bwd_kernel(const __grid_constant__ CUtensorMap m_dpo_hi, const __grid_constan
               if (cb >= ncol) break;
               float v[32];
               tmem_ld_groups(t_main, t_main + 128, cb, cb + 8, cb + 16, cb + 24, v);
-              xpose8(v, lane);
+              xpose_vec4(v, lane);
+              const int n = c * 128 + cb + (lane >> 2) * 4;            // first of this lane's 4 columns of [dz | pad | dzx | pad]
 #pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                const int n = c * 128 + cb + g * 8 + c8;            // column of [dz | pad | dzx | pad]
-#pragma unroll
-                for (int rg = 0; rg < 8; ++rg) {
-                  const int r = eq * 32 + rg * 4 + rl, m = row0 + r;
-                  if (m < a.B) {
-                    const float val = v[g * 8 + rg];
-                    if (NP > 1) {
-                      a.part[(((size_t)cid * NP + s_rank * KSPLIT + ks) * BM + r) * a.KPp + n] = val;
-                    } else if (n < a.zp) {
-                      a.dz_all[((size_t)t * a.B + m) * a.zp + n] = val;
-                      const float hi = split_hi(val);
-                      a.dzo_hi[(size_t)m * a.zp + n] = hi;
-                      a.dzo_lo[(size_t)m * a.zp + n] = split_lo(val, hi);
-                    } else if (n >= a.KZP && n < a.KZP + a.zxp) {
-                      a.dzx_all[((size_t)t * a.B + m) * a.zxp + (n - a.KZP)] = val;
-                    }
+              for (int rg = 0; rg < 8; ++rg) {
+                const int r = eq * 32 + rg * 4 + rl, m = row0 + r;
+                if (m < a.B) {
+                  const float4 val = make_float4(v[rg * 4], v[rg * 4 + 1], v[rg * 4 + 2], v[rg * 4 + 3]);
+                  if (NP > 1) {
+                    *reinterpret_cast<float4*>(a.part + (((size_t)cid * NP + s_rank * KSPLIT + ks) * BM + r) * a.KPp + n) = val;
+                  } else if (n < a.zp) {                               // zp, KZP, zxp are multiples of 4
+                    *reinterpret_cast<float4*>(a.dz_all + ((size_t)t * a.B + m) * a.zp + n) = val;
+                    float4 hi, lo;
+                    hi.x = split_hi(val.x); hi.y = split_hi(val.y); hi.z = split_hi(val.z); hi.w = split_hi(val.w);
+                    lo.x = split_lo(val.x, hi.x); lo.y = split_lo(val.y, hi.y); lo.z = split_lo(val.z, hi.z); lo.w = split_lo(val.w, hi.w);
+                    *reinterpret_cast<float4*>(a.dzo_hi + (size_t)m * a.zp + n) = hi;
+                    *reinterpret_cast<float4*>(a.dzo_lo + (size_t)m * a.zp + n) = lo;
+                  } else if (n >= a.KZP && n < a.KZP + a.zxp) {
+                    *reinterpret_cast<float4*>(a.dzx_all + ((size_t)t * a.B + m) * a.zxp + (n - a.KZP)) = val;
                   }
                 }
               }
@@ -779,30 +801,34 @@ r2_bwd_kernel(const __grid_constant__ CUtensorMap m_dpo_hi, const __grid_constan
           const int rpc = (rows_valid + CS - 1) / CS;
           const int r_lo = s_rank * rpc, r_hi = min(rows_valid, r_lo + rpc);
           const int et = threadIdx.x - 64;
-          const int wcols = a.zp + a.zxp;
-          const int nel = (r_hi - r_lo) * wcols;
+          const int zp4 = a.zp >> 2, w4 = (a.zp + a.zxp) >> 2;               // float4 columns: dz then dzx
+          const int nel = (r_hi - r_lo) * w4;
           const float* pbase = a.part + (size_t)cid * NP * BM * a.KPp;
           const size_t pstride = (size_t)BM * a.KPp;
           for (int e = et; e < nel; e += 32 * kEpiWarps) {
-            const int r = r_lo + e / wcols, cc = e - (e / wcols) * wcols;
-            const int n = cc < a.zp ? cc : a.KZP + (cc - a.zp);
+            const int r = r_lo + e / w4, c4 = e - (e / w4) * w4;
+            const int n = c4 < zp4 ? c4 * 4 : a.KZP + (c4 - zp4) * 4;
             const float* src = pbase + (size_t)r * a.KPp + n;
-            float v = 0.f;
-            int p = 0;
-            for (; p + 4 <= NP; p += 4) {
-              const float p0 = __ldcg(src + (size_t)p * pstride), p1 = __ldcg(src + (size_t)(p + 1) * pstride);
-              const float p2 = __ldcg(src + (size_t)(p + 2) * pstride), p3 = __ldcg(src + (size_t)(p + 3) * pstride);
-              v += p0; v += p1; v += p2; v += p3;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int p0 = 0; p0 < NP; p0 += 8) {                              // eight 16-byte loads in flight; fixed summation order
+              float4 pv[8];
+#pragma unroll
+              for (int q = 0; q < 8; ++q)
+                pv[q] = p0 + q < NP ? __ldcg(reinterpret_cast<const float4*>(src + (size_t)(p0 + q) * pstride)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+              for (int q = 0; q < 8; ++q) { v.x += pv[q].x; v.y += pv[q].y; v.z += pv[q].z; v.w += pv[q].w; }
             }
-            for (; p < NP; ++p) v += __ldcg(src + (size_t)p * pstride);
             const int m = row0 + r;
-            if (cc < a.zp) {
-              a.dz_all[((size_t)t * a.B + m) * a.zp + cc] = v;
-              const float hi = split_hi(v);
-              a.dzo_hi[(size_t)m * a.zp + cc] = hi;
-              a.dzo_lo[(size_t)m * a.zp + cc] = split_lo(v, hi);
+            if (c4 < zp4) {
+              const int cc = c4 * 4;
+              *reinterpret_cast<float4*>(a.dz_all + ((size_t)t * a.B + m) * a.zp + cc) = v;
+              float4 hi, lo;
+              hi.x = split_hi(v.x); hi.y = split_hi(v.y); hi.z = split_hi(v.z); hi.w = split_hi(v.w);
+              lo.x = split_lo(v.x, hi.x); lo.y = split_lo(v.y, hi.y); lo.z = split_lo(v.z, hi.z); lo.w = split_lo(v.w, hi.w);
+              *reinterpret_cast<float4*>(a.dzo_hi + (size_t)m * a.zp + cc) = hi;
+              *reinterpret_cast<float4*>(a.dzo_lo + (size_t)m * a.zp + cc) = lo;
             } else {
-              a.dzx_all[((size_t)t * a.B + m) * a.zxp + (cc - a.zp)] = v;
+              *reinterpret_cast<float4*>(a.dzx_all + ((size_t)t * a.B + m) * a.zxp + (c4 - zp4) * 4) = v;
             }
           }
           fence_proxy_async_all();
