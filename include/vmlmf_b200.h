@@ -154,6 +154,14 @@ int vmlmf_gemm_nt(const float* A, long long lda, const float* B, long long ldb, 
                   const float* bias, int M, int N, int K, int accumulate, void* workspace,
                   long long workspace_bytes, void* stream);
 
+/* C[M,N] (+)= At[K,M]^T Bt[K,N]: both operands stored with the contraction index as the ROW (activations [rows, features]);
+ * the tensor cores read them as MN-major operands, no transposed copy is made.  This is the weight-gradient product
+ * dW = dY^T X of a linear layer (V/models/vmlmf_lm.py:357 under autograd) and of the low-rank factors.  Row pitches in
+ * floats, rows 16-byte aligned; returns VMLMF_EUNSUPPORTED when an operand misses that.  Long contractions are split and
+ * summed in a fixed order; `workspace` as for vmlmf_gemm_nt.                                                          */
+int vmlmf_gemm_tn(const float* At, long long lda, const float* Bt, long long ldb, float* C, long long ldc,
+                  int M, int N, long long K, int accumulate, void* workspace, long long workspace_bytes, void* stream);
+
 /* ---- callers either side of the recurrence (SURVEY.md 8 rows f1 / f2 and the Net head, a4) ---------------- */
 
 /* Softmax-NLL over rows of scores[rows, C] (row pitch ld floats), labels int64 in [0, C):

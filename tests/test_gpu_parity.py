@@ -159,12 +159,17 @@ def test_lm_model_cfg4_size_vs_cpu_oracle(B, monkeypatch, r1_path):
     T, V, H, R = 35, 10000, 650, 300
     assert _lib.plan(T, B, H, H, R, R).path in _lib.LARGE_PATHS
     calls = {"gemm": 0}
-    real_gemm = functional.gemm_nt
+    real_nt, real_tn = functional.gemm_nt, functional.gemm_tn
 
-    def counting_gemm(*a, **k):
+    def counting_nt(*a, **k):
         calls["gemm"] += 1
-        return real_gemm(*a, **k)
-    monkeypatch.setattr(functional, "gemm_nt", counting_gemm)
+        return real_nt(*a, **k)
+
+    def counting_tn(*a, **k):
+        calls["gemm"] += 1
+        return real_tn(*a, **k)
+    monkeypatch.setattr(functional, "gemm_nt", counting_nt)
+    monkeypatch.setattr(functional, "gemm_tn", counting_tn)
     torch.manual_seed(3)
     m = vb.Model(V, H, 2, 0.0, 0.05, w_rank=R, u_ranks=[R], lstm_type="vmlmf")
     g = torch.Generator().manual_seed(11)
@@ -181,7 +186,7 @@ def test_lm_model_cfg4_size_vs_cpu_oracle(B, monkeypatch, r1_path):
     sg, new_g = m(tok.to(DEV), [(h.to(DEV), c.to(DEV)) for h, c in st])
     loss = vb.nll_loss(sg, y.to(DEV))
     loss.backward()
-    assert calls["gemm"] >= 3, "the vocabulary projection must run on the tcgen05 GEMM (forward, dX, dW)"
+    assert calls["gemm"] >= 3, "the vocabulary projection must run on the tcgen05 GEMMs (forward, dX: gemm_nt; dW: gemm_tn)"
     assert_close(sg.detach().cpu().numpy(), so.detach().numpy(), TOL, "scores")
     for l in range(2):
         assert_close(new_g[l][0].detach().cpu().numpy(), new_o[l][0].detach().numpy(), TOL, f"hT{l}")
@@ -489,3 +494,20 @@ def test_bench_size_gradients_vs_fp64_spec(split, monkeypatch, r1_path):
     assert_close(hT.detach().cpu().numpy(), hT64, 4e-6, "hT")
     for k, t in zip(names, tp):
         assert_close(t.grad.cpu().numpy(), g64[k], 4e-6, f"d{k}")
+
+
+@pytest.mark.parametrize("K,M,N", [(700, 2688, 300), (32, 32, 32), (4099, 130, 36), (8, 128, 128), (20000, 64, 8)])
+def test_tensor_core_tn_gemm_matches_fp64(K, M, N, r1_path):
+    """vmlmf_gemm_tn (C = At^T Bt with MN-major tensor-core operands, no transposed copies): the shape of every
+    weight-gradient contraction of the backward.  Against an fp64 product."""
+    if r1_path != "auto":
+        pytest.skip("independent of the recurrence regime")
+    from vmlmf_b200.functional import gemm_tn
+    g = torch.Generator(device=DEV).manual_seed(K + M)
+    at = torch.randn(K, M, device=DEV, generator=g)
+    bt = torch.randn(K, N, device=DEV, generator=g)
+    got = gemm_tn(at, bt)
+    ref = at.double().t() @ bt.double()
+    assert_close(got.cpu().numpy(), ref.cpu().numpy(), 3e-6, "At^T Bt")
+    acc = gemm_tn(at, bt, out=got.clone(), accumulate=True)
+    assert_close(acc.cpu().numpy(), (2 * ref).cpu().numpy(), 3e-6, "accumulate")

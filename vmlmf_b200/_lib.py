@@ -35,6 +35,7 @@ SIGNATURES = {
     "vmlmf_pack_plain_fwd": [_P] * 11 + [_I] * 4 + [_P],
     "vmlmf_pack_plain_bwd": [_P] * 14 + [_I] * 4 + [_P],
     "vmlmf_gemm_nt": [_P, _LL, _P, _LL, _P, _LL, _P, _I, _I, _I, _I, _P, _LL, _P],
+    "vmlmf_gemm_tn": [_P, _LL, _P, _LL, _P, _LL, _I, _I, _LL, _I, _P, _LL, _P],
     "vmlmf_xproj_fwd": [_P, _LL, _LL, _P, _P, _I, _I, _I, _I, _I, _P],
     "vmlmf_seq_fwd": [C.POINTER(Plan), _P, _LL, _LL] + [_P] * 10 + [_P, _LL, _LL] + [_P] * 6 + [_I] * 6 + [_P],
     "vmlmf_seq_bwd": [C.POINTER(Plan), _P, _LL, _LL] + [_P] * 9 + [_P, _LL, _LL] + [_P] * 3 + [_P, _LL, _LL]

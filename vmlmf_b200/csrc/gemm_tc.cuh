@@ -396,6 +396,153 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   }
 }
 
+// ------------------------------------------------------------------------------------------------- TN kernel
+// C[M,N] = At[K,M]^T Bt[K,N]: both operands stored with the CONTRACTION index as the row (row-major activations
+// [T*B rows, features]), i.e. MN-major tensor-core operands.  This is the shape of every weight-gradient contraction
+// of the backward (dBm = dPre^T Z, dVx = dPre^T ZX, ...: V/models/vmlmf.py:98-99 replayed by autograd): reading the
+// activations in place removes the transposed copies a K-major kernel needs.
+// Shared-memory tile of one operand: four blocks of [32 K rows][32 features = 128 bytes] (one TMA box each), blocks 4096
+// bytes apart (leading byte offset).  MN-major 32-bit operands have exactly one legal swizzle: 128-byte rows swizzled in
+// 32-byte chunks with a 4-row period (descriptor layout type 1, TMA mode SWIZZLE_128B_ATOM_32B), so the K groups are 4
+// rows = 512 bytes apart (stride byte offset); one tf32 MMA (K = 8) consumes two of them, the k-step advance is 1024 bytes.
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)(4096 >> 4) << 16;                  // leading byte offset: next 32-feature block along M / N
+  d |= (uint64_t)(512 >> 4) << 32;                   // stride byte offset: next group of 4 K rows
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;                            // SWIZZLE_128B_BASE32B
+  return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc_mn(int M, int N) { return make_idesc(M, N) | (1u << 15) | (1u << 16); }
+
+template <class Epi>
+__global__ void __launch_bounds__(kThreads, 1) gemm_tn_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                              const __grid_constant__ CUtensorMap mapB, int M, int N,
+                                                              int K, int kb_per_split, Epi epi) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* full = bars;
+  uint64_t* split = bars + kStages;
+  uint64_t* empty = bars + 2 * kStages;
+  uint64_t* accf = bars + 3 * kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kStages + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BM;
+  const int n0 = blockIdx.x * BN;
+  const int nkb_total = (K + BK - 1) / BK;
+  const int kb0 = blockIdx.z * kb_per_split;
+  const int nkb = (nkb_total - kb0) < kb_per_split ? (nkb_total - kb0) : kb_per_split;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&split[s], 4); mbar_init(&empty[s], 1); }
+    mbar_init(accf, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % kStages, it = kb / kStages;
+        if (it > 0) mbar_wait(&empty[s], (it - 1) & 1);
+        uint8_t* st = smem + s * kStageBytes;
+        mbar_arrive_expect_tx(&full[s], 2 * kTileBytes);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          tma_load_2d(st + i * 4096, &mapA, m0 + 32 * i, (kb0 + kb) * BK, &full[s]);
+          tma_load_2d(st + 2 * kTileBytes + i * 4096, &mapB, n0 + 32 * i, (kb0 + kb) * BK, &full[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_mn(BM, BN);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % kStages, it = kb / kStages;
+        mbar_wait(&split[s], it & 1);
+        tc_fence_after();
+        const uint32_t a_hi = smem_u32(smem + s * kStageBytes), a_lo = a_hi + kTileBytes;
+        const uint32_t b_hi = a_hi + 2 * kTileBytes, b_lo = a_hi + 3 * kTileBytes;
+#pragma unroll
+        for (int k = 0; k < BK / 8; ++k) {
+          const uint32_t off = k * 1024;                 // next group of 8 K rows
+          const int kk = kb * (BK / 8) + k;
+          mma_tf32_ss(tmem_d + 3 * BN, make_desc_mn(a_lo + off), make_desc_mn(b_hi + off), idesc, kk ? 1u : 0u);
+          mma_tf32_ss(tmem_d + 3 * BN, make_desc_mn(a_hi + off), make_desc_mn(b_lo + off), idesc, 1u);
+          mma_tf32_ss(tmem_d + (kk % 3) * BN, make_desc_mn(a_hi + off), make_desc_mn(b_hi + off), idesc, kk >= 3 ? 1u : 0u);
+        }
+        mma_commit(&empty[s]);
+      }
+      mma_commit(accf);
+    }
+  } else {
+    const int sw = warp - 2;
+    const int st_tid = sw * 32 + lane;
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % kStages, it = kb / kStages;
+      mbar_wait(&full[s], it & 1);
+      float4* a_hi = reinterpret_cast<float4*>(smem + s * kStageBytes);
+      float4* a_lo = a_hi + kTileBytes / 16;
+      float4* b_hi = a_hi + 2 * kTileBytes / 16;
+      float4* b_lo = a_hi + 3 * kTileBytes / 16;
+#pragma unroll 4
+      for (int i = st_tid; i < kTileBytes / 16; i += 128) {
+        const float4 va = a_hi[i], vb = b_hi[i];
+        float4 ha, la, hb, lb;
+        ha.x = tf32r(va.x); ha.y = tf32r(va.y); ha.z = tf32r(va.z); ha.w = tf32r(va.w);
+        la.x = tf32r(va.x - ha.x); la.y = tf32r(va.y - ha.y); la.z = tf32r(va.z - ha.z); la.w = tf32r(va.w - ha.w);
+        hb.x = tf32r(vb.x); hb.y = tf32r(vb.y); hb.z = tf32r(vb.z); hb.w = tf32r(vb.w);
+        lb.x = tf32r(vb.x - hb.x); lb.y = tf32r(vb.y - hb.y); lb.z = tf32r(vb.z - hb.z); lb.w = tf32r(vb.w - hb.w);
+        a_hi[i] = ha; a_lo[i] = la; b_hi[i] = hb; b_lo[i] = lb;
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&split[s]);
+    }
+    mbar_wait(accf, 0);
+    tc_fence_after();
+    const int lane_grp = warp & 3;
+    const uint32_t tbase = tmem_d + ((uint32_t)(lane_grp * 32) << 16);
+    const int nks = nkb * (BK / 8);
+    const int nhi = nks < 3 ? nks : 3;
+    float* S = reinterpret_cast<float*>(smem);
+    {
+      float* srow = S + (size_t)(lane_grp * 32 + lane) * kEpiPitch;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 8) {
+        float v[8];
+        tmem_ld8(tbase + c, nhi, v);
+        reinterpret_cast<float4*>(srow + c)[0] = make_float4(v[0], v[1], v[2], v[3]);
+        reinterpret_cast<float4*>(srow + c)[1] = make_float4(v[4], v[5], v[6], v[7]);
+      }
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    for (int r = sw; r < BM; r += 4) {
+      const int m = m0 + r;
+      if (m >= M) break;
+      const float* srow = S + (size_t)r * kEpiPitch + lane;
+      const float v[4] = {srow[0], srow[32], srow[64], srow[96]};
+      epi(m, n0, N, lane, v);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(kTmemCols));
+  }
+}
+
 // ------------------------------------------------------------------------------------------------- host
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -476,6 +623,46 @@ inline int gemm_tc(const float* A, long long lda, const float* Bm, long long ldb
   const int kbs = ceil_div(nkb, splits);
   dim3 grid(ntn, ceil_div(M, BM), ceil_div(nkb, kbs));
   kern<<<grid, kThreads, kSmemBytes, st>>>(ma, mb, M, N, K, kbs, epi);
+  return (int)cudaGetLastError();
+}
+
+
+// [rows, cols] fp32 matrix, row pitch ld floats, viewed as an MN-major operand: box = 32 columns x 32 rows
+inline int make_map_tn(CUtensorMap* map, const float* p, long long rows, long long cols, long long ld) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return kTcNoFit;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {32, BK};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(p), dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : kTcNoFit;
+}
+// C[M,N] = At[K rows, M cols]^T Bt[K rows, N cols]   (row pitches lda, ldb floats; both 16-byte aligned rows)
+template <class Epi>
+inline int gemm_tn(const float* At, long long lda, const float* Bt, long long ldb, int M, int N, long long K, Epi epi,
+                   cudaStream_t st, int splits = 1) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if (!tc_operand_ok(At, lda) || !tc_operand_ok(Bt, ldb) || K > 0x7fffffffLL) return kTcNoFit;
+  CUtensorMap ma, mb;
+  int rc = make_map_tn(&ma, At, K, M, lda);
+  if (rc) return rc;
+  rc = make_map_tn(&mb, Bt, K, N, ldb);
+  if (rc) return rc;
+  auto kern = gemm_tn_kernel<Epi>;
+  static PerDevice attr_pd;
+  int& attr = attr_pd.cur();
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) return (int)e;
+    attr = 1;
+  }
+  const int nkb = ceil_div((int)K, BK);
+  const int kbs = ceil_div(nkb, splits);
+  dim3 grid(ceil_div(N, BN), ceil_div(M, BM), ceil_div(nkb, kbs));
+  kern<<<grid, kThreads, kSmemBytes, st>>>(ma, mb, M, N, (int)K, kbs, epi);
   return (int)cudaGetLastError();
 }
 

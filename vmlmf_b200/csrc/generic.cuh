@@ -472,6 +472,11 @@ inline bool g_simt_only() {
   const char* e = getenv("VMLMF_G_SIMT");
   return e && e[0] == '1';
 }
+// VMLMF_TN_OFF=1 keeps the transposed-copy path of the time-parallel gradient GEMMs (A/B measurements, tests)
+inline bool g_tn_off() {
+  const char* e = getenv("VMLMF_TN_OFF");
+  return e && e[0] == '1';
+}
 inline float* align4(float* p) { return reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(p) + 15) & ~(uintptr_t)15); }
 
 // out[M, N] (row pitch ldo) (+)= A[M,K] B[N,K]^T on the tensor cores, split over K when the tile grid alone would
@@ -531,6 +536,26 @@ inline int gemm_nt_public(const float* A, long long lda, const float* Bm, long l
   }
   return gemm_launch<false, true>(plain_view(A, lda), plain_view(Bm, ldb), M, N, K, 1, NIdent{},
                                   EpiBias{plain_view(C, ldc), bias, accumulate}, st);
+}
+
+// public TN GEMM (vmlmf_gemm_tn): tensor cores only (the operands must meet the TMA constraints)
+inline int gemm_tn_public(const float* At, long long lda, const float* Bt, long long ldb, float* C, long long ldc, int M, int N,
+                          long long K, int accumulate, float* part, long long part_floats, cudaStream_t st) {
+  if (!tc::encode_fn() || !tc::tc_operand_ok(At, lda) || !tc::tc_operand_ok(Bt, ldb) || K > 0x7fffffffLL) return VMLMF_EUNSUPPORTED;
+  int splits = tc::tc_splits(M, N, (int)K, 32);
+  const int acc_splits = tc_accuracy_splits(M, N, K);
+  if (splits < acc_splits) splits = acc_splits;
+  while (splits > 1 && (!part || (long long)splits * M * N > part_floats)) --splits;
+  if (splits <= 1) {
+    const int rc = tc::gemm_tn(At, lda, Bt, ldb, M, N, K, tc::EpiBiasTC{C, ldc, nullptr, accumulate}, st);
+    return rc == tc::kTcNoFit ? VMLMF_EUNSUPPORTED : rc;
+  }
+  const int nkb = ceil_div((int)K, tc::BK), kbs = ceil_div(nkb, splits), nz = ceil_div(nkb, kbs);
+  int rc = tc::gemm_tn(At, lda, Bt, ldb, M, N, K, tc::EpiPartialTC{part, M, N}, st, splits);
+  if (rc) return rc == tc::kTcNoFit ? VMLMF_EUNSUPPORTED : rc;
+  const long long n = (long long)M * N;
+  splitk_reduce_bias_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(part, nz, M, N, nullptr, C, ldc, accumulate);
+  return (int)cudaGetLastError();
 }
 
 // ZX = X Ux, pad columns zeroed
@@ -709,15 +734,36 @@ inline int generic_bwd_tp(TpArgs& a, cudaStream_t st) {
   };
   float* gBm = (G == H) ? a.dBm : a.gtmp;
   float* gVx = (G == H) ? a.dVx : a.gtmp;
+  // C[M,N] = At[rows, M]^T Bt[rows, N] straight from the row-major activations (MN-major tensor-core operands)
+  auto tc_direct = [&](const float* At, long long lda, const float* Bt, long long ldb, int M, int N, float* out) -> int {
+    int splits = tc::tc_splits(M, N, (int)rows, 32);
+    const int acc_splits = tc_accuracy_splits(M, N, rows);
+    if (splits < acc_splits) splits = acc_splits;
+    while (splits > 1 && (long long)splits * M * N > a.n_part) --splits;
+    const int nkb = ceil_div((int)rows, tc::BK), kbs = ceil_div(nkb, splits), nz = ceil_div(nkb, kbs);
+    int rc = tc::gemm_tn(At, lda, Bt, ldb, M, N, rows, tc::EpiPartialTC{part, M, N}, st, splits);
+    if (rc) return rc;
+    return reduce_to(nz, (long long)M * N, out);
+  };
+  const bool direct = tc_tp && !g_tn_off() && tc::tc_operand_ok(a.dpre, 4 * G) && tc::tc_operand_ok(a.z, a.zp) &&
+                      tc::tc_operand_ok(a.zx, a.zxp);
   if (tc_tp) {
-    // dBm = dPre^T Z, dVx = dPre^T ZX share the transposed dPre
-    G_TRY(transpose_rows_launch(dPv, nullptr, 0, 0, rows, 4 * G, tA, a.ldt, st));
-    G_TRY(transpose_rows_launch(Zv, nullptr, 0, 0, rows, RH, tB, a.ldt, st));
-    G_TRY(tc_tn(4 * G, RH, gBm));
-    G_TRY(finish_gate(gBm, a.dBm, RH));
-    G_TRY(transpose_rows_launch(ZXv, nullptr, 0, 0, rows, RX, tB, a.ldt, st));
-    G_TRY(tc_tn(4 * G, RX, gVx));
-    G_TRY(finish_gate(gVx, a.dVx, RX));
+    if (direct) {
+      // dBm = dPre^T Z, dVx = dPre^T ZX: no transposed copies
+      G_TRY(tc_direct(a.dpre, 4 * G, a.z, a.zp, 4 * G, RH, gBm));
+      G_TRY(finish_gate(gBm, a.dBm, RH));
+      G_TRY(tc_direct(a.dpre, 4 * G, a.zx, a.zxp, 4 * G, RX, gVx));
+      G_TRY(finish_gate(gVx, a.dVx, RX));
+    } else {
+      // dBm = dPre^T Z, dVx = dPre^T ZX share the transposed dPre
+      G_TRY(transpose_rows_launch(dPv, nullptr, 0, 0, rows, 4 * G, tA, a.ldt, st));
+      G_TRY(transpose_rows_launch(Zv, nullptr, 0, 0, rows, RH, tB, a.ldt, st));
+      G_TRY(tc_tn(4 * G, RH, gBm));
+      G_TRY(finish_gate(gBm, a.dBm, RH));
+      G_TRY(transpose_rows_launch(ZXv, nullptr, 0, 0, rows, RX, tB, a.ldt, st));
+      G_TRY(tc_tn(4 * G, RX, gVx));
+      G_TRY(finish_gate(gVx, a.dVx, RX));
+    }
     // dA = Hprev^T dZ: row (t,b) of Hprev is y[t-1,b], or h0[b] / 0 at t = 0
     G_TRY(transpose_rows_launch(Yv, a.h0, H, B, rows, H, tA, a.ldt, st));
     G_TRY(transpose_rows_launch(plain_view(a.dz, a.zp), nullptr, 0, 0, rows, RH, tB, a.ldt, st));

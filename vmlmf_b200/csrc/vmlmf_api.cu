@@ -187,6 +187,13 @@ int vmlmf_gemm_nt(const float* A, long long lda, const float* B, long long ldb, 
                         workspace ? workspace_bytes / (long long)sizeof(float) : 0, (cudaStream_t)stream);
 }
 
+int vmlmf_gemm_tn(const float* At, long long lda, const float* Bt, long long ldb, float* C, long long ldc, int M, int N,
+                  long long K, int accumulate, void* workspace, long long workspace_bytes, void* stream) {
+  if (!At || !Bt || !C || M <= 0 || N <= 0 || K <= 0 || lda < M || ldb < N || ldc < N) return VMLMF_EINVAL;
+  return gemm_tn_public(At, lda, Bt, ldb, C, ldc, M, N, K, accumulate, (float*)workspace,
+                        workspace ? workspace_bytes / (long long)sizeof(float) : 0, (cudaStream_t)stream);
+}
+
 int vmlmf_xproj_fwd(const float* x, long long xs_t, long long xs_b, const float* Ux, float* zx, int T,
                     int B, int I, int RX, int zx_pitch, void* stream) {
   if (!x || !Ux || !zx || T <= 0 || B <= 0 || I <= 0 || RX <= 0) return VMLMF_EINVAL;

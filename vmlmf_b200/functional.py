@@ -289,6 +289,25 @@ def gemm_nt(a, b, bias=None, out=None, accumulate=False):
     return out
 
 
+def gemm_tn(at, bt, out=None, accumulate=False):
+    """out[M,N] (+)= at[K,M]^T @ bt[K,N] on the tcgen05 3xTF32 GEMM with MN-major operands (vmlmf_gemm_tn): the
+    contraction runs over the ROWS of both inputs, which are read in place -- no transposed copies.  fp32-accurate."""
+    _require_cuda(at, bt)
+    (k, m), n = at.shape, bt.shape[1]
+    a2, lda = _pad4(at)
+    b2, ldb = _pad4(bt)
+    if out is None:
+        out = at.new_empty((m, n))
+    nsp = max(min(32, max(1, -(-k // 128))), min(128, -(-k // 1536)))
+    nsp = max(1, min(nsp, (1 << 24) // max(1, m * n)))
+    ws = at.new_empty((nsp * m * n,)) if m * n <= (1 << 24) else None
+    with torch.cuda.device_of(at):
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _lib.check(_lib.lib().vmlmf_gemm_tn(_ptr(a2), lda, _ptr(b2), ldb, _ptr(out), out.stride(0), m, n, k,
+                                            1 if accumulate else 0, _ptr(ws), 0 if ws is None else ws.numel() * 4, st))
+    return out
+
+
 class LinearTCFunction(torch.autograd.Function):
     """y = x w^T + b with all three GEMMs (forward, dX, dW) on the tensor-core kernel.
     Replaces `torch.addmm(self.b, x, self.w.t())` of the LM head (V/models/vmlmf_lm.py:357) and its autograd."""
@@ -303,7 +322,7 @@ class LinearTCFunction(torch.autograd.Function):
         x, w = ctx.saved_tensors
         dy = dy.contiguous()
         dx = gemm_nt(dy, w.t().contiguous()) if ctx.needs_input_grad[0] else None          # [M,N] x [K,N]^T
-        dw = gemm_nt(dy.t().contiguous(), x.t().contiguous()) if ctx.needs_input_grad[1] else None   # [N,M] x [K,M]^T
+        dw = gemm_tn(dy, x) if ctx.needs_input_grad[1] else None                            # dy^T x, operands read in place
         db = dy.sum(0) if ctx.needs_input_grad[2] else None
         return dx, dw, db
 
