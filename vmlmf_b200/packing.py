@@ -36,6 +36,12 @@ def pack_plain(u_x, u_h, v_x, v_h, b_x, b_h, dia_x, dia_h):
     return u_x, v_x, dx, u_h, v_h, dh, b_x.reshape(-1) + b_h.reshape(-1) * 1.0
 
 
+def _reorder_gates(t, dim):
+    """chunks of `dim` (size 4) taken in GROUP_Q_OF_K order, without an index tensor (an index list would be built on the
+    host and copied to the device on every call, which also breaks CUDA-graph capture)"""
+    return torch.stack([t.select(dim, q) for q in GROUP_Q_OF_K], dim)
+
+
 def _gate_perm(hidden, device):
     return torch.cat([torch.arange(q * hidden, (q + 1) * hidden, device=device) for q in GROUP_Q_OF_K])
 
@@ -58,7 +64,7 @@ def pack_group(layers, g, with_vm=True):
             blk[(j + off) % g, :, j, :] = u[j]
         a_cols.append(blk.reshape(hidden, g * r))
         # Bm: rows (k, j, m), columns (j', r) non-zero for j'==j
-        vq = v.view(g, r, 4, hg)[:, :, list(GROUP_Q_OF_K), :]      # [j, r, k, m]
+        vq = _reorder_gates(v.view(g, r, 4, hg), 2)                 # [j, r, k, m]
         bb = u.new_zeros(4, g, hg, g, r)                           # [k, j, m, j', r]
         for j in range(g):
             bb[:, j, :, j, :] = vq[j].permute(1, 2, 0)             # [k, m, r]
@@ -70,7 +76,7 @@ def pack_group(layers, g, with_vm=True):
     if with_vm:
         dx = layers["dia_x"].reshape(1, n_in) - _diag_corr(u_x, v_x, n_in)
         u0, v0 = layers["u_h_0"], layers["v_h_0"]
-        v0q = v0.view(g, v0.shape[1], 4, hg)[:, :, list(GROUP_Q_OF_K), :]      # [j, r, k, m]
+        v0q = _reorder_gates(v0.view(g, v0.shape[1], 4, hg), 2)                # [j, r, k, m]
         corr = torch.einsum("jmr,jrkm->kjm", u0, v0q).reshape(4, hidden)   # diag of offset-0 blocks (:101-110)
         dh = layers["dia_h"].reshape(1, hidden) - corr
         return u_x, v_x, dx, a, bm, dh, bx + bh[perm]
