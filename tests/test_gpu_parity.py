@@ -511,3 +511,88 @@ def test_tensor_core_tn_gemm_matches_fp64(K, M, N, r1_path):
     assert_close(got.cpu().numpy(), ref.cpu().numpy(), 3e-6, "At^T Bt")
     acc = gemm_tn(at, bt, out=got.clone(), accumulate=True)
     assert_close(acc.cpu().numpy(), (2 * ref).cpu().numpy(), 3e-6, "accumulate")
+
+
+# ----------------------------- regime R2 specifics ----------------------------- #
+
+def test_r2_inference_matches_training_forward_and_ksplit(monkeypatch, r1_path):
+    """The persistent tcgen05 recurrence without saved state (inference) gives the training forward's values bit for bit;
+    a forced group of 2 CTAs at H = 1024 makes the backward split its 4*HS = 2048-long contraction into four accumulation
+    segments (KSPLIT = 4) and sum 8 partials per tile -- checked against the fp64 numpy spec."""
+    if r1_path != "auto":
+        pytest.skip("regime R2 does not depend on the R1 kernel choice")
+    from vmlmf_b200 import _lib
+    monkeypatch.setenv("VMLMF_R2_CLUSTER", "2")
+    T, B, I, H, RX, RH = 3, 70, 9, 1024, 16, 24
+    assert _lib.plan(T, B, I, H, RX, RH).path == _lib.PATH_R2
+    rng = np.random.default_rng(5)
+    cp = _rand_canon(rng, I, H, RX, RH, 0.05)
+    x = rng.standard_normal((T, B, I)).astype(np.float32)
+    dy = rng.standard_normal((T, B, H)).astype(np.float32)
+    cp64 = {k: v.astype(np.float64) for k, v in cp.items()}
+    y64, hT64, cT64, saved = cn.forward(cp64, x.astype(np.float64))
+    g64 = cn.backward(cp64, x.astype(np.float64), y64, saved, dy.astype(np.float64), None, None)
+    names = ("Ux", "Vx", "Dx", "A", "Bm", "Dh", "bias")
+    tp = [torch.from_numpy(cp[k]).to(DEV).requires_grad_(True) for k in names]
+    xt = torch.from_numpy(x).to(DEV)
+    with torch.no_grad():
+        y0, h0, c0 = vmlmf_sequence(xt, None, None, tp, batch_first=False)
+    y1, h1, c1 = vmlmf_sequence(xt, None, None, tp, batch_first=False)
+    assert torch.equal(y0, y1) and torch.equal(h0, h1) and torch.equal(c0, c1)
+    y1.backward(torch.from_numpy(dy).to(DEV))
+    assert_close(y1.detach().cpu().numpy(), y64, TOL, "y")
+    for k, t in zip(names, tp):
+        assert_close(t.grad.cpu().numpy(), g64[k], TOL, f"d{k}")
+
+
+def test_lm_dense_lstm_baseline_runs_through_the_fused_kernels(r1_path):
+    """The LM's "custom" dense LSTM layer (V/models/vmlmf_lm.py:283-339) on the canonical kernels against its eager formula."""
+    if r1_path != "auto":
+        pytest.skip("independent of the R1 kernel choice")
+    torch.manual_seed(2)
+    T, B, H = 5, 9, 40
+    layer = vb.vmlmf_lm.LSTM(H, H)
+    for p in layer.parameters():
+        torch.nn.init.uniform_(p, -0.2, 0.2)
+    x = torch.randn(T, B, H)
+    h0, c0 = torch.randn(B, H) * 0.3, torch.randn(B, H) * 0.3
+    w = torch.randn(T, B, H)
+    ref_in = [t.clone().double().requires_grad_(True) for t in (x, h0, c0)]
+    ref_layer = vb.vmlmf_lm.LSTM(H, H).double()
+    ref_layer.load_state_dict({k: v.double() for k, v in layer.state_dict().items()})
+    out_r, (hr, cr) = ref_layer(ref_in[0], (ref_in[1], ref_in[2]))          # host tensors: the eager loop
+    ((out_r * w.double()).sum() + hr.sum() + cr.sum()).backward()
+    layer = layer.to(DEV)
+    got_in = [t.clone().to(DEV).requires_grad_(True) for t in (x, h0, c0)]
+    out_g, (hg, cg) = layer(got_in[0], (got_in[1], got_in[2]))
+    ((out_g * w.to(DEV)).sum() + hg.sum() + cg.sum()).backward()
+    assert_close(out_g.detach().cpu().numpy(), out_r.detach().numpy(), TOL, "out")
+    for a, b, nm in zip(got_in, ref_in, ("dx", "dh0", "dc0")):
+        assert_close(a.grad.cpu().numpy(), b.grad.numpy(), TOL, nm)
+    for (k, p), (_, q) in zip(layer.named_parameters(), ref_layer.named_parameters()):
+        assert_close(p.grad.cpu().numpy(), q.grad.numpy(), TOL, f"grad {k}")
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_second_device_after_first(r1_path):
+    """Function attributes and occupancy are per device: a call on cuda:1 after cuda:0 must set them again
+    (every regime: SIMT, warp-MMA, R2, the tail kernels)."""
+    if r1_path != "auto":
+        pytest.skip("one pass is enough")
+    outs = []
+    for d in ("cuda:0", "cuda:1"):
+        torch.manual_seed(4)
+        small = vb.Net(9, [32], w_rank=8, u_rank=[6], cell=vb.MyVMLMFCell).to(d)
+        big = vb.Net(77, [256], w_rank=8, u_rank=[6], cell=vb.MyVMLMFCell).to(d)
+        wide = vb.Net(9, [320], w_rank=20, u_rank=[24], cell=vb.MyVMLMFCell).to(d)
+        g = torch.Generator().manual_seed(1)
+        res = []
+        for net, shape in ((small, (6, 10, 9)), (big, (1600, 4, 77)), (wide, (130, 3, 9))):
+            x = torch.randn(*shape, generator=g).to(d).requires_grad_(True)
+            out = net(x)
+            vb.cross_entropy(out, torch.zeros(shape[0], dtype=torch.long, device=d)).backward()
+            res += [out.detach().cpu(), x.grad.cpu()]
+        torch.cuda.synchronize(d)
+        outs.append(res)
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)

@@ -84,3 +84,56 @@ def test_single_process_bucket_is_a_noop_collective():
     flat = bucket.all_reduce()
     assert flat.numel() == sum(p.numel() for p in net.rnn.parameters()) and bool((flat == 1).all())
     assert shard_batch(torch.arange(6)).tolist() == [0, 1, 2, 3, 4, 5]
+
+
+# ---- LM data-parallel semantics (V/train_test/lm_test.py:140-153, :204): local loss = token-mean x LOCAL batch, gradients
+# SUMMED over ranks (GradBucket(average=False)) = gradient of token-mean x GLOBAL batch; the clip uses the norm of the
+# reduced gradient.  Stand-in model on CPU, the oracle's lm_nll_loss as the loss.
+
+class _ToyLM(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        torch.manual_seed(9)
+        self.emb = torch.nn.Parameter(0.3 * torch.randn(11, 6))
+        self.fc = torch.nn.Parameter(0.3 * torch.randn(11, 6))
+
+    def forward(self, tok):                    # [T,B] -> scores [T*B, V]
+        return torch.tanh(self.emb[tok]).reshape(-1, 6) @ self.fc.t()
+
+
+def _lm_worker(rank, world, port, out):
+    from oracle import vmlmf_oracle as vo
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        net = _ToyLM()
+        g = torch.Generator().manual_seed(3)
+        tok = torch.randint(0, 11, (5, 8), generator=g)
+        y = torch.randint(0, 11, (5, 8), generator=g)
+        bucket = GradBucket(net, average=False)
+        bucket.zero()
+        vo.lm_nll_loss(net(shard_batch(tok, 1)), shard_batch(y, 1)).backward()      # token streams sharded along the batch axis
+        flat = bucket.all_reduce()
+        norm = flat.norm()
+        coef = torch.clamp(5.0 / (norm + 1e-6), max=1.0)                            # clip_grad_norm_ on the REDUCED gradient
+        if rank == 0:
+            torch.save({"emb": net.emb.grad.clone(), "fc": net.fc.grad.clone(), "norm": norm, "coef": coef}, out)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_lm_loss_sum_over_ranks_equals_global_batch(tmp_path):
+    from oracle import vmlmf_oracle as vo
+    out = str(tmp_path / "lm.pt")
+    mp.spawn(_lm_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    got = torch.load(out)
+    ref = _ToyLM()
+    g = torch.Generator().manual_seed(3)
+    tok = torch.randint(0, 11, (5, 8), generator=g)
+    y = torch.randint(0, 11, (5, 8), generator=g)
+    vo.lm_nll_loss(ref(tok), y).backward()                                          # token-mean x GLOBAL batch on one process
+    assert torch.allclose(got["emb"], ref.emb.grad, rtol=1e-5, atol=1e-7)
+    assert torch.allclose(got["fc"], ref.fc.grad, rtol=1e-5, atol=1e-7)
+    ref_norm = torch.cat([ref.emb.grad.reshape(-1), ref.fc.grad.reshape(-1)]).norm()
+    assert torch.allclose(got["norm"], ref_norm, rtol=1e-5)

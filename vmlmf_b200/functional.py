@@ -420,9 +420,13 @@ class HeadLinearFunction(torch.autograd.Function):
 
 
 def head_linear(h, w, b):
-    """nn.Linear for a narrow head (out_features <= 32, in_features <= 1024) on CUDA fp32; other shapes -> F.linear."""
-    if h.is_cuda and h.dim() == 2 and w.shape[0] <= 32 and w.shape[1] <= 1024 and h.dtype == torch.float32:
-        return HeadLinearFunction.apply(h, w, b)
+    """nn.Linear on CUDA fp32: the narrow-head kernels (out_features <= 32, in_features <= 1024: the reference's 18-way
+    head at every hidden size it ships) or, for wider shapes, the tcgen05 GEMMs of linear_tc.  Host tensors (module
+    construction / state_dict tests) go to F.linear; no library GEMM runs on the device path."""
+    if h.is_cuda and h.dim() == 2 and h.dtype == torch.float32:
+        if w.shape[0] <= 32 and w.shape[1] <= 1024:
+            return HeadLinearFunction.apply(h, w, b)
+        return linear_tc(h, w, b)
     return torch.nn.functional.linear(h, w, b)
 
 

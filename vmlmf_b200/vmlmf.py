@@ -4,7 +4,8 @@ signatures, parameter names/shapes, state_dict keys, forward signatures and retu
 MyVMLMFCell / MyLSTM / Net run on the fused sm_100a kernels: MyLSTM.forward issues ONE fused call
 per layer instead of the reference's `for t in range(seqlen): h, c = cell(...)` loop
 (V/models/vmlmf.py:308-310).  MyLSTMCell (the uncompressed / plain low-rank baseline,
-V/models/vmlmf.py:127-238) is out of the hot path and stays an eager PyTorch cell.
+V/models/vmlmf.py:127-238) runs through the same kernels as a canonical recurrence without vector-multiplication
+terms (identity first factor on a dense side), so compressed-vs-dense comparisons share one code path.
 """
 from __future__ import annotations
 

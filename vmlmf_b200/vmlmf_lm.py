@@ -129,8 +129,10 @@ class MyVMLSTMGroup(nn.Module):
 
 
 class LSTM(nn.Module):
-    """Plain dense LSTM layer, the reference's "custom" baseline (V/models/vmlmf_lm.py:283-339).
-    Eager PyTorch; not part of the accelerated path."""
+    """Plain dense LSTM layer, the reference's "custom" baseline (V/models/vmlmf_lm.py:283-339).  On CUDA it runs through the
+    same fused kernels as the compressed layers, as a canonical recurrence with identity first factors and no
+    vector-multiplication terms (pre = x W_x^T + h W_h^T + b_x + b_h; +25 % GEMM work for the identity products, like for
+    like otherwise), so compressed-vs-dense speed comparisons use one code path.  Host tensors keep the eager loop."""
 
     def __init__(self, input_size, hidden_size, dropout=0):
         super().__init__()
@@ -143,8 +145,18 @@ class LSTM(nn.Module):
     def __repr__(self):
         return f"LSTM(input: {self.input_size}, hidden: {self.hidden_size})"
 
+    def canonical(self):
+        eye_x = torch.eye(self.input_size, device=self.w_x.device, dtype=self.w_x.dtype)
+        eye_h = eye_x if self.input_size == self.hidden_size else torch.eye(self.hidden_size, device=self.w_x.device, dtype=self.w_x.dtype)
+        zx = self.w_x.new_zeros(4, self.input_size)
+        zh = self.w_x.new_zeros(4, self.hidden_size)
+        return eye_x, self.w_x, zx, eye_h, self.w_h, zh, self.b_x + self.b_h * 1.0
+
     def forward(self, x, states):
         h, c = states
+        if x.is_cuda and x.dtype == torch.float32 and self.input_size <= self.hidden_size:
+            out, h1, c1 = vmlmf_sequence(x, h, c, self.canonical(), batch_first=False)
+            return out, (h1, c1)
         gx_all = torch.addmm(self.b_x, x.reshape(-1, x.size(2)), self.w_x.t()).view(x.size(0), x.size(1), -1)
         outs = []
         for gx in gx_all.unbind(0):
@@ -166,11 +178,11 @@ class Linear(nn.Module):
 
     def forward(self, x):
         x2 = x.reshape(-1, x.size(2))
-        if x2.is_cuda and x2.dtype == torch.float32 and x2.size(0) >= 512:
-            # large vocabulary projection: fp32-accurate tcgen05 GEMMs (forward, dX, dW)
+        if x2.is_cuda and x2.dtype == torch.float32:
+            # vocabulary projection on the fp32-accurate tcgen05 GEMMs (forward, dX: vmlmf_gemm_nt; dW: vmlmf_gemm_tn)
             from .functional import linear_tc
             return linear_tc(x2, self.w, self.b)
-        return torch.addmm(self.b, x2, self.w.t())
+        return torch.addmm(self.b, x2, self.w.t())      # host tensors (state_dict / shape tests): no kernel of ours involved
 
     def __repr__(self):
         return f"FC(input: {self.input_size}, output: {self.hidden_size})"
