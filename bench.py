@@ -265,7 +265,7 @@ class Workload:
         if c["kind"] == "har":
             cell_cls = vb.MyVMLMFCellg2 if c["cell"] == "group" else vb.MyVMLMFCell
             self.net = vb.Net(c["I"], [c["H"]], w_rank=c["wr"], u_rank=c["ur"], cell=cell_cls).to(dev)
-            self.bucket = GradBucket(self.net, average=True)          # batch-MEAN loss: average over ranks
+            self.bucket = GradBucket(self.net, average=True, symmetric=world > 1)   # batch-MEAN loss: average over ranks; peer-mapped bucket
             self.opt = vb.FlatAdam(self.bucket, lr=0.002)
             self.loss_fn = vb.cross_entropy
             self.states = None
@@ -415,7 +415,9 @@ def measure(w, K, W, use_graph, want_e2e, rank, world, dist):
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     out = {"ms_per_step": ms_total / K, "value": world * w.B * K / (ms_total * 1e-3), "kernel_ms": kernel_ms,
-           "graphs": len(graphs), "collective_in_graph": graph_ok["collective_in_graph"]}
+           "graphs": len(graphs), "collective_in_graph": graph_ok["collective_in_graph"],
+           "collective": ("fused into the optimizer step over NVLink peer memory (vmlmf_p2p_adam_step)" if w.bucket.fused_reduce
+                          else ("ncclAllReduce of the flat bucket" if world > 1 else None))}
 
     if want_e2e:
         loader = SyntheticLoader(w.make_batch, dev, pool=4, source="host", seed=1234 + rank)
@@ -628,7 +630,7 @@ def run_ours(args):
         "data": "synthetic",
         "config": {"workload": c["desc"], "name": name, "per_gpu_batch": B, "global_batch": B * world, "seq_len": c["T"],
                    "parallelism": f"dp{world}", "cuda_graph": bool(use_graph), "cuda_graphs": m["graphs"],
-                   "collective_in_graph": m["collective_in_graph"],
+                   "collective_in_graph": m["collective_in_graph"], "collective": m["collective"],
                    "l2_policy": "inputs larger than L2 (4 rotating resident batches; saved state per step >> 126 MB)"},
         "clocks": clocks,
         "e2e": m.get("e2e"),

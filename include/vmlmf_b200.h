@@ -195,6 +195,14 @@ int vmlmf_head_bwd(const float* h, long long ldh, const float* W, const float* d
  * is read from the device scalar step_dev (float; lets a CUDA graph replay advance it) or, if NULL, from `step`. */
 int vmlmf_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                     float eps, const float* step_dev, int step, void* stream);
+/* Data-parallel Adam step with the gradient all-reduce FUSED in, over NVLink peer memory (one-shot all-reduce): peer_grads is
+ * a device array of `world` pointers, peer_grads[r] = rank r's flat gradient bucket of n floats mapped into this process
+ * (torch symmetric memory / cudaIpc).  Every rank adds the buckets in rank order (bit-identical replicas), multiplies by
+ * `scale` (1/world for the batch-mean HAR loss, V/train_test/train.py:63) and applies Adam as vmlmf_adam_step does.  The
+ * caller brackets the call with cross-rank barriers on the stream (all buckets written before / all read after).  Meant for
+ * the small factor-gradient buckets (latency-bound); large buckets (the LM's 67.7 MB) belong on ncclAllReduce.            */
+int vmlmf_p2p_adam_step(float* p, float* m, float* v, const float* const* peer_grads, int world, long long n, float scale,
+                        float lr, float beta1, float beta2, float eps, const float* step_dev, int step, void* stream);
 /* clip_grad_norm_(max_norm) then `param -= lr * param.grad` (V/train_test/lm_test.py:203-209) in two launches:
  * coef = min(1, max_norm / (||g||_2 + 1e-6)) (max_norm <= 0: no clipping); scale_grads != 0 also writes g *= coef
  * back like clip_grad_norm_ does.  norm_out (device scalar, may be NULL) receives ||g||_2.

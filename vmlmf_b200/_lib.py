@@ -47,6 +47,7 @@ SIGNATURES = {
     "vmlmf_head_bwd_workspace_bytes": [_I, _I, _I],                          # returns long long
     "vmlmf_head_bwd": [_P, _LL, _P, _P, _P, _LL, _P, _P, _P, _I, _I, _I, _P],
     "vmlmf_adam_step": [_P, _P, _P, _P, _LL, _F, _F, _F, _F, _P, _I, _P],
+    "vmlmf_p2p_adam_step": [_P, _P, _P, _P, _I, _LL, _F, _F, _F, _F, _F, _P, _I, _P],
     "vmlmf_sgd_clip_workspace_bytes": [_LL],                                 # returns long long
     "vmlmf_sgd_clip_step": [_P, _P, _LL, _F, _F, _I, _P, _P, _P],
 }

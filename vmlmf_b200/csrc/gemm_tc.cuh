@@ -339,6 +339,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     // ---- epilogue: TMEM -> registers -> shared memory (row per thread), then one row per warp with lane <-> column
     mbar_wait(accf, 0);
     tc_fence_after();
+    // the staging tile below reuses the pipeline stages these same four warps wrote (hi / lo split): ordered through the
+    // mbarrier chain already, the CTA-level barrier makes that ordering explicit (and visible to racecheck)
+    asm volatile("bar.sync 1, 128;" ::: "memory");
     const int lane_grp = warp & 3;                       // TMEM lane quarter this warp may access
     const uint32_t tbase = tmem_d + ((uint32_t)(lane_grp * 32) << 16);
     const int nks = nkb * (BK / 8);
@@ -511,6 +514,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tn_kernel(const __grid_const
     }
     mbar_wait(accf, 0);
     tc_fence_after();
+    asm volatile("bar.sync 1, 128;" ::: "memory");       // see gemm_tc_kernel: staging reuses the stages these warps wrote
     const int lane_grp = warp & 3;
     const uint32_t tbase = tmem_d + ((uint32_t)(lane_grp * 32) << 16);
     const int nks = nkb * (BK / 8);

@@ -118,7 +118,15 @@ __global__ void __launch_bounds__(512, 1) seq_bwd_fused_kernel(const SeqBwdFused
 
   // ---- tensor memory: accumulator space, 64 columns per warp ----
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(tslot)), "r"(tmem_cols));
+    const uint32_t ts = (uint32_t)__cvta_generic_to_shared(tslot);
+    // the column count as an immediate (tmem_cols is a power of two in [32, 512])
+    switch (tmem_cols) {
+      case 32: asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 32;" ::"r"(ts)); break;
+      case 64: asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;" ::"r"(ts)); break;
+      case 128: asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(ts)); break;
+      case 256: asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(ts)); break;
+      default: asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(ts)); break;
+    }
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   // ---- prologue (as K3a) ----

@@ -305,6 +305,41 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
   }
 }
 
+// Data-parallel Adam: the gradient all-reduce fused into the optimizer step over NVLink peer memory (one-shot all-reduce).
+// peer[r] is rank r's flat gradient bucket, mapped into this process (symmetric memory); every rank reads all `world`
+// buckets and adds them in rank order, so the reduced gradient -- and with it the updated replica -- is bit-identical on
+// every rank.  For the small factor-gradient buckets of the HAR nets (94 KB at cfg2) the step is latency-bound: this is one
+// kernel between two cross-rank barriers instead of ncclAllReduce + scale + Adam.  Loads bypass L1 (peer data changes every step).
+__device__ __forceinline__ float ld_peer(const float* p) {
+  float v;
+  asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__global__ void __launch_bounds__(kTailThreads)
+p2p_adam_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, const float* const* __restrict__ peer,
+                int world, long long n, float scale, float lr, float b1, float b2, float eps,
+                const float* __restrict__ step_dev, int step_host) {
+  __shared__ float sc[2];
+  __shared__ const float* sp[16];
+  if (threadIdx.x == 0) {
+    const double t = step_dev ? (double)*step_dev : (double)step_host;
+    sc[0] = (float)((double)lr / (1.0 - pow((double)b1, t)));
+    sc[1] = (float)(1.0 / sqrt(1.0 - pow((double)b2, t)));
+  }
+  if (threadIdx.x < world) sp[threadIdx.x] = peer[threadIdx.x];
+  __syncthreads();
+  const float step_size = sc[0], inv_bc2_sqrt = sc[1];
+  for (long long i = (long long)blockIdx.x * kTailThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kTailThreads) {
+    float gi = 0.f;
+    for (int r = 0; r < world; ++r) gi += ld_peer(sp[r] + i);              // fixed rank order
+    gi *= scale;
+    const float mi = fmaf(gi - m[i], 1.f - b1, m[i]);
+    const float vi = fmaf(gi * gi, 1.f - b2, b2 * v[i]);
+    m[i] = mi; v[i] = vi;
+    p[i] -= step_size * (mi / (sqrtf(vi) * inv_bc2_sqrt + eps));
+  }
+}
+
 // sum of squares of g, one partial per block (fixed grid-stride order)
 __global__ void __launch_bounds__(kTailThreads) sumsq_kernel(const float* __restrict__ g, long long n,
                                                              float* __restrict__ partials) {

@@ -459,6 +459,14 @@ int vmlmf_adam_step(float* p, const float* g, float* m, float* v, long long n, f
   return (int)cudaGetLastError();
 }
 
+int vmlmf_p2p_adam_step(float* p, float* m, float* v, const float* const* peer_grads, int world, long long n, float scale,
+                        float lr, float beta1, float beta2, float eps, const float* step_dev, int step, void* stream) {
+  if (!p || !m || !v || !peer_grads || world < 1 || world > 16 || n <= 0 || (!step_dev && step < 1)) return VMLMF_EINVAL;
+  p2p_adam_kernel<<<tail_grid(n), kTailThreads, 0, (cudaStream_t)stream>>>(p, m, v, peer_grads, world, n, scale, lr, beta1, beta2,
+                                                                          eps, step_dev, step);
+  return (int)cudaGetLastError();
+}
+
 long long vmlmf_sgd_clip_workspace_bytes(long long n) { return n <= 0 ? 0 : (long long)tail_grid(n) * (long long)sizeof(float); }
 
 int vmlmf_sgd_clip_step(float* p, float* g, long long n, float lr, float max_norm, int scale_grads, float* norm_out,

@@ -60,11 +60,19 @@ class FlatAdam(_FlatOptimizer):
         self.lr, self.betas, self.eps = lr, betas, eps
         self.m = self.v = self.t = None
 
+    P2P_MAX_BYTES = 2 << 20      # one-shot all-reduce: every rank reads world x bucket over NVLink
+
     def _build(self):
         super()._build()
         self.m = torch.zeros_like(self.pflat)
         self.v = torch.zeros_like(self.pflat)
         self.t = torch.zeros((), dtype=torch.float32, device=self.pflat.device)
+        b = self.bucket
+        # data parallel with a peer-mapped bucket: fuse the all-reduce into this step (vmlmf_p2p_adam_step)
+        if b.symm is not None and b.nbytes <= self.P2P_MAX_BYTES and b.symm.world_size <= 16:
+            b.fused_reduce = True
+            off = int(getattr(b.symm, "offset", 0))     # the bucket's byte offset inside the symmetric allocation
+            self.peer_ptrs = torch.tensor([int(q) + off for q in b.symm.buffer_ptrs], dtype=torch.int64, device=self.pflat.device)
 
     @torch.no_grad()
     def step(self):
@@ -72,6 +80,18 @@ class FlatAdam(_FlatOptimizer):
             self._build()
         g = self.bucket.pack()
         self.t += 1
+        b = self.bucket
+        if b.fused_reduce:
+            h = b.symm
+            scale = 1.0 / h.world_size if b.average else 1.0
+            with torch.cuda.device_of(g):
+                st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+                h.barrier(channel=0)                    # every rank's bucket is complete
+                _lib.check(_lib.lib().vmlmf_p2p_adam_step(_ptr(self.pflat), _ptr(self.m), _ptr(self.v), _ptr(self.peer_ptrs),
+                                                          h.world_size, g.numel(), scale, self.lr, self.betas[0], self.betas[1],
+                                                          self.eps, _ptr(self.t), 0, st))
+                h.barrier(channel=1)                    # every rank has read every bucket: the next backward may overwrite it
+            return
         with torch.cuda.device_of(g):
             st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
             _lib.check(_lib.lib().vmlmf_adam_step(_ptr(self.pflat), _ptr(g), _ptr(self.m), _ptr(self.v), g.numel(),

@@ -23,18 +23,37 @@ class GradBucket:
     bucket with one multi-tensor launch and re-points `.grad` at the bucket slices, which is what callers see
     afterwards (reduced / clipped values)."""
 
-    def __init__(self, module, average=True):
+    def __init__(self, module, average=True, symmetric=False):
         self.module = module
         self.average = average
         self.flat = None
         self.params = []
         self.views = []
+        # symmetric=True: allocate the bucket as NVLink peer-mapped symmetric memory so that an optimizer can read every
+        # rank's gradients directly (optim.FlatAdam fuses the all-reduce into its step); falls back to a plain buffer
+        # when symmetric memory is not available (single process, no NVLink peer access)
+        self.symmetric = symmetric
+        self.symm = None          # torch symmetric-memory handle once rendezvoused
+        self.fused_reduce = False # set by an optimizer that performs the reduction itself
 
     def _build(self):
         self.params = [p for p in self.module.parameters() if p.grad is not None]
         n = sum(p.numel() for p in self.params)
         ref = self.params[0]
-        self.flat = torch.zeros(n, dtype=ref.dtype, device=ref.device)
+        self.flat = None
+        if self.symmetric and ref.is_cuda and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                flat = symm_mem.empty(n, dtype=ref.dtype, device=ref.device)
+                self.symm = symm_mem.rendezvous(flat, dist.group.WORLD.group_name)
+                flat.zero_()
+                self.flat = flat
+            except Exception as e:                      # no peer access / backend missing: plain bucket + NCCL
+                import sys
+                sys.stderr.write(f"vmlmf_b200.parallel: symmetric memory unavailable ({type(e).__name__}: {e}); using NCCL\n")
+                self.symm = None
+        if self.flat is None:
+            self.flat = torch.zeros(n, dtype=ref.dtype, device=ref.device)
         off = 0
         self.views = []
         for p in self.params:
@@ -69,6 +88,8 @@ class GradBucket:
     def all_reduce(self):
         """sum (or mean) the bucket over all ranks; packs first; no collective for a single process"""
         self.pack()
+        if self.fused_reduce:                           # the optimizer step reads every rank's bucket itself
+            return self.flat
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
             if self.average:
