@@ -126,13 +126,13 @@ int map_3d(CUtensorMap* m, const float* p, long long cols, long long d1, long lo
 // Cooperative launch: every CTA of the grid is resident at once (grid <= SMs, one CTA per SM by shared-memory size), which
 // the group barriers inside the kernels rely on.
 template <class Kern, class... Args>
-int launch_coop(Kern kern, int grid, cudaStream_t st, Args... args) {
+int launch_coop(Kern kern, int grid, int smem_bytes, cudaStream_t st, Args... args) {
   // set on every launch: kernels that differ only in a template flag share this function's instantiation (same pointer
   // type), and the attribute is per device; the call is a few microseconds against a launch that runs T timesteps
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
   if (e != cudaSuccess) return (int)e;
   void* argv[] = {(void*)&args...};
-  return (int)cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(kThreads), argv, kSmemBytes, st);
+  return (int)cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(kThreads), argv, smem_bytes, st);
 }
 
 }  // namespace
@@ -254,9 +254,9 @@ int launch_fwd(const FwdCall& c, void* workspace, cudaStream_t st) {
   if (me != cudaSuccess) return (int)me;
   const int grid = g.ncl * g.CS;
   if (save)
-    return launch_coop(r2_fwd_kernel<true>, grid, st, m_hop_hi, m_hop_lo, m_at_hi, m_at_lo, m_zop_hi, m_zop_lo,
+    return launch_coop(r2_fwd_kernel<true>, grid, kSmemBytes, st, m_hop_hi, m_hop_lo, m_at_hi, m_at_lo, m_zop_hi, m_zop_lo,
                        m_zx_hi, m_zx_lo, m_w2_hi, m_w2_lo, a);
-  return launch_coop(r2_fwd_kernel<false>, grid, st, m_hop_hi, m_hop_lo, m_at_hi, m_at_lo, m_zop_hi, m_zop_lo,
+  return launch_coop(r2_fwd_kernel<false>, grid, kSmemBytes, st, m_hop_hi, m_hop_lo, m_at_hi, m_at_lo, m_zop_hi, m_zop_lo,
                      m_zx_hi, m_zx_lo, m_w2_hi, m_w2_lo, a);
 }
 
@@ -290,7 +290,7 @@ int launch_bwd(const BwdCall& c, void* workspace, BwdOut* out, cudaStream_t st) 
   a.sync = reinterpret_cast<unsigned int*>(ws + g.b_sync);
   e = cudaMemsetAsync(a.sync, 0, 32 * sizeof(unsigned int) * (size_t)g.ncl, st);
   if (e != cudaSuccess) return (int)e;
-  return launch_coop(r2_bwd_kernel, g.ncl * g.CS, st, m_dpo_hi, m_dpo_lo, m_w2t_hi, m_w2t_lo, m_dzo_hi, m_dzo_lo,
+  return launch_coop(r2_bwd_kernel, g.ncl * g.CS, kSmemBytesBwd, st, m_dpo_hi, m_dpo_lo, m_w2t_hi, m_w2t_lo, m_dzo_hi, m_dzo_lo,
                      m_ap_hi, m_ap_lo, a);
 }
 

@@ -54,8 +54,10 @@ constexpr int kStages = 3;
 constexpr int kTile = BM * BK * 4;           // 16 KB: one [128 x 32] fp32 operand tile
 constexpr int kStageBytes = 4 * kTile;       // A hi | A lo | B hi | B lo
 constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*alignment*/ + 256 /*barriers*/;
+constexpr int kXposeBytes = 32 * 32 * 4;     // backward: per-epilogue-warp [32 rows][32 units] transpose tile (XOR swizzled)
 constexpr int kEpiWarps = 8;                 // two per tensor-memory lane quarter
 constexpr int kThreads = 64 + 32 * kEpiWarps;
+constexpr int kSmemBytesBwd = kSmemBytes + kEpiWarps * kXposeBytes;
 constexpr int kMaxGroup = 64;                // CTAs per batch tile
 
 // ------------------------------------------------------------------------------------------------- PTX
@@ -595,20 +597,21 @@ struct BwdArgs {
 // gate-gradient algebra of one (row m, unit j) at step tq, in two halves so that a warp can have the loads of eight
 // cells in flight before the first store (the scratch buffers it writes may alias what it reads as far as the compiler
 // can tell, so loads are hoisted by hand).  Saved activations go through the read-only path.
-struct PwIn { float gi, gf, go, gn, ct, cp, dhs, dcin; };
-// dhs = dy_t + (dh seed, or the Dh term kept in dhrun); dcin = dc seed or dcrun
+struct PwIn { float gi, gf, go, gn, ct, cp, dyv, dhs, dcin; };
+// loads only, no arithmetic on the loaded values (a use would make the warp wait for the load right here and defeat the
+// prefetch): dyv = dy_t, dhs = dh seed or the Dh term kept in dhrun, dcin = dc seed or dcrun
 __device__ __forceinline__ void pw_load(const BwdArgs& a, int tq, int m, int j, bool seed, PwIn& in) {
   const size_t rowq = (size_t)tq * a.B + m;
   const float* g = a.gates + rowq * 4 * a.H + j;
   in.gi = __ldg(g); in.gf = __ldg(g + a.H); in.go = __ldg(g + 2 * a.H); in.gn = __ldg(g + 3 * a.H);
   in.ct = __ldg(a.cs + rowq * a.H + j);
   in.cp = tq > 0 ? __ldg(a.cs + (rowq - a.B) * a.H + j) : (a.c0 ? __ldg(a.c0 + (size_t)m * a.H + j) : 0.f);
-  const float dyv = a.dy ? __ldg(a.dy + (long long)tq * a.dys_t + (long long)m * a.dys_b + j) : 0.f;
+  in.dyv = a.dy ? __ldg(a.dy + (long long)tq * a.dys_t + (long long)m * a.dys_b + j) : 0.f;
   if (seed) {
-    in.dhs = dyv + (a.dhT ? __ldg(a.dhT + (size_t)m * a.H + j) : 0.f);
+    in.dhs = a.dhT ? __ldg(a.dhT + (size_t)m * a.H + j) : 0.f;
     in.dcin = a.dcT ? __ldg(a.dcT + (size_t)m * a.H + j) : 0.f;
   } else {
-    in.dhs = dyv + a.dhrun[(size_t)m * a.Hp + j];
+    in.dhs = a.dhrun[(size_t)m * a.Hp + j];
     in.dcin = a.dcrun[(size_t)m * a.Hp + j];
   }
 }
@@ -646,6 +649,9 @@ r2_bwd_kernel(const __grid_constant__ CUtensorMap m_dpo_hi, const __grid_constan
   const Smem sm = carve(smem_raw);
   Bars* bars = sm.bars;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // per-epilogue-warp transpose tile behind the barriers: accumulator rows (thread = batch row) -> lane = hidden unit, so
+  // that every global access of the gate-gradient algebra is one full 128-byte line (32 consecutive units of one row)
+  float* const xt = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sm.bars) + 256) + (warp >= 2 ? (warp - 2) * (kXposeBytes / 4) : 0);
   const int CS = a.CS, KSPLIT = a.KSPLIT, NP = CS * KSPLIT;
   const int s_rank = (int)blockIdx.x % CS, cid = (int)blockIdx.x / CS, ncl = (int)gridDim.x / CS;
   const int ntiles = (a.B + BM - 1) / BM;
@@ -685,22 +691,25 @@ r2_bwd_kernel(const __grid_constant__ CUtensorMap m_dpo_hi, const __grid_constan
     // ---- seed: gate-gradient algebra of the last step with dh = dhT, dc = dcT ----
     if (warp >= 2) {
       const int tq = a.T - 1;
-      for (int ug = ehalf; ug * 8 < uvalid; ug += 2) {
-        const int j = u0 + ug * 8 + c8;
+      for (int ub = ehalf * 32; ub < uvalid; ub += 64) {          // lane = unit: 128-byte lines
+        const int j = u0 + ub + lane;
         if (j < a.H) {
           float dhc[4];
 #pragma unroll
           for (int k = 0; k < 4; ++k) dhc[k] = __ldg(a.Dh + k * a.H + j);
-          PwIn in[8];
+#pragma unroll 1
+          for (int r0 = 0; r0 < 32; r0 += 4) {
+            PwIn in[4];
 #pragma unroll
-          for (int rg = 0; rg < 8; ++rg) {
-            const int m = row0 + eq * 32 + rg * 4 + rl;
-            if (m < a.B) pw_load(a, tq, m, j, true, in[rg]);
-          }
+            for (int u = 0; u < 4; ++u) {
+              const int m = row0 + eq * 32 + r0 + u;
+              if (m < a.B) pw_load(a, tq, m, j, true, in[u]);
+            }
 #pragma unroll
-          for (int rg = 0; rg < 8; ++rg) {
-            const int m = row0 + eq * 32 + rg * 4 + rl;
-            if (m < a.B) pw_finish(a, tq, m, j, in[rg], in[rg].dhs, dhc);
+            for (int u = 0; u < 4; ++u) {
+              const int m = row0 + eq * 32 + r0 + u;
+              if (m < a.B) pw_finish(a, tq, m, j, in[u], in[u].dyv + in[u].dhs, dhc);
+            }
           }
         }
       }
@@ -742,10 +751,12 @@ r2_bwd_kernel(const __grid_constant__ CUtensorMap m_dpo_hi, const __grid_constan
                 const int s = n_tile % kStages, it = n_tile / kStages;
                 mbar_wait(&bars->full[s], it & 1);
                 tc_fence_after();
+                if (ka == ka0) R2_TRACE(10);
                 issue_tile(smem_u32(sm.stages + s * kStageBytes), acc_main, acc_cross, idesc, tile_ksteps(uvalid, kt), ka == ka0);
                 mma_commit(&bars->empty[s]);
               }
               mma_commit(&bars->accf[buf]);
+              R2_TRACE(11);
             }
           }
         }
@@ -757,6 +768,7 @@ r2_bwd_kernel(const __grid_constant__ CUtensorMap m_dpo_hi, const __grid_constan
             const int buf = n_chunk & 1, use = n_chunk >> 1;
             mbar_wait(&bars->accf[buf], use & 1);
             tc_fence_after();
+            if (warp == 2) R2_TRACE(20);
             const uint32_t t_main = tmem_d + ((uint32_t)(eq * 32) << 16) + buf * 256;
 #pragma unroll 1
             for (int pp = 0; pp < 2; ++pp) {
@@ -792,10 +804,12 @@ r2_bwd_kernel(const __grid_constant__ CUtensorMap m_dpo_hi, const __grid_constan
           }
         }
         fence_proxy_async_all();
+        if (warp == 2) R2_TRACE(21);
       }
       // ======================================= exchange =======================================
       if (NP > 1) {
         if (CS > 1) group_sync(sync_ctr, epoch, CS); else __syncthreads();
+        if (warp == 2) R2_TRACE(30);
         if (warp >= 2) {
           const int rows_valid = min(BM, a.B - row0);
           const int rpc = (rows_valid + CS - 1) / CS;
@@ -832,8 +846,10 @@ r2_bwd_kernel(const __grid_constant__ CUtensorMap m_dpo_hi, const __grid_constan
             }
           }
           fence_proxy_async_all();
+          if (warp == 2) R2_TRACE(31);
         }
         if (CS > 1) group_sync(sync_ctr, epoch, CS); else __syncthreads();
+        if (warp == 2) R2_TRACE(32);
       } else {
         __syncthreads();
       }
@@ -866,53 +882,78 @@ r2_bwd_kernel(const __grid_constant__ CUtensorMap m_dpo_hi, const __grid_constan
               const int s = n_tile % kStages, it = n_tile / kStages;
               mbar_wait(&bars->full[s], it & 1);
               tc_fence_after();
+              if (kt == 0) R2_TRACE(12);
               issue_tile(smem_u32(sm.stages + s * kStageBytes), acc_main, acc_cross, idesc, tile_ksteps(a.RH, kt), kt == 0);
               mma_commit(&bars->empty[s]);
             }
             mma_commit(&bars->accf[buf]);
+            R2_TRACE(13);
           }
         }
         __syncwarp();
       } else {
         for (int c = 0; c < nch2; ++c, ++n_chunk) {
           const int buf = n_chunk & 1, use = n_chunk >> 1;
+          // this warp's two 32-unit passes of the chunk.  The accumulator arrives with thread = batch row; a swizzled
+          // shared tile private to the warp turns it into lane = hidden unit, and the rows are then walked four at a time
+          // (runtime loop: the body holds the gate-gradient algebra of four cells and stays inside the instruction cache) with
+          // the next four rows' saved activations already requested.
+          if (warp == 2) R2_TRACE(22);
           mbar_wait(&bars->accf[buf], use & 1);
           tc_fence_after();
+          if (warp == 2) R2_TRACE(23);
           const uint32_t t_main = tmem_d + ((uint32_t)(eq * 32) << 16) + buf * 256;
-          // this warp's eight 8-unit groups of the chunk, one per (deliberately not unrolled) iteration: the body holds the
-          // gate-gradient algebra of eight cells and must stay inside the instruction cache
 #pragma unroll 1
-          for (int gg = 0; gg < 8; ++gg) {
-            const int cb = (ehalf * 8 + gg) * 8;
+          for (int pp = 0; pp < 2; ++pp) {
+            const int cb = (ehalf * 2 + pp) * 32;
             if (c * 128 + cb >= uvalid) break;
-            float v[8];
-            tmem_ld_group(t_main, t_main + 128, cb, v);
-            xpose8_group(v, lane);
-            const int j = u0 + c * 128 + cb + c8;
-            if (j < a.H) {
-              if (t > 0) {
-                float dhc[4];
+            {
+              float v[32];
+              tmem_ld_groups(t_main, t_main + 128, cb, cb + 8, cb + 16, cb + 24, v);
+              __syncwarp();                                      // the previous pass's readers are done with the tile
 #pragma unroll
-                for (int k = 0; k < 4; ++k) dhc[k] = __ldg(a.Dh + k * a.H + j);
-                PwIn in[8];
+              for (int cc = 0; cc < 32; ++cc) xt[lane * 32 + ((cc ^ lane) & 31)] = v[cc];
+              __syncwarp();
+            }
+            const int j = u0 + c * 128 + cb + lane;
+            const bool act = j < a.H;
+            const int mbase = row0 + eq * 32;
+            if (t > 0) {
+              float dhc[4];
 #pragma unroll
-                for (int rg = 0; rg < 8; ++rg) {
-                  const int m = row0 + eq * 32 + rg * 4 + rl;
-                  if (m < a.B) pw_load(a, t - 1, m, j, false, in[rg]);
+              for (int k = 0; k < 4; ++k) dhc[k] = act ? __ldg(a.Dh + k * a.H + j) : 0.f;
+              PwIn pa[4];
+              if (act) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                  if (mbase + u < a.B) pw_load(a, t - 1, mbase + u, j, false, pa[u]);
+              }
+#pragma unroll 1
+              for (int r0 = 0; r0 < 32; r0 += 4) {
+                if (mbase + r0 >= a.B) break;
+                PwIn pn[4];
+                if (act && r0 + 4 < 32) {
+#pragma unroll
+                  for (int u = 0; u < 4; ++u)
+                    if (mbase + r0 + 4 + u < a.B) pw_load(a, t - 1, mbase + r0 + 4 + u, j, false, pn[u]);
                 }
+                if (act) {
 #pragma unroll
-                for (int rg = 0; rg < 8; ++rg) {
-                  const int m = row0 + eq * 32 + rg * 4 + rl;
-                  if (m < a.B) pw_finish(a, t - 1, m, j, in[rg], in[rg].dhs + v[rg], dhc);
-                }
-              } else {
-#pragma unroll
-                for (int rg = 0; rg < 8; ++rg) {
-                  const int m = row0 + eq * 32 + rg * 4 + rl;
-                  if (m < a.B) {
-                    if (a.dh0) a.dh0[(size_t)m * a.H + j] = a.dhrun[(size_t)m * a.Hp + j] + v[rg];
-                    if (a.dc0) a.dc0[(size_t)m * a.H + j] = a.dcrun[(size_t)m * a.Hp + j];
+                  for (int u = 0; u < 4; ++u) {
+                    const int r = r0 + u, m = mbase + r;
+                    if (m < a.B) pw_finish(a, t - 1, m, j, pa[u], pa[u].dyv + pa[u].dhs + xt[r * 32 + ((lane ^ r) & 31)], dhc);
                   }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) pa[u] = pn[u];
+              }
+            } else if (act) {
+#pragma unroll 4
+              for (int r = 0; r < 32; ++r) {
+                const int m = mbase + r;
+                if (m < a.B) {
+                  if (a.dh0) a.dh0[(size_t)m * a.H + j] = a.dhrun[(size_t)m * a.Hp + j] + xt[r * 32 + ((lane ^ r) & 31)];
+                  if (a.dc0) a.dc0[(size_t)m * a.H + j] = a.dcrun[(size_t)m * a.Hp + j];
                 }
               }
             }
@@ -920,10 +961,13 @@ r2_bwd_kernel(const __grid_constant__ CUtensorMap m_dpo_hi, const __grid_constan
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&bars->acce[buf]);
+          if (warp == 2) R2_TRACE(24);
         }
         fence_proxy_async_all();
+        if (warp == 2) R2_TRACE(25);
       }
       __syncthreads();
+      if (warp == 2) R2_TRACE(40);
     }
   }
   tc_fence_before();
