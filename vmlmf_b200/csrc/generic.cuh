@@ -327,6 +327,61 @@ static __global__ void colreduce_kernel(const ColRedArgs a) {
   p[4 * a.H + n] = sh;
   if (j < a.I) p[8 * a.H + k * a.I + j] = sx;
 }
+// one thread per FOUR consecutive columns of a gate (16-byte loads of dPre, h_{t-1} and x); needs H % 4 == 0, G % 4 == 0,
+// I % 4 == 0 or I handled by the tail lanes scalar-wise -- the launcher falls back to the scalar kernel otherwise
+static __global__ void colreduce4_kernel(const ColRedArgs a) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;          // column quad of dPre
+  const int hq = a.H >> 2;
+  if (q >= 4 * hq) return;
+  const int k = q / hq, j = (q - k * hq) * 4;
+  const long long rows = (long long)a.T * a.B;
+  const long long r0 = (long long)blockIdx.y * a.rows_per_split;
+  const long long r1 = r0 + a.rows_per_split < rows ? r0 + a.rows_per_split : rows;
+  const int nx = a.I - j < 0 ? 0 : (a.I - j > 4 ? 4 : a.I - j);  // how many of the four columns have an input-side term
+  const bool x_vec = nx == 4 && ((a.X.s_t | a.X.s_b) & 3) == 0 && (reinterpret_cast<uintptr_t>(a.X.p) & 15) == 0;
+  const bool y_vec = ((a.Y.s_t | a.Y.s_b) & 3) == 0 && (reinterpret_cast<uintptr_t>(a.Y.p) & 15) == 0;
+  float4 sb = make_float4(0.f, 0.f, 0.f, 0.f), sh = sb, sx = sb;
+  int t = (int)(r0 / a.B), b = (int)(r0 - (long long)t * a.B);
+  const float* dp = a.dpre + (size_t)r0 * 4 * a.G + (size_t)k * a.G + j;
+  const size_t dstep = (size_t)4 * a.G;
+  for (long long r = r0; r < r1; r += 2) {
+    float4 d[2], hp[2], xv[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      d[u] = hp[u] = xv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r + u < r1) {
+        d[u] = *reinterpret_cast<const float4*>(dp + u * dstep);
+        const float* hrow = t > 0 ? a.Y.p + (long long)(t - 1) * a.Y.s_t + (long long)b * a.Y.s_b
+                                  : (a.h0 ? a.h0 + (size_t)b * a.H : nullptr);
+        if (hrow) {
+          if (t > 0 ? y_vec : true) hp[u] = *reinterpret_cast<const float4*>(hrow + j);
+          else hp[u] = make_float4(hrow[j], hrow[j + 1], hrow[j + 2], hrow[j + 3]);
+        }
+        if (nx) {
+          const float* xr = a.X.p + (long long)t * a.X.s_t + (long long)b * a.X.s_b + j;
+          if (x_vec) xv[u] = *reinterpret_cast<const float4*>(xr);
+          else { xv[u].x = xr[0]; if (nx > 1) xv[u].y = xr[1]; if (nx > 2) xv[u].z = xr[2]; if (nx > 3) xv[u].w = xr[3]; }
+        }
+        if (++b == a.B) { b = 0; ++t; }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {           // fixed order; absent rows add zeros
+      sb.x += d[u].x; sb.y += d[u].y; sb.z += d[u].z; sb.w += d[u].w;
+      sh.x = fmaf(d[u].x, hp[u].x, sh.x); sh.y = fmaf(d[u].y, hp[u].y, sh.y);
+      sh.z = fmaf(d[u].z, hp[u].z, sh.z); sh.w = fmaf(d[u].w, hp[u].w, sh.w);
+      sx.x = fmaf(d[u].x, xv[u].x, sx.x); sx.y = fmaf(d[u].y, xv[u].y, sx.y);
+      sx.z = fmaf(d[u].z, xv[u].z, sx.z); sx.w = fmaf(d[u].w, xv[u].w, sx.w);
+    }
+    dp += 2 * dstep;
+  }
+  float* p = a.part + (size_t)blockIdx.y * (8 * a.H + 4 * a.I);
+  const int n = k * a.H + j;
+  p[n] = sb.x; p[n + 1] = sb.y; p[n + 2] = sb.z; p[n + 3] = sb.w;
+  p[4 * a.H + n] = sh.x; p[4 * a.H + n + 1] = sh.y; p[4 * a.H + n + 2] = sh.z; p[4 * a.H + n + 3] = sh.w;
+  const float sxa[4] = {sx.x, sx.y, sx.z, sx.w};
+  for (int e = 0; e < nx; ++e) p[8 * a.H + k * a.I + j + e] = sxa[e];
+}
 static __global__ void colreduce_final_kernel(const float* __restrict__ part, int nsplit, int H, int I,
                                               float* dbias, float* dDh, float* dDx) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x, tot = 8 * H + 4 * I;
@@ -840,7 +895,11 @@ inline int generic_bwd_tp(TpArgs& a, cudaStream_t st) {
     if (rps < 1) rps = 1;
     const int nsp = (int)((rows + rps - 1) / rps);
     ColRedArgs ca{a.dpre, Yv, a.h0, Xv, part, T, B, H, I, rps, G};
-    colreduce_kernel<<<dim3(ceil_div(4 * H, 128), nsp), 128, 0, st>>>(ca);
+    const bool quad = (H & 3) == 0 && (G & 3) == 0 && (reinterpret_cast<uintptr_t>(a.dpre) & 15) == 0 &&
+                      (!a.h0 || (reinterpret_cast<uintptr_t>(a.h0) & 15) == 0) && ((a.ys_t | a.ys_b) & 3) == 0 &&
+                      (reinterpret_cast<uintptr_t>(a.y) & 15) == 0;
+    if (quad) colreduce4_kernel<<<dim3(ceil_div(H, 128), nsp), 128, 0, st>>>(ca);
+    else colreduce_kernel<<<dim3(ceil_div(4 * H, 128), nsp), 128, 0, st>>>(ca);
     G_TRY((int)cudaGetLastError());
     colreduce_final_kernel<<<ceil_div(8 * H + 4 * I, 256), 256, 0, st>>>(part, nsp, H, I, a.dbias, a.dDh, a.dDx);
     G_TRY((int)cudaGetLastError());
