@@ -68,6 +68,13 @@ def _require_cuda(*ts):
             raise RuntimeError("vmlmf_b200: fp32 only (the reference computes in fp32)")
 
 
+def _xproj_on_tensor_cores(x, batch_first, T, B, I, RX, plan):
+    """the x projection as one tcgen05 GEMM: time-major contiguous input (row t*B+b = the order zx is consumed in), a
+    product big enough for 128 x 128 tiles, and an unpadded zx (RX % 4 == 0: the GEMM writes exactly RX columns)"""
+    return (plan.path == _lib.PATH_R2 and not batch_first and x.is_contiguous() and I >= 128 and RX >= 32 and
+            T * B >= 256 and plan.zx_pitch == RX)
+
+
 def _seq_forward(x, h0, c0, canon, batch_first, need_grad, need_y):
     """xproj + the whole time loop of one layer through the C ABI.  Returns (y, hT, cT, saved) where `saved` is what
     _seq_backward needs (None when nothing is kept)."""
@@ -102,7 +109,19 @@ def _seq_forward(x, h0, c0, canon, batch_first, need_grad, need_y):
     with torch.cuda.device_of(x):
         st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         with _timed("xproj_fwd"):
-            _lib.check(lib.vmlmf_xproj_fwd(_ptr(x), xs_t, xs_b, _ptr(Ux), _ptr(zx), T, B, I, RX, plan.zx_pitch, st))
+            if _xproj_on_tensor_cores(x, batch_first, T, B, I, RX, plan):
+                # wide time-major inputs (the LM layers: x[T,B,650] Ux[650,300]): ZX = X Ux on the tcgen05 GEMM.  Rows of 650
+                # floats are not 16-byte multiples (TMA), so x is copied once into a pitch-padded buffer (46 MB at B=512
+                # against a 7 GFLOP product that the SIMT fallback takes 0.55 ms for)
+                ip = (I + 3) // 4 * 4
+                xp = x.new_zeros((T * B, ip)) if ip != I else None
+                if xp is not None:
+                    xp[:, :I].copy_(x.reshape(T * B, I))
+                uxt = x.new_zeros((RX, ip))
+                uxt[:, :I].copy_(Ux.t())
+                gemm_nt(xp if xp is not None else x.reshape(T * B, I), uxt, out=zx)
+            else:
+                _lib.check(lib.vmlmf_xproj_fwd(_ptr(x), xs_t, xs_b, _ptr(Ux), _ptr(zx), T, B, I, RX, plan.zx_pitch, st))
         with _timed("seq_fwd"):
             _lib.check(lib.vmlmf_seq_fwd(C.byref(plan), _ptr(x), xs_t, xs_b, _ptr(zx), _ptr(Ux), _ptr(Vx), _ptr(Dx),
                                          _ptr(A), _ptr(Bm), _ptr(Dh), _ptr(bias), _ptr(h0), _ptr(c0), _ptr(y), ys_t,
