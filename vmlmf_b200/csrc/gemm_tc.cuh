@@ -63,6 +63,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {}
 }
 __device__ __forceinline__ float tf32r(float v) { return tf32_rna(v); }
+// v minus its tf32 truncation (exact; |result| < 2^-10 |v|)
+__device__ __forceinline__ float tf32_lo(float v) { return v - __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
@@ -325,12 +327,22 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
 #pragma unroll 4
       for (int i = st_tid; i < kTileBytes / 16; i += 128) {
         const float4 va = a_hi[i], vb = b_hi[i];
+#ifdef VMLMF_SPLIT_ROUND
         float4 ha, la, hb, lb;
         ha.x = tf32r(va.x); ha.y = tf32r(va.y); ha.z = tf32r(va.z); ha.w = tf32r(va.w);
         la.x = tf32r(va.x - ha.x); la.y = tf32r(va.y - ha.y); la.z = tf32r(va.z - ha.z); la.w = tf32r(va.w - ha.w);
         hb.x = tf32r(vb.x); hb.y = tf32r(vb.y); hb.z = tf32r(vb.z); hb.w = tf32r(vb.w);
         lb.x = tf32r(vb.x - hb.x); lb.y = tf32r(vb.y - hb.y); lb.z = tf32r(vb.z - hb.z); lb.w = tf32r(vb.w - hb.w);
         a_hi[i] = ha; a_lo[i] = la; b_hi[i] = hb; b_lo[i] = lb;
+#else
+        // The tensor core reads the top 19 bits of a tf32 operand and ignores the low 13 mantissa bits, so the raw fp32 tile
+        // the TMA delivered IS its own (truncated) hi part: only the remainder is computed and written -- a third less
+        // shared-memory traffic in the stage that bounds this kernel (same trick as the mma.sync kernels, seq_mma.cuh:split4).
+        float4 la, lb;
+        la.x = tf32_lo(va.x); la.y = tf32_lo(va.y); la.z = tf32_lo(va.z); la.w = tf32_lo(va.w);
+        lb.x = tf32_lo(vb.x); lb.y = tf32_lo(vb.y); lb.z = tf32_lo(vb.z); lb.w = tf32_lo(vb.w);
+        a_lo[i] = la; b_lo[i] = lb;
+#endif
       }
       fence_proxy_async();                               // generic-proxy writes -> visible to the tensor-core (async) proxy
       __syncwarp();
@@ -501,12 +513,22 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tn_kernel(const __grid_const
 #pragma unroll 4
       for (int i = st_tid; i < kTileBytes / 16; i += 128) {
         const float4 va = a_hi[i], vb = b_hi[i];
+#ifdef VMLMF_SPLIT_ROUND
         float4 ha, la, hb, lb;
         ha.x = tf32r(va.x); ha.y = tf32r(va.y); ha.z = tf32r(va.z); ha.w = tf32r(va.w);
         la.x = tf32r(va.x - ha.x); la.y = tf32r(va.y - ha.y); la.z = tf32r(va.z - ha.z); la.w = tf32r(va.w - ha.w);
         hb.x = tf32r(vb.x); hb.y = tf32r(vb.y); hb.z = tf32r(vb.z); hb.w = tf32r(vb.w);
         lb.x = tf32r(vb.x - hb.x); lb.y = tf32r(vb.y - hb.y); lb.z = tf32r(vb.z - hb.z); lb.w = tf32r(vb.w - hb.w);
         a_hi[i] = ha; a_lo[i] = la; b_hi[i] = hb; b_lo[i] = lb;
+#else
+        // The tensor core reads the top 19 bits of a tf32 operand and ignores the low 13 mantissa bits, so the raw fp32 tile
+        // the TMA delivered IS its own (truncated) hi part: only the remainder is computed and written -- a third less
+        // shared-memory traffic in the stage that bounds this kernel (same trick as the mma.sync kernels, seq_mma.cuh:split4).
+        float4 la, lb;
+        la.x = tf32_lo(va.x); la.y = tf32_lo(va.y); la.z = tf32_lo(va.z); la.w = tf32_lo(va.w);
+        lb.x = tf32_lo(vb.x); lb.y = tf32_lo(vb.y); lb.z = tf32_lo(vb.z); lb.w = tf32_lo(vb.w);
+        a_lo[i] = la; b_lo[i] = lb;
+#endif
       }
       fence_proxy_async();
       __syncwarp();

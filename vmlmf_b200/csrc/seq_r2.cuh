@@ -94,8 +94,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+// tf32 hi / lo parts of an fp32 operand.  The tensor core reads the top 19 bits of a 32-bit tf32 container and ignores the low
+// 13 mantissa bits, so the raw value is its own (truncated) hi part; lo = v - trunc(v) is exact in fp32 and < 2^-10 |v|
+// (measured: same end-to-end error as round-to-nearest splitting, tests/test_gpu_parity.py; -DVMLMF_SPLIT_ROUND restores it).
+#ifdef VMLMF_SPLIT_ROUND
 __device__ __forceinline__ float split_hi(float v) { return tf32_rna(v); }
 __device__ __forceinline__ float split_lo(float v, float hi) { return tf32_rna(v - hi); }
+#else
+__device__ __forceinline__ float split_hi(float v) { return v; }
+__device__ __forceinline__ float split_lo(float v, float) { return v - __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
+#endif
 
 // Debug-only cycle trace (-DVMLMF_R2_TRACE, tools/trace_r2.py): lane 0 of each role of CTA 0 appends (event, clock64) pairs
 // for a few timesteps.  Compiled out of the shipped library.
