@@ -108,6 +108,20 @@ inline int ew_grid(long long n) {
 int map_2d(CUtensorMap* m, const float* p, long long cols, long long rows, long long ld) {
   return tc::make_map_2d(m, p, rows, cols, ld);                       // box 32 x 128
 }
+// [d3][d2][d1][cols] view, strides in floats; box = 32 x 1 x box2 x 1
+int map_4d(CUtensorMap* m, const float* p, long long cols, long long d1, long long d2, long long d3, long long s1, long long s2,
+           long long s3, int box2) {
+  tc::EncodeTiledFn fn = tc::encode_fn();
+  if (!fn) return tc::kTcNoFit;
+  cuuint64_t dims[4] = {(cuuint64_t)cols, (cuuint64_t)d1, (cuuint64_t)d2, (cuuint64_t)d3};
+  cuuint64_t strides[3] = {(cuuint64_t)s1 * 4, (cuuint64_t)s2 * 4, (cuuint64_t)s3 * 4};
+  cuuint32_t box[4] = {BK, 1, (cuuint32_t)box2, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(p), dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : tc::kTcNoFit;
+}
 // [d2][d1][cols] view, strides in floats; box = 32 x box1 x box2
 int map_3d(CUtensorMap* m, const float* p, long long cols, long long d1, long long d2, long long s1, long long s2,
            int box1, int box2) {
@@ -263,17 +277,24 @@ int launch_fwd(const FwdCall& c, void* workspace, cudaStream_t st) {
 int launch_bwd(const BwdCall& c, void* workspace, BwdOut* out, cudaStream_t st) {
   const Geom g = geom(c.T, c.B, c.I, c.H, c.RX, c.RH);
   float* ws = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
-  float *dpo_hi = ws + g.b_dpo_hi, *dpo_lo = ws + g.b_dpo_lo, *dzo_hi = ws + g.b_dzo_hi, *dzo_lo = ws + g.b_dzo_lo;
+  float *dpo_lo = ws + g.b_dpo_lo, *dzo_hi = ws + g.b_dzo_hi, *dzo_lo = ws + g.b_dzo_lo, *dpre = ws + g.b_dpre;
   float *w2t_hi = ws + g.b_w2t_hi, *w2t_lo = ws + g.b_w2t_lo, *ap_hi = ws + g.b_ap_hi, *ap_lo = ws + g.b_ap_lo;
-  // the operand copy of dPre keeps zeros in its pad units (never written by the kernel; dpo_hi and dpo_lo are adjacent)
-  cudaError_t e = cudaMemsetAsync(dpo_hi, 0, (size_t)(g.b_dzo_hi - g.b_dpo_hi) * sizeof(float), st);
+  // pad units (H <= j < Hp) are never written by the kernel but are read as tensor-core operands (against zero weights):
+  // they must hold finite values.  The lo copy is small; of dPre itself only the pad columns are cleared.
+  cudaError_t e = cudaMemsetAsync(dpo_lo, 0, (size_t)c.B * 4 * g.Hp * sizeof(float), st);
   if (e != cudaSuccess) return (int)e;
+  if (g.Hp > c.H) {
+    e = cudaMemset2DAsync(dpre + c.H, (size_t)g.Hp * sizeof(float), 0, (size_t)(g.Hp - c.H) * sizeof(float),
+                          (size_t)c.T * c.B * 4, st);
+    if (e != cudaSuccess) return (int)e;
+  }
   pack_bwd_kernel<<<ew_grid((long long)g.KPp * 4 * g.Hp + (long long)g.Hp * g.KZP), 256, 0, st>>>(
       c.A, c.Bm, c.Vx, w2t_hi, w2t_lo, ap_hi, ap_lo, c.H, c.RH, c.RX, g.Hp, g.KZP, g.KPp);
   int rc = (int)cudaGetLastError();
   if (rc) return rc;
-  CUtensorMap m_dpo_hi, m_dpo_lo, m_w2t_hi, m_w2t_lo, m_dzo_hi, m_dzo_lo, m_ap_hi, m_ap_lo;
-  if (map_3d(&m_dpo_hi, dpo_hi, g.Hp, 4, c.B, g.Hp, 4LL * g.Hp, 1, BM) || map_3d(&m_dpo_lo, dpo_lo, g.Hp, 4, c.B, g.Hp, 4LL * g.Hp, 1, BM) ||
+  CUtensorMap m_dpre, m_dpo_lo, m_w2t_hi, m_w2t_lo, m_dzo_hi, m_dzo_lo, m_ap_hi, m_ap_lo;
+  if (map_4d(&m_dpre, dpre, g.Hp, 4, c.B, c.T, g.Hp, 4LL * g.Hp, 4LL * g.Hp * c.B, BM) ||
+      map_3d(&m_dpo_lo, dpo_lo, g.Hp, 4, c.B, g.Hp, 4LL * g.Hp, 1, BM) ||
       map_3d(&m_w2t_hi, w2t_hi, g.Hp, 4, g.KPp, g.Hp, 4LL * g.Hp, 1, 128) || map_3d(&m_w2t_lo, w2t_lo, g.Hp, 4, g.KPp, g.Hp, 4LL * g.Hp, 1, 128) ||
       map_2d(&m_dzo_hi, dzo_hi, g.zp, c.B, g.zp) || map_2d(&m_dzo_lo, dzo_lo, g.zp, c.B, g.zp) ||
       map_2d(&m_ap_hi, ap_hi, g.KZP, g.Hp, g.KZP) || map_2d(&m_ap_lo, ap_lo, g.KZP, g.Hp, g.KZP))
@@ -281,8 +302,8 @@ int launch_bwd(const BwdCall& c, void* workspace, BwdOut* out, cudaStream_t st) 
   BwdArgs a;
   a.gates = c.gates; a.cs = c.cs; a.c0 = c.c0; a.dy = c.dy; a.dys_t = c.dys_t; a.dys_b = c.dys_b;
   a.dhT = c.dhT; a.dcT = c.dcT; a.Dh = c.Dh; a.dh0 = c.dh0; a.dc0 = c.dc0;
-  a.dpre = ws + g.b_dpre; a.dz_all = ws + g.b_dz; a.dzx_all = ws + g.b_dzx;
-  a.dpo_hi = dpo_hi; a.dpo_lo = dpo_lo; a.dzo_hi = dzo_hi; a.dzo_lo = dzo_lo;
+  a.dpre = dpre; a.dz_all = ws + g.b_dz; a.dzx_all = ws + g.b_dzx;
+  a.dpo_lo = dpo_lo; a.dzo_hi = dzo_hi; a.dzo_lo = dzo_lo;
   a.dhrun = ws + g.b_dhrun; a.dcrun = ws + g.b_dcrun; a.part = ws + g.b_part;
   a.T = c.T; a.B = c.B; a.H = c.H; a.RX = c.RX; a.RH = c.RH;
   a.Hp = g.Hp; a.HS = g.HS; a.CS = g.CS; a.zp = g.zp; a.zxp = g.zxp; a.KZP = g.KZP; a.KPp = g.KPp; a.KSPLIT = g.KSPLIT;
@@ -290,7 +311,7 @@ int launch_bwd(const BwdCall& c, void* workspace, BwdOut* out, cudaStream_t st) 
   a.sync = reinterpret_cast<unsigned int*>(ws + g.b_sync);
   e = cudaMemsetAsync(a.sync, 0, 32 * sizeof(unsigned int) * (size_t)g.ncl, st);
   if (e != cudaSuccess) return (int)e;
-  return launch_coop(r2_bwd_kernel, g.ncl * g.CS, kSmemBytesBwd, st, m_dpo_hi, m_dpo_lo, m_w2t_hi, m_w2t_lo, m_dzo_hi, m_dzo_lo,
+  return launch_coop(r2_bwd_kernel, g.ncl * g.CS, kSmemBytesBwd, st, m_dpre, m_dpo_lo, m_w2t_hi, m_w2t_lo, m_dzo_hi, m_dzo_lo,
                      m_ap_hi, m_ap_lo, a);
 }
 

@@ -593,7 +593,7 @@ struct BwdArgs {
   float* dpre;                // [T*B, 4, Hp]
   float* dz_all;              // [T*B, zp]
   float* dzx_all;             // [T*B, zxp]
-  float *dpo_hi, *dpo_lo;     // [B, 4, Hp]   tf32 operand copy of dPre_t
+  float* dpo_lo;              // [B, 4, Hp]   tf32 lo part of dPre_t (the hi part is dPre itself: the tensor core truncates)
   float *dzo_hi, *dzo_lo;     // [B, zp]      tf32 operand copy of dz_t
   float *dhrun, *dcrun;       // [B, Hp]
   float* part;                // [groups, NP, 128, KPp]   NP = CS * KSPLIT partials
@@ -633,15 +633,12 @@ __device__ __forceinline__ void pw_finish(const BwdArgs& a, int tq, int m, int j
   d[2] = dh * tcv * in.go * (1.f - in.go);
   d[3] = dc * in.gi * (1.f - in.gn * in.gn);
   float* o = a.dpre + rowq * 4 * a.Hp + j;
-  float* oh = a.dpo_hi + (size_t)m * 4 * a.Hp + j;
   float* ol = a.dpo_lo + (size_t)m * 4 * a.Hp + j;
   float sdh = 0.f;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    o[(size_t)k * a.Hp] = d[k];
-    const float hi = split_hi(d[k]);
-    oh[(size_t)k * a.Hp] = hi;
-    ol[(size_t)k * a.Hp] = split_lo(d[k], hi);
+    o[(size_t)k * a.Hp] = d[k];                               // exact copy for the time-parallel GEMMs AND the hi operand of phase 1
+    ol[(size_t)k * a.Hp] = split_lo(d[k], d[k]);
     sdh = fmaf(d[k], dhc[k], sdh);
   }
   a.dcrun[(size_t)m * a.Hp + j] = dc * in.gf;
@@ -649,7 +646,7 @@ __device__ __forceinline__ void pw_finish(const BwdArgs& a, int tq, int m, int j
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
-r2_bwd_kernel(const __grid_constant__ CUtensorMap m_dpo_hi, const __grid_constant__ CUtensorMap m_dpo_lo,
+r2_bwd_kernel(const __grid_constant__ CUtensorMap m_dpre, const __grid_constant__ CUtensorMap m_dpo_lo,
               const __grid_constant__ CUtensorMap m_w2t_hi, const __grid_constant__ CUtensorMap m_w2t_lo,
               const __grid_constant__ CUtensorMap m_dzo_hi, const __grid_constant__ CUtensorMap m_dzo_lo,
               const __grid_constant__ CUtensorMap m_ap_hi, const __grid_constant__ CUtensorMap m_ap_lo, const BwdArgs a) {
@@ -736,7 +733,7 @@ r2_bwd_kernel(const __grid_constant__ CUtensorMap m_dpo_hi, const __grid_constan
               if (it > 0) mbar_wait(&bars->empty[s], (it - 1) & 1);
               uint8_t* st = sm.stages + s * kStageBytes;
               mbar_arrive_expect_tx(&bars->full[s], kStageBytes);
-              tma_load_3d(st, &m_dpo_hi, u0 + kt * BK, k, row0, &bars->full[s]);
+              tma_load_4d(st, &m_dpre, u0 + kt * BK, k, row0, t, &bars->full[s]);
               tma_load_3d(st + kTile, &m_dpo_lo, u0 + kt * BK, k, row0, &bars->full[s]);
               tma_load_3d(st + 2 * kTile, &m_w2t_hi, u0 + kt * BK, k, c * 128, &bars->full[s]);
               tma_load_3d(st + 3 * kTile, &m_w2t_lo, u0 + kt * BK, k, c * 128, &bars->full[s]);
