@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define VMLMF_ABI_VERSION 3
+#define VMLMF_ABI_VERSION 4
 
 enum {
   VMLMF_OK = 0,
@@ -195,6 +195,14 @@ int vmlmf_head_bwd(const float* h, long long ldh, const float* W, const float* d
  * is read from the device scalar step_dev (float; lets a CUDA graph replay advance it) or, if NULL, from `step`. */
 int vmlmf_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                     float eps, const float* step_dev, int step, void* stream);
+/* LM input side: Embed (index -> row of W[V,E], V/models/vmlmf_lm.py:33-51) and the dropout applied to it (:436) in one pass:
+ *   out[r, c] = W[tok[r], c] * (mask ? mask[r, c] * scale : 1)   c < E;   0 for E <= c < ldo
+ * out has row pitch ldo (>= E): with ldo % 4 == 0 the result is directly the TMA A operand of the x-projection GEMM (rows of
+ * E = 650 floats are not 16-byte multiples).  mask: uint8 [rows, E], 1 = keep, or NULL (eval / p = 0); scale = 1/(1-p).
+ * An out-of-range token yields NaN rows (the eager indexing this replaces device-asserts).                              */
+int vmlmf_embed_dropout_fwd(const long long* tok, const float* W, const unsigned char* mask, float scale, float* out,
+                            long long ldo, long long rows, int E, int V, void* stream);
+
 /* Data-parallel Adam step with the gradient all-reduce FUSED in, over NVLink peer memory (one-shot all-reduce): peer_grads is
  * a device array of `world` pointers, peer_grads[r] = rank r's flat gradient bucket of n floats mapped into this process
  * (torch symmetric memory / cudaIpc).  Every rank adds the buckets in rank order (bit-identical replicas), multiplies by

@@ -166,3 +166,35 @@ def test_graphed_step_with_static_inputs_reads_the_callers_buffers():
     assert abs(l1 - float(l2)) <= 1e-5 * max(1.0, abs(float(l2)))
     for (k, p1), (_, p2) in zip(net1.named_parameters(), net2.named_parameters()):
         _close(p1, p2, 2e-5, k)
+
+
+@pytest.mark.parametrize("p", [0.0, 0.5])
+def test_fused_embed_dropout_matches_indexing(p):
+    """vmlmf_embed_dropout_fwd (Embed + dropout of the LM input, V/models/vmlmf_lm.py:48,:436): every element is either 0
+    or w[token] / (1 - p), the view is backed by a pitch-padded buffer with zero pad columns, and the weight gradient is
+    the dense embedding backward of the masked upstream gradient."""
+    from vmlmf_b200.functional import embed_dropout
+    torch.manual_seed(5)
+    V, E, T, B = 37, 650, 6, 5
+    w = (torch.randn(V, E, device=DEV) + 3.0).requires_grad_(True)          # no exact zeros: the mask is recoverable from the output
+    tok = torch.randint(0, V, (T, B), device=DEV)
+    out = embed_dropout(tok, w, p, training=True)
+    assert out.shape == (T, B, E) and out.stride(-1) == 1 and out.stride(1) % 4 == 0
+    dense = w.detach()[tok]
+    keep = out.detach() != 0
+    scale = 1.0 / (1.0 - p)
+    _close(out.detach()[keep], dense[keep] * scale, 1e-6, "kept values")
+    if p == 0.0:
+        assert bool(keep.all())
+    else:
+        frac = keep.float().mean().item()
+        assert abs(frac - (1 - p)) < 0.03, f"keep fraction {frac}"
+    pad = out.detach().as_strided((T * B, out.stride(1)), (out.stride(1), 1))[:, E:]
+    assert pad.numel() == 0 or bool((pad == 0).all())
+    up = torch.randn(T, B, E, device=DEV)
+    (out * up).sum().backward()
+    ref = torch.zeros_like(w)
+    ref.index_add_(0, tok.reshape(-1), (up * keep * scale).reshape(-1, E))
+    _close(w.grad, ref, 1e-5, "dW")
+    ev = embed_dropout(tok, w.detach(), p, training=False)
+    assert torch.equal(ev, dense)                                            # eval: plain gather

@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvmlmf_b200.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 PATH_R1, PATH_G, PATH_R1M, PATH_R2 = 1, 2, 3, 4
 LARGE_PATHS = (PATH_G, PATH_R2)      # regimes for shapes beyond the register-resident kernels
@@ -47,6 +47,7 @@ SIGNATURES = {
     "vmlmf_head_bwd_workspace_bytes": [_I, _I, _I],                          # returns long long
     "vmlmf_head_bwd": [_P, _LL, _P, _P, _P, _LL, _P, _P, _P, _I, _I, _I, _P],
     "vmlmf_adam_step": [_P, _P, _P, _P, _LL, _F, _F, _F, _F, _P, _I, _P],
+    "vmlmf_embed_dropout_fwd": [_P, _P, _P, _F, _P, _LL, _LL, _I, _I, _P],
     "vmlmf_p2p_adam_step": [_P, _P, _P, _P, _I, _LL, _F, _F, _F, _F, _F, _P, _I, _P],
     "vmlmf_sgd_clip_workspace_bytes": [_LL],                                 # returns long long
     "vmlmf_sgd_clip_step": [_P, _P, _LL, _F, _F, _I, _P, _P, _P],

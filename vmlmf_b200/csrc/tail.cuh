@@ -340,6 +340,26 @@ p2p_adam_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict_
   }
 }
 
+// LM input side: out[r, c] = W[tok[r], c] * (mask ? mask[r, c] * scale : 1) for c < E, 0 for E <= c < ldo.
+// Embed (index -> row, V/models/vmlmf_lm.py:48) and the dropout that follows it (:436) in one pass, written into a
+// pitch-padded buffer (ldo % 4 == 0) so that the x-projection GEMM can read it in place as its TMA A operand.
+__global__ void __launch_bounds__(kTailThreads)
+embed_dropout_kernel(const long long* __restrict__ tok, const float* __restrict__ W, const unsigned char* __restrict__ mask,
+                     float scale, float* __restrict__ out, long long ldo, long long rows, int E, int V) {
+  const long long n = rows * ldo;
+  for (long long i = (long long)blockIdx.x * kTailThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kTailThreads) {
+    const long long r = i / ldo;
+    const int c = (int)(i - r * ldo);
+    float v = 0.f;
+    if (c < E) {
+      const long long t = tok[r];
+      v = (t >= 0 && t < V) ? __ldg(W + t * E + c) : __int_as_float(0x7fc00000);   // out-of-range token: NaN, no stray read
+      if (mask) v = mask[r * E + c] ? v * scale : 0.f;
+    }
+    out[i] = v;
+  }
+}
+
 // sum of squares of g, one partial per block (fixed grid-stride order)
 __global__ void __launch_bounds__(kTailThreads) sumsq_kernel(const float* __restrict__ g, long long n,
                                                              float* __restrict__ partials) {

@@ -459,6 +459,13 @@ int vmlmf_adam_step(float* p, const float* g, float* m, float* v, long long n, f
   return (int)cudaGetLastError();
 }
 
+int vmlmf_embed_dropout_fwd(const long long* tok, const float* W, const unsigned char* mask, float scale, float* out,
+                            long long ldo, long long rows, int E, int V, void* stream) {
+  if (!tok || !W || !out || rows <= 0 || E <= 0 || V <= 0 || ldo < E) return VMLMF_EINVAL;
+  embed_dropout_kernel<<<tail_grid(rows * ldo), kTailThreads, 0, (cudaStream_t)stream>>>(tok, W, mask, scale, out, ldo, rows, E, V);
+  return (int)cudaGetLastError();
+}
+
 int vmlmf_p2p_adam_step(float* p, float* m, float* v, const float* const* peer_grads, int world, long long n, float scale,
                         float lr, float beta1, float beta2, float eps, const float* step_dev, int step, void* stream) {
   if (!p || !m || !v || !peer_grads || world < 1 || world > 16 || n <= 0 || (!step_dev && step < 1)) return VMLMF_EINVAL;

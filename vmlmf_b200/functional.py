@@ -71,7 +71,8 @@ def _require_cuda(*ts):
 def _xproj_on_tensor_cores(x, batch_first, T, B, I, RX, plan):
     """the x projection as one tcgen05 GEMM: time-major contiguous input (row t*B+b = the order zx is consumed in), a
     product big enough for 128 x 128 tiles, and an unpadded zx (RX % 4 == 0: the GEMM writes exactly RX columns)"""
-    return (plan.path == _lib.PATH_R2 and not batch_first and x.is_contiguous() and I >= 128 and RX >= 32 and
+    rows_uniform = x.stride(1) * B == x.stride(0) or T == 1          # row t*B+b lives at (t*B+b) * pitch
+    return (plan.path == _lib.PATH_R2 and not batch_first and rows_uniform and I >= 128 and RX >= 32 and
             T * B >= 256 and plan.zx_pitch == RX)
 
 
@@ -114,12 +115,16 @@ def _seq_forward(x, h0, c0, canon, batch_first, need_grad, need_y):
                 # floats are not 16-byte multiples (TMA), so x is copied once into a pitch-padded buffer (46 MB at B=512
                 # against a 7 GFLOP product that the SIMT fallback takes 0.55 ms for)
                 ip = (I + 3) // 4 * 4
-                xp = x.new_zeros((T * B, ip)) if ip != I else None
-                if xp is not None:
-                    xp[:, :I].copy_(x.reshape(T * B, I))
+                pitch = x.stride(1)
+                if pitch % 4 == 0 and pitch >= ip and x.data_ptr() % 16 == 0:
+                    # already pitch-padded with zero pad columns (functional.embed_dropout): read in place
+                    xa = x.as_strided((T * B, ip), (pitch, 1)) if pitch > I else x.reshape(T * B, I)
+                else:
+                    xa = x.new_zeros((T * B, ip))
+                    xa[:, :I].copy_(x.reshape(T * B, I))
                 uxt = x.new_zeros((RX, ip))
                 uxt[:, :I].copy_(Ux.t())
-                gemm_nt(xp if xp is not None else x.reshape(T * B, I), uxt, out=zx)
+                gemm_nt(xa, uxt, out=zx)
             else:
                 _lib.check(lib.vmlmf_xproj_fwd(_ptr(x), xs_t, xs_b, _ptr(Ux), _ptr(zx), T, B, I, RX, plan.zx_pitch, st))
         with _timed("seq_fwd"):
@@ -387,6 +392,47 @@ class SoftmaxNLLFunction(torch.autograd.Function):
                                                         _ptr(dloss), ctx.scale, _ptr(dscores), dscores.stride(0),
                                                         rows, ncls, st))
         return dscores, None, None
+
+
+class EmbedDropoutFunction(torch.autograd.Function):
+    """x = dropout(w[tokens]) (V/models/vmlmf_lm.py:48, :436) in one kernel, written into a buffer whose row pitch is a
+    multiple of four floats: the returned [.., E] view is what the first layer's x-projection GEMM reads in place as its TMA
+    operand.  Backward is the deterministic dense embedding backward of the masked upstream gradient."""
+
+    @staticmethod
+    def forward(ctx, tokens, w, p, training):
+        _require_cuda(w)
+        if not tokens.is_cuda:
+            tokens = tokens.to(w.device)                  # the reference indexes a CUDA table with CPU indices (lm_test.py:200)
+        tok = tokens.reshape(-1).to(torch.int64).contiguous()
+        rows, (vocab, emb) = tok.numel(), w.shape
+        pitch = (emb + 3) // 4 * 4
+        w = w.contiguous()
+        mask = None
+        scale = 1.0
+        if training and p > 0.0:
+            mask = (torch.rand((rows, emb), device=w.device) >= p).to(torch.uint8)
+            scale = 1.0 / (1.0 - p)
+        buf = w.new_empty((rows, pitch))
+        with torch.cuda.device_of(w):
+            st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            _lib.check(_lib.lib().vmlmf_embed_dropout_fwd(_ptr(tok), _ptr(w), _ptr(mask), scale, _ptr(buf), pitch, rows, emb, vocab, st))
+        ctx.save_for_backward(tok, mask)
+        ctx.scale, ctx.vocab = scale, vocab
+        return buf[:, :emb].view(*tokens.shape, emb) if pitch == emb else buf.view(*tokens.shape, pitch)[..., :emb]
+
+    @staticmethod
+    def backward(ctx, dout):
+        tok, mask = ctx.saved_tensors
+        g = dout.reshape(tok.numel(), -1)
+        if mask is not None:
+            g = g * mask * ctx.scale
+        dw = torch.ops.aten.embedding_dense_backward(g.contiguous(), tok, ctx.vocab, -1, False)
+        return None, dw, None, None
+
+
+def embed_dropout(tokens, w, p=0.0, training=False):
+    return EmbedDropoutFunction.apply(tokens, w, float(p), bool(training))
 
 
 def cross_entropy(logits, target):

@@ -233,7 +233,12 @@ class Model(nn.Module):
         return [(h.detach(), c.detach()) for (h, c) in states]
 
     def forward(self, x, states):
-        x = self.dropout(self.embed(x))
+        if self.embed.w.is_cuda and self.embed.w.dtype == torch.float32:
+            # Embed + dropout fused, output pitch-padded for the TMA-fed x projection of the first layer
+            from .functional import embed_dropout
+            x = embed_dropout(x, self.embed.w, self.dropout.p, self.training)
+        else:
+            x = self.dropout(self.embed(x))
         for i, rnn in enumerate(self.rnns):
             x, states[i] = rnn(x, states[i])
             x = self.dropout(x)
