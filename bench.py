@@ -48,6 +48,8 @@ CONFIGS = {
                  desc="cfg3: group-structured VMLMF cell Net(9,[128],8,[2,4],cell=MyVMLMFCellg2) on HAR windows [8192,128,9], train step"),
     "cfg4": dict(kind="lm", V=10000, H=650, layers=2, wr=300, ur=[300], T=35, batch=512, dropout=0.5,
                  desc="cfg4: vmlmf_lm Model(10000,650,2,0.5,0.05,300,[300],'vmlmf') on PTB-shaped synthetic tokens [35,B], B=512 per GPU, train step (fwd+nll_loss+bwd+clip 5+SGD), carried state"),
+    "cfg4_b20": dict(kind="lm", V=10000, H=650, layers=2, wr=300, ur=[300], T=35, batch=20, dropout=0.5,
+                     desc="cfg4 at the reference's own batch: Model(10000,650,2,0.5,0.05,300,[300],'vmlmf'), tokens [35,20] (lm_test.py defaults), train step"),
     "cfg5": dict(kind="har", I=9, H=1024, wr=64, ur=[64], T=128, classes=6, batch=2048, cell="plain",
                  desc="cfg5: scaling-sweep point Net(9,[1024],w_rank=64,u_rank=[64]) on windows [2048,128,9], train step"),
     "cfg5b": dict(kind="har", I=9, H=4096, wr=256, ur=[256], T=128, classes=6, batch=1024, cell="plain",
@@ -183,7 +185,7 @@ def cpu_train_rate(cfg_name, batch, steps, warmup, budget_s=60.0):
     return done * batch / dt, dt / done * 1e3, done, torch.get_num_threads()
 
 
-CPU_BATCH = {"cfg1": 64, "cfg2": 1024, "cfg3": 512, "cfg4": 20, "cfg5": 64, "cfg5b": 16}
+CPU_BATCH = {"cfg1": 64, "cfg2": 1024, "cfg3": 512, "cfg4": 20, "cfg4_b20": 20, "cfg5": 64, "cfg5b": 16}
 
 
 def run_reference(args):
@@ -255,13 +257,10 @@ def bind_to_gpu_numa_node(index):
     """pin this rank's CPU affinity to the NUMA node its GPU hangs off, so that the pinned host batches it allocates next are
     node-local (8 ranks x 70 MB per 1.3 ms step otherwise all stream from whichever node the launcher started on)"""
     try:
-        import torch
-        bus = torch.cuda.get_device_properties(index).pci_bus_id if hasattr(torch.cuda.get_device_properties(index), "pci_bus_id") else None
-        if bus is None:
-            out = subprocess.run(["nvidia-smi", "-i", str(index), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
-                                 capture_output=True, text=True, timeout=10).stdout.strip()
-            bus = out
-        bus = str(bus).lower()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = vis.split(",")[index] if vis else str(index)
+        bus = subprocess.run(["nvidia-smi", "-i", phys, "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=10).stdout.strip().lower()
         if len(bus.split(":")[0]) == 8:               # nvidia-smi prints an 8-digit domain, sysfs uses 4
             bus = bus[4:]
         node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
@@ -616,7 +615,7 @@ def run_ours(args):
         # ---------------- every BASELINE config, same measurement, fewer steps ----------------
         if not args.no_configs:
             configs = []
-            for cn in ("cfg1", "cfg2", "cfg3", "cfg4", "cfg5", "cfg5b"):
+            for cn in ("cfg1", "cfg2", "cfg3", "cfg4", "cfg4_b20", "cfg5", "cfg5b"):
                 try:
                     if cn == name:
                         wc, mc = w, m

@@ -198,3 +198,33 @@ def test_fused_embed_dropout_matches_indexing(p):
     _close(w.grad, ref, 1e-5, "dW")
     ev = embed_dropout(tok, w.detach(), p, training=False)
     assert torch.equal(ev, dense)                                            # eval: plain gather
+
+
+def test_fast_tf32_mode():
+    """Optional single-pass TF32 mode of the tcgen05 GEMMs (vb.set_fast_tf32): stated bound 2e-3 relative against an fp64
+    product (1e-5 class in the default mode), and the decisions taken from the result (row-wise argmax of an LM-head sized
+    product) do not change on margins above that bound."""
+    from vmlmf_b200.functional import gemm_nt, gemm_tn
+    g = torch.Generator(device=DEV).manual_seed(3)
+    x = torch.randn(700, 650, device=DEV, generator=g)
+    w = torch.randn(1000, 650, device=DEV, generator=g) * 0.05
+    ref = x.double() @ w.double().t()
+    try:
+        vb.set_fast_tf32(False)
+        acc = gemm_nt(x, w)
+        vb.set_fast_tf32(True)
+        fast = gemm_nt(x, w)
+        fast_tn = gemm_tn(x, x[:, :96].contiguous())
+    finally:
+        vb.set_fast_tf32(False)
+    e_acc = max(rel_err(acc.cpu().numpy(), ref.cpu().numpy()))
+    e_fast = max(rel_err(fast.cpu().numpy(), ref.cpu().numpy()))
+    e_tn = max(rel_err(fast_tn.cpu().numpy(), (x.double().t() @ x[:, :96].double()).cpu().numpy()))
+    assert e_acc <= 3e-6, e_acc
+    assert 1e-5 < e_fast <= 2e-3, f"single-pass TF32 error {e_fast:.2e} outside the stated window"
+    assert e_tn <= 2e-3, e_tn
+    top2 = ref.topk(2, dim=1).values
+    clear = (top2[:, 0] - top2[:, 1]) > 4e-3 * ref.abs().max()           # rows whose decision margin exceeds the error bound
+    assert bool(clear.any())
+    assert torch.equal(fast.argmax(1)[clear], ref.argmax(1)[clear])
+    assert torch.equal(acc.argmax(1), ref.argmax(1))
