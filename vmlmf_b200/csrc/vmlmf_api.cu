@@ -116,7 +116,7 @@ int vmlmf_seq_plan(int T, int B, int I, int H, int RX, int RH, vmlmf_plan* plan)
     plan->xp_cols = 0;
     plan->fwd_workspace_bytes = 0;
     const GradLayout L(I, H, RX, RH);
-    const long long ntiles = ceil_div(B, kBwdBT);
+    const long long ntiles = ceil_div(B, r1_bwd_bt(B, c.rh_t));
     const long long cap = (long long)num_sms() * kMaxCtasPerSM;
     plan->bwd_workspace_bytes = (ntiles < cap ? ntiles : cap) * L.total * (long long)sizeof(float);
     plan->reserved[0] = c.rh_t;
