@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define VMLMF_ABI_VERSION 4
+#define VMLMF_ABI_VERSION 5
 
 enum {
   VMLMF_OK = 0,
@@ -51,9 +51,12 @@ enum {
   VMLMF_PATH_G = 2,   /* generic: time-parallel XP GEMM + one fused launch per timestep        */
   VMLMF_PATH_R1M = 3, /* persistent warp-MMA (mma.sync 3xTF32) recurrence, CTA = 16 sequences;
                          needs H % 4 == 0, H <= 256, RH <= 16, RH + RX + 1 <= 32               */
-  VMLMF_PATH_R2 = 4   /* persistent tcgen05 recurrence for every other shape (large H, high ranks):
+  VMLMF_PATH_R2 = 4,  /* persistent tcgen05 recurrence for every other shape (large H, high ranks):
                          a thread-block cluster owns a 128-sequence tile for all T steps, the hidden
                          units are split over the cluster's CTAs, operands arrive as TMA tiles     */
+  VMLMF_PATH_R3 = 5   /* the same recurrence for small batches (B <= 32, e.g. the LM at the reference's
+                         20 streams): one group of ceil(H/8) CTAs, each keeps its rows of the factors
+                         resident in shared memory for all T steps; only activations move per step  */
 };
 
 typedef struct vmlmf_plan {

@@ -545,6 +545,59 @@ def test_r2_inference_matches_training_forward_and_ksplit(monkeypatch, r1_path):
         assert_close(t.grad.cpu().numpy(), g64[k], TOL, f"d{k}")
 
 
+# ----------------------------- regime R3 specifics ----------------------------- #
+
+@pytest.mark.parametrize("T,B,I,H,RX,RH,bf,state", [
+    (5, 20, 650, 650, 300, 300, False, True),    # the LM layer at the reference's batch (V/train_test/lm_test.py: 20 streams)
+    (4, 32, 9, 1024, 64, 64, True, True),        # a full 32-row tile, 128 CTAs
+    (3, 7, 16, 100, 20, 130, False, False),      # H not a multiple of 8 (last CTA owns 4 units), two 128-column z chunks
+    (6, 3, 30, 520, 8, 500, True, True),         # four z chunks (all k-step slots of the stationary phase Z tile), 16 K tiles
+    (2, 1, 12, 16, 5, 20, False, True),          # two CTAs, a single sequence
+])
+def test_r3_small_batch_regime_vs_numpy_spec(T, B, I, H, RX, RH, bf, state, r1_path):
+    """Regime R3 (B <= 32: one group of ceil(H/8) CTAs with the factors resident in shared memory; XP and dzx formed by
+    time-parallel GEMMs around the launch) against the fp64 numpy spec, forward and every gradient."""
+    if r1_path != "auto":
+        pytest.skip("regime R3 does not depend on the R1 kernel choice")
+    from vmlmf_b200 import _lib
+    assert _lib.plan(T, B, I, H, RX, RH).path == _lib.PATH_R3
+    test_canonical_kernels_vs_numpy_spec(T, B, I, H, RX, RH, bf, state, scale=0.05 if H >= 300 else 0.2)
+
+
+def test_r3_inference_bitwise_and_agrees_with_r2(monkeypatch, r1_path):
+    """Inference (no saved state) gives the training forward's values bit for bit; the large-batch regime R2 on the same
+    inputs agrees to fp32 round-off (different summation order of the same 3xTF32 products)."""
+    if r1_path != "auto":
+        pytest.skip("regime R3 does not depend on the R1 kernel choice")
+    from vmlmf_b200 import _lib
+    T, B, I, H, RX, RH = 6, 20, 650, 650, 300, 300
+    rng = np.random.default_rng(9)
+    cp = _rand_canon(rng, I, H, RX, RH, 0.05)
+    names = ("Ux", "Vx", "Dx", "A", "Bm", "Dh", "bias")
+    tp = [torch.from_numpy(cp[k]).to(DEV).requires_grad_(True) for k in names]
+    xt = torch.from_numpy(rng.standard_normal((T, B, I)).astype(np.float32)).to(DEV)
+    h0 = torch.from_numpy((rng.standard_normal((B, H)) * .5).astype(np.float32)).to(DEV)
+    c0 = torch.from_numpy((rng.standard_normal((B, H)) * .5).astype(np.float32)).to(DEV)
+    dy = torch.from_numpy(rng.standard_normal((T, B, H)).astype(np.float32)).to(DEV)
+    assert _lib.plan(T, B, I, H, RX, RH).path == _lib.PATH_R3
+    with torch.no_grad():
+        y0, hT0, cT0 = vmlmf_sequence(xt, h0, c0, tp, batch_first=False)
+    y1, hT1, cT1 = vmlmf_sequence(xt, h0, c0, tp, batch_first=False)
+    assert torch.equal(y0, y1) and torch.equal(hT0, hT1) and torch.equal(cT0, cT1)
+    y1.backward(dy)
+    g3 = [t.grad.clone() for t in tp]
+    for t in tp:
+        t.grad = None
+    monkeypatch.setenv("VMLMF_NO_R3", "1")
+    assert _lib.plan(T, B, I, H, RX, RH).path == _lib.PATH_R2
+    y2, hT2, cT2 = vmlmf_sequence(xt, h0, c0, tp, batch_first=False)
+    y2.backward(dy)
+    assert_close(y1.detach().cpu().numpy(), y2.detach().cpu().numpy().astype(np.float64), TOL, "y R3 vs R2")
+    assert_close(cT1.detach().cpu().numpy(), cT2.detach().cpu().numpy().astype(np.float64), TOL, "cT R3 vs R2")
+    for k, a, t in zip(names, g3, tp):
+        assert_close(a.cpu().numpy(), t.grad.cpu().numpy().astype(np.float64), TOL, f"d{k} R3 vs R2")
+
+
 def test_lm_dense_lstm_baseline_runs_through_the_fused_kernels(r1_path):
     """The LM's "custom" dense LSTM layer (V/models/vmlmf_lm.py:283-339) on the canonical kernels against its eager formula."""
     if r1_path != "auto":

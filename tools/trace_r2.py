@@ -7,7 +7,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 csrc = os.path.join(ROOT, "vmlmf_b200", "csrc")
 out = "/tmp/libvmlmf_trace.so"
-srcs = ["vmlmf_api.cu", "seq_r1_rx4.cu", "seq_r1_rx8.cu", "seq_r1_rx16.cu", "seq_mma.cu", "seq_bwd_mma.cu", "seq_bwd_fused.cu", "seq_r2.cu"]
+srcs = ["vmlmf_api.cu", "seq_r1_rx4.cu", "seq_r1_rx8.cu", "seq_r1_rx16.cu", "seq_mma.cu", "seq_bwd_mma.cu", "seq_bwd_fused.cu", "seq_r2.cu", "seq_r3.cu"]
 subprocess.check_call(["nvcc", "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC",
                        "--expt-relaxed-constexpr", "-DVMLMF_R2_TRACE", "-shared", "-o", out] + srcs, cwd=csrc)
 import torch
@@ -28,6 +28,7 @@ if bwd:
         p.requires_grad_(True)
     y, hT, cT = vmlmf_sequence(x, None, None, canon, False)
     ctypes.CDLL(out).vmlmf_r2_trace_read(tr_buf0, 4096)          # drop the forward's events
+    ctypes.CDLL(out).vmlmf_r3_trace_read(tr_buf0, 4096)
     (y.sum() + hT.sum()).backward()
 else:
     with torch.no_grad():
@@ -35,7 +36,7 @@ else:
 torch.cuda.synchronize()
 tr_buf = (ctypes.c_longlong * 8192)()
 h = ctypes.CDLL(out)
-getn = h.vmlmf_r2_trace_read
+getn = h.vmlmf_r3_trace_read if _lib.plan(T, B, I, H, RX, RH).path == _lib.PATH_R3 else h.vmlmf_r2_trace_read
 getn.argtypes = [ctypes.c_void_p, ctypes.c_int]
 getn.restype = ctypes.c_int
 n = getn(tr_buf, 4096)

@@ -10,10 +10,10 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvmlmf_b200.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 
-PATH_R1, PATH_G, PATH_R1M, PATH_R2 = 1, 2, 3, 4
-LARGE_PATHS = (PATH_G, PATH_R2)      # regimes for shapes beyond the register-resident kernels
+PATH_R1, PATH_G, PATH_R1M, PATH_R2, PATH_R3 = 1, 2, 3, 4, 5
+LARGE_PATHS = (PATH_G, PATH_R2, PATH_R3)      # regimes for shapes beyond the register-resident kernels
 
 
 class Plan(C.Structure):

@@ -724,6 +724,7 @@ struct TpArgs {
   float* tA; float* tB; float* gtmp;   // transposed operands [4G, ldt], [max(RH,RX), ldt]; [4G, max(RH,RX)] when G != H
   long long ldt; float* unused;
   int T, B, I, H, RX, RH; bool use_tc;
+  bool vxt_padded = false;             // vxt already holds Vx^T in dPre's gate-padded layout [RX, 4G] (regime R3)
 };
 // dst[k*H + j, :] = src[k*G + j, :]  (rows of R floats)
 static __global__ void compact_gate_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, int H, int G, int R) {
@@ -860,7 +861,12 @@ inline int generic_bwd_tp(TpArgs& a, cudaStream_t st) {
   if (!a.have_dzx) {
     if (a.zxp > RX) G_TRY((int)cudaMemsetAsync(a.dzx, 0, (size_t)rows * a.zxp * sizeof(float), st));
     int rc = tc::kTcNoFit;
-    if (a.use_tc && tc::tc_operand_ok(a.dpre, 4 * G) && tc::tc_operand_ok(a.dzx, a.zxp)) {
+    if (a.vxt_padded) {
+      // pad units of dPre are zero, pad columns of vxt are zero: contract over the whole padded gate axis
+      if (!(a.use_tc && tc::tc_operand_ok(a.dpre, 4 * G) && tc::tc_operand_ok(a.dzx, a.zxp))) return VMLMF_EUNSUPPORTED;
+      rc = tc::gemm_tc(a.dpre, 4 * G, a.vxt, 4 * G, (int)rows, RX, 4 * G, tc::EpiStoreTC{a.dzx, a.zxp, 0}, st);
+      if (rc == tc::kTcNoFit) return VMLMF_EUNSUPPORTED;
+    } else if (a.use_tc && tc::tc_operand_ok(a.dpre, 4 * G) && tc::tc_operand_ok(a.dzx, a.zxp)) {
       G_TRY(transpose_launch(a.Vx, 4 * H, RX, a.vxt, 4 * H, st));
       rc = tc::gemm_tc(a.dpre, 4 * G, a.vxt, 4 * H, (int)rows, RX, 4 * H, tc::EpiStoreTC{a.dzx, a.zxp, 0}, st);
     }

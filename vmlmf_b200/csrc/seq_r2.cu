@@ -311,7 +311,7 @@ int launch_bwd(const BwdCall& c, void* workspace, BwdOut* out, cudaStream_t st) 
   a.sync = reinterpret_cast<unsigned int*>(ws + g.b_sync);
   e = cudaMemsetAsync(a.sync, 0, 32 * sizeof(unsigned int) * (size_t)g.ncl, st);
   if (e != cudaSuccess) return (int)e;
-  return launch_coop(r2_bwd_kernel, g.ncl * g.CS, kSmemBytesBwd, st, m_dpre, m_dpo_lo, m_w2t_hi, m_w2t_lo, m_dzo_hi, m_dzo_lo,
+  return launch_coop(r2_bwd_kernel<0>, g.ncl * g.CS, kSmemBytesBwd, st, m_dpre, m_dpo_lo, m_w2t_hi, m_w2t_lo, m_dzo_hi, m_dzo_lo,
                      m_ap_hi, m_ap_lo, a);
 }
 

@@ -108,8 +108,8 @@ __device__ __forceinline__ float split_lo(float v, float) { return v - __uint_as
 // Debug-only cycle trace (-DVMLMF_R2_TRACE, tools/trace_r2.py): lane 0 of each role of CTA 0 appends (event, clock64) pairs
 // for a few timesteps.  Compiled out of the shipped library.
 #ifdef VMLMF_R2_TRACE
-__device__ long long g_r2_trace[8192];
-__device__ int g_r2_trace_n;
+static __device__ long long g_r2_trace[8192];
+static __device__ int g_r2_trace_n;
 #define R2_TRACE(ev)                                                                      \
   do {                                                                                    \
     if (blockIdx.x == 0 && lane == 0 && t >= 8 && t < 11) {                               \
@@ -608,7 +608,8 @@ struct BwdArgs {
 struct PwIn { float gi, gf, go, gn, ct, cp, dyv, dhs, dcin; };
 // loads only, no arithmetic on the loaded values (a use would make the warp wait for the load right here and defeat the
 // prefetch): dyv = dy_t, dhs = dh seed or the Dh term kept in dhrun, dcin = dc seed or dcrun
-__device__ __forceinline__ void pw_load(const BwdArgs& a, int tq, int m, int j, bool seed, PwIn& in) {
+template <class Args>
+__device__ __forceinline__ void pw_load(const Args& a, int tq, int m, int j, bool seed, PwIn& in) {
   const size_t rowq = (size_t)tq * a.B + m;
   const float* g = a.gates + rowq * 4 * a.H + j;
   in.gi = __ldg(g); in.gf = __ldg(g + a.H); in.go = __ldg(g + 2 * a.H); in.gn = __ldg(g + 3 * a.H);
@@ -645,6 +646,7 @@ __device__ __forceinline__ void pw_finish(const BwdArgs& a, int tq, int m, int j
   a.dhrun[(size_t)m * a.Hp + j] = sdh;
 }
 
+template <int kVariant>      // a template only for linkage: the header is included by two translation units
 __global__ void __launch_bounds__(kThreads, 1)
 r2_bwd_kernel(const __grid_constant__ CUtensorMap m_dpre, const __grid_constant__ CUtensorMap m_dpo_lo,
               const __grid_constant__ CUtensorMap m_w2t_hi, const __grid_constant__ CUtensorMap m_w2t_lo,

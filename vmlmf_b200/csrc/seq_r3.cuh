@@ -1,0 +1,643 @@
+// seq_r3.cuh -- regime R3: the persistent tcgen05 recurrence for SMALL batches (B <= 32), weight-stationary.
+//
+// The LM at the reference's own batch (V/lm_test.py: 20 streams, H=650, ranks 300; time loop V/models/vmlmf_lm.py:272-280,
+// step :222-269) is a latency chain, not a throughput problem: one 128-row tensor-core tile is 84 % padding, and in regime
+// R2 every CTA re-streams its 0.6 MB slice of the factors through TMA on every timestep.  Here the factors never move:
+//   * ONE group of CS = ceil(H / 8) CTAs (cooperative launch, one per SM) owns the whole batch for all T steps; CTA s owns
+//     the 8 hidden units [8s, 8s+8) and keeps ITS rows of the factors in shared memory for the whole call
+//     (forward: Bm rows of its 4 x 8 gate outputs [32 x RH] + its 8 rows of A; backward: the same two slices transposed),
+//     as tf32 hi / lo pairs: ~110 KB per CTA at the LM shape, 9 MB over the group;
+//   * per step only activations move: the CTA's [32 x 8] slice of h (phase Z), the reduced z [32 x RH] (phase G);
+//     TMA boxes are 32 rows (the tensor core still computes 128-row tiles -- rows 32..127 of the A operand are whatever
+//     follows the tile in shared memory, they only reach accumulator lanes 32..127, which nobody reads);
+//   * the x side is taken out of the serial loop: XP = zx Vx^T + bias + x (.) Dx is one time-parallel tcgen05 GEMM before the
+//     launch (700 rows at the LM batch), the gate epilogue adds it; likewise dzx = dPre Vx after the backward launch.
+// Per timestep and CTA (3xTF32, accumulators in tensor memory):
+//   phase Z   partial z_s[32, RH] = h_{t-1}[:, 8 units] * A[8 units, :]          1 k-step, N = RH in 128-column chunks
+//   exchange  z = sum_s z_s: partials through L2, fixed-order reduce spread over ALL CTAs of the group (each CTA sums a
+//             1/CS share of the [B, RH] outputs: 8 lanes x (CS/8) partials each, then a butterfly), two group barriers
+//   phase G   pre[32, 4 x 8] = z * Bm[4 x 8 rows, :]^T                            K = RH, N = 32
+// Backward mirrors it: phase 1 (dz partial = dPre_t[:, 4 x 8] * Bm[4 x 8 rows, :], K = 32), exchange, phase 2
+// (dh_{t-1}[32, 8] = dz_t * A[8 units, :]^T, K = RH, N = 16), gate-gradient algebra of step t-1 in the epilogue.
+// Warp roles as in seq_r2.cuh: warp 0 TMA producer, warp 1 MMA issuer, warps 2-9 epilogue -- only warps 4 and 8 own
+// tensor-memory lanes 0..31 (the batch rows), the others help with the reduce.
+#pragma once
+#include "seq_r2.cuh"
+
+namespace vmlmf {
+namespace r3 {
+
+using namespace r2;
+
+constexpr int UB = 8;                        // hidden units per CTA
+constexpr int RB = 32;                       // batch rows (one tensor-memory lane quarter, one TMA box)
+constexpr int kATile = RB * BK * 4;          // 4 KB: [32 rows x 32 fp32] activation tile (hi or lo)
+constexpr int kAStage = 2 * kATile;          // hi | lo
+constexpr int kPTile = BM * BK * 4;          // 16 KB: [128 rows x 32 fp32] weight tile
+constexpr int kApTile = 16 * BK * 4;         // 2 KB: [16 rows x 32 fp32] (phase 2 B operand: 8 units + 8 spare rows)
+constexpr int kMaxStages = 16;
+constexpr int kBarBytes = 512;
+constexpr int kSmemMax = 232448 - 1024;      // 227 KB minus the alignment slack
+
+struct Bars3 {
+  uint64_t full[kMaxStages];
+  uint64_t empty[kMaxStages];
+  uint64_t accf[2];
+  uint64_t acce[2];
+  uint64_t wbar;               // stationary weights landed
+  uint32_t tmem_slot;
+};
+static_assert(sizeof(Bars3) <= kBarBytes, "barrier block");
+
+// position of (gate k, unit j) inside a row of the slice-major operand buffers: CTA s = j / 8 owns 32 consecutive floats
+__host__ __device__ __forceinline__ int slice_col(int k, int j) { return (j >> 3) * 32 + k * 8 + (j & 7); }
+
+// Fixed-order sum of the CS partial copies of a [rows, 4 * w4] matrix (partial q at part + q * RB * pitch).  Output element e
+// (one float4) belongs to CTA e / epc; inside the CTA eight adjacent lanes share one output, lane pg adding the partials
+// q = pg, pg + 8, ... in order, then a butterfly over the eight lanes (same order every run: deterministic).
+template <class Store>
+__device__ __forceinline__ void reduce_partials(const float* part, int CS, int s_rank, int rows, int pitch, int w4, Store&& store) {
+  const int et = (int)threadIdx.x - 64;
+  const int o = et >> 3, pg = et & 7;
+  const int E = rows * w4;
+  const int epc = (E + CS - 1) / CS;
+  const int e0 = s_rank * epc;
+  const int cnt = min(epc, E - e0);
+  const size_t qstride4 = (size_t)RB * pitch / 4;
+  for (int base = 0; base < cnt; base += 32) {
+    const int oo = base + o;
+    const bool on = oo < cnt;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int r = 0, c4 = 0;
+    if (on) {
+      const int e = e0 + oo;
+      r = e / w4;
+      c4 = e - r * w4;
+      const float4* src = reinterpret_cast<const float4*>(part + (size_t)r * pitch) + c4;
+      for (int q = pg; q < CS; q += 32) {
+        float4 pv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) pv[i] = q + 8 * i < CS ? __ldcg(src + (size_t)(q + 8 * i) * qstride4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { acc.x += pv[i].x; acc.y += pv[i].y; acc.z += pv[i].z; acc.w += pv[i].w; }
+      }
+    }
+#pragma unroll
+    for (int d = 1; d < 8; d <<= 1) {
+      acc.x += __shfl_xor_sync(0xffffffffu, acc.x, d);
+      acc.y += __shfl_xor_sync(0xffffffffu, acc.y, d);
+      acc.z += __shfl_xor_sync(0xffffffffu, acc.z, d);
+      acc.w += __shfl_xor_sync(0xffffffffu, acc.w, d);
+    }
+    if (on && pg == 0) store(r, c4 * 4, acc);
+  }
+}
+__device__ __forceinline__ void store_split4(float* hi_p, float* lo_p, const float4 v) {
+  float4 hi, lo;
+  hi.x = split_hi(v.x); hi.y = split_hi(v.y); hi.z = split_hi(v.z); hi.w = split_hi(v.w);
+  lo.x = split_lo(v.x, hi.x); lo.y = split_lo(v.y, hi.y); lo.z = split_lo(v.z, hi.z); lo.w = split_lo(v.w, hi.w);
+  *reinterpret_cast<float4*>(hi_p) = hi;
+  *reinterpret_cast<float4*>(lo_p) = lo;
+}
+// the three MMAs of one tf32 k-step: cross terms first (small), then hi * hi
+__device__ __forceinline__ void issue_kstep(uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, uint32_t acc_main,
+                                            uint32_t acc_cross, uint32_t idesc, bool first) {
+  const uint32_t acc = first ? 0u : 1u;
+  mma_tf32_ss(acc_cross, make_desc(a_lo), make_desc(b_hi), idesc, acc);
+  mma_tf32_ss(acc_cross, make_desc(a_hi), make_desc(b_lo), idesc, 1u);
+  mma_tf32_ss(acc_main, make_desc(a_hi), make_desc(b_hi), idesc, acc);
+}
+__device__ __forceinline__ void init_common(Bars3* bars, int S, int warp) {
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&bars->accf[b], 1); mbar_init(&bars->acce[b], 2); }
+    mbar_init(&bars->wbar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_slot)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+}
+
+// ------------------------------------------------------------------------------------------------- forward
+struct FwdArgs3 {
+  const float* xp;            // [T*B, 4H]  zx Vx^T + bias + x (.) Dx
+  const float* Dh; const float* h0; const float* c0;
+  float* y; long long ys_t, ys_b;
+  float *hT, *cT;
+  float* gates;               // [T,B,4,H] or null (inference)
+  float* cs;                  // [T,B,H] when saving, else a [2,B,H] ping-pong scratch
+  float* z;                   // [T*B, zp] saved z (null in inference)
+  float *hop_hi, *hop_lo;     // [B, Hp]
+  float *zop_hi, *zop_lo;     // [B, zp]
+  float* zpart;               // [CS, 32, zp]
+  unsigned int* sync;         // group barrier counter (one 128-byte line), zeroed before the launch
+  int T, B, H, RH;
+  int Hp, CS, zp, S;          // S = activation ring stages
+};
+
+template <bool SAVE>
+__global__ void __launch_bounds__(kThreads, 1)
+r3_fwd_kernel(const __grid_constant__ CUtensorMap m_hop_hi, const __grid_constant__ CUtensorMap m_hop_lo,
+              const __grid_constant__ CUtensorMap m_p_hi, const __grid_constant__ CUtensorMap m_p_lo,
+              const __grid_constant__ CUtensorMap m_zop_hi, const __grid_constant__ CUtensorMap m_zop_lo,
+              const __grid_constant__ CUtensorMap m_w2_hi, const __grid_constant__ CUtensorMap m_w2_lo, const FwdArgs3 a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* const base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S = a.S, CS = a.CS;
+  const int RHr = (a.RH + 7) & ~7;
+  const int nzc = (RHr + 127) / 128;                         // phase Z chunks (128 z columns each; <= 4: one k-step slot each)
+  const int nkz = (a.RH + BK - 1) / BK;                      // phase G K tiles
+  // shared memory: activation ring | phase Z weights (hi, lo) | phase G weights (nkz x (hi | lo)) | barriers
+  uint8_t* const ring = base;
+  uint8_t* const p_hi = base + S * kAStage;
+  uint8_t* const p_lo = p_hi + kPTile;
+  uint8_t* const w2s = p_lo + kPTile;
+  Bars3* const bars = reinterpret_cast<Bars3*>(w2s + nkz * kAStage);
+  const int s_rank = (int)blockIdx.x;
+  const int u0 = s_rank * UB;
+  unsigned int epoch = 0;
+
+  init_common(bars, S, warp);
+  const uint32_t tmem_d = bars->tmem_slot;
+
+  if (warp == 0 && lane == 0) {                              // the CTA's factor rows: loaded once, resident for all T steps
+    mbar_arrive_expect_tx(&bars->wbar, 2 * kPTile + nkz * kAStage);
+    tma_load_2d(p_hi, &m_p_hi, 0, s_rank * BM, &bars->wbar);
+    tma_load_2d(p_lo, &m_p_lo, 0, s_rank * BM, &bars->wbar);
+    for (int kt = 0; kt < nkz; ++kt) {
+      tma_load_2d(w2s + kt * kAStage, &m_w2_hi, kt * BK, s_rank * 32, &bars->wbar);
+      tma_load_2d(w2s + kt * kAStage + kATile, &m_w2_lo, kt * BK, s_rank * 32, &bars->wbar);
+    }
+  }
+
+  const int eq = warp & 3, ehalf = (warp - 2) >> 2;          // epilogue: tensor-memory lane quarter, column half
+  const bool epi = warp >= 2 && eq == 0;                     // warps 4 and 8 own lanes 0..31 = the batch rows
+  const int rl = lane & 3, c8 = lane >> 2;
+  uint32_t n_tile = 0, n_chunk = 0;
+  bool wready = false;
+
+  for (int t = 0; t < a.T; ++t) {
+    // ======================================= phase Z =======================================
+    if (warp == 0) {
+      if (lane == 0) {
+        fence_proxy_async_all();
+        R2_TRACE(1);
+        const int s = n_tile % S, it = n_tile / S;
+        if (it > 0) mbar_wait(&bars->empty[s], (it - 1) & 1);
+        mbar_arrive_expect_tx(&bars->full[s], kAStage);
+        tma_load_2d(ring + s * kAStage, &m_hop_hi, u0, 0, &bars->full[s]);
+        tma_load_2d(ring + s * kAStage + kATile, &m_hop_lo, u0, 0, &bars->full[s]);
+        ++n_tile;
+      }
+      __syncwarp();
+    } else if (warp == 1) {
+      if (lane == 0) {
+        if (!wready) { mbar_wait(&bars->wbar, 0); wready = true; }
+        const int s = n_tile % S, it = n_tile / S;
+        const uint32_t a_hi = smem_u32(ring + s * kAStage), a_lo = a_hi + kATile;
+        for (int zc = 0; zc < nzc; ++zc, ++n_chunk) {
+          const int buf = n_chunk & 1, use = n_chunk >> 1;
+          if (use > 0) mbar_wait(&bars->acce[buf], (use - 1) & 1);
+          if (zc == 0) { mbar_wait(&bars->full[s], it & 1); R2_TRACE(10); }
+          tc_fence_after();
+          const int ncol = min(128, RHr - zc * 128);
+          const uint32_t idesc = make_idesc(BM, (ncol + 15) & ~15);
+          const uint32_t acc_main = tmem_d + buf * 256, acc_cross = acc_main + 128;
+          // chunk zc of the z columns sits in k-step slot zc of the packed tile (seq_r2.cu: pack3_fwd_kernel)
+          issue_kstep(a_hi, a_lo, smem_u32(p_hi) + zc * 32, smem_u32(p_lo) + zc * 32, acc_main, acc_cross, idesc, true);
+          mma_commit(&bars->accf[buf]);
+        }
+        mma_commit(&bars->empty[s]);
+        R2_TRACE(11);
+        ++n_tile;
+      }
+      __syncwarp();
+    } else if (epi) {
+      for (int zc = 0; zc < nzc; ++zc, ++n_chunk) {
+        const int buf = n_chunk & 1, use = n_chunk >> 1;
+        mbar_wait(&bars->accf[buf], use & 1);
+        tc_fence_after();
+        if (warp == 4) R2_TRACE(20);
+        const int ncol = min(128, RHr - zc * 128);
+        const uint32_t t_main = tmem_d + buf * 256;
+#pragma unroll 1
+        for (int pp = 0; pp < 2; ++pp) {
+          const int cb = (ehalf * 2 + pp) * 32;
+          if (cb >= ncol) break;
+          float v[32];
+          tmem_ld_groups(t_main, t_main + 128, cb, cb + 8, cb + 16, cb + 24, v);
+          xpose_vec4(v, lane);
+          const int c = zc * 128 + cb + (lane >> 2) * 4;
+          if (c < a.zp) {
+#pragma unroll
+            for (int rg = 0; rg < 8; ++rg) {
+              const int r = rg * 4 + rl;
+              if (r < a.B)
+                *reinterpret_cast<float4*>(a.zpart + ((size_t)s_rank * RB + r) * a.zp + c) =
+                    make_float4(v[rg * 4], v[rg * 4 + 1], v[rg * 4 + 2], v[rg * 4 + 3]);
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->acce[buf]);
+      }
+    }
+    // ======================================= exchange =======================================
+    if (warp == 4) R2_TRACE(21);
+    group_sync(a.sync, epoch, CS);
+    if (warp == 4) R2_TRACE(30);
+    if (warp >= 2) {
+      reduce_partials(a.zpart, CS, s_rank, a.B, a.zp, a.zp >> 2, [&](int r, int c, const float4 v) {
+        if (SAVE) *reinterpret_cast<float4*>(a.z + ((size_t)t * a.B + r) * a.zp + c) = v;
+        store_split4(a.zop_hi + (size_t)r * a.zp + c, a.zop_lo + (size_t)r * a.zp + c, v);
+      });
+      fence_proxy_async_all();
+      if (warp == 4) R2_TRACE(31);
+    }
+    group_sync(a.sync, epoch, CS);
+    if (warp == 4) R2_TRACE(32);
+    // ======================================= phase G =======================================
+    if (warp == 0) {
+      if (lane == 0) {
+        fence_proxy_async_all();
+        for (int kt = 0; kt < nkz; ++kt, ++n_tile) {
+          const int s = n_tile % S, it = n_tile / S;
+          if (it > 0) mbar_wait(&bars->empty[s], (it - 1) & 1);
+          mbar_arrive_expect_tx(&bars->full[s], kAStage);
+          tma_load_2d(ring + s * kAStage, &m_zop_hi, kt * BK, 0, &bars->full[s]);
+          tma_load_2d(ring + s * kAStage + kATile, &m_zop_lo, kt * BK, 0, &bars->full[s]);
+        }
+      }
+      __syncwarp();
+    } else if (warp == 1) {
+      if (lane == 0) {
+        const uint32_t idesc = make_idesc(BM, 32);
+        const int buf = n_chunk & 1, use = n_chunk >> 1;
+        if (use > 0) mbar_wait(&bars->acce[buf], (use - 1) & 1);
+        tc_fence_after();
+        const uint32_t acc_main = tmem_d + buf * 256, acc_cross = acc_main + 128;
+        for (int kt = 0; kt < nkz; ++kt, ++n_tile) {
+          const int s = n_tile % S, it = n_tile / S;
+          mbar_wait(&bars->full[s], it & 1);
+          tc_fence_after();
+          if (kt == 0) R2_TRACE(12);
+          const uint32_t a_hi = smem_u32(ring + s * kAStage), a_lo = a_hi + kATile;
+          const uint32_t b_hi = smem_u32(w2s + kt * kAStage), b_lo = b_hi + kATile;
+          const int ks = tile_ksteps(a.RH, kt);
+          for (int k = 0; k < ks; ++k)
+            issue_kstep(a_hi + k * 32, a_lo + k * 32, b_hi + k * 32, b_lo + k * 32, acc_main, acc_cross, idesc, kt == 0 && k == 0);
+          mma_commit(&bars->empty[s]);
+        }
+        mma_commit(&bars->accf[buf]);
+        R2_TRACE(13);
+        ++n_chunk;
+      }
+      __syncwarp();
+    } else if (epi) {
+      const int buf = n_chunk & 1, use = n_chunk >> 1;
+      if (ehalf == 0) {
+        // lane (c8, rl) owns unit j for the 8 rows rg*4 + rl; the chunk's 32 columns are [gate k][unit]
+        const float* hprev = t ? a.y + (size_t)(t - 1) * a.ys_t : a.h0;
+        const long long hp_sb = t ? a.ys_b : a.H;
+        const float* cprev = SAVE ? (t ? a.cs + (size_t)(t - 1) * a.B * a.H : a.c0) : (t ? a.cs + (size_t)((t - 1) & 1) * a.B * a.H : a.c0);
+        float* cout = SAVE ? a.cs + (size_t)t * a.B * a.H : a.cs + (size_t)(t & 1) * a.B * a.H;
+        float* y_t = a.y + (size_t)t * a.ys_t;
+        const bool last = (t == a.T - 1);
+        const int j = u0 + c8;
+        const bool act = j < a.H;
+        float dh[4], hp[8], cp[8], xq[8][4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) dh[k] = act ? __ldg(a.Dh + k * a.H + j) : 0.f;
+#pragma unroll
+        for (int rg = 0; rg < 8; ++rg) {
+          const int m = rg * 4 + rl;
+          const bool ok = act && m < a.B;
+          hp[rg] = (ok && hprev) ? hprev[(size_t)m * hp_sb + j] : 0.f;
+          cp[rg] = (ok && cprev) ? cprev[(size_t)m * a.H + j] : 0.f;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) xq[rg][k] = ok ? __ldg(a.xp + ((size_t)t * a.B + m) * 4 * a.H + (size_t)k * a.H + j) : 0.f;
+        }
+        R2_TRACE(22);
+        mbar_wait(&bars->accf[buf], use & 1);
+        tc_fence_after();
+        R2_TRACE(23);
+        const uint32_t t_main = tmem_d + buf * 256;
+        float v[32];
+        tmem_ld_groups(t_main, t_main + 128, 0, 8, 16, 24, v);
+        xpose8(v, lane);                                       // -> v[k*8 + rg] = (row rg*4 + rl, unit c8, gate k)
+        if (act) {
+#pragma unroll
+          for (int rg = 0; rg < 8; ++rg) {
+            const int m = rg * 4 + rl;
+            if (m < a.B) {
+              float pre[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) pre[k] = v[k * 8 + rg] + xq[rg][k] + hp[rg] * dh[k];
+              const float gi = sigmoidf_acc(pre[0]), gf = sigmoidf_acc(pre[1]);
+              const float go = sigmoidf_acc(pre[2]), gn = tanhf_acc(pre[3]);
+              const float c = fmaf(gf, cp[rg], gi * gn);
+              const float h = go * tanhf_acc(c);
+              y_t[(size_t)m * a.ys_b + j] = h;
+              const float hi = split_hi(h);
+              a.hop_hi[(size_t)m * a.Hp + j] = hi;
+              a.hop_lo[(size_t)m * a.Hp + j] = split_lo(h, hi);
+              cout[(size_t)m * a.H + j] = c;
+              if (SAVE) {
+                float* gp = a.gates + ((size_t)t * a.B + m) * 4 * a.H + j;
+                gp[0] = gi; gp[a.H] = gf; gp[2 * a.H] = go; gp[3 * a.H] = gn;
+              }
+              if (last) { a.hT[(size_t)m * a.H + j] = h; a.cT[(size_t)m * a.H + j] = c; }
+            }
+          }
+        }
+      } else {
+        mbar_wait(&bars->accf[buf], use & 1);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->acce[buf]);
+      ++n_chunk;
+      fence_proxy_async_all();
+      if (warp == 4) R2_TRACE(24);
+    }
+    __syncthreads();       // h_t operand columns of this CTA are complete before its next phase Z load
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(512));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------- backward
+struct BwdArgs3 {
+  const float* gates;         // [T,B,4,H]
+  const float* cs;            // [T,B,H]
+  const float* c0;            // [B,H] or null
+  const float* dy; long long dys_t, dys_b;      // or null
+  const float *dhT, *dcT;     // [B,H] or null
+  const float* Dh;
+  float *dh0, *dc0;           // [B,H] or null
+  float* dpre;                // [T*B, 4, Hp]   exact copy for the time-parallel weight-gradient GEMMs
+  float* dz_all;              // [T*B, zp]
+  float *dpo_hi, *dpo_lo;     // [B, 4*Hp]      slice-major tf32 operand copy of dPre_t (slice_col)
+  float *dzo_hi, *dzo_lo;     // [B, zp]        tf32 operand copy of dz_t
+  float *dhrun, *dcrun;       // [B, Hp]
+  float* part;                // [CS, 32, zp]
+  unsigned int* sync;
+  int T, B, H, RH;
+  int Hp, CS, zp, S;
+};
+
+__device__ __forceinline__ void pw_finish3(const BwdArgs3& a, int tq, int m, int j, const PwIn& in, float dh, const float (&dhc)[4]) {
+  const size_t rowq = (size_t)tq * a.B + m;
+  const float tcv = tanhf_acc(in.ct);
+  const float dc = fmaf(dh * in.go, 1.f - tcv * tcv, in.dcin);
+  float d[4];
+  d[0] = dc * in.gn * in.gi * (1.f - in.gi);
+  d[1] = dc * in.cp * in.gf * (1.f - in.gf);
+  d[2] = dh * tcv * in.go * (1.f - in.go);
+  d[3] = dc * in.gi * (1.f - in.gn * in.gn);
+  float* o = a.dpre + rowq * 4 * a.Hp + j;
+  float sdh = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    o[(size_t)k * a.Hp] = d[k];
+    const size_t oc = (size_t)m * 4 * a.Hp + slice_col(k, j);
+    a.dpo_hi[oc] = d[k];                                        // the tensor core truncates: the value is its own hi part
+    a.dpo_lo[oc] = split_lo(d[k], d[k]);
+    sdh = fmaf(d[k], dhc[k], sdh);
+  }
+  a.dcrun[(size_t)m * a.Hp + j] = dc * in.gf;
+  a.dhrun[(size_t)m * a.Hp + j] = sdh;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+r3_bwd_kernel(const __grid_constant__ CUtensorMap m_dpo_hi, const __grid_constant__ CUtensorMap m_dpo_lo,
+              const __grid_constant__ CUtensorMap m_w2t_hi, const __grid_constant__ CUtensorMap m_w2t_lo,
+              const __grid_constant__ CUtensorMap m_dzo_hi, const __grid_constant__ CUtensorMap m_dzo_lo,
+              const __grid_constant__ CUtensorMap m_ap_hi, const __grid_constant__ CUtensorMap m_ap_lo, const BwdArgs3 a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* const base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S = a.S, CS = a.CS;
+  const int RHr = (a.RH + 7) & ~7;
+  const int nch1 = (RHr + 127) / 128;                        // phase 1 chunks (128 dz columns)
+  const int nkz = (a.RH + BK - 1) / BK;                      // phase 2 K tiles
+  // shared memory: activation ring | phase 1 weights (nch1 x (hi | lo) 16 KB tiles) | phase 2 weights (nkz x (hi | lo) 2 KB) | barriers
+  uint8_t* const ring = base;
+  uint8_t* const w2ts = base + S * kAStage;
+  uint8_t* const aps = w2ts + nch1 * 2 * kPTile;
+  Bars3* const bars = reinterpret_cast<Bars3*>(aps + nkz * 2 * kApTile);
+  const int s_rank = (int)blockIdx.x;
+  const int u0 = s_rank * UB;
+  unsigned int epoch = 0;
+
+  init_common(bars, S, warp);
+  const uint32_t tmem_d = bars->tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    mbar_arrive_expect_tx(&bars->wbar, nch1 * 2 * kPTile + nkz * 2 * kApTile);
+    for (int c = 0; c < nch1; ++c) {
+      tma_load_2d(w2ts + c * 2 * kPTile, &m_w2t_hi, s_rank * 32, c * BM, &bars->wbar);
+      tma_load_2d(w2ts + c * 2 * kPTile + kPTile, &m_w2t_lo, s_rank * 32, c * BM, &bars->wbar);
+    }
+    for (int kt = 0; kt < nkz; ++kt) {
+      tma_load_2d(aps + kt * 2 * kApTile, &m_ap_hi, kt * BK, u0, &bars->wbar);
+      tma_load_2d(aps + kt * 2 * kApTile + kApTile, &m_ap_lo, kt * BK, u0, &bars->wbar);
+    }
+  }
+
+  const int eq = warp & 3, ehalf = (warp - 2) >> 2;
+  const bool epi = warp >= 2 && eq == 0;
+  const int rl = lane & 3, c8 = lane >> 2;
+  const int j = u0 + c8;                                     // this lane's hidden unit in the gate-gradient algebra
+  const bool act = j < a.H;
+  float dhc[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) dhc[k] = act ? __ldg(a.Dh + k * a.H + j) : 0.f;
+  uint32_t n_tile = 0, n_chunk = 0;
+  bool wready = false;
+
+  // ---- seed: gate-gradient algebra of the last step with dh = dhT (+ dy), dc = dcT ----
+  if (epi && ehalf == 0 && act) {
+    PwIn in[8];
+#pragma unroll
+    for (int rg = 0; rg < 8; ++rg)
+      if (rg * 4 + rl < a.B) pw_load(a, a.T - 1, rg * 4 + rl, j, true, in[rg]);
+#pragma unroll
+    for (int rg = 0; rg < 8; ++rg)
+      if (rg * 4 + rl < a.B) pw_finish3(a, a.T - 1, rg * 4 + rl, j, in[rg], in[rg].dyv + in[rg].dhs, dhc);
+  }
+  fence_proxy_async_all();
+  __syncthreads();
+
+  for (int t = a.T - 1; t >= 0; --t) {
+    // ======================================= phase 1 =======================================
+    if (warp == 0) {
+      if (lane == 0) {
+        fence_proxy_async_all();
+        const int s = n_tile % S, it = n_tile / S;
+        if (it > 0) mbar_wait(&bars->empty[s], (it - 1) & 1);
+        mbar_arrive_expect_tx(&bars->full[s], kAStage);
+        tma_load_2d(ring + s * kAStage, &m_dpo_hi, s_rank * 32, 0, &bars->full[s]);
+        tma_load_2d(ring + s * kAStage + kATile, &m_dpo_lo, s_rank * 32, 0, &bars->full[s]);
+        ++n_tile;
+      }
+      __syncwarp();
+    } else if (warp == 1) {
+      if (lane == 0) {
+        if (!wready) { mbar_wait(&bars->wbar, 0); wready = true; }
+        const int s = n_tile % S, it = n_tile / S;
+        const uint32_t a_hi = smem_u32(ring + s * kAStage), a_lo = a_hi + kATile;
+        for (int c = 0; c < nch1; ++c, ++n_chunk) {
+          const int buf = n_chunk & 1, use = n_chunk >> 1;
+          if (use > 0) mbar_wait(&bars->acce[buf], (use - 1) & 1);
+          if (c == 0) mbar_wait(&bars->full[s], it & 1);
+          tc_fence_after();
+          const int ncol = min(128, RHr - c * 128);
+          const uint32_t idesc = make_idesc(BM, (ncol + 15) & ~15);
+          const uint32_t acc_main = tmem_d + buf * 256, acc_cross = acc_main + 128;
+          const uint32_t b_hi = smem_u32(w2ts + c * 2 * kPTile), b_lo = b_hi + kPTile;
+          for (int k = 0; k < 4; ++k)
+            issue_kstep(a_hi + k * 32, a_lo + k * 32, b_hi + k * 32, b_lo + k * 32, acc_main, acc_cross, idesc, k == 0);
+          mma_commit(&bars->accf[buf]);
+        }
+        mma_commit(&bars->empty[s]);
+        ++n_tile;
+      }
+      __syncwarp();
+    } else if (epi) {
+      for (int c = 0; c < nch1; ++c, ++n_chunk) {
+        const int buf = n_chunk & 1, use = n_chunk >> 1;
+        mbar_wait(&bars->accf[buf], use & 1);
+        tc_fence_after();
+        const int ncol = min(128, RHr - c * 128);
+        const uint32_t t_main = tmem_d + buf * 256;
+#pragma unroll 1
+        for (int pp = 0; pp < 2; ++pp) {
+          const int cb = (ehalf * 2 + pp) * 32;
+          if (cb >= ncol) break;
+          float v[32];
+          tmem_ld_groups(t_main, t_main + 128, cb, cb + 8, cb + 16, cb + 24, v);
+          xpose_vec4(v, lane);
+          const int n = c * 128 + cb + (lane >> 2) * 4;
+          if (n < a.zp) {
+#pragma unroll
+            for (int rg = 0; rg < 8; ++rg) {
+              const int r = rg * 4 + rl;
+              if (r < a.B)
+                *reinterpret_cast<float4*>(a.part + ((size_t)s_rank * RB + r) * a.zp + n) =
+                    make_float4(v[rg * 4], v[rg * 4 + 1], v[rg * 4 + 2], v[rg * 4 + 3]);
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->acce[buf]);
+      }
+    }
+    // ======================================= exchange =======================================
+    group_sync(a.sync, epoch, CS);
+    if (warp >= 2) {
+      reduce_partials(a.part, CS, s_rank, a.B, a.zp, a.zp >> 2, [&](int r, int c, const float4 v) {
+        *reinterpret_cast<float4*>(a.dz_all + ((size_t)t * a.B + r) * a.zp + c) = v;
+        store_split4(a.dzo_hi + (size_t)r * a.zp + c, a.dzo_lo + (size_t)r * a.zp + c, v);
+      });
+      fence_proxy_async_all();
+    }
+    group_sync(a.sync, epoch, CS);
+    // ======================================= phase 2 =======================================
+    if (warp == 0) {
+      if (lane == 0) {
+        fence_proxy_async_all();
+        for (int kt = 0; kt < nkz; ++kt, ++n_tile) {
+          const int s = n_tile % S, it = n_tile / S;
+          if (it > 0) mbar_wait(&bars->empty[s], (it - 1) & 1);
+          mbar_arrive_expect_tx(&bars->full[s], kAStage);
+          tma_load_2d(ring + s * kAStage, &m_dzo_hi, kt * BK, 0, &bars->full[s]);
+          tma_load_2d(ring + s * kAStage + kATile, &m_dzo_lo, kt * BK, 0, &bars->full[s]);
+        }
+      }
+      __syncwarp();
+    } else if (warp == 1) {
+      if (lane == 0) {
+        const uint32_t idesc = make_idesc(BM, 16);
+        const int buf = n_chunk & 1, use = n_chunk >> 1;
+        if (use > 0) mbar_wait(&bars->acce[buf], (use - 1) & 1);
+        tc_fence_after();
+        const uint32_t acc_main = tmem_d + buf * 256, acc_cross = acc_main + 128;
+        for (int kt = 0; kt < nkz; ++kt, ++n_tile) {
+          const int s = n_tile % S, it = n_tile / S;
+          mbar_wait(&bars->full[s], it & 1);
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(ring + s * kAStage), a_lo = a_hi + kATile;
+          const uint32_t b_hi = smem_u32(aps + kt * 2 * kApTile), b_lo = b_hi + kApTile;
+          const int ks = tile_ksteps(a.RH, kt);
+          for (int k = 0; k < ks; ++k)
+            issue_kstep(a_hi + k * 32, a_lo + k * 32, b_hi + k * 32, b_lo + k * 32, acc_main, acc_cross, idesc, kt == 0 && k == 0);
+          mma_commit(&bars->empty[s]);
+        }
+        mma_commit(&bars->accf[buf]);
+        ++n_chunk;
+      }
+      __syncwarp();
+    } else if (epi) {
+      const int buf = n_chunk & 1, use = n_chunk >> 1;
+      if (ehalf == 0) {
+        // the saved activations of step t-1 are requested before the accumulator is waited for
+        PwIn in[8];
+        if (t > 0 && act) {
+#pragma unroll
+          for (int rg = 0; rg < 8; ++rg)
+            if (rg * 4 + rl < a.B) pw_load(a, t - 1, rg * 4 + rl, j, false, in[rg]);
+        }
+        mbar_wait(&bars->accf[buf], use & 1);
+        tc_fence_after();
+        const uint32_t t_main = tmem_d + buf * 256;
+        float v[8];
+        tmem_ld_group(t_main, t_main + 128, 0, v);
+        xpose8_group(v, lane);                                  // -> v[rg] = dh_{t-1}(row rg*4 + rl, unit c8) without the Dh term
+        if (act) {
+#pragma unroll
+          for (int rg = 0; rg < 8; ++rg) {
+            const int m = rg * 4 + rl;
+            if (m < a.B) {
+              if (t > 0) {
+                pw_finish3(a, t - 1, m, j, in[rg], in[rg].dyv + in[rg].dhs + v[rg], dhc);
+              } else {
+                if (a.dh0) a.dh0[(size_t)m * a.H + j] = a.dhrun[(size_t)m * a.Hp + j] + v[rg];
+                if (a.dc0) a.dc0[(size_t)m * a.H + j] = a.dcrun[(size_t)m * a.Hp + j];
+              }
+            }
+          }
+        }
+      } else {
+        mbar_wait(&bars->accf[buf], use & 1);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->acce[buf]);
+      ++n_chunk;
+      fence_proxy_async_all();
+    }
+    __syncthreads();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(512));
+  }
+}
+
+}  // namespace r3
+}  // namespace vmlmf

@@ -127,7 +127,14 @@ int vmlmf_seq_plan(int T, int B, int I, int H, int RX, int RH, vmlmf_plan* plan)
   if (grc) return grc;
   // beyond the register-resident kernels: the persistent tcgen05 recurrence (one launch for all T steps) when TMA is
   // available; the launch-per-timestep generic regime otherwise.  Pitches and the saved-state layouts are shared.
-  if (r2::fits(T, B, I, H, RX, RH)) {
+  if (r3::fits(T, B, I, H, RX, RH)) {
+    // small batches: weight-stationary variant (factors resident in shared memory, XP / dzx time-parallel around the launch)
+    plan->path = VMLMF_PATH_R3;
+    plan->xp_cols = 0;
+    const r3::Geom g = r3::geom(T, B, I, H, RX, RH);
+    plan->fwd_workspace_bytes = (g.fwd_floats + 128) * (long long)sizeof(float);
+    plan->bwd_workspace_bytes = (g.bwd_floats + tp_scratch(T, B, I, H, g.Hp, RX, RH).total + 192) * (long long)sizeof(float);
+  } else if (r2::fits(T, B, I, H, RX, RH)) {
     plan->path = VMLMF_PATH_R2;
     plan->xp_cols = 0;
     const r2::Geom g = r2::geom(T, B, I, H, RX, RH);
@@ -244,7 +251,7 @@ int vmlmf_seq_fwd(const vmlmf_plan* plan, const float* x, long long xs_t, long l
   if (save && !(gates && cs && z)) return VMLMF_EINVAL;
   // y may be null for a last-step-only caller (V/models/vmlmf.py:354-355 reads y[:, -1] alone): inference on the
   // persistent kernels only -- backward and the generic regime read h_{t-1} back from y
-  if (!y && (save || plan->path == VMLMF_PATH_G || plan->path == VMLMF_PATH_R2)) return VMLMF_EINVAL;
+  if (!y && (save || plan->path == VMLMF_PATH_G || plan->path == VMLMF_PATH_R2 || plan->path == VMLMF_PATH_R3)) return VMLMF_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
   if (plan->path == VMLMF_PATH_R1) {
     const R1Choice c = choose_r1(I, H, RX, RH);
@@ -272,6 +279,21 @@ int vmlmf_seq_fwd(const vmlmf_plan* plan, const float* x, long long xs_t, long l
     if (!workspace) return VMLMF_EWORKSPACE;
     r2::FwdCall c{x, xs_t, xs_b, zx, Vx, Dx, A, Bm, Dh, bias, h0, c0, y, ys_t, ys_b, hT, cT, gates, cs, z, T, B, I, H, RX, RH};
     return r2::launch_fwd(c, workspace, st);
+  }
+  if (plan->path == VMLMF_PATH_R3) {
+    if (!r3::fits(T, B, I, H, RX, RH) || plan->zx_pitch != round_up(RX, 4) || plan->z_pitch != round_up(RH, 4)) return VMLMF_EPLAN;
+    if (!workspace) return VMLMF_EWORKSPACE;
+    const r3::Geom g = r3::geom(T, B, I, H, RX, RH);
+    float* xp = r3::ws_base(workspace) + g.o_xp;
+    // time-parallel: XP = ZX Vx^T + bias + x (.) Dx (tcgen05 3xTF32 GEMM; SIMT when an operand misses the TMA constraints)
+    const int rows = T * B;
+    int rc3 = tc::gemm_tc(zx, plan->zx_pitch, Vx, RX, rows, 4 * H, RX, tc::EpiXPTC{xp, bias, x, xs_t, xs_b, B, Dx, H, I}, st);
+    if (rc3 == tc::kTcNoFit)
+      rc3 = gemm_launch<false, true>(plain_view(zx, plan->zx_pitch), plain_view(Vx, RX), rows, 4 * H, RX, 1, NIdent{},
+                                     EpiXP{xp, bias, tb_view(x, xs_t, xs_b, B), Dx, H, I}, st);
+    if (rc3) return rc3;
+    r3::FwdCall c{xp, A, Bm, Dh, h0, c0, y, ys_t, ys_b, hT, cT, gates, cs, z, T, B, I, H, RX, RH};
+    return r3::launch_fwd(c, workspace, st);
   }
   if (plan->path == VMLMF_PATH_G)
     return generic_seq_fwd(plan, x, xs_t, xs_b, zx, Ux, Vx, Dx, A, Bm, Dh, bias, h0, c0, y, ys_t, ys_b, hT, cT,
@@ -342,6 +364,23 @@ int vmlmf_seq_bwd(const vmlmf_plan* plan, const float* x, long long xs_t, long l
     tp.tA = align4(part + ts.n_part);
     tp.tB = align4(tp.tA + ts.n_tA);
     tp.gtmp = align4(tp.tB + ts.n_tB);
+    return generic_bwd_tp(tp, st);
+  }
+  if (plan->path == VMLMF_PATH_R3) {
+    if (!r3::fits(T, B, I, H, RX, RH) || plan->zx_pitch != round_up(RX, 4) || plan->z_pitch != round_up(RH, 4)) return VMLMF_EPLAN;
+    r3::BwdCall bc{Vx, A, Bm, Dh, c0, gates, cs, dy, dys_t, dys_b, dhT, dcT, dh0, dc0, T, B, I, H, RX, RH};
+    r3::BwdOut bo;
+    int rc3 = r3::launch_bwd(bc, workspace, &bo, st);
+    if (rc3) return rc3;
+    const TpScratch ts = tp_scratch(T, B, I, H, bo.G, RX, RH);
+    float* part = align4(bo.after);
+    TpArgs tp{bo.dpre, bo.G, z, plan->z_pitch, zx, plan->zx_pitch, bo.dz, bo.dzx, false, x, xs_t, xs_b, y, ys_t, ys_b, h0, Ux, Vx, Dx,
+              dx, dxs_t, dxs_b, dUx, dVx, dDx, dA, dBm, dDh, dbias, part, ts.n_part, bo.vxt, nullptr, nullptr, nullptr, ts.ldt, nullptr,
+              T, B, I, H, RX, RH, true};
+    tp.tA = align4(part + ts.n_part);
+    tp.tB = align4(tp.tA + ts.n_tA);
+    tp.gtmp = align4(tp.tB + ts.n_tB);
+    tp.vxt_padded = true;
     return generic_bwd_tp(tp, st);
   }
   if (plan->path == VMLMF_PATH_G)

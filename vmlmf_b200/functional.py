@@ -72,7 +72,7 @@ def _xproj_on_tensor_cores(x, batch_first, T, B, I, RX, plan):
     """the x projection as one tcgen05 GEMM: time-major contiguous input (row t*B+b = the order zx is consumed in), a
     product big enough for 128 x 128 tiles, and an unpadded zx (RX % 4 == 0: the GEMM writes exactly RX columns)"""
     rows_uniform = x.stride(1) * B == x.stride(0) or T == 1          # row t*B+b lives at (t*B+b) * pitch
-    return (plan.path == _lib.PATH_R2 and not batch_first and rows_uniform and I >= 128 and RX >= 32 and
+    return (plan.path in (_lib.PATH_R2, _lib.PATH_R3) and not batch_first and rows_uniform and I >= 128 and RX >= 32 and
             T * B >= 256 and plan.zx_pitch == RX)
 
 
