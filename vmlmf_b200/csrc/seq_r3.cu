@@ -139,22 +139,22 @@ Geom geom(int T, int B, int I, int H, int RX, int RH) {
   const int stat_f = 2 * kPTile + g.nkz * kAStage;
   const int stat_b = g.nch * 2 * kPTile + g.nkz * 2 * kApTile;
   auto stages = [](int stat) {
-    int s = (kSmemMax - kBarBytes - stat) / kAStage;
+    int s = (kSmemMax - kBarBytes - kXbufBytes - stat) / kAStage;
     return s > kMaxStages ? kMaxStages : s;
   };
   g.S_fwd = stages(stat_f);
   g.S_bwd = stages(stat_b);
   if (g.S_fwd > g.nkz + 1) g.S_fwd = g.nkz + 1;
   if (g.S_bwd > g.nkz + 1) g.S_bwd = g.nkz + 1;
-  g.smem_fwd = g.S_fwd * kAStage + stat_f + kBarBytes + 1024;
-  g.smem_bwd = g.S_bwd * kAStage + stat_b + kBarBytes + 1024;
+  g.smem_fwd = g.S_fwd * kAStage + stat_f + kBarBytes + kXbufBytes + 1024;
+  g.smem_bwd = g.S_bwd * kAStage + stat_b + kBarBytes + kXbufBytes + 1024;
   long long o = 0;
   g.o_xp = o; o += al64((long long)T * B * 4 * H);
   g.o_hop_hi = o; o += al64((long long)B * g.Hp);
   g.o_hop_lo = o; o += al64((long long)B * g.Hp);
   g.o_zop_hi = o; o += al64((long long)B * g.zp);
   g.o_zop_lo = o; o += al64((long long)B * g.zp);
-  g.o_zpart = o; o += al64((long long)g.CS * RB * g.zp);
+  g.o_zpart = o; o += al64(2LL * g.CS * RB * g.zp);      // hi*hi + hi*lo and lo*hi partials per CTA
   g.o_p_hi = o; o += al64((long long)g.CS * 128 * 32);
   g.o_p_lo = o; o += al64((long long)g.CS * 128 * 32);
   g.o_w2_hi = o; o += al64((long long)g.CS * 32 * g.KZP);
@@ -172,7 +172,7 @@ Geom geom(int T, int B, int I, int H, int RX, int RH) {
   g.b_dzo_lo = o; o += al64((long long)B * g.zp);
   g.b_dhrun = o; o += al64((long long)B * g.Hp);
   g.b_dcrun = o; o += al64((long long)B * g.Hp);
-  g.b_part = o; o += al64((long long)g.CS * RB * g.zp);
+  g.b_part = o; o += al64(2LL * g.CS * RB * g.zp);
   g.b_w2t_hi = o; o += al64((long long)g.KZP * 4 * g.Hp);
   g.b_w2t_lo = o; o += al64((long long)g.KZP * 4 * g.Hp);
   g.b_ap_hi = o; o += al64((long long)g.Hp * g.KZP);
@@ -273,15 +273,16 @@ int launch_bwd(const BwdCall& c, void* workspace, BwdOut* out, cudaStream_t st) 
 }  // namespace vmlmf
 
 #ifdef VMLMF_R2_TRACE
-// debug builds only (tools/trace_r2.py): this translation unit's copy of the cycle trace
+// debug builds only (tools/trace_r2.py): this translation unit's copy of the cycle trace (10 warps x 96 slots, zero = unused)
 extern "C" int vmlmf_r3_trace_read(long long* dst, int max_events) {
-  int n = 0;
+  static long long host[2 * 960];
   cudaDeviceSynchronize();
-  cudaMemcpyFromSymbol(&n, vmlmf::r2::g_r2_trace_n, sizeof(int));
-  if (n > max_events) n = max_events;
-  cudaMemcpyFromSymbol(dst, vmlmf::r2::g_r2_trace, (size_t)n * 2 * sizeof(long long));
-  const int zero = 0;
-  cudaMemcpyToSymbol(vmlmf::r2::g_r2_trace_n, &zero, sizeof(int));
+  cudaMemcpyFromSymbol(host, vmlmf::r2::g_r2_trace, sizeof(host));
+  int n = 0;
+  for (int i = 0; i < 960 && n < max_events; ++i)
+    if (host[2 * i + 1] != 0) { dst[2 * n] = host[2 * i]; dst[2 * n + 1] = host[2 * i + 1]; ++n; }
+  static long long zeros[2 * 960];
+  cudaMemcpyToSymbol(vmlmf::r2::g_r2_trace, zeros, sizeof(zeros));
   return n;
 }
 #endif

@@ -29,6 +29,20 @@ namespace r3 {
 
 using namespace r2;
 
+// Debug-only cycle trace (-DVMLMF_R2_TRACE): lane 0 of a warp of CTA 0 appends (event, clock) pairs to the warp's own slice of
+// the trace buffer -- a plain store, no atomics, so that tracing does not stretch the latency chain it measures.
+#ifdef VMLMF_R2_TRACE
+#define R3_TRACE(ev)                                                                                           \
+  do {                                                                                                         \
+    if (blockIdx.x == 0 && lane == 0 && t >= 8 && t < 11 && trc < 96) {                                        \
+      const int i__ = warp * 96 + trc++;                                                                       \
+      g_r2_trace[2 * i__] = (ev) + 1000 * t; g_r2_trace[2 * i__ + 1] = clock64();                              \
+    }                                                                                                          \
+  } while (0)
+#else
+#define R3_TRACE(ev) do {} while (0)
+#endif
+
 constexpr int UB = 8;                        // hidden units per CTA
 constexpr int RB = 32;                       // batch rows (one tensor-memory lane quarter, one TMA box)
 constexpr int kATile = RB * BK * 4;          // 4 KB: [32 rows x 32 fp32] activation tile (hi or lo)
@@ -37,6 +51,7 @@ constexpr int kPTile = BM * BK * 4;          // 16 KB: [128 rows x 32 fp32] weig
 constexpr int kApTile = 16 * BK * 4;         // 2 KB: [16 rows x 32 fp32] (phase 2 B operand: 8 units + 8 spare rows)
 constexpr int kMaxStages = 16;
 constexpr int kBarBytes = 512;
+constexpr int kXbufBytes = 32 * 32 * 4;        // cross-term hand-over between the two epilogue lane quarters (pointwise phases)
 constexpr int kSmemMax = 232448 - 1024;      // 227 KB minus the alignment slack
 
 struct Bars3 {
@@ -52,11 +67,11 @@ static_assert(sizeof(Bars3) <= kBarBytes, "barrier block");
 // position of (gate k, unit j) inside a row of the slice-major operand buffers: CTA s = j / 8 owns 32 consecutive floats
 __host__ __device__ __forceinline__ int slice_col(int k, int j) { return (j >> 3) * 32 + k * 8 + (j & 7); }
 
-// Fixed-order sum of the CS partial copies of a [rows, 4 * w4] matrix (partial q at part + q * RB * pitch).  Output element e
+// Fixed-order sum of the NP partial copies of a [rows, 4 * w4] matrix (partial q at part + q * RB * pitch).  Output element e
 // (one float4) belongs to CTA e / epc; inside the CTA eight adjacent lanes share one output, lane pg adding the partials
 // q = pg, pg + 8, ... in order, then a butterfly over the eight lanes (same order every run: deterministic).
-template <class Store>
-__device__ __forceinline__ void reduce_partials(const float* part, int CS, int s_rank, int rows, int pitch, int w4, Store&& store) {
+template <class Store, class Trace>
+__device__ __forceinline__ void reduce_partials(const float* part, int NP, int CS, int s_rank, int rows, int pitch, int w4, Store&& store, Trace&& tr) {
   const int et = (int)threadIdx.x - 64;
   const int o = et >> 3, pg = et & 7;
   const int E = rows * w4;
@@ -74,14 +89,15 @@ __device__ __forceinline__ void reduce_partials(const float* part, int CS, int s
       r = e / w4;
       c4 = e - r * w4;
       const float4* src = reinterpret_cast<const float4*>(part + (size_t)r * pitch) + c4;
-      for (int q = pg; q < CS; q += 32) {
-        float4 pv[4];
+      for (int q = pg; q < NP; q += 192) {
+        float4 pv[24];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) pv[i] = q + 8 * i < CS ? __ldcg(src + (size_t)(q + 8 * i) * qstride4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < 24; ++i) pv[i] = q + 8 * i < NP ? __ldcg(src + (size_t)(q + 8 * i) * qstride4) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { acc.x += pv[i].x; acc.y += pv[i].y; acc.z += pv[i].z; acc.w += pv[i].w; }
+        for (int i = 0; i < 24; ++i) { acc.x += pv[i].x; acc.y += pv[i].y; acc.z += pv[i].z; acc.w += pv[i].w; }
       }
     }
+    tr(33);
 #pragma unroll
     for (int d = 1; d < 8; d <<= 1) {
       acc.x += __shfl_xor_sync(0xffffffffu, acc.x, d);
@@ -89,7 +105,9 @@ __device__ __forceinline__ void reduce_partials(const float* part, int CS, int s
       acc.z += __shfl_xor_sync(0xffffffffu, acc.z, d);
       acc.w += __shfl_xor_sync(0xffffffffu, acc.w, d);
     }
+    tr(34);
     if (on && pg == 0) store(r, c4 * 4, acc);
+    tr(35);
   }
 }
 __device__ __forceinline__ void store_split4(float* hi_p, float* lo_p, const float4 v) {
@@ -99,18 +117,66 @@ __device__ __forceinline__ void store_split4(float* hi_p, float* lo_p, const flo
   *reinterpret_cast<float4*>(hi_p) = hi;
   *reinterpret_cast<float4*>(lo_p) = lo;
 }
-// the three MMAs of one tf32 k-step: cross terms first (small), then hi * hi
-__device__ __forceinline__ void issue_kstep(uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, uint32_t acc_main,
-                                            uint32_t acc_cross, uint32_t idesc, bool first) {
-  const uint32_t acc = first ? 0u : 1u;
-  mma_tf32_ss(acc_cross, make_desc(a_lo), make_desc(b_hi), idesc, acc);
-  mma_tf32_ss(acc_cross, make_desc(a_hi), make_desc(b_lo), idesc, 1u);
-  mma_tf32_ss(acc_main, make_desc(a_hi), make_desc(b_hi), idesc, acc);
+// 32 lanes x 32 consecutive fp32 columns of the accumulator -> 32 registers per thread
+__device__ __forceinline__ void tmem_ld32_raw(uint32_t taddr, float (&v)[32]) {
+  float g0[8], g1[8], g2[8], g3[8];
+  tc::tmem_ld8_raw(taddr, g0); tc::tmem_ld8_raw(taddr + 8, g1); tc::tmem_ld8_raw(taddr + 16, g2); tc::tmem_ld8_raw(taddr + 24, g3);
+  tc::tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { v[i] = g0[i]; v[8 + i] = g1[i]; v[16 + i] = g2[i]; v[24 + i] = g3[i]; }
+}
+// ONE MMA per tf32 k-step computes all three 3xTF32 products.  The batch fills 32 of the 128 accumulator rows and every operand
+// lives in shared memory as a hi tile directly followed by its lo tile, so
+//   * the A descriptor at the hi tile makes rows 0..31 = a_hi and rows 32..63 = a_lo (rows 64..127: don't care);
+//   * the B descriptor at the hi tile with N doubled makes columns [0, n) = b_hi and [NB, NB + n) = b_lo (NB = rows of the hi tile).
+// Accumulator: lanes 0..31 x [0, n) = hi*hi, lanes 0..31 x [NB, NB+n) = hi*lo, lanes 32..63 x [0, n) = lo*hi (lo*lo is computed
+// and ignored).  The three terms stay in separate accumulator cells as before (the tensor core's accumulate truncates: the
+// small terms must not ride on the large sum).  A tf32 MMA with a 128-row shared-memory A operand costs ~110 cycles whatever
+// N is (measured: the same per-instruction time at N = 32 and N = 128), so this is a 3x cut of the tensor time of a step.
+__device__ __forceinline__ void issue_ktile(uint32_t a_addr, uint32_t b_addr, uint32_t acc, uint32_t idesc, int ksteps, bool first) {
+  const uint64_t da = make_desc(a_addr), db = make_desc(b_addr);
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (k < ksteps) mma_tf32_ss(acc, da + 2 * k, db + 2 * k, idesc, (first && k == 0) ? 0u : 1u);
+}
+// The long contractions (K = RH: phase G, phase 2) are a chain of MMAs into one accumulator, and a dependent tf32 MMA issues only
+// every ~190 cycles (measured; the math of a 128 x 64 x 8 tile is ~30).  K-step k of every K tile therefore goes to its own
+// accumulator (column offset k * nw): four independent chains, summed by the epilogue.
+__device__ __forceinline__ void issue_ktile_split(uint32_t a_addr, uint32_t b_addr, uint32_t acc, uint32_t nw, uint32_t idesc,
+                                                  int ksteps, bool first) {
+  const uint64_t da = make_desc(a_addr), db = make_desc(b_addr);
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (k < ksteps) mma_tf32_ss(acc + k * nw, da + 2 * k, db + 2 * k, idesc, first ? 0u : 1u);
+}
+// accumulator chunk -> row-major partial buffer without a transpose: tcgen05.ld hands lane r the row r, 32 consecutive
+// columns; each lane stores its own 128 bytes (eight float4).  Twice the store sectors of a transposed write, a fifth of
+// the instructions -- the epilogue of a 20-row batch is latency, not bandwidth.
+__device__ __forceinline__ void store_partial_rows(uint32_t t_main, int cb, float* row_ptr, int c0, int zp, bool row_ok) {
+  float v[32];
+  tmem_ld_groups(t_main, t_main + 128, cb, cb + 8, cb + 16, cb + 24, v);      // hi*hi + hi*lo
+  if (row_ok) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (c0 + 4 * i < zp)
+        *reinterpret_cast<float4*>(row_ptr + c0 + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  }
+}
+// the lo*hi term of the same chunk: accumulator lanes 32..63 (read by a warp of lane quarter 1), stored as a partial of its own
+__device__ __forceinline__ void store_cross_rows(uint32_t t_q1, int cb, float* row_ptr, int c0, int zp, bool row_ok) {
+  float v[32];
+  tmem_ld32_raw(t_q1 + cb, v);
+  if (row_ok) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (c0 + 4 * i < zp)
+        *reinterpret_cast<float4*>(row_ptr + c0 + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  }
 }
 __device__ __forceinline__ void init_common(Bars3* bars, int S, int warp) {
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&bars->accf[b], 1); mbar_init(&bars->acce[b], 2); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&bars->accf[b], 1); mbar_init(&bars->acce[b], 4); }
     mbar_init(&bars->wbar, 1);
     fence_barrier_init();
   }
@@ -152,13 +218,15 @@ r3_fwd_kernel(const __grid_constant__ CUtensorMap m_hop_hi, const __grid_constan
   const int S = a.S, CS = a.CS;
   const int RHr = (a.RH + 7) & ~7;
   const int nzc = (RHr + 127) / 128;                         // phase Z chunks (128 z columns each; <= 4: one k-step slot each)
-  const int nkz = (a.RH + BK - 1) / BK;                      // phase G K tiles
+  const int nkz = (a.RH + BK - 1) / BK;
+  const int nacc = min(4, (a.RH + 7) / 8);                   // independent accumulation chains of the K = RH phases                      // phase G K tiles
   // shared memory: activation ring | phase Z weights (hi, lo) | phase G weights (nkz x (hi | lo)) | barriers
   uint8_t* const ring = base;
   uint8_t* const p_hi = base + S * kAStage;
   uint8_t* const p_lo = p_hi + kPTile;
   uint8_t* const w2s = p_lo + kPTile;
   Bars3* const bars = reinterpret_cast<Bars3*>(w2s + nkz * kAStage);
+  float* const xbuf = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + kBarBytes);
   const int s_rank = (int)blockIdx.x;
   const int u0 = s_rank * UB;
   unsigned int epoch = 0;
@@ -177,17 +245,19 @@ r3_fwd_kernel(const __grid_constant__ CUtensorMap m_hop_hi, const __grid_constan
   }
 
   const int eq = warp & 3, ehalf = (warp - 2) >> 2;          // epilogue: tensor-memory lane quarter, column half
-  const bool epi = warp >= 2 && eq == 0;                     // warps 4 and 8 own lanes 0..31 = the batch rows
+  const bool epi = warp >= 2 && eq <= 1;                     // warps 4, 8: accumulator lanes 0..31 (hi rows); 5, 9: lanes 32..63 (lo rows)
   const int rl = lane & 3, c8 = lane >> 2;
   uint32_t n_tile = 0, n_chunk = 0;
   bool wready = false;
+  int trc = 0;
+  (void)trc;
 
   for (int t = 0; t < a.T; ++t) {
     // ======================================= phase Z =======================================
     if (warp == 0) {
       if (lane == 0) {
         fence_proxy_async_all();
-        R2_TRACE(1);
+        R3_TRACE(1);
         const int s = n_tile % S, it = n_tile / S;
         if (it > 0) mbar_wait(&bars->empty[s], (it - 1) & 1);
         mbar_arrive_expect_tx(&bars->full[s], kAStage);
@@ -200,21 +270,20 @@ r3_fwd_kernel(const __grid_constant__ CUtensorMap m_hop_hi, const __grid_constan
       if (lane == 0) {
         if (!wready) { mbar_wait(&bars->wbar, 0); wready = true; }
         const int s = n_tile % S, it = n_tile / S;
-        const uint32_t a_hi = smem_u32(ring + s * kAStage), a_lo = a_hi + kATile;
+        const uint32_t a_addr = smem_u32(ring + s * kAStage), p_addr = smem_u32(p_hi);
         for (int zc = 0; zc < nzc; ++zc, ++n_chunk) {
           const int buf = n_chunk & 1, use = n_chunk >> 1;
           if (use > 0) mbar_wait(&bars->acce[buf], (use - 1) & 1);
-          if (zc == 0) { mbar_wait(&bars->full[s], it & 1); R2_TRACE(10); }
+          if (zc == 0) { mbar_wait(&bars->full[s], it & 1); R3_TRACE(10); }
           tc_fence_after();
           const int ncol = min(128, RHr - zc * 128);
-          const uint32_t idesc = make_idesc(BM, (ncol + 15) & ~15);
-          const uint32_t acc_main = tmem_d + buf * 256, acc_cross = acc_main + 128;
-          // chunk zc of the z columns sits in k-step slot zc of the packed tile (seq_r2.cu: pack3_fwd_kernel)
-          issue_kstep(a_hi, a_lo, smem_u32(p_hi) + zc * 32, smem_u32(p_lo) + zc * 32, acc_main, acc_cross, idesc, true);
+          const uint32_t idesc = make_idesc(BM, 128 + ((ncol + 15) & ~15));      // [p_hi rows | p_lo rows]
+          // chunk zc of the z columns sits in k-step slot zc of the packed tile (seq_r3.cu: pack3_fwd_kernel)
+          mma_tf32_ss(tmem_d + buf * 256, make_desc(a_addr), make_desc(p_addr + zc * 32), idesc, 0u);
           mma_commit(&bars->accf[buf]);
         }
         mma_commit(&bars->empty[s]);
-        R2_TRACE(11);
+        R3_TRACE(11);
         ++n_tile;
       }
       __syncwarp();
@@ -223,26 +292,15 @@ r3_fwd_kernel(const __grid_constant__ CUtensorMap m_hop_hi, const __grid_constan
         const int buf = n_chunk & 1, use = n_chunk >> 1;
         mbar_wait(&bars->accf[buf], use & 1);
         tc_fence_after();
-        if (warp == 4) R2_TRACE(20);
+        if (warp == 4) R3_TRACE(20);
         const int ncol = min(128, RHr - zc * 128);
         const uint32_t t_main = tmem_d + buf * 256;
 #pragma unroll 1
         for (int pp = 0; pp < 2; ++pp) {
           const int cb = (ehalf * 2 + pp) * 32;
           if (cb >= ncol) break;
-          float v[32];
-          tmem_ld_groups(t_main, t_main + 128, cb, cb + 8, cb + 16, cb + 24, v);
-          xpose_vec4(v, lane);
-          const int c = zc * 128 + cb + (lane >> 2) * 4;
-          if (c < a.zp) {
-#pragma unroll
-            for (int rg = 0; rg < 8; ++rg) {
-              const int r = rg * 4 + rl;
-              if (r < a.B)
-                *reinterpret_cast<float4*>(a.zpart + ((size_t)s_rank * RB + r) * a.zp + c) =
-                    make_float4(v[rg * 4], v[rg * 4 + 1], v[rg * 4 + 2], v[rg * 4 + 3]);
-            }
-          }
+          if (eq == 0) store_partial_rows(t_main, cb, a.zpart + ((size_t)s_rank * RB + lane) * a.zp, zc * 128 + cb, a.zp, lane < a.B);
+          else store_cross_rows(t_main + (32u << 16), cb, a.zpart + ((size_t)(CS + s_rank) * RB + lane) * a.zp, zc * 128 + cb, a.zp, lane < a.B);
         }
         tc_fence_before();
         __syncwarp();
@@ -250,19 +308,19 @@ r3_fwd_kernel(const __grid_constant__ CUtensorMap m_hop_hi, const __grid_constan
       }
     }
     // ======================================= exchange =======================================
-    if (warp == 4) R2_TRACE(21);
+    if (warp == 4) R3_TRACE(21);
     group_sync(a.sync, epoch, CS);
-    if (warp == 4) R2_TRACE(30);
+    if (warp == 4) R3_TRACE(30);
     if (warp >= 2) {
-      reduce_partials(a.zpart, CS, s_rank, a.B, a.zp, a.zp >> 2, [&](int r, int c, const float4 v) {
+      reduce_partials(a.zpart, 2 * CS, CS, s_rank, a.B, a.zp, a.zp >> 2, [&](int r, int c, const float4 v) {
         if (SAVE) *reinterpret_cast<float4*>(a.z + ((size_t)t * a.B + r) * a.zp + c) = v;
         store_split4(a.zop_hi + (size_t)r * a.zp + c, a.zop_lo + (size_t)r * a.zp + c, v);
-      });
+      }, [&](int ev) { if (warp == 4) R3_TRACE(ev); });
       fence_proxy_async_all();
-      if (warp == 4) R2_TRACE(31);
+      if (warp == 4) R3_TRACE(31);
     }
     group_sync(a.sync, epoch, CS);
-    if (warp == 4) R2_TRACE(32);
+    if (warp == 4) R3_TRACE(32);
     // ======================================= phase G =======================================
     if (warp == 0) {
       if (lane == 0) {
@@ -273,36 +331,47 @@ r3_fwd_kernel(const __grid_constant__ CUtensorMap m_hop_hi, const __grid_constan
           mbar_arrive_expect_tx(&bars->full[s], kAStage);
           tma_load_2d(ring + s * kAStage, &m_zop_hi, kt * BK, 0, &bars->full[s]);
           tma_load_2d(ring + s * kAStage + kATile, &m_zop_lo, kt * BK, 0, &bars->full[s]);
+          R3_TRACE(200 + kt);
         }
       }
       __syncwarp();
     } else if (warp == 1) {
       if (lane == 0) {
-        const uint32_t idesc = make_idesc(BM, 32);
+        const uint32_t idesc = make_idesc(BM, 64);               // [32 hi rows | 32 lo rows] of the CTA's Bm slice
         const int buf = n_chunk & 1, use = n_chunk >> 1;
         if (use > 0) mbar_wait(&bars->acce[buf], (use - 1) & 1);
         tc_fence_after();
-        const uint32_t acc_main = tmem_d + buf * 256, acc_cross = acc_main + 128;
         for (int kt = 0; kt < nkz; ++kt, ++n_tile) {
           const int s = n_tile % S, it = n_tile / S;
           mbar_wait(&bars->full[s], it & 1);
           tc_fence_after();
-          if (kt == 0) R2_TRACE(12);
-          const uint32_t a_hi = smem_u32(ring + s * kAStage), a_lo = a_hi + kATile;
-          const uint32_t b_hi = smem_u32(w2s + kt * kAStage), b_lo = b_hi + kATile;
-          const int ks = tile_ksteps(a.RH, kt);
-          for (int k = 0; k < ks; ++k)
-            issue_kstep(a_hi + k * 32, a_lo + k * 32, b_hi + k * 32, b_lo + k * 32, acc_main, acc_cross, idesc, kt == 0 && k == 0);
+          R3_TRACE(100 + kt);
+          issue_ktile_split(smem_u32(ring + s * kAStage), smem_u32(w2s + kt * kAStage), tmem_d + buf * 256, 64, idesc, tile_ksteps(a.RH, kt), kt == 0);
           mma_commit(&bars->empty[s]);
         }
         mma_commit(&bars->accf[buf]);
-        R2_TRACE(13);
+        R3_TRACE(13);
         ++n_chunk;
       }
       __syncwarp();
     } else if (epi) {
       const int buf = n_chunk & 1, use = n_chunk >> 1;
-      if (ehalf == 0) {
+      if (ehalf == 0 && eq == 1) {
+        // lo*hi term (accumulator lanes 32..63) -> shared memory, [column][row]: conflict free for writer and reader
+        mbar_wait(&bars->accf[buf], use & 1);
+        tc_fence_after();
+        float v[32];
+        tmem_ld32_raw(tmem_d + (32u << 16) + buf * 256, v);
+        for (int ac = 1; ac < nacc; ++ac) {
+          float w[32];
+          tmem_ld32_raw(tmem_d + (32u << 16) + buf * 256 + ac * 64, w);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] += w[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) xbuf[i * 32 + lane] = v[i];
+        asm volatile("bar.sync 1, 64;" ::: "memory");
+      } else if (ehalf == 0) {
         // lane (c8, rl) owns unit j for the 8 rows rg*4 + rl; the chunk's 32 columns are [gate k][unit]
         const float* hprev = t ? a.y + (size_t)(t - 1) * a.ys_t : a.h0;
         const long long hp_sb = t ? a.ys_b : a.H;
@@ -324,13 +393,22 @@ r3_fwd_kernel(const __grid_constant__ CUtensorMap m_hop_hi, const __grid_constan
 #pragma unroll
           for (int k = 0; k < 4; ++k) xq[rg][k] = ok ? __ldg(a.xp + ((size_t)t * a.B + m) * 4 * a.H + (size_t)k * a.H + j) : 0.f;
         }
-        R2_TRACE(22);
+        R3_TRACE(22);
         mbar_wait(&bars->accf[buf], use & 1);
         tc_fence_after();
-        R2_TRACE(23);
+        R3_TRACE(23);
         const uint32_t t_main = tmem_d + buf * 256;
         float v[32];
-        tmem_ld_groups(t_main, t_main + 128, 0, 8, 16, 24, v);
+        tmem_ld_groups(t_main, t_main + 32, 0, 8, 16, 24, v);     // hi*hi + hi*lo of this row, first k-step chain
+        for (int ac = 1; ac < nacc; ++ac) {
+          float w[32];
+          tmem_ld_groups(t_main + ac * 64, t_main + ac * 64 + 32, 0, 8, 16, 24, w);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] += w[i];
+        }
+        asm volatile("bar.sync 1, 64;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] += xbuf[i * 32 + lane]; // + lo*hi
         xpose8(v, lane);                                       // -> v[k*8 + rg] = (row rg*4 + rl, unit c8, gate k)
         if (act) {
 #pragma unroll
@@ -365,7 +443,7 @@ r3_fwd_kernel(const __grid_constant__ CUtensorMap m_hop_hi, const __grid_constan
       if (lane == 0) mbar_arrive(&bars->acce[buf]);
       ++n_chunk;
       fence_proxy_async_all();
-      if (warp == 4) R2_TRACE(24);
+      if (warp == 4) R3_TRACE(24);
     }
     __syncthreads();       // h_t operand columns of this CTA are complete before its next phase Z load
   }
@@ -431,12 +509,14 @@ r3_bwd_kernel(const __grid_constant__ CUtensorMap m_dpo_hi, const __grid_constan
   const int S = a.S, CS = a.CS;
   const int RHr = (a.RH + 7) & ~7;
   const int nch1 = (RHr + 127) / 128;                        // phase 1 chunks (128 dz columns)
-  const int nkz = (a.RH + BK - 1) / BK;                      // phase 2 K tiles
+  const int nkz = (a.RH + BK - 1) / BK;
+  const int nacc = min(4, (a.RH + 7) / 8);                   // independent accumulation chains of the K = RH phases                      // phase 2 K tiles
   // shared memory: activation ring | phase 1 weights (nch1 x (hi | lo) 16 KB tiles) | phase 2 weights (nkz x (hi | lo) 2 KB) | barriers
   uint8_t* const ring = base;
   uint8_t* const w2ts = base + S * kAStage;
   uint8_t* const aps = w2ts + nch1 * 2 * kPTile;
   Bars3* const bars = reinterpret_cast<Bars3*>(aps + nkz * 2 * kApTile);
+  float* const xbuf = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + kBarBytes);
   const int s_rank = (int)blockIdx.x;
   const int u0 = s_rank * UB;
   unsigned int epoch = 0;
@@ -457,7 +537,7 @@ r3_bwd_kernel(const __grid_constant__ CUtensorMap m_dpo_hi, const __grid_constan
   }
 
   const int eq = warp & 3, ehalf = (warp - 2) >> 2;
-  const bool epi = warp >= 2 && eq == 0;
+  const bool epi = warp >= 2 && eq <= 1;
   const int rl = lane & 3, c8 = lane >> 2;
   const int j = u0 + c8;                                     // this lane's hidden unit in the gate-gradient algebra
   const bool act = j < a.H;
@@ -466,9 +546,11 @@ r3_bwd_kernel(const __grid_constant__ CUtensorMap m_dpo_hi, const __grid_constan
   for (int k = 0; k < 4; ++k) dhc[k] = act ? __ldg(a.Dh + k * a.H + j) : 0.f;
   uint32_t n_tile = 0, n_chunk = 0;
   bool wready = false;
+  int trc = 0;
+  (void)trc;
 
   // ---- seed: gate-gradient algebra of the last step with dh = dhT (+ dy), dc = dcT ----
-  if (epi && ehalf == 0 && act) {
+  if (epi && ehalf == 0 && eq == 0 && act) {
     PwIn in[8];
 #pragma unroll
     for (int rg = 0; rg < 8; ++rg)
@@ -485,6 +567,7 @@ r3_bwd_kernel(const __grid_constant__ CUtensorMap m_dpo_hi, const __grid_constan
     if (warp == 0) {
       if (lane == 0) {
         fence_proxy_async_all();
+        R3_TRACE(1);
         const int s = n_tile % S, it = n_tile / S;
         if (it > 0) mbar_wait(&bars->empty[s], (it - 1) & 1);
         mbar_arrive_expect_tx(&bars->full[s], kAStage);
@@ -497,21 +580,19 @@ r3_bwd_kernel(const __grid_constant__ CUtensorMap m_dpo_hi, const __grid_constan
       if (lane == 0) {
         if (!wready) { mbar_wait(&bars->wbar, 0); wready = true; }
         const int s = n_tile % S, it = n_tile / S;
-        const uint32_t a_hi = smem_u32(ring + s * kAStage), a_lo = a_hi + kATile;
+        const uint32_t a_addr = smem_u32(ring + s * kAStage);
         for (int c = 0; c < nch1; ++c, ++n_chunk) {
           const int buf = n_chunk & 1, use = n_chunk >> 1;
           if (use > 0) mbar_wait(&bars->acce[buf], (use - 1) & 1);
-          if (c == 0) mbar_wait(&bars->full[s], it & 1);
+          if (c == 0) { mbar_wait(&bars->full[s], it & 1); R3_TRACE(10); }
           tc_fence_after();
           const int ncol = min(128, RHr - c * 128);
-          const uint32_t idesc = make_idesc(BM, (ncol + 15) & ~15);
-          const uint32_t acc_main = tmem_d + buf * 256, acc_cross = acc_main + 128;
-          const uint32_t b_hi = smem_u32(w2ts + c * 2 * kPTile), b_lo = b_hi + kPTile;
-          for (int k = 0; k < 4; ++k)
-            issue_kstep(a_hi + k * 32, a_lo + k * 32, b_hi + k * 32, b_lo + k * 32, acc_main, acc_cross, idesc, k == 0);
+          const uint32_t idesc = make_idesc(BM, 128 + ((ncol + 15) & ~15));      // [w2t hi rows | w2t lo rows]
+          issue_ktile(a_addr, smem_u32(w2ts + c * 2 * kPTile), tmem_d + buf * 256, idesc, 4, true);
           mma_commit(&bars->accf[buf]);
         }
         mma_commit(&bars->empty[s]);
+        R3_TRACE(11);
         ++n_tile;
       }
       __syncwarp();
@@ -520,25 +601,15 @@ r3_bwd_kernel(const __grid_constant__ CUtensorMap m_dpo_hi, const __grid_constan
         const int buf = n_chunk & 1, use = n_chunk >> 1;
         mbar_wait(&bars->accf[buf], use & 1);
         tc_fence_after();
+        if (warp == 4) R3_TRACE(20);
         const int ncol = min(128, RHr - c * 128);
         const uint32_t t_main = tmem_d + buf * 256;
 #pragma unroll 1
         for (int pp = 0; pp < 2; ++pp) {
           const int cb = (ehalf * 2 + pp) * 32;
           if (cb >= ncol) break;
-          float v[32];
-          tmem_ld_groups(t_main, t_main + 128, cb, cb + 8, cb + 16, cb + 24, v);
-          xpose_vec4(v, lane);
-          const int n = c * 128 + cb + (lane >> 2) * 4;
-          if (n < a.zp) {
-#pragma unroll
-            for (int rg = 0; rg < 8; ++rg) {
-              const int r = rg * 4 + rl;
-              if (r < a.B)
-                *reinterpret_cast<float4*>(a.part + ((size_t)s_rank * RB + r) * a.zp + n) =
-                    make_float4(v[rg * 4], v[rg * 4 + 1], v[rg * 4 + 2], v[rg * 4 + 3]);
-            }
-          }
+          if (eq == 0) store_partial_rows(t_main, cb, a.part + ((size_t)s_rank * RB + lane) * a.zp, c * 128 + cb, a.zp, lane < a.B);
+          else store_cross_rows(t_main + (32u << 16), cb, a.part + ((size_t)(CS + s_rank) * RB + lane) * a.zp, c * 128 + cb, a.zp, lane < a.B);
         }
         tc_fence_before();
         __syncwarp();
@@ -546,15 +617,19 @@ r3_bwd_kernel(const __grid_constant__ CUtensorMap m_dpo_hi, const __grid_constan
       }
     }
     // ======================================= exchange =======================================
+    if (warp == 4) R3_TRACE(21);
     group_sync(a.sync, epoch, CS);
+    if (warp == 4) R3_TRACE(30);
     if (warp >= 2) {
-      reduce_partials(a.part, CS, s_rank, a.B, a.zp, a.zp >> 2, [&](int r, int c, const float4 v) {
+      reduce_partials(a.part, 2 * CS, CS, s_rank, a.B, a.zp, a.zp >> 2, [&](int r, int c, const float4 v) {
         *reinterpret_cast<float4*>(a.dz_all + ((size_t)t * a.B + r) * a.zp + c) = v;
         store_split4(a.dzo_hi + (size_t)r * a.zp + c, a.dzo_lo + (size_t)r * a.zp + c, v);
-      });
+      }, [&](int ev) { if (warp == 4) R3_TRACE(ev); });
       fence_proxy_async_all();
+      if (warp == 4) R3_TRACE(31);
     }
     group_sync(a.sync, epoch, CS);
+    if (warp == 4) R3_TRACE(32);
     // ======================================= phase 2 =======================================
     if (warp == 0) {
       if (lane == 0) {
@@ -570,29 +645,42 @@ r3_bwd_kernel(const __grid_constant__ CUtensorMap m_dpo_hi, const __grid_constan
       __syncwarp();
     } else if (warp == 1) {
       if (lane == 0) {
-        const uint32_t idesc = make_idesc(BM, 16);
+        const uint32_t idesc = make_idesc(BM, 32);               // [16 hi rows | 16 lo rows] of the CTA's A slice
         const int buf = n_chunk & 1, use = n_chunk >> 1;
         if (use > 0) mbar_wait(&bars->acce[buf], (use - 1) & 1);
         tc_fence_after();
-        const uint32_t acc_main = tmem_d + buf * 256, acc_cross = acc_main + 128;
         for (int kt = 0; kt < nkz; ++kt, ++n_tile) {
           const int s = n_tile % S, it = n_tile / S;
           mbar_wait(&bars->full[s], it & 1);
           tc_fence_after();
-          const uint32_t a_hi = smem_u32(ring + s * kAStage), a_lo = a_hi + kATile;
-          const uint32_t b_hi = smem_u32(aps + kt * 2 * kApTile), b_lo = b_hi + kApTile;
-          const int ks = tile_ksteps(a.RH, kt);
-          for (int k = 0; k < ks; ++k)
-            issue_kstep(a_hi + k * 32, a_lo + k * 32, b_hi + k * 32, b_lo + k * 32, acc_main, acc_cross, idesc, kt == 0 && k == 0);
+          R3_TRACE(100 + kt);
+          issue_ktile_split(smem_u32(ring + s * kAStage), smem_u32(aps + kt * 2 * kApTile), tmem_d + buf * 256, 32, idesc, tile_ksteps(a.RH, kt), kt == 0);
           mma_commit(&bars->empty[s]);
         }
         mma_commit(&bars->accf[buf]);
+        R3_TRACE(13);
         ++n_chunk;
       }
       __syncwarp();
     } else if (epi) {
       const int buf = n_chunk & 1, use = n_chunk >> 1;
-      if (ehalf == 0) {
+      if (ehalf == 0 && eq == 1) {
+        mbar_wait(&bars->accf[buf], use & 1);
+        tc_fence_after();
+        float v[8];
+        tc::tmem_ld8_raw(tmem_d + (32u << 16) + buf * 256, v);   // lo*hi term of the 8 units
+        tc::tmem_ld_wait();
+        for (int ac = 1; ac < nacc; ++ac) {
+          float w[8];
+          tc::tmem_ld8_raw(tmem_d + (32u << 16) + buf * 256 + ac * 32, w);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] += w[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) xbuf[i * 32 + lane] = v[i];
+        asm volatile("bar.sync 1, 64;" ::: "memory");
+      } else if (ehalf == 0) {
         // the saved activations of step t-1 are requested before the accumulator is waited for
         PwIn in[8];
         if (t > 0 && act) {
@@ -600,11 +688,22 @@ r3_bwd_kernel(const __grid_constant__ CUtensorMap m_dpo_hi, const __grid_constan
           for (int rg = 0; rg < 8; ++rg)
             if (rg * 4 + rl < a.B) pw_load(a, t - 1, rg * 4 + rl, j, false, in[rg]);
         }
+        R3_TRACE(22);
         mbar_wait(&bars->accf[buf], use & 1);
         tc_fence_after();
+        R3_TRACE(23);
         const uint32_t t_main = tmem_d + buf * 256;
         float v[8];
-        tmem_ld_group(t_main, t_main + 128, 0, v);
+        tmem_ld_group(t_main, t_main + 16, 0, v);               // hi*hi + hi*lo, first k-step chain
+        for (int ac = 1; ac < nacc; ++ac) {
+          float w[8];
+          tmem_ld_group(t_main + ac * 32, t_main + ac * 32 + 16, 0, w);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] += w[i];
+        }
+        asm volatile("bar.sync 1, 64;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] += xbuf[i * 32 + lane];  // + lo*hi
         xpose8_group(v, lane);                                  // -> v[rg] = dh_{t-1}(row rg*4 + rl, unit c8) without the Dh term
         if (act) {
 #pragma unroll
@@ -628,6 +727,7 @@ r3_bwd_kernel(const __grid_constant__ CUtensorMap m_dpo_hi, const __grid_constan
       if (lane == 0) mbar_arrive(&bars->acce[buf]);
       ++n_chunk;
       fence_proxy_async_all();
+      if (warp == 4) R3_TRACE(24);
     }
     __syncthreads();
   }
