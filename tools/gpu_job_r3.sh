@@ -1,8 +1,8 @@
 set -x
-timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "r3_ or generic_regime or lm_model_cfg4" > gpurun_out/r3_tests.log 2>&1
+timeout 1500 python -m pytest tests -x -q -m gpu > gpurun_out/r3_tests.log 2>&1
 tail -5 gpurun_out/r3_tests.log
-timeout 600 python tools/trace_r2.py 20 12 650 650 300 300 > gpurun_out/trace_r3_lm20_fwd.log 2>&1
-timeout 600 python tools/trace_r2.py 20 12 650 650 300 300 bwd > gpurun_out/trace_r3_lm20_bwd.log 2>&1
 timeout 300 python tools/time_r2.py 20 35 650 650 300 300 > gpurun_out/r3_time.log 2>&1
-timeout 300 python tools/time_r2.py 32 128 9 1024 64 64 >> gpurun_out/r3_time.log 2>&1
+timeout 300 python tools/time_r2.py 512 35 650 650 300 300 >> gpurun_out/r3_time.log 2>&1
+timeout 300 python tools/time_r2.py 2048 128 9 1024 64 64 3 >> gpurun_out/r3_time.log 2>&1
+timeout 300 python tools/time_r2.py 8192 24 77 256 32 32 >> gpurun_out/r3_time.log 2>&1
 cat gpurun_out/r3_time.log

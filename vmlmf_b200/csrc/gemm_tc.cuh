@@ -81,6 +81,16 @@ __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarr
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// One lane of a fully active warp.  The producer / MMA warps run their loops with all 32 lanes in warp-uniform control flow and
+// elect right at the asynchronous instructions: inside an `if (lane == 0)` region the compiler keeps descriptors and addresses
+// in per-thread registers and wraps every tcgen05.mma / TMA in an elect + R2UR.BROADCAST + loop sequence (~135 cycles per MMA
+// measured, ~45-60 for the uniform form: tools/ubench_mma.cu).  The warp index must come from warp_index() for that.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ int warp_index() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
 // shared-memory matrix descriptor: K-major tile, rows of 128 bytes, SWIZZLE_128B, 8-row groups 1024 bytes apart
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   uint64_t d = 0;
@@ -254,7 +264,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   uint64_t* accf = bars + 3 * kStages;          // accumulator complete
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kStages + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_index(), lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * BM;
   const int n_tile = blockIdx.x;
   // split-K: blockIdx.z owns k-blocks [kb0, kb0 + nkb)
@@ -278,11 +288,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
 
   if (warp == 0) {
     // ================= TMA producer =================
-    if (lane == 0) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % kStages, it = kb / kStages;
-        if (it > 0) mbar_wait(&empty[s], (it - 1) & 1);
-        uint8_t* st = smem + s * kStageBytes;
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % kStages, it = kb / kStages;
+      if (it > 0) mbar_wait(&empty[s], (it - 1) & 1);
+      uint8_t* st = smem + s * kStageBytes;
+      if (elect_one()) {
         mbar_arrive_expect_tx(&full[s], 2 * kTileBytes);
         tma_load_2d(st, &mapA, (kb0 + kb) * BK, m0, &full[s]);
         if (Epi::kGate) tma_load_3d(st + 2 * kTileBytes, &mapB, (kb0 + kb) * BK, n_tile * 32, 0, &full[s]);
@@ -291,32 +301,36 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(BM, BN);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % kStages, it = kb / kStages;
-        mbar_wait(&split[s], it & 1);
-        tc_fence_after();
-        const uint32_t a_hi = smem_u32(smem + s * kStageBytes), a_lo = a_hi + kTileBytes;
-        const uint32_t b_hi = a_hi + 2 * kTileBytes, b_lo = a_hi + 3 * kTileBytes;
-        // The tensor core adds into the fp32 accumulator with truncation, so the error grows with the number of
-        // accumulations into one accumulator (measured ~3e-8 relative per add).  The large hi*hi products are
-        // spread round-robin over three accumulators, the small cross terms go to a fourth; the epilogue adds
-        // the four in fp32.
+    const uint32_t idesc = make_idesc(BM, BN);
+    int rr = 0;                                          // kk % 3 without a division in the issue loop
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % kStages, it = kb / kStages;
+      mbar_wait(&split[s], it & 1);
+      tc_fence_after();
+      const uint32_t a_addr = smem_u32(smem + s * kStageBytes);
+      // descriptors of the four operand tiles; a k-step (8 tf32 = 32 bytes inside the 128-byte swizzle row) adds 2
+      const uint64_t da_hi = make_desc(a_addr), da_lo = make_desc(a_addr + kTileBytes);
+      const uint64_t db_hi = make_desc(a_addr + 2 * kTileBytes), db_lo = make_desc(a_addr + 3 * kTileBytes);
+      // The tensor core adds into the fp32 accumulator with truncation, so the error grows with the number of
+      // accumulations into one accumulator (measured ~3e-8 relative per add).  The large hi*hi products are
+      // spread round-robin over three accumulators, the small cross terms go to a fourth; the epilogue adds
+      // the four in fp32.
+      if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < BK / 8; ++k) {               // 8 tf32 = 32 bytes per k-step inside the 128-byte swizzle row
-          const uint32_t off = k * 32;
+        for (int k = 0; k < BK / 8; ++k) {
           const int kk = kb * (BK / 8) + k;
           if (!fast) {                                     // fast mode (single-pass TF32): no error-compensation terms
-            mma_tf32_ss(tmem_d + 3 * BN, make_desc(a_lo + off), make_desc(b_hi + off), idesc, kk ? 1u : 0u);
-            mma_tf32_ss(tmem_d + 3 * BN, make_desc(a_hi + off), make_desc(b_lo + off), idesc, 1u);
+            mma_tf32_ss(tmem_d + 3 * BN, da_lo + 2 * k, db_hi + 2 * k, idesc, kk ? 1u : 0u);
+            mma_tf32_ss(tmem_d + 3 * BN, da_hi + 2 * k, db_lo + 2 * k, idesc, 1u);
           }
-          mma_tf32_ss(tmem_d + (kk % 3) * BN, make_desc(a_hi + off), make_desc(b_hi + off), idesc, kk >= 3 ? 1u : 0u);
+          const int r3 = (rr + k) % 3;                     // rr in 0..2, k a constant: folds to compares
+          mma_tf32_ss(tmem_d + r3 * BN, da_hi + 2 * k, db_hi + 2 * k, idesc, kk >= 3 ? 1u : 0u);
         }
         mma_commit(&empty[s]);                           // stage reusable once these MMAs have read it
       }
-      mma_commit(accf);                                  // accumulator complete
+      rr = (rr + BK / 8) % 3;
     }
+    if (elect_one()) mma_commit(accf);                   // accumulator complete
   } else {
     // ================= split warps, then epilogue =================
     const int sw = warp - 2;                             // 0..3
@@ -449,7 +463,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tn_kernel(const __grid_const
   uint64_t* accf = bars + 3 * kStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kStages + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_index(), lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * BM;
   const int n0 = blockIdx.x * BN;
   const int nkb_total = (K + BK - 1) / BK;
@@ -471,11 +485,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tn_kernel(const __grid_const
   const uint32_t tmem_d = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % kStages, it = kb / kStages;
-        if (it > 0) mbar_wait(&empty[s], (it - 1) & 1);
-        uint8_t* st = smem + s * kStageBytes;
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % kStages, it = kb / kStages;
+      if (it > 0) mbar_wait(&empty[s], (it - 1) & 1);
+      uint8_t* st = smem + s * kStageBytes;
+      if (elect_one()) {
         mbar_arrive_expect_tx(&full[s], 2 * kTileBytes);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -485,28 +499,32 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tn_kernel(const __grid_const
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_mn(BM, BN);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % kStages, it = kb / kStages;
-        mbar_wait(&split[s], it & 1);
-        tc_fence_after();
-        const uint32_t a_hi = smem_u32(smem + s * kStageBytes), a_lo = a_hi + kTileBytes;
-        const uint32_t b_hi = a_hi + 2 * kTileBytes, b_lo = a_hi + 3 * kTileBytes;
+    const uint32_t idesc = make_idesc_mn(BM, BN);
+    int rr = 0;
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % kStages, it = kb / kStages;
+      mbar_wait(&split[s], it & 1);
+      tc_fence_after();
+      const uint32_t a_addr = smem_u32(smem + s * kStageBytes);
+      // a k-step is the next group of 8 K rows: 1024 bytes = 64 descriptor units
+      const uint64_t da_hi = make_desc_mn(a_addr), da_lo = make_desc_mn(a_addr + kTileBytes);
+      const uint64_t db_hi = make_desc_mn(a_addr + 2 * kTileBytes), db_lo = make_desc_mn(a_addr + 3 * kTileBytes);
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < BK / 8; ++k) {
-          const uint32_t off = k * 1024;                 // next group of 8 K rows
           const int kk = kb * (BK / 8) + k;
           if (!fast) {
-            mma_tf32_ss(tmem_d + 3 * BN, make_desc_mn(a_lo + off), make_desc_mn(b_hi + off), idesc, kk ? 1u : 0u);
-            mma_tf32_ss(tmem_d + 3 * BN, make_desc_mn(a_hi + off), make_desc_mn(b_lo + off), idesc, 1u);
+            mma_tf32_ss(tmem_d + 3 * BN, da_lo + 64 * k, db_hi + 64 * k, idesc, kk ? 1u : 0u);
+            mma_tf32_ss(tmem_d + 3 * BN, da_hi + 64 * k, db_lo + 64 * k, idesc, 1u);
           }
-          mma_tf32_ss(tmem_d + (kk % 3) * BN, make_desc_mn(a_hi + off), make_desc_mn(b_hi + off), idesc, kk >= 3 ? 1u : 0u);
+          const int r3 = (rr + k) % 3;
+          mma_tf32_ss(tmem_d + r3 * BN, da_hi + 64 * k, db_hi + 64 * k, idesc, kk >= 3 ? 1u : 0u);
         }
         mma_commit(&empty[s]);
       }
-      mma_commit(accf);
+      rr = (rr + BK / 8) % 3;
     }
+    if (elect_one()) mma_commit(accf);
   } else {
     const int sw = warp - 2;
     const int st_tid = sw * 32 + lane;

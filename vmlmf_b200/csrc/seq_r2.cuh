@@ -33,6 +33,7 @@
 namespace vmlmf {
 namespace r2 {
 
+using tc::elect_one;
 using tc::fence_barrier_init;
 using tc::make_desc;
 using tc::make_idesc;
@@ -47,6 +48,7 @@ using tc::tc_fence_after;
 using tc::tc_fence_before;
 using tc::tma_load_2d;
 using tc::tma_load_3d;
+using tc::warp_index;
 
 constexpr int BM = 128;                      // batch rows per tile (= TMEM lanes)
 constexpr int BK = 32;                       // fp32 per K tile (128 bytes = one swizzle row)
@@ -148,17 +150,26 @@ __device__ __forceinline__ int tile_ksteps(int valid, int kt) {
   return left >= BK ? 4 : (left + 7) / 8;
 }
 
-// the 3 x ksteps MMAs of one K tile: cross terms first (small), then hi*hi
+// the 3 x ksteps MMAs of one K tile: cross terms first (small), then hi*hi.  Called by all lanes of the MMA warp (warp-uniform
+// operands live in uniform registers); one elected lane issues.  A k-step advances the descriptors' start address by 32 bytes.
 __device__ __forceinline__ void issue_tile(uint32_t stage_addr, uint32_t acc_main, uint32_t acc_cross, uint32_t idesc,
                                            int ksteps, bool first) {
-  const uint32_t a_hi = stage_addr, a_lo = stage_addr + kTile, b_hi = stage_addr + 2 * kTile, b_lo = stage_addr + 3 * kTile;
-  for (int k = 0; k < ksteps; ++k) {
-    const uint32_t off = k * 32;
-    const uint32_t acc = (first && k == 0) ? 0u : 1u;
-    mma_tf32_ss(acc_cross, make_desc(a_lo + off), make_desc(b_hi + off), idesc, acc);
-    mma_tf32_ss(acc_cross, make_desc(a_hi + off), make_desc(b_lo + off), idesc, 1u);
-    mma_tf32_ss(acc_main, make_desc(a_hi + off), make_desc(b_hi + off), idesc, acc);
+  const uint64_t a_hi = make_desc(stage_addr), a_lo = make_desc(stage_addr + kTile);
+  const uint64_t b_hi = make_desc(stage_addr + 2 * kTile), b_lo = make_desc(stage_addr + 3 * kTile);
+  if (elect_one()) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (k < ksteps) {
+        const uint32_t acc = (first && k == 0) ? 0u : 1u;
+        mma_tf32_ss(acc_cross, a_lo + 2 * k, b_hi + 2 * k, idesc, acc);
+        mma_tf32_ss(acc_cross, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+        mma_tf32_ss(acc_main, a_hi + 2 * k, b_hi + 2 * k, idesc, acc);
+      }
+    }
   }
+}
+__device__ __forceinline__ void commit_elect(uint64_t* bar) {
+  if (elect_one()) mma_commit(bar);
 }
 
 // ---- epilogue data movement without shared memory ----
@@ -270,7 +281,7 @@ r2_fwd_kernel(const __grid_constant__ CUtensorMap m_hop_hi, const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   const Smem sm = carve(smem_raw);
   Bars* bars = sm.bars;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_index(), lane = threadIdx.x & 31;      // broadcast: role branches are warp-uniform for the compiler
   const int CS = a.CS;
   const int s_rank = (int)blockIdx.x % CS, cid = (int)blockIdx.x / CS, ncl = (int)gridDim.x / CS;
   const int ntiles = (a.B + BM - 1) / BM;
@@ -312,45 +323,41 @@ r2_fwd_kernel(const __grid_constant__ CUtensorMap m_hop_hi, const __grid_constan
     for (int t = 0; t < a.T; ++t) {
       // ======================================= phase Z =======================================
       if (warp == 0) {
-        if (lane == 0) {
-          fence_proxy_async_all();
-          R2_TRACE(1);
-          for (int zc = 0; zc < nzc; ++zc)
-            for (int kt = 0; kt < nkh; ++kt, ++n_tile) {
-              const int s = n_tile % kStages, it = n_tile / kStages;
-              if (it > 0) mbar_wait(&bars->empty[s], (it - 1) & 1);
-              uint8_t* st = sm.stages + s * kStageBytes;
+        fence_proxy_async_all();
+        R2_TRACE(1);
+        for (int zc = 0; zc < nzc; ++zc)
+          for (int kt = 0; kt < nkh; ++kt, ++n_tile) {
+            const int s = n_tile % kStages, it = n_tile / kStages;
+            if (it > 0) mbar_wait(&bars->empty[s], (it - 1) & 1);
+            uint8_t* st = sm.stages + s * kStageBytes;
+            if (elect_one()) {
               mbar_arrive_expect_tx(&bars->full[s], kStageBytes);
               tma_load_2d(st, &m_hop_hi, u0 + kt * BK, row0, &bars->full[s]);
               tma_load_2d(st + kTile, &m_hop_lo, u0 + kt * BK, row0, &bars->full[s]);
               tma_load_2d(st + 2 * kTile, &m_at_hi, u0 + kt * BK, zc * 128, &bars->full[s]);
               tma_load_2d(st + 3 * kTile, &m_at_lo, u0 + kt * BK, zc * 128, &bars->full[s]);
             }
-          R2_TRACE(2);
-        }
-        __syncwarp();
-      } else if (warp == 1) {
-        if (lane == 0) {
-          for (int zc = 0; zc < nzc; ++zc, ++n_chunk) {
-            const int buf = n_chunk & 1, use = n_chunk >> 1;
-            if (use > 0) mbar_wait(&bars->acce[buf], (use - 1) & 1);
-            tc_fence_after();
-            const int ncol = min(128, RHr - zc * 128);
-            const uint32_t idesc = make_idesc(BM, (ncol + 15) & ~15);
-            const uint32_t acc_main = tmem_d + buf * 256, acc_cross = acc_main + 128;
-            for (int kt = 0; kt < nkh; ++kt, ++n_tile) {
-              const int s = n_tile % kStages, it = n_tile / kStages;
-              mbar_wait(&bars->full[s], it & 1);
-              tc_fence_after();
-              if (kt == 0) R2_TRACE(10);
-              issue_tile(smem_u32(sm.stages + s * kStageBytes), acc_main, acc_cross, idesc, tile_ksteps(uvalid, kt), kt == 0);
-              mma_commit(&bars->empty[s]);
-            }
-            mma_commit(&bars->accf[buf]);
-            R2_TRACE(11);
           }
+        R2_TRACE(2);
+      } else if (warp == 1) {
+        for (int zc = 0; zc < nzc; ++zc, ++n_chunk) {
+          const int buf = n_chunk & 1, use = n_chunk >> 1;
+          if (use > 0) mbar_wait(&bars->acce[buf], (use - 1) & 1);
+          tc_fence_after();
+          const int ncol = min(128, RHr - zc * 128);
+          const uint32_t idesc = make_idesc(BM, (ncol + 15) & ~15);
+          const uint32_t acc_main = tmem_d + buf * 256, acc_cross = acc_main + 128;
+          for (int kt = 0; kt < nkh; ++kt, ++n_tile) {
+            const int s = n_tile % kStages, it = n_tile / kStages;
+            mbar_wait(&bars->full[s], it & 1);
+            tc_fence_after();
+            if (kt == 0) R2_TRACE(10);
+            issue_tile(smem_u32(sm.stages + s * kStageBytes), acc_main, acc_cross, idesc, tile_ksteps(uvalid, kt), kt == 0);
+            commit_elect(&bars->empty[s]);
+          }
+          commit_elect(&bars->accf[buf]);
+          R2_TRACE(11);
         }
-        __syncwarp();
       } else {
         for (int zc = 0; zc < nzc; ++zc, ++n_chunk) {
           const int buf = n_chunk & 1, use = n_chunk >> 1;
@@ -438,14 +445,14 @@ r2_fwd_kernel(const __grid_constant__ CUtensorMap m_hop_hi, const __grid_constan
       }
       // ======================================= phase G =======================================
       if (warp == 0) {
-        if (lane == 0) {
-          fence_proxy_async_all();
-          R2_TRACE(3);
-          for (int gc = 0; gc < ngc; ++gc)
-            for (int kt = 0; kt < nkz + nkx; ++kt, ++n_tile) {
-              const int s = n_tile % kStages, it = n_tile / kStages;
-              if (it > 0) mbar_wait(&bars->empty[s], (it - 1) & 1);
-              uint8_t* st = sm.stages + s * kStageBytes;
+        fence_proxy_async_all();
+        R2_TRACE(3);
+        for (int gc = 0; gc < ngc; ++gc)
+          for (int kt = 0; kt < nkz + nkx; ++kt, ++n_tile) {
+            const int s = n_tile % kStages, it = n_tile / kStages;
+            if (it > 0) mbar_wait(&bars->empty[s], (it - 1) & 1);
+            uint8_t* st = sm.stages + s * kStageBytes;
+            if (elect_one()) {
               mbar_arrive_expect_tx(&bars->full[s], kStageBytes);
               if (kt < nkz) {
                 tma_load_2d(st, &m_zop_hi, kt * BK, row0, &bars->full[s]);
@@ -460,31 +467,27 @@ r2_fwd_kernel(const __grid_constant__ CUtensorMap m_hop_hi, const __grid_constan
                 tma_load_3d(st + 3 * kTile, &m_w2_lo, a.KZP + kx * BK, u0 + gc * 32, 0, &bars->full[s]);
               }
             }
-          R2_TRACE(4);
-        }
-        __syncwarp();
-      } else if (warp == 1) {
-        if (lane == 0) {
-          const uint32_t idesc = make_idesc(BM, 128);
-          for (int gc = 0; gc < ngc; ++gc, ++n_chunk) {
-            const int buf = n_chunk & 1, use = n_chunk >> 1;
-            if (use > 0) mbar_wait(&bars->acce[buf], (use - 1) & 1);
-            tc_fence_after();
-            const uint32_t acc_main = tmem_d + buf * 256, acc_cross = acc_main + 128;
-            for (int kt = 0; kt < nkz + nkx; ++kt, ++n_tile) {
-              const int s = n_tile % kStages, it = n_tile / kStages;
-              mbar_wait(&bars->full[s], it & 1);
-              tc_fence_after();
-              const int ks = kt < nkz ? tile_ksteps(a.RH, kt) : tile_ksteps(a.RX, kt - nkz);
-              if (kt == 0) R2_TRACE(12);
-              issue_tile(smem_u32(sm.stages + s * kStageBytes), acc_main, acc_cross, idesc, ks, kt == 0);
-              mma_commit(&bars->empty[s]);
-            }
-            mma_commit(&bars->accf[buf]);
-            R2_TRACE(13);
           }
+        R2_TRACE(4);
+      } else if (warp == 1) {
+        const uint32_t idesc = make_idesc(BM, 128);
+        for (int gc = 0; gc < ngc; ++gc, ++n_chunk) {
+          const int buf = n_chunk & 1, use = n_chunk >> 1;
+          if (use > 0) mbar_wait(&bars->acce[buf], (use - 1) & 1);
+          tc_fence_after();
+          const uint32_t acc_main = tmem_d + buf * 256, acc_cross = acc_main + 128;
+          for (int kt = 0; kt < nkz + nkx; ++kt, ++n_tile) {
+            const int s = n_tile % kStages, it = n_tile / kStages;
+            mbar_wait(&bars->full[s], it & 1);
+            tc_fence_after();
+            const int ks = kt < nkz ? tile_ksteps(a.RH, kt) : tile_ksteps(a.RX, kt - nkz);
+            if (kt == 0) R2_TRACE(12);
+            issue_tile(smem_u32(sm.stages + s * kStageBytes), acc_main, acc_cross, idesc, ks, kt == 0);
+            commit_elect(&bars->empty[s]);
+          }
+          commit_elect(&bars->accf[buf]);
+          R2_TRACE(13);
         }
-        __syncwarp();
       } else {
         const float* hprev = t ? a.y + (size_t)(t - 1) * a.ys_t : a.h0;
         const long long hp_sb = t ? a.ys_b : a.H;
@@ -655,7 +658,7 @@ r2_bwd_kernel(const __grid_constant__ CUtensorMap m_dpre, const __grid_constant_
   extern __shared__ uint8_t smem_raw[];
   const Smem sm = carve(smem_raw);
   Bars* bars = sm.bars;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_index(), lane = threadIdx.x & 31;      // broadcast: role branches are warp-uniform for the compiler
   // per-epilogue-warp transpose tile behind the barriers: accumulator rows (thread = batch row) -> lane = hidden unit, so
   // that every global access of the gate-gradient algebra is one full 128-byte line (32 consecutive units of one row)
   float* const xt = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sm.bars) + 256) + (warp >= 2 ? (warp - 2) * (kXposeBytes / 4) : 0);
@@ -726,48 +729,44 @@ r2_bwd_kernel(const __grid_constant__ CUtensorMap m_dpre, const __grid_constant_
     for (int t = a.T - 1; t >= 0; --t) {
       // ======================================= phase 1 =======================================
       if (warp == 0) {
-        if (lane == 0) {
-          fence_proxy_async_all();
-          for (int c = 0; c < nch1; ++c)
-            for (int ka = 0; ka < KT; ++ka, ++n_tile) {
-              const int k = ka / nkh, kt = ka - k * nkh;
-              const int s = n_tile % kStages, it = n_tile / kStages;
-              if (it > 0) mbar_wait(&bars->empty[s], (it - 1) & 1);
-              uint8_t* st = sm.stages + s * kStageBytes;
+        fence_proxy_async_all();
+        for (int c = 0; c < nch1; ++c)
+          for (int ka = 0; ka < KT; ++ka, ++n_tile) {
+            const int k = ka / nkh, kt = ka - k * nkh;
+            const int s = n_tile % kStages, it = n_tile / kStages;
+            if (it > 0) mbar_wait(&bars->empty[s], (it - 1) & 1);
+            uint8_t* st = sm.stages + s * kStageBytes;
+            if (elect_one()) {
               mbar_arrive_expect_tx(&bars->full[s], kStageBytes);
               tma_load_4d(st, &m_dpre, u0 + kt * BK, k, row0, t, &bars->full[s]);
               tma_load_3d(st + kTile, &m_dpo_lo, u0 + kt * BK, k, row0, &bars->full[s]);
               tma_load_3d(st + 2 * kTile, &m_w2t_hi, u0 + kt * BK, k, c * 128, &bars->full[s]);
               tma_load_3d(st + 3 * kTile, &m_w2t_lo, u0 + kt * BK, k, c * 128, &bars->full[s]);
             }
-        }
-        __syncwarp();
+          }
       } else if (warp == 1) {
-        if (lane == 0) {
-          for (int c = 0; c < nch1; ++c) {
-            const int ncol = min(128, a.KPp - c * 128);
-            const uint32_t idesc = make_idesc(BM, ncol);
-            for (int ks = 0; ks < KSPLIT; ++ks, ++n_chunk) {
-              const int buf = n_chunk & 1, use = n_chunk >> 1;
-              if (use > 0) mbar_wait(&bars->acce[buf], (use - 1) & 1);
+        for (int c = 0; c < nch1; ++c) {
+          const int ncol = min(128, a.KPp - c * 128);
+          const uint32_t idesc = make_idesc(BM, ncol);
+          for (int ks = 0; ks < KSPLIT; ++ks, ++n_chunk) {
+            const int buf = n_chunk & 1, use = n_chunk >> 1;
+            if (use > 0) mbar_wait(&bars->acce[buf], (use - 1) & 1);
+            tc_fence_after();
+            const uint32_t acc_main = tmem_d + buf * 256, acc_cross = acc_main + 128;
+            const int ka0 = ks * kseg, ka1 = min(KT, ka0 + kseg);
+            for (int ka = ka0; ka < ka1; ++ka, ++n_tile) {
+              const int kt = ka % nkh;
+              const int s = n_tile % kStages, it = n_tile / kStages;
+              mbar_wait(&bars->full[s], it & 1);
               tc_fence_after();
-              const uint32_t acc_main = tmem_d + buf * 256, acc_cross = acc_main + 128;
-              const int ka0 = ks * kseg, ka1 = min(KT, ka0 + kseg);
-              for (int ka = ka0; ka < ka1; ++ka, ++n_tile) {
-                const int kt = ka % nkh;
-                const int s = n_tile % kStages, it = n_tile / kStages;
-                mbar_wait(&bars->full[s], it & 1);
-                tc_fence_after();
-                if (ka == ka0) R2_TRACE(10);
-                issue_tile(smem_u32(sm.stages + s * kStageBytes), acc_main, acc_cross, idesc, tile_ksteps(uvalid, kt), ka == ka0);
-                mma_commit(&bars->empty[s]);
-              }
-              mma_commit(&bars->accf[buf]);
-              R2_TRACE(11);
+              if (ka == ka0) R2_TRACE(10);
+              issue_tile(smem_u32(sm.stages + s * kStageBytes), acc_main, acc_cross, idesc, tile_ksteps(uvalid, kt), ka == ka0);
+              commit_elect(&bars->empty[s]);
             }
+            commit_elect(&bars->accf[buf]);
+            R2_TRACE(11);
           }
         }
-        __syncwarp();
       } else {
         for (int c = 0; c < nch1; ++c) {
           const int ncol = min(128, a.KPp - c * 128);
@@ -862,42 +861,38 @@ r2_bwd_kernel(const __grid_constant__ CUtensorMap m_dpre, const __grid_constant_
       }
       // ======================================= phase 2 =======================================
       if (warp == 0) {
-        if (lane == 0) {
-          fence_proxy_async_all();
-          for (int c = 0; c < nch2; ++c)
-            for (int kt = 0; kt < nkz; ++kt, ++n_tile) {
-              const int s = n_tile % kStages, it = n_tile / kStages;
-              if (it > 0) mbar_wait(&bars->empty[s], (it - 1) & 1);
-              uint8_t* st = sm.stages + s * kStageBytes;
+        fence_proxy_async_all();
+        for (int c = 0; c < nch2; ++c)
+          for (int kt = 0; kt < nkz; ++kt, ++n_tile) {
+            const int s = n_tile % kStages, it = n_tile / kStages;
+            if (it > 0) mbar_wait(&bars->empty[s], (it - 1) & 1);
+            uint8_t* st = sm.stages + s * kStageBytes;
+            if (elect_one()) {
               mbar_arrive_expect_tx(&bars->full[s], kStageBytes);
               tma_load_2d(st, &m_dzo_hi, kt * BK, row0, &bars->full[s]);
               tma_load_2d(st + kTile, &m_dzo_lo, kt * BK, row0, &bars->full[s]);
               tma_load_2d(st + 2 * kTile, &m_ap_hi, kt * BK, u0 + c * 128, &bars->full[s]);
               tma_load_2d(st + 3 * kTile, &m_ap_lo, kt * BK, u0 + c * 128, &bars->full[s]);
             }
-        }
-        __syncwarp();
-      } else if (warp == 1) {
-        if (lane == 0) {
-          const uint32_t idesc = make_idesc(BM, 128);
-          for (int c = 0; c < nch2; ++c, ++n_chunk) {
-            const int buf = n_chunk & 1, use = n_chunk >> 1;
-            if (use > 0) mbar_wait(&bars->acce[buf], (use - 1) & 1);
-            tc_fence_after();
-            const uint32_t acc_main = tmem_d + buf * 256, acc_cross = acc_main + 128;
-            for (int kt = 0; kt < nkz; ++kt, ++n_tile) {
-              const int s = n_tile % kStages, it = n_tile / kStages;
-              mbar_wait(&bars->full[s], it & 1);
-              tc_fence_after();
-              if (kt == 0) R2_TRACE(12);
-              issue_tile(smem_u32(sm.stages + s * kStageBytes), acc_main, acc_cross, idesc, tile_ksteps(a.RH, kt), kt == 0);
-              mma_commit(&bars->empty[s]);
-            }
-            mma_commit(&bars->accf[buf]);
-            R2_TRACE(13);
           }
+      } else if (warp == 1) {
+        const uint32_t idesc = make_idesc(BM, 128);
+        for (int c = 0; c < nch2; ++c, ++n_chunk) {
+          const int buf = n_chunk & 1, use = n_chunk >> 1;
+          if (use > 0) mbar_wait(&bars->acce[buf], (use - 1) & 1);
+          tc_fence_after();
+          const uint32_t acc_main = tmem_d + buf * 256, acc_cross = acc_main + 128;
+          for (int kt = 0; kt < nkz; ++kt, ++n_tile) {
+            const int s = n_tile % kStages, it = n_tile / kStages;
+            mbar_wait(&bars->full[s], it & 1);
+            tc_fence_after();
+            if (kt == 0) R2_TRACE(12);
+            issue_tile(smem_u32(sm.stages + s * kStageBytes), acc_main, acc_cross, idesc, tile_ksteps(a.RH, kt), kt == 0);
+            commit_elect(&bars->empty[s]);
+          }
+          commit_elect(&bars->accf[buf]);
+          R2_TRACE(13);
         }
-        __syncwarp();
       } else {
         for (int c = 0; c < nch2; ++c, ++n_chunk) {
           const int buf = n_chunk & 1, use = n_chunk >> 1;

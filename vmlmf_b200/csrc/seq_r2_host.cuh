@@ -50,11 +50,10 @@ namespace vmlmf {
 namespace r3 {
 
 struct Geom {
-  int CS, Hp, zp, zxp, RHr, KZP, nkz, nch, S_fwd, S_bwd, smem_fwd, smem_bwd;
-  long long o_xp, o_hop_hi, o_hop_lo, o_zop_hi, o_zop_lo, o_zpart, o_p_hi, o_p_lo, o_w2_hi, o_w2_lo, o_cbuf, o_sync;
+  int CS, Hp, zp, zxp, RHr, KZP, nkz, nch, S_fwd, G_fwd, S_bwd, G_bwd, smem_fwd, smem_bwd;
+  long long o_xp, o_hop, o_zop, o_zpart, o_p_hi, o_p_lo, o_w2_hi, o_w2_lo, o_cbuf, o_sync;
   long long fwd_floats;
-  long long b_dpre, b_dz, b_dzx, b_dpo_hi, b_dpo_lo, b_dzo_hi, b_dzo_lo, b_dhrun, b_dcrun, b_part, b_w2t_hi, b_w2t_lo,
-      b_ap_hi, b_ap_lo, b_vxt, b_sync;
+  long long b_dpre, b_dz, b_dzx, b_dpo, b_dzo, b_dhrun, b_dcrun, b_part, b_w2t_hi, b_w2t_lo, b_ap_hi, b_ap_lo, b_vxt, b_sync;
   long long bwd_floats;      // recurrence part; the time-parallel GEMMs' scratch follows it
 };
 Geom geom(int T, int B, int I, int H, int RX, int RH);

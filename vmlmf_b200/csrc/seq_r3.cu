@@ -67,15 +67,15 @@ __global__ void pack3_bwd_kernel(const float* __restrict__ A, const float* __res
     }
   }
 }
-// hop[b, j] = h0[b, j] (0 when h0 is null or j >= H), as tf32 hi / lo
-__global__ void prep3_state_kernel(const float* __restrict__ h0, float* __restrict__ hop_hi, float* __restrict__ hop_lo,
-                                   int B, int H, int Hp) {
-  const long long n = (long long)B * Hp;
+// hop tile of CTA j / 8 (tile-major, zeroed before): [hi | lo][row b][column j % 8] = h0[b, j]
+__global__ void prep3_state_kernel(const float* __restrict__ h0, float* __restrict__ hop, int B, int H) {
+  const long long n = (long long)B * H;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const int b = (int)(i / Hp), j = (int)(i % Hp);
-    const float v = (h0 && j < H) ? h0[(size_t)b * H + j] : 0.f;
-    hop_hi[i] = split_hi(v);
-    hop_lo[i] = split_lo(v, v);
+    const int b = (int)(i / H), j = (int)(i % H);
+    const float v = h0[i];
+    float* t = hop + (size_t)(j >> 3) * kTileFloats + b * 32 + (j & 7);
+    t[0] = split_hi(v);
+    t[1024] = split_lo(v, v);
   }
 }
 // vxt[r, k*G + j] = Vx[kH + j, r]  (zero for j >= H): the B operand of dzx = dPre Vx with dPre in its gate-padded layout
@@ -134,27 +134,29 @@ Geom geom(int T, int B, int I, int H, int RX, int RH) {
   g.KZP = round_up(RH, 32);
   g.nkz = ceil_div(RH, BK);
   g.nch = ceil_div(g.RHr, 128);
-  // shared memory: stationary factor rows + as many 8 KB activation stages as still fit (the per-step loads are latency
-  // bound: the deeper the ring, the fewer round trips)
+  // shared memory: stationary factor rows + an activation ring of S stages of G K tiles (8 KB each); one TMA box and one
+  // barrier per stage, so the bigger the stage the fewer barrier round trips of the issuing thread
   const int stat_f = 2 * kPTile + g.nkz * kAStage;
   const int stat_b = g.nch * 2 * kPTile + g.nkz * 2 * kApTile;
-  auto stages = [](int stat) {
-    int s = (kSmemMax - kBarBytes - kXbufBytes - stat) / kAStage;
-    return s > kMaxStages ? kMaxStages : s;
+  auto ring = [&](int stat, int* S, int* G) {
+    const int room = kSmemMax - kBarBytes - kXbufBytes - stat;
+    for (int gg = 4; gg >= 1; gg >>= 1) {
+      int ss = room / (gg * kAStage);
+      if (ss > kMaxStages) ss = kMaxStages;
+      const int need = ceil_div(g.nkz, gg) + 1;            // every stage of a step resident at once is as deep as it gets
+      if (ss > need) ss = need;
+      if (ss >= 2 || gg == 1) { *S = ss; *G = gg; return; }
+    }
   };
-  g.S_fwd = stages(stat_f);
-  g.S_bwd = stages(stat_b);
-  if (g.S_fwd > g.nkz + 1) g.S_fwd = g.nkz + 1;
-  if (g.S_bwd > g.nkz + 1) g.S_bwd = g.nkz + 1;
-  g.smem_fwd = g.S_fwd * kAStage + stat_f + kBarBytes + kXbufBytes + 1024;
-  g.smem_bwd = g.S_bwd * kAStage + stat_b + kBarBytes + kXbufBytes + 1024;
+  ring(stat_f, &g.S_fwd, &g.G_fwd);
+  ring(stat_b, &g.S_bwd, &g.G_bwd);
+  g.smem_fwd = g.S_fwd * g.G_fwd * kAStage + stat_f + kBarBytes + kXbufBytes + 1024;
+  g.smem_bwd = g.S_bwd * g.G_bwd * kAStage + stat_b + kBarBytes + kXbufBytes + 1024;
   long long o = 0;
   g.o_xp = o; o += al64((long long)T * B * 4 * H);
-  g.o_hop_hi = o; o += al64((long long)B * g.Hp);
-  g.o_hop_lo = o; o += al64((long long)B * g.Hp);
-  g.o_zop_hi = o; o += al64((long long)B * g.zp);
-  g.o_zop_lo = o; o += al64((long long)B * g.zp);
-  g.o_zpart = o; o += al64(2LL * g.CS * RB * g.zp);      // hi*hi + hi*lo and lo*hi partials per CTA
+  g.o_hop = o; o += al64((long long)g.CS * kTileFloats);
+  g.o_zop = o; o += al64((long long)g.nkz * kTileFloats);
+  g.o_zpart = o; o += al64((long long)g.CS * RB * g.zp);
   g.o_p_hi = o; o += al64((long long)g.CS * 128 * 32);
   g.o_p_lo = o; o += al64((long long)g.CS * 128 * 32);
   g.o_w2_hi = o; o += al64((long long)g.CS * 32 * g.KZP);
@@ -166,13 +168,11 @@ Geom geom(int T, int B, int I, int H, int RX, int RH) {
   g.b_dpre = o; o += al64((long long)T * B * 4 * g.Hp);
   g.b_dz = o; o += al64((long long)T * B * g.zp);
   g.b_dzx = o; o += al64((long long)T * B * g.zxp);
-  g.b_dpo_hi = o; o += al64((long long)B * 4 * g.Hp);
-  g.b_dpo_lo = o; o += al64((long long)B * 4 * g.Hp);
-  g.b_dzo_hi = o; o += al64((long long)B * g.zp);
-  g.b_dzo_lo = o; o += al64((long long)B * g.zp);
+  g.b_dpo = o; o += al64((long long)g.CS * kTileFloats);
+  g.b_dzo = o; o += al64((long long)g.nkz * kTileFloats);
   g.b_dhrun = o; o += al64((long long)B * g.Hp);
   g.b_dcrun = o; o += al64((long long)B * g.Hp);
-  g.b_part = o; o += al64(2LL * g.CS * RB * g.zp);
+  g.b_part = o; o += al64((long long)g.CS * RB * g.zp);
   g.b_w2t_hi = o; o += al64((long long)g.KZP * 4 * g.Hp);
   g.b_w2t_lo = o; o += al64((long long)g.KZP * 4 * g.Hp);
   g.b_ap_hi = o; o += al64((long long)g.Hp * g.KZP);
@@ -197,45 +197,45 @@ bool fits(int T, int B, int I, int H, int RX, int RH) {
 int launch_fwd(const FwdCall& c, void* workspace, cudaStream_t st) {
   const Geom g = geom(c.T, c.B, c.I, c.H, c.RX, c.RH);
   float* ws = ws_base(workspace);
-  float *hop_hi = ws + g.o_hop_hi, *hop_lo = ws + g.o_hop_lo, *zop_hi = ws + g.o_zop_hi, *zop_lo = ws + g.o_zop_lo;
+  float *hop = ws + g.o_hop, *zop = ws + g.o_zop;
   float *p_hi = ws + g.o_p_hi, *p_lo = ws + g.o_p_lo, *w2_hi = ws + g.o_w2_hi, *w2_lo = ws + g.o_w2_lo;
   const bool save = c.gates != nullptr;
+  // rows >= B, pad columns and pad units of the operand tiles are never written by the kernel: zero them once (hop and zop are adjacent)
+  cudaError_t me = cudaMemsetAsync(hop, 0, (size_t)(g.o_zpart - g.o_hop) * sizeof(float), st);
+  if (me != cudaSuccess) return (int)me;
   pack3_fwd_kernel<<<ew_grid((long long)g.CS * 128 * 32 + (long long)g.CS * 32 * g.KZP), 256, 0, st>>>(
       c.A, c.Bm, p_hi, p_lo, w2_hi, w2_lo, c.H, c.RH, g.CS, g.KZP);
-  prep3_state_kernel<<<ew_grid((long long)c.B * g.Hp), 256, 0, st>>>(c.h0, hop_hi, hop_lo, c.B, c.H, g.Hp);
+  if (c.h0) prep3_state_kernel<<<ew_grid((long long)c.B * c.H), 256, 0, st>>>(c.h0, hop, c.B, c.H);
   int rc = (int)cudaGetLastError();
   if (rc) return rc;
-  CUtensorMap m_hop_hi, m_hop_lo, m_p_hi, m_p_lo, m_zop_hi, m_zop_lo, m_w2_hi, m_w2_lo;
-  if (map2(&m_hop_hi, hop_hi, g.Hp, c.B, g.Hp, RB) || map2(&m_hop_lo, hop_lo, g.Hp, c.B, g.Hp, RB) ||
+  CUtensorMap m_hop, m_zop, m_p_hi, m_p_lo, m_w2_hi, m_w2_lo;
+  if (map2(&m_hop, hop, 32, (long long)g.CS * 64, 32, 64) || map2(&m_zop, zop, 32, (long long)g.nkz * 64, 32, 64 * g.G_fwd) ||
       map2(&m_p_hi, p_hi, 32, (long long)g.CS * 128, 32, BM) || map2(&m_p_lo, p_lo, 32, (long long)g.CS * 128, 32, BM) ||
-      map2(&m_zop_hi, zop_hi, g.zp, c.B, g.zp, RB) || map2(&m_zop_lo, zop_lo, g.zp, c.B, g.zp, RB) ||
       map2(&m_w2_hi, w2_hi, g.KZP, (long long)g.CS * 32, g.KZP, 32) || map2(&m_w2_lo, w2_lo, g.KZP, (long long)g.CS * 32, g.KZP, 32))
     return VMLMF_EUNSUPPORTED;
   FwdArgs3 a;
   a.xp = c.xp; a.Dh = c.Dh; a.h0 = c.h0; a.c0 = c.c0;
   a.y = c.y; a.ys_t = c.ys_t; a.ys_b = c.ys_b; a.hT = c.hT; a.cT = c.cT;
   a.gates = c.gates; a.cs = save ? c.cs : ws + g.o_cbuf; a.z = c.z;
-  a.hop_hi = hop_hi; a.hop_lo = hop_lo; a.zop_hi = zop_hi; a.zop_lo = zop_lo; a.zpart = ws + g.o_zpart;
+  a.hop = hop; a.zop = zop; a.zpart = ws + g.o_zpart;
   a.sync = reinterpret_cast<unsigned int*>(ws + g.o_sync);
   a.T = c.T; a.B = c.B; a.H = c.H; a.RH = c.RH;
-  a.Hp = g.Hp; a.CS = g.CS; a.zp = g.zp; a.S = g.S_fwd;
-  cudaError_t me = cudaMemsetAsync(a.sync, 0, 32 * sizeof(unsigned int), st);
+  a.CS = g.CS; a.zp = g.zp; a.S = g.S_fwd; a.G = g.G_fwd;
+  me = cudaMemsetAsync(a.sync, 0, 32 * sizeof(unsigned int), st);
   if (me != cudaSuccess) return (int)me;
   if (save)
-    return launch_coop(r3_fwd_kernel<true>, g.CS, g.smem_fwd, st, m_hop_hi, m_hop_lo, m_p_hi, m_p_lo, m_zop_hi, m_zop_lo,
-                       m_w2_hi, m_w2_lo, a);
-  return launch_coop(r3_fwd_kernel<false>, g.CS, g.smem_fwd, st, m_hop_hi, m_hop_lo, m_p_hi, m_p_lo, m_zop_hi, m_zop_lo,
-                     m_w2_hi, m_w2_lo, a);
+    return launch_coop(r3_fwd_kernel<true>, g.CS, g.smem_fwd, st, m_hop, m_zop, m_p_hi, m_p_lo, m_w2_hi, m_w2_lo, a);
+  return launch_coop(r3_fwd_kernel<false>, g.CS, g.smem_fwd, st, m_hop, m_zop, m_p_hi, m_p_lo, m_w2_hi, m_w2_lo, a);
 }
 
 int launch_bwd(const BwdCall& c, void* workspace, BwdOut* out, cudaStream_t st) {
   const Geom g = geom(c.T, c.B, c.I, c.H, c.RX, c.RH);
   float* ws = ws_base(workspace);
-  float *dpre = ws + g.b_dpre, *dpo_hi = ws + g.b_dpo_hi, *dpo_lo = ws + g.b_dpo_lo, *dzo_hi = ws + g.b_dzo_hi, *dzo_lo = ws + g.b_dzo_lo;
+  float *dpre = ws + g.b_dpre, *dpo = ws + g.b_dpo, *dzo = ws + g.b_dzo;
   float *w2t_hi = ws + g.b_w2t_hi, *w2t_lo = ws + g.b_w2t_lo, *ap_hi = ws + g.b_ap_hi, *ap_lo = ws + g.b_ap_lo;
-  // pad units (H <= j < Hp) are never written by the kernel but are read as operands (against zero weights) and by the
-  // time-parallel GEMMs: they must hold zeros
-  cudaError_t e = cudaMemsetAsync(dpo_hi, 0, 2 * (size_t)al64((long long)c.B * 4 * g.Hp) * sizeof(float), st);
+  // rows >= B / pad columns / pad units of the operand tiles and the pad units of dPre (read by the time-parallel GEMMs) are
+  // never written by the kernel: they must hold zeros (dpo and dzo are adjacent)
+  cudaError_t e = cudaMemsetAsync(dpo, 0, (size_t)(g.b_dhrun - g.b_dpo) * sizeof(float), st);
   if (e != cudaSuccess) return (int)e;
   if (g.Hp > c.H) {
     e = cudaMemset2DAsync(dpre + c.H, (size_t)g.Hp * sizeof(float), 0, (size_t)(g.Hp - c.H) * sizeof(float),
@@ -246,27 +246,25 @@ int launch_bwd(const BwdCall& c, void* workspace, BwdOut* out, cudaStream_t st) 
       c.A, c.Bm, w2t_hi, w2t_lo, ap_hi, ap_lo, c.H, c.RH, g.Hp, g.KZP);
   int rc = (int)cudaGetLastError();
   if (rc) return rc;
-  CUtensorMap m_dpo_hi, m_dpo_lo, m_w2t_hi, m_w2t_lo, m_dzo_hi, m_dzo_lo, m_ap_hi, m_ap_lo;
-  if (map2(&m_dpo_hi, dpo_hi, 4LL * g.Hp, c.B, 4LL * g.Hp, RB) || map2(&m_dpo_lo, dpo_lo, 4LL * g.Hp, c.B, 4LL * g.Hp, RB) ||
+  CUtensorMap m_dpo, m_dzo, m_w2t_hi, m_w2t_lo, m_ap_hi, m_ap_lo;
+  if (map2(&m_dpo, dpo, 32, (long long)g.CS * 64, 32, 64) || map2(&m_dzo, dzo, 32, (long long)g.nkz * 64, 32, 64 * g.G_bwd) ||
       map2(&m_w2t_hi, w2t_hi, 4LL * g.Hp, g.KZP, 4LL * g.Hp, BM) || map2(&m_w2t_lo, w2t_lo, 4LL * g.Hp, g.KZP, 4LL * g.Hp, BM) ||
-      map2(&m_dzo_hi, dzo_hi, g.zp, c.B, g.zp, RB) || map2(&m_dzo_lo, dzo_lo, g.zp, c.B, g.zp, RB) ||
       map2(&m_ap_hi, ap_hi, g.KZP, g.Hp, g.KZP, 16) || map2(&m_ap_lo, ap_lo, g.KZP, g.Hp, g.KZP, 16))
     return VMLMF_EUNSUPPORTED;
   BwdArgs3 a;
   a.gates = c.gates; a.cs = c.cs; a.c0 = c.c0; a.dy = c.dy; a.dys_t = c.dys_t; a.dys_b = c.dys_b;
   a.dhT = c.dhT; a.dcT = c.dcT; a.Dh = c.Dh; a.dh0 = c.dh0; a.dc0 = c.dc0;
-  a.dpre = dpre; a.dz_all = ws + g.b_dz; a.dpo_hi = dpo_hi; a.dpo_lo = dpo_lo; a.dzo_hi = dzo_hi; a.dzo_lo = dzo_lo;
+  a.dpre = dpre; a.dz_all = ws + g.b_dz; a.dpo = dpo; a.dzo = dzo;
   a.dhrun = ws + g.b_dhrun; a.dcrun = ws + g.b_dcrun; a.part = ws + g.b_part;
   a.sync = reinterpret_cast<unsigned int*>(ws + g.b_sync);
   a.T = c.T; a.B = c.B; a.H = c.H; a.RH = c.RH;
-  a.Hp = g.Hp; a.CS = g.CS; a.zp = g.zp; a.S = g.S_bwd;
+  a.Hp = g.Hp; a.CS = g.CS; a.zp = g.zp; a.S = g.S_bwd; a.G = g.G_bwd;
   float* vxt = ws + g.b_vxt;
   vxt_pad_kernel<<<ew_grid((long long)c.RX * 4 * g.Hp), 256, 0, st>>>(c.Vx, vxt, c.H, g.Hp, c.RX);
   out->dpre = dpre; out->G = g.Hp; out->dz = a.dz_all; out->dzx = ws + g.b_dzx; out->vxt = vxt; out->after = ws + g.bwd_floats;
   e = cudaMemsetAsync(a.sync, 0, 32 * sizeof(unsigned int), st);
   if (e != cudaSuccess) return (int)e;
-  return launch_coop(r3_bwd_kernel, g.CS, g.smem_bwd, st, m_dpo_hi, m_dpo_lo, m_w2t_hi, m_w2t_lo, m_dzo_hi, m_dzo_lo, m_ap_hi,
-                     m_ap_lo, a);
+  return launch_coop(r3_bwd_kernel, g.CS, g.smem_bwd, st, m_dpo, m_dzo, m_w2t_hi, m_w2t_lo, m_ap_hi, m_ap_lo, a);
 }
 
 }  // namespace r3

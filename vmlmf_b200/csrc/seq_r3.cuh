@@ -46,12 +46,13 @@ using namespace r2;
 constexpr int UB = 8;                        // hidden units per CTA
 constexpr int RB = 32;                       // batch rows (one tensor-memory lane quarter, one TMA box)
 constexpr int kATile = RB * BK * 4;          // 4 KB: [32 rows x 32 fp32] activation tile (hi or lo)
-constexpr int kAStage = 2 * kATile;          // hi | lo
+constexpr int kAStage = 2 * kATile;          // one K tile of an activation: hi | lo
+constexpr int kTileFloats = kAStage / 4;     // 2048
 constexpr int kPTile = BM * BK * 4;          // 16 KB: [128 rows x 32 fp32] weight tile
 constexpr int kApTile = 16 * BK * 4;         // 2 KB: [16 rows x 32 fp32] (phase 2 B operand: 8 units + 8 spare rows)
-constexpr int kMaxStages = 16;
+constexpr int kMaxStages = 4;
 constexpr int kBarBytes = 512;
-constexpr int kXbufBytes = 32 * 32 * 4;        // cross-term hand-over between the two epilogue lane quarters (pointwise phases)
+constexpr int kXbufBytes = 4 * 32 * 32 * 4;  // lo*hi hand-over between the lane quarters: 2 warp pairs x 2 buffers x [32 x 32] fp32
 constexpr int kSmemMax = 232448 - 1024;      // 227 KB minus the alignment slack
 
 struct Bars3 {
@@ -64,8 +65,14 @@ struct Bars3 {
 };
 static_assert(sizeof(Bars3) <= kBarBytes, "barrier block");
 
-// position of (gate k, unit j) inside a row of the slice-major operand buffers: CTA s = j / 8 owns 32 consecutive floats
-__host__ __device__ __forceinline__ int slice_col(int k, int j) { return (j >> 3) * 32 + k * 8 + (j & 7); }
+// Activations that feed the tensor core live in global memory TILE-MAJOR: [K tile][hi | lo][32 rows][32 fp32] -- exactly the
+// bytes of the shared-memory stage, so that ONE TMA box (32 columns x 64 * G rows of a [tiles * 64, 32] view) brings G K tiles
+// with one barrier.  (A barrier wait + tcgen05 fence + commit costs ~250 cycles of the single issuing thread per use, an MMA
+// ~50: tools/ubench_mma.cu.  Per-K-tile barriers made the MMA phases 3x longer than their instructions.)
+// element (plane p, row r, column c) of a row-major [32, K] activation:
+__host__ __device__ __forceinline__ size_t tile_off(int p, int r, int c) { return ((size_t)(c >> 5) * 2 + p) * 1024 + r * 32 + (c & 31); }
+// (gate k, unit j) inside the K = 32 slice of CTA j / 8 (phase 1 A operand; slice-major weight rows use the same order)
+__host__ __device__ __forceinline__ int slice_col(int k, int j) { return k * 8 + (j & 7); }
 
 // Fixed-order sum of the NP partial copies of a [rows, 4 * w4] matrix (partial q at part + q * RB * pitch).  Output element e
 // (one float4) belongs to CTA e / epc; inside the CTA eight adjacent lanes share one output, lane pg adding the partials
@@ -89,12 +96,12 @@ __device__ __forceinline__ void reduce_partials(const float* part, int NP, int C
       r = e / w4;
       c4 = e - r * w4;
       const float4* src = reinterpret_cast<const float4*>(part + (size_t)r * pitch) + c4;
-      for (int q = pg; q < NP; q += 192) {
-        float4 pv[24];
+      for (int q = pg; q < NP; q += 96) {
+        float4 pv[12];
 #pragma unroll
-        for (int i = 0; i < 24; ++i) pv[i] = q + 8 * i < NP ? __ldcg(src + (size_t)(q + 8 * i) * qstride4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < 12; ++i) pv[i] = q + 8 * i < NP ? __ldcg(src + (size_t)(q + 8 * i) * qstride4) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int i = 0; i < 24; ++i) { acc.x += pv[i].x; acc.y += pv[i].y; acc.z += pv[i].z; acc.w += pv[i].w; }
+        for (int i = 0; i < 12; ++i) { acc.x += pv[i].x; acc.y += pv[i].y; acc.z += pv[i].z; acc.w += pv[i].w; }
       }
     }
     tr(33);
@@ -105,17 +112,15 @@ __device__ __forceinline__ void reduce_partials(const float* part, int NP, int C
       acc.z += __shfl_xor_sync(0xffffffffu, acc.z, d);
       acc.w += __shfl_xor_sync(0xffffffffu, acc.w, d);
     }
-    tr(34);
     if (on && pg == 0) store(r, c4 * 4, acc);
-    tr(35);
   }
 }
-__device__ __forceinline__ void store_split4(float* hi_p, float* lo_p, const float4 v) {
-  float4 hi, lo;
-  hi.x = split_hi(v.x); hi.y = split_hi(v.y); hi.z = split_hi(v.z); hi.w = split_hi(v.w);
-  lo.x = split_lo(v.x, hi.x); lo.y = split_lo(v.y, hi.y); lo.z = split_lo(v.z, hi.z); lo.w = split_lo(v.w, hi.w);
-  *reinterpret_cast<float4*>(hi_p) = hi;
-  *reinterpret_cast<float4*>(lo_p) = lo;
+// v and its tf32 lo part into the tile-major operand buffer (4 consecutive columns never straddle a tile: c % 4 == 0)
+__device__ __forceinline__ void store_split4(float* op, int r, int c, const float4 v) {
+  float4 lo;
+  lo.x = split_lo(v.x, v.x); lo.y = split_lo(v.y, v.y); lo.z = split_lo(v.z, v.z); lo.w = split_lo(v.w, v.w);
+  *reinterpret_cast<float4*>(op + tile_off(0, r, c)) = v;           // the tensor core truncates: the value is its own hi part
+  *reinterpret_cast<float4*>(op + tile_off(1, r, c)) = lo;
 }
 // 32 lanes x 32 consecutive fp32 columns of the accumulator -> 32 registers per thread
 __device__ __forceinline__ void tmem_ld32_raw(uint32_t taddr, float (&v)[32]) {
@@ -125,52 +130,79 @@ __device__ __forceinline__ void tmem_ld32_raw(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) { v[i] = g0[i]; v[8 + i] = g1[i]; v[16 + i] = g2[i]; v[24 + i] = g3[i]; }
 }
+// The producer and the MMA warp run their loops with all 32 lanes (warp-uniform control flow, warp-uniform operands) and
+// elect one lane right at each asynchronous instruction.  Inside an `if (lane == 0)` region the compiler keeps descriptors
+// and addresses in per-thread registers and wraps EVERY tcgen05.mma / TMA in an elect + five R2UR.BROADCAST + loop sequence
+// (~135 cycles per MMA measured, against ~45 for the uniform form: tools/ubench_mma.cu).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void mma_elect(uint32_t acc, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  if (elect_one()) mma_tf32_ss(acc, da, db, idesc, accumulate);
+}
+__device__ __forceinline__ void commit_elect(uint64_t* bar) {
+  if (elect_one()) mma_commit(bar);
+}
 // ONE MMA per tf32 k-step computes all three 3xTF32 products.  The batch fills 32 of the 128 accumulator rows and every operand
 // lives in shared memory as a hi tile directly followed by its lo tile, so
 //   * the A descriptor at the hi tile makes rows 0..31 = a_hi and rows 32..63 = a_lo (rows 64..127: don't care);
 //   * the B descriptor at the hi tile with N doubled makes columns [0, n) = b_hi and [NB, NB + n) = b_lo (NB = rows of the hi tile).
 // Accumulator: lanes 0..31 x [0, n) = hi*hi, lanes 0..31 x [NB, NB+n) = hi*lo, lanes 32..63 x [0, n) = lo*hi (lo*lo is computed
 // and ignored).  The three terms stay in separate accumulator cells as before (the tensor core's accumulate truncates: the
-// small terms must not ride on the large sum).  A tf32 MMA with a 128-row shared-memory A operand costs ~110 cycles whatever
-// N is (measured: the same per-instruction time at N = 32 and N = 128), so this is a 3x cut of the tensor time of a step.
+// small terms must not ride on the large sum).
 __device__ __forceinline__ void issue_ktile(uint32_t a_addr, uint32_t b_addr, uint32_t acc, uint32_t idesc, int ksteps, bool first) {
   const uint64_t da = make_desc(a_addr), db = make_desc(b_addr);
+  if (elect_one()) {                                         // one election per K tile: elect.sync itself is ~25 cycles
 #pragma unroll
-  for (int k = 0; k < 4; ++k)
-    if (k < ksteps) mma_tf32_ss(acc, da + 2 * k, db + 2 * k, idesc, (first && k == 0) ? 0u : 1u);
+    for (int k = 0; k < 4; ++k)
+      if (k < ksteps) mma_tf32_ss(acc, da + 2 * k, db + 2 * k, idesc, (first && k == 0) ? 0u : 1u);
+  }
 }
-// The long contractions (K = RH: phase G, phase 2) are a chain of MMAs into one accumulator, and a dependent tf32 MMA issues only
-// every ~190 cycles (measured; the math of a 128 x 64 x 8 tile is ~30).  K-step k of every K tile therefore goes to its own
-// accumulator (column offset k * nw): four independent chains, summed by the epilogue.
+// K-step k of every K tile of the long contractions (K = RH) goes to its own accumulator (column offset k * nw): four
+// independent chains, summed by the epilogue.
 __device__ __forceinline__ void issue_ktile_split(uint32_t a_addr, uint32_t b_addr, uint32_t acc, uint32_t nw, uint32_t idesc,
                                                   int ksteps, bool first) {
   const uint64_t da = make_desc(a_addr), db = make_desc(b_addr);
+  if (elect_one()) {
+    if (ksteps == 4) {                                       // every tile but the last: straight-line
 #pragma unroll
-  for (int k = 0; k < 4; ++k)
-    if (k < ksteps) mma_tf32_ss(acc + k * nw, da + 2 * k, db + 2 * k, idesc, first ? 0u : 1u);
-}
-// accumulator chunk -> row-major partial buffer without a transpose: tcgen05.ld hands lane r the row r, 32 consecutive
-// columns; each lane stores its own 128 bytes (eight float4).  Twice the store sectors of a transposed write, a fifth of
-// the instructions -- the epilogue of a 20-row batch is latency, not bandwidth.
-__device__ __forceinline__ void store_partial_rows(uint32_t t_main, int cb, float* row_ptr, int c0, int zp, bool row_ok) {
-  float v[32];
-  tmem_ld_groups(t_main, t_main + 128, cb, cb + 8, cb + 16, cb + 24, v);      // hi*hi + hi*lo
-  if (row_ok) {
+      for (int k = 0; k < 4; ++k) mma_tf32_ss(acc + k * nw, da + 2 * k, db + 2 * k, idesc, first ? 0u : 1u);
+    } else {
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-      if (c0 + 4 * i < zp)
-        *reinterpret_cast<float4*>(row_ptr + c0 + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      for (int k = 0; k < 3; ++k)
+        if (k < ksteps) mma_tf32_ss(acc + k * nw, da + 2 * k, db + 2 * k, idesc, first ? 0u : 1u);
+    }
   }
 }
-// the lo*hi term of the same chunk: accumulator lanes 32..63 (read by a warp of lane quarter 1), stored as a partial of its own
-__device__ __forceinline__ void store_cross_rows(uint32_t t_q1, int cb, float* row_ptr, int c0, int zp, bool row_ok) {
-  float v[32];
-  tmem_ld32_raw(t_q1 + cb, v);
-  if (row_ok) {
+// One 32-column pass of a partial-product chunk.  Lane quarter 0 (warps 4, 8) holds hi*hi + hi*lo of row `lane`, lane quarter 1
+// (warps 5, 9) the lo*hi term of the same row: the quarter-1 warp hands its 32 values over through shared memory ([column][row]:
+// conflict free both ways, two buffers alternate so that one named barrier per pass is enough) and the quarter-0 warp stores
+// the finished partial row -- 128 contiguous bytes per lane, no transpose: the epilogue of a 20-row batch is latency, not
+// bandwidth.
+__device__ __forceinline__ void partial_pass(uint32_t t_main, int cb, int eq, int pair, int& xph, float* xbuf, int lane,
+                                             float* row_ptr, int c0, int zp, bool row_ok) {
+  float* xb = xbuf + (pair * 2 + (xph & 1)) * 1024;
+  ++xph;
+  if (eq == 1) {
+    float v[32];
+    tmem_ld32_raw(t_main + (32u << 16) + cb, v);
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-      if (c0 + 4 * i < zp)
-        *reinterpret_cast<float4*>(row_ptr + c0 + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    for (int i = 0; i < 32; ++i) xb[i * 32 + lane] = v[i];
+    if (pair == 0) asm volatile("bar.sync 1, 64;" ::: "memory"); else asm volatile("bar.sync 2, 64;" ::: "memory");
+  } else {
+    float v[32];
+    tmem_ld_groups(t_main, t_main + 128, cb, cb + 8, cb + 16, cb + 24, v);      // hi*hi + hi*lo
+    if (pair == 0) asm volatile("bar.sync 1, 64;" ::: "memory"); else asm volatile("bar.sync 2, 64;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] += xb[i * 32 + lane];
+    if (row_ok) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (c0 + 4 * i < zp)
+          *reinterpret_cast<float4*>(row_ptr + c0 + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    }
   }
 }
 __device__ __forceinline__ void init_common(Bars3* bars, int S, int warp) {
@@ -198,31 +230,33 @@ struct FwdArgs3 {
   float* gates;               // [T,B,4,H] or null (inference)
   float* cs;                  // [T,B,H] when saving, else a [2,B,H] ping-pong scratch
   float* z;                   // [T*B, zp] saved z (null in inference)
-  float *hop_hi, *hop_lo;     // [B, Hp]
-  float *zop_hi, *zop_lo;     // [B, zp]
+  float* hop;                 // [CS][hi | lo][32][32] tile-major: CTA s's units in columns 0..7 of its tile
+  float* zop;                 // [nkz][hi | lo][32][32] tile-major z_t
   float* zpart;               // [CS, 32, zp]
   unsigned int* sync;         // group barrier counter (one 128-byte line), zeroed before the launch
   int T, B, H, RH;
-  int Hp, CS, zp, S;          // S = activation ring stages
+  int CS, zp, S, G;           // S = activation ring stages of G K tiles each
 };
 
 template <bool SAVE>
 __global__ void __launch_bounds__(kThreads, 1)
-r3_fwd_kernel(const __grid_constant__ CUtensorMap m_hop_hi, const __grid_constant__ CUtensorMap m_hop_lo,
+r3_fwd_kernel(const __grid_constant__ CUtensorMap m_hop, const __grid_constant__ CUtensorMap m_zop,
               const __grid_constant__ CUtensorMap m_p_hi, const __grid_constant__ CUtensorMap m_p_lo,
-              const __grid_constant__ CUtensorMap m_zop_hi, const __grid_constant__ CUtensorMap m_zop_lo,
               const __grid_constant__ CUtensorMap m_w2_hi, const __grid_constant__ CUtensorMap m_w2_lo, const FwdArgs3 a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* const base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int S = a.S, CS = a.CS;
+  // the warp index through a broadcast: the compiler then knows the role branches are warp-uniform (uniform registers inside)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const int S = a.S, CS = a.CS, G = a.G;
+  const int stage_bytes = G * kAStage;
   const int RHr = (a.RH + 7) & ~7;
   const int nzc = (RHr + 127) / 128;                         // phase Z chunks (128 z columns each; <= 4: one k-step slot each)
-  const int nkz = (a.RH + BK - 1) / BK;
-  const int nacc = min(4, (a.RH + 7) / 8);                   // independent accumulation chains of the K = RH phases                      // phase G K tiles
-  // shared memory: activation ring | phase Z weights (hi, lo) | phase G weights (nkz x (hi | lo)) | barriers
+  const int nkz = (a.RH + BK - 1) / BK;                      // phase G K tiles
+  const int ngr = (nkz + G - 1) / G;                         // ... in groups of G per stage
+  const int nacc = min(4, (a.RH + 7) / 8);                   // independent accumulation chains of phase G
+  // shared memory: activation ring | phase Z weights (hi, lo) | phase G weights (nkz x (hi | lo)) | barriers | hand-over buffers
   uint8_t* const ring = base;
-  uint8_t* const p_hi = base + S * kAStage;
+  uint8_t* const p_hi = base + S * stage_bytes;
   uint8_t* const p_lo = p_hi + kPTile;
   uint8_t* const w2s = p_lo + kPTile;
   Bars3* const bars = reinterpret_cast<Bars3*>(w2s + nkz * kAStage);
@@ -247,46 +281,42 @@ r3_fwd_kernel(const __grid_constant__ CUtensorMap m_hop_hi, const __grid_constan
   const int eq = warp & 3, ehalf = (warp - 2) >> 2;          // epilogue: tensor-memory lane quarter, column half
   const bool epi = warp >= 2 && eq <= 1;                     // warps 4, 8: accumulator lanes 0..31 (hi rows); 5, 9: lanes 32..63 (lo rows)
   const int rl = lane & 3, c8 = lane >> 2;
-  uint32_t n_tile = 0, n_chunk = 0;
+  uint32_t n_stage = 0, n_chunk = 0;
   bool wready = false;
+  int xph = 0;
   int trc = 0;
   (void)trc;
 
   for (int t = 0; t < a.T; ++t) {
     // ======================================= phase Z =======================================
     if (warp == 0) {
-      if (lane == 0) {
-        fence_proxy_async_all();
-        R3_TRACE(1);
-        const int s = n_tile % S, it = n_tile / S;
-        if (it > 0) mbar_wait(&bars->empty[s], (it - 1) & 1);
+      fence_proxy_async_all();
+      R3_TRACE(1);
+      const int s = n_stage % S, it = n_stage / S;
+      if (it > 0) mbar_wait(&bars->empty[s], (it - 1) & 1);
+      if (elect_one()) {
         mbar_arrive_expect_tx(&bars->full[s], kAStage);
-        tma_load_2d(ring + s * kAStage, &m_hop_hi, u0, 0, &bars->full[s]);
-        tma_load_2d(ring + s * kAStage + kATile, &m_hop_lo, u0, 0, &bars->full[s]);
-        ++n_tile;
+        tma_load_2d(ring + s * stage_bytes, &m_hop, 0, s_rank * 64, &bars->full[s]);
       }
-      __syncwarp();
+      ++n_stage;
     } else if (warp == 1) {
-      if (lane == 0) {
-        if (!wready) { mbar_wait(&bars->wbar, 0); wready = true; }
-        const int s = n_tile % S, it = n_tile / S;
-        const uint32_t a_addr = smem_u32(ring + s * kAStage), p_addr = smem_u32(p_hi);
-        for (int zc = 0; zc < nzc; ++zc, ++n_chunk) {
-          const int buf = n_chunk & 1, use = n_chunk >> 1;
-          if (use > 0) mbar_wait(&bars->acce[buf], (use - 1) & 1);
-          if (zc == 0) { mbar_wait(&bars->full[s], it & 1); R3_TRACE(10); }
-          tc_fence_after();
-          const int ncol = min(128, RHr - zc * 128);
-          const uint32_t idesc = make_idesc(BM, 128 + ((ncol + 15) & ~15));      // [p_hi rows | p_lo rows]
-          // chunk zc of the z columns sits in k-step slot zc of the packed tile (seq_r3.cu: pack3_fwd_kernel)
-          mma_tf32_ss(tmem_d + buf * 256, make_desc(a_addr), make_desc(p_addr + zc * 32), idesc, 0u);
-          mma_commit(&bars->accf[buf]);
-        }
-        mma_commit(&bars->empty[s]);
-        R3_TRACE(11);
-        ++n_tile;
+      if (!wready) { mbar_wait(&bars->wbar, 0); wready = true; }
+      const int s = n_stage % S, it = n_stage / S;
+      const uint32_t a_addr = smem_u32(ring + s * stage_bytes), p_addr = smem_u32(p_hi);
+      for (int zc = 0; zc < nzc; ++zc, ++n_chunk) {
+        const int buf = n_chunk & 1, use = n_chunk >> 1;
+        if (use > 0) mbar_wait(&bars->acce[buf], (use - 1) & 1);
+        if (zc == 0) { mbar_wait(&bars->full[s], it & 1); R3_TRACE(10); }
+        tc_fence_after();
+        const int ncol = min(128, RHr - zc * 128);
+        const uint32_t idesc = make_idesc(BM, 128 + ((ncol + 15) & ~15));      // [p_hi rows | p_lo rows]
+        // chunk zc of the z columns sits in k-step slot zc of the packed tile (seq_r3.cu: pack3_fwd_kernel)
+        mma_elect(tmem_d + buf * 256, make_desc(a_addr), make_desc(p_addr + zc * 32), idesc, 0u);
+        commit_elect(&bars->accf[buf]);
       }
-      __syncwarp();
+      commit_elect(&bars->empty[s]);
+      R3_TRACE(11);
+      ++n_stage;
     } else if (epi) {
       for (int zc = 0; zc < nzc; ++zc, ++n_chunk) {
         const int buf = n_chunk & 1, use = n_chunk >> 1;
@@ -299,8 +329,7 @@ r3_fwd_kernel(const __grid_constant__ CUtensorMap m_hop_hi, const __grid_constan
         for (int pp = 0; pp < 2; ++pp) {
           const int cb = (ehalf * 2 + pp) * 32;
           if (cb >= ncol) break;
-          if (eq == 0) store_partial_rows(t_main, cb, a.zpart + ((size_t)s_rank * RB + lane) * a.zp, zc * 128 + cb, a.zp, lane < a.B);
-          else store_cross_rows(t_main + (32u << 16), cb, a.zpart + ((size_t)(CS + s_rank) * RB + lane) * a.zp, zc * 128 + cb, a.zp, lane < a.B);
+          partial_pass(t_main, cb, eq, ehalf, xph, xbuf, lane, a.zpart + ((size_t)s_rank * RB + lane) * a.zp, zc * 128 + cb, a.zp, lane < a.B);
         }
         tc_fence_before();
         __syncwarp();
@@ -312,9 +341,9 @@ r3_fwd_kernel(const __grid_constant__ CUtensorMap m_hop_hi, const __grid_constan
     group_sync(a.sync, epoch, CS);
     if (warp == 4) R3_TRACE(30);
     if (warp >= 2) {
-      reduce_partials(a.zpart, 2 * CS, CS, s_rank, a.B, a.zp, a.zp >> 2, [&](int r, int c, const float4 v) {
+      reduce_partials(a.zpart, CS, CS, s_rank, a.B, a.zp, a.zp >> 2, [&](int r, int c, const float4 v) {
         if (SAVE) *reinterpret_cast<float4*>(a.z + ((size_t)t * a.B + r) * a.zp + c) = v;
-        store_split4(a.zop_hi + (size_t)r * a.zp + c, a.zop_lo + (size_t)r * a.zp + c, v);
+        store_split4(a.zop, r, c, v);
       }, [&](int ev) { if (warp == 4) R3_TRACE(ev); });
       fence_proxy_async_all();
       if (warp == 4) R3_TRACE(31);
@@ -323,37 +352,37 @@ r3_fwd_kernel(const __grid_constant__ CUtensorMap m_hop_hi, const __grid_constan
     if (warp == 4) R3_TRACE(32);
     // ======================================= phase G =======================================
     if (warp == 0) {
-      if (lane == 0) {
-        fence_proxy_async_all();
-        for (int kt = 0; kt < nkz; ++kt, ++n_tile) {
-          const int s = n_tile % S, it = n_tile / S;
-          if (it > 0) mbar_wait(&bars->empty[s], (it - 1) & 1);
-          mbar_arrive_expect_tx(&bars->full[s], kAStage);
-          tma_load_2d(ring + s * kAStage, &m_zop_hi, kt * BK, 0, &bars->full[s]);
-          tma_load_2d(ring + s * kAStage + kATile, &m_zop_lo, kt * BK, 0, &bars->full[s]);
-          R3_TRACE(200 + kt);
+      fence_proxy_async_all();
+      for (int g = 0; g < ngr; ++g, ++n_stage) {
+        const int s = n_stage % S, it = n_stage / S;
+        if (it > 0) mbar_wait(&bars->empty[s], (it - 1) & 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&bars->full[s], stage_bytes);
+          tma_load_2d(ring + s * stage_bytes, &m_zop, 0, g * G * 64, &bars->full[s]);
         }
+        R3_TRACE(200 + g);
       }
-      __syncwarp();
     } else if (warp == 1) {
-      if (lane == 0) {
-        const uint32_t idesc = make_idesc(BM, 64);               // [32 hi rows | 32 lo rows] of the CTA's Bm slice
-        const int buf = n_chunk & 1, use = n_chunk >> 1;
-        if (use > 0) mbar_wait(&bars->acce[buf], (use - 1) & 1);
+      const uint32_t idesc = make_idesc(BM, 64);               // [32 hi rows | 32 lo rows] of the CTA's Bm slice
+      const int buf = n_chunk & 1, use = n_chunk >> 1;
+      if (use > 0) mbar_wait(&bars->acce[buf], (use - 1) & 1);
+      tc_fence_after();
+      for (int g = 0; g < ngr; ++g, ++n_stage) {
+        const int s = n_stage % S, it = n_stage / S;
+        mbar_wait(&bars->full[s], it & 1);
         tc_fence_after();
-        for (int kt = 0; kt < nkz; ++kt, ++n_tile) {
-          const int s = n_tile % S, it = n_tile / S;
-          mbar_wait(&bars->full[s], it & 1);
-          tc_fence_after();
-          R3_TRACE(100 + kt);
-          issue_ktile_split(smem_u32(ring + s * kAStage), smem_u32(w2s + kt * kAStage), tmem_d + buf * 256, 64, idesc, tile_ksteps(a.RH, kt), kt == 0);
-          mma_commit(&bars->empty[s]);
+        R3_TRACE(100 + g);
+        const int nt = min(G, nkz - g * G);
+        for (int tl = 0; tl < nt; ++tl) {
+          const int kt = g * G + tl;
+          issue_ktile_split(smem_u32(ring + s * stage_bytes + tl * kAStage), smem_u32(w2s + kt * kAStage), tmem_d + buf * 256, 64, idesc,
+                            tile_ksteps(a.RH, kt), kt == 0);
         }
-        mma_commit(&bars->accf[buf]);
-        R3_TRACE(13);
-        ++n_chunk;
+        commit_elect(&bars->empty[s]);
       }
-      __syncwarp();
+      commit_elect(&bars->accf[buf]);
+      R3_TRACE(13);
+      ++n_chunk;
     } else if (epi) {
       const int buf = n_chunk & 1, use = n_chunk >> 1;
       if (ehalf == 0 && eq == 1) {
@@ -368,8 +397,9 @@ r3_fwd_kernel(const __grid_constant__ CUtensorMap m_hop_hi, const __grid_constan
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] += w[i];
         }
+        float* xb = xbuf + (xph & 1) * 1024;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) xbuf[i * 32 + lane] = v[i];
+        for (int i = 0; i < 32; ++i) xb[i * 32 + lane] = v[i];
         asm volatile("bar.sync 1, 64;" ::: "memory");
       } else if (ehalf == 0) {
         // lane (c8, rl) owns unit j for the 8 rows rg*4 + rl; the chunk's 32 columns are [gate k][unit]
@@ -406,11 +436,13 @@ r3_fwd_kernel(const __grid_constant__ CUtensorMap m_hop_hi, const __grid_constan
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] += w[i];
         }
+        const float* xb = xbuf + (xph & 1) * 1024;
         asm volatile("bar.sync 1, 64;" ::: "memory");
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] += xbuf[i * 32 + lane]; // + lo*hi
+        for (int i = 0; i < 32; ++i) v[i] += xb[i * 32 + lane]; // + lo*hi
         xpose8(v, lane);                                       // -> v[k*8 + rg] = (row rg*4 + rl, unit c8, gate k)
         if (act) {
+          float* hop_t = a.hop + (size_t)s_rank * kTileFloats;
 #pragma unroll
           for (int rg = 0; rg < 8; ++rg) {
             const int m = rg * 4 + rl;
@@ -423,9 +455,8 @@ r3_fwd_kernel(const __grid_constant__ CUtensorMap m_hop_hi, const __grid_constan
               const float c = fmaf(gf, cp[rg], gi * gn);
               const float h = go * tanhf_acc(c);
               y_t[(size_t)m * a.ys_b + j] = h;
-              const float hi = split_hi(h);
-              a.hop_hi[(size_t)m * a.Hp + j] = hi;
-              a.hop_lo[(size_t)m * a.Hp + j] = split_lo(h, hi);
+              hop_t[m * 32 + c8] = h;                            // hi part = the value itself (the tensor core truncates)
+              hop_t[1024 + m * 32 + c8] = split_lo(h, h);
               cout[(size_t)m * a.H + j] = c;
               if (SAVE) {
                 float* gp = a.gates + ((size_t)t * a.B + m) * 4 * a.H + j;
@@ -438,6 +469,7 @@ r3_fwd_kernel(const __grid_constant__ CUtensorMap m_hop_hi, const __grid_constan
       } else {
         mbar_wait(&bars->accf[buf], use & 1);
       }
+      if (ehalf == 0) ++xph;                                   // warps 4 and 5 used one hand-over buffer
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->acce[buf]);
@@ -466,13 +498,13 @@ struct BwdArgs3 {
   float *dh0, *dc0;           // [B,H] or null
   float* dpre;                // [T*B, 4, Hp]   exact copy for the time-parallel weight-gradient GEMMs
   float* dz_all;              // [T*B, zp]
-  float *dpo_hi, *dpo_lo;     // [B, 4*Hp]      slice-major tf32 operand copy of dPre_t (slice_col)
-  float *dzo_hi, *dzo_lo;     // [B, zp]        tf32 operand copy of dz_t
+  float* dpo;                 // [CS][hi | lo][32][32] tile-major tf32 operand copy of dPre_t: CTA s's (gate, unit) slice
+  float* dzo;                 // [nkz][hi | lo][32][32] tile-major tf32 operand copy of dz_t
   float *dhrun, *dcrun;       // [B, Hp]
   float* part;                // [CS, 32, zp]
   unsigned int* sync;
   int T, B, H, RH;
-  int Hp, CS, zp, S;
+  int Hp, CS, zp, S, G;
 };
 
 __device__ __forceinline__ void pw_finish3(const BwdArgs3& a, int tq, int m, int j, const PwIn& in, float dh, const float (&dhc)[4]) {
@@ -485,13 +517,13 @@ __device__ __forceinline__ void pw_finish3(const BwdArgs3& a, int tq, int m, int
   d[2] = dh * tcv * in.go * (1.f - in.go);
   d[3] = dc * in.gi * (1.f - in.gn * in.gn);
   float* o = a.dpre + rowq * 4 * a.Hp + j;
+  float* op = a.dpo + (size_t)(j >> 3) * kTileFloats + m * 32;
   float sdh = 0.f;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     o[(size_t)k * a.Hp] = d[k];
-    const size_t oc = (size_t)m * 4 * a.Hp + slice_col(k, j);
-    a.dpo_hi[oc] = d[k];                                        // the tensor core truncates: the value is its own hi part
-    a.dpo_lo[oc] = split_lo(d[k], d[k]);
+    op[slice_col(k, j)] = d[k];                                 // the tensor core truncates: the value is its own hi part
+    op[1024 + slice_col(k, j)] = split_lo(d[k], d[k]);
     sdh = fmaf(d[k], dhc[k], sdh);
   }
   a.dcrun[(size_t)m * a.Hp + j] = dc * in.gf;
@@ -499,21 +531,23 @@ __device__ __forceinline__ void pw_finish3(const BwdArgs3& a, int tq, int m, int
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
-r3_bwd_kernel(const __grid_constant__ CUtensorMap m_dpo_hi, const __grid_constant__ CUtensorMap m_dpo_lo,
+r3_bwd_kernel(const __grid_constant__ CUtensorMap m_dpo, const __grid_constant__ CUtensorMap m_dzo,
               const __grid_constant__ CUtensorMap m_w2t_hi, const __grid_constant__ CUtensorMap m_w2t_lo,
-              const __grid_constant__ CUtensorMap m_dzo_hi, const __grid_constant__ CUtensorMap m_dzo_lo,
               const __grid_constant__ CUtensorMap m_ap_hi, const __grid_constant__ CUtensorMap m_ap_lo, const BwdArgs3 a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* const base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int S = a.S, CS = a.CS;
+  // the warp index through a broadcast: the compiler then knows the role branches are warp-uniform (uniform registers inside)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const int S = a.S, CS = a.CS, G = a.G;
+  const int stage_bytes = G * kAStage;
   const int RHr = (a.RH + 7) & ~7;
   const int nch1 = (RHr + 127) / 128;                        // phase 1 chunks (128 dz columns)
-  const int nkz = (a.RH + BK - 1) / BK;
-  const int nacc = min(4, (a.RH + 7) / 8);                   // independent accumulation chains of the K = RH phases                      // phase 2 K tiles
-  // shared memory: activation ring | phase 1 weights (nch1 x (hi | lo) 16 KB tiles) | phase 2 weights (nkz x (hi | lo) 2 KB) | barriers
+  const int nkz = (a.RH + BK - 1) / BK;                      // phase 2 K tiles
+  const int ngr = (nkz + G - 1) / G;
+  const int nacc = min(4, (a.RH + 7) / 8);                   // independent accumulation chains of phase 2
+  // shared memory: activation ring | phase 1 weights (nch1 x (hi | lo) 16 KB tiles) | phase 2 weights (nkz x (hi | lo) 2 KB) | barriers | hand-over
   uint8_t* const ring = base;
-  uint8_t* const w2ts = base + S * kAStage;
+  uint8_t* const w2ts = base + S * stage_bytes;
   uint8_t* const aps = w2ts + nch1 * 2 * kPTile;
   Bars3* const bars = reinterpret_cast<Bars3*>(aps + nkz * 2 * kApTile);
   float* const xbuf = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + kBarBytes);
@@ -544,8 +578,9 @@ r3_bwd_kernel(const __grid_constant__ CUtensorMap m_dpo_hi, const __grid_constan
   float dhc[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) dhc[k] = act ? __ldg(a.Dh + k * a.H + j) : 0.f;
-  uint32_t n_tile = 0, n_chunk = 0;
+  uint32_t n_stage = 0, n_chunk = 0;
   bool wready = false;
+  int xph = 0;
   int trc = 0;
   (void)trc;
 
@@ -565,37 +600,32 @@ r3_bwd_kernel(const __grid_constant__ CUtensorMap m_dpo_hi, const __grid_constan
   for (int t = a.T - 1; t >= 0; --t) {
     // ======================================= phase 1 =======================================
     if (warp == 0) {
-      if (lane == 0) {
-        fence_proxy_async_all();
-        R3_TRACE(1);
-        const int s = n_tile % S, it = n_tile / S;
-        if (it > 0) mbar_wait(&bars->empty[s], (it - 1) & 1);
+      fence_proxy_async_all();
+      R3_TRACE(1);
+      const int s = n_stage % S, it = n_stage / S;
+      if (it > 0) mbar_wait(&bars->empty[s], (it - 1) & 1);
+      if (elect_one()) {
         mbar_arrive_expect_tx(&bars->full[s], kAStage);
-        tma_load_2d(ring + s * kAStage, &m_dpo_hi, s_rank * 32, 0, &bars->full[s]);
-        tma_load_2d(ring + s * kAStage + kATile, &m_dpo_lo, s_rank * 32, 0, &bars->full[s]);
-        ++n_tile;
+        tma_load_2d(ring + s * stage_bytes, &m_dpo, 0, s_rank * 64, &bars->full[s]);
       }
-      __syncwarp();
+      ++n_stage;
     } else if (warp == 1) {
-      if (lane == 0) {
-        if (!wready) { mbar_wait(&bars->wbar, 0); wready = true; }
-        const int s = n_tile % S, it = n_tile / S;
-        const uint32_t a_addr = smem_u32(ring + s * kAStage);
-        for (int c = 0; c < nch1; ++c, ++n_chunk) {
-          const int buf = n_chunk & 1, use = n_chunk >> 1;
-          if (use > 0) mbar_wait(&bars->acce[buf], (use - 1) & 1);
-          if (c == 0) { mbar_wait(&bars->full[s], it & 1); R3_TRACE(10); }
-          tc_fence_after();
-          const int ncol = min(128, RHr - c * 128);
-          const uint32_t idesc = make_idesc(BM, 128 + ((ncol + 15) & ~15));      // [w2t hi rows | w2t lo rows]
-          issue_ktile(a_addr, smem_u32(w2ts + c * 2 * kPTile), tmem_d + buf * 256, idesc, 4, true);
-          mma_commit(&bars->accf[buf]);
-        }
-        mma_commit(&bars->empty[s]);
-        R3_TRACE(11);
-        ++n_tile;
+      if (!wready) { mbar_wait(&bars->wbar, 0); wready = true; }
+      const int s = n_stage % S, it = n_stage / S;
+      const uint32_t a_addr = smem_u32(ring + s * stage_bytes);
+      for (int c = 0; c < nch1; ++c, ++n_chunk) {
+        const int buf = n_chunk & 1, use = n_chunk >> 1;
+        if (use > 0) mbar_wait(&bars->acce[buf], (use - 1) & 1);
+        if (c == 0) { mbar_wait(&bars->full[s], it & 1); R3_TRACE(10); }
+        tc_fence_after();
+        const int ncol = min(128, RHr - c * 128);
+        const uint32_t idesc = make_idesc(BM, 128 + ((ncol + 15) & ~15));      // [w2t hi rows | w2t lo rows]
+        issue_ktile(a_addr, smem_u32(w2ts + c * 2 * kPTile), tmem_d + buf * 256, idesc, 4, true);
+        commit_elect(&bars->accf[buf]);
       }
-      __syncwarp();
+      commit_elect(&bars->empty[s]);
+      R3_TRACE(11);
+      ++n_stage;
     } else if (epi) {
       for (int c = 0; c < nch1; ++c, ++n_chunk) {
         const int buf = n_chunk & 1, use = n_chunk >> 1;
@@ -608,8 +638,7 @@ r3_bwd_kernel(const __grid_constant__ CUtensorMap m_dpo_hi, const __grid_constan
         for (int pp = 0; pp < 2; ++pp) {
           const int cb = (ehalf * 2 + pp) * 32;
           if (cb >= ncol) break;
-          if (eq == 0) store_partial_rows(t_main, cb, a.part + ((size_t)s_rank * RB + lane) * a.zp, c * 128 + cb, a.zp, lane < a.B);
-          else store_cross_rows(t_main + (32u << 16), cb, a.part + ((size_t)(CS + s_rank) * RB + lane) * a.zp, c * 128 + cb, a.zp, lane < a.B);
+          partial_pass(t_main, cb, eq, ehalf, xph, xbuf, lane, a.part + ((size_t)s_rank * RB + lane) * a.zp, c * 128 + cb, a.zp, lane < a.B);
         }
         tc_fence_before();
         __syncwarp();
@@ -621,9 +650,9 @@ r3_bwd_kernel(const __grid_constant__ CUtensorMap m_dpo_hi, const __grid_constan
     group_sync(a.sync, epoch, CS);
     if (warp == 4) R3_TRACE(30);
     if (warp >= 2) {
-      reduce_partials(a.part, 2 * CS, CS, s_rank, a.B, a.zp, a.zp >> 2, [&](int r, int c, const float4 v) {
+      reduce_partials(a.part, CS, CS, s_rank, a.B, a.zp, a.zp >> 2, [&](int r, int c, const float4 v) {
         *reinterpret_cast<float4*>(a.dz_all + ((size_t)t * a.B + r) * a.zp + c) = v;
-        store_split4(a.dzo_hi + (size_t)r * a.zp + c, a.dzo_lo + (size_t)r * a.zp + c, v);
+        store_split4(a.dzo, r, c, v);
       }, [&](int ev) { if (warp == 4) R3_TRACE(ev); });
       fence_proxy_async_all();
       if (warp == 4) R3_TRACE(31);
@@ -632,36 +661,36 @@ r3_bwd_kernel(const __grid_constant__ CUtensorMap m_dpo_hi, const __grid_constan
     if (warp == 4) R3_TRACE(32);
     // ======================================= phase 2 =======================================
     if (warp == 0) {
-      if (lane == 0) {
-        fence_proxy_async_all();
-        for (int kt = 0; kt < nkz; ++kt, ++n_tile) {
-          const int s = n_tile % S, it = n_tile / S;
-          if (it > 0) mbar_wait(&bars->empty[s], (it - 1) & 1);
-          mbar_arrive_expect_tx(&bars->full[s], kAStage);
-          tma_load_2d(ring + s * kAStage, &m_dzo_hi, kt * BK, 0, &bars->full[s]);
-          tma_load_2d(ring + s * kAStage + kATile, &m_dzo_lo, kt * BK, 0, &bars->full[s]);
+      fence_proxy_async_all();
+      for (int g = 0; g < ngr; ++g, ++n_stage) {
+        const int s = n_stage % S, it = n_stage / S;
+        if (it > 0) mbar_wait(&bars->empty[s], (it - 1) & 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&bars->full[s], stage_bytes);
+          tma_load_2d(ring + s * stage_bytes, &m_dzo, 0, g * G * 64, &bars->full[s]);
         }
       }
-      __syncwarp();
     } else if (warp == 1) {
-      if (lane == 0) {
-        const uint32_t idesc = make_idesc(BM, 32);               // [16 hi rows | 16 lo rows] of the CTA's A slice
-        const int buf = n_chunk & 1, use = n_chunk >> 1;
-        if (use > 0) mbar_wait(&bars->acce[buf], (use - 1) & 1);
+      const uint32_t idesc = make_idesc(BM, 32);               // [16 hi rows | 16 lo rows] of the CTA's A slice
+      const int buf = n_chunk & 1, use = n_chunk >> 1;
+      if (use > 0) mbar_wait(&bars->acce[buf], (use - 1) & 1);
+      tc_fence_after();
+      for (int g = 0; g < ngr; ++g, ++n_stage) {
+        const int s = n_stage % S, it = n_stage / S;
+        mbar_wait(&bars->full[s], it & 1);
         tc_fence_after();
-        for (int kt = 0; kt < nkz; ++kt, ++n_tile) {
-          const int s = n_tile % S, it = n_tile / S;
-          mbar_wait(&bars->full[s], it & 1);
-          tc_fence_after();
-          R3_TRACE(100 + kt);
-          issue_ktile_split(smem_u32(ring + s * kAStage), smem_u32(aps + kt * 2 * kApTile), tmem_d + buf * 256, 32, idesc, tile_ksteps(a.RH, kt), kt == 0);
-          mma_commit(&bars->empty[s]);
+        R3_TRACE(100 + g);
+        const int nt = min(G, nkz - g * G);
+        for (int tl = 0; tl < nt; ++tl) {
+          const int kt = g * G + tl;
+          issue_ktile_split(smem_u32(ring + s * stage_bytes + tl * kAStage), smem_u32(aps + kt * 2 * kApTile), tmem_d + buf * 256, 32, idesc,
+                            tile_ksteps(a.RH, kt), kt == 0);
         }
-        mma_commit(&bars->accf[buf]);
-        R3_TRACE(13);
-        ++n_chunk;
+        commit_elect(&bars->empty[s]);
       }
-      __syncwarp();
+      commit_elect(&bars->accf[buf]);
+      R3_TRACE(13);
+      ++n_chunk;
     } else if (epi) {
       const int buf = n_chunk & 1, use = n_chunk >> 1;
       if (ehalf == 0 && eq == 1) {
@@ -677,8 +706,9 @@ r3_bwd_kernel(const __grid_constant__ CUtensorMap m_dpo_hi, const __grid_constan
 #pragma unroll
           for (int i = 0; i < 8; ++i) v[i] += w[i];
         }
+        float* xb = xbuf + (xph & 1) * 1024;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) xbuf[i * 32 + lane] = v[i];
+        for (int i = 0; i < 8; ++i) xb[i * 32 + lane] = v[i];
         asm volatile("bar.sync 1, 64;" ::: "memory");
       } else if (ehalf == 0) {
         // the saved activations of step t-1 are requested before the accumulator is waited for
@@ -701,9 +731,10 @@ r3_bwd_kernel(const __grid_constant__ CUtensorMap m_dpo_hi, const __grid_constan
 #pragma unroll
           for (int i = 0; i < 8; ++i) v[i] += w[i];
         }
+        const float* xb = xbuf + (xph & 1) * 1024;
         asm volatile("bar.sync 1, 64;" ::: "memory");
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] += xbuf[i * 32 + lane];  // + lo*hi
+        for (int i = 0; i < 8; ++i) v[i] += xb[i * 32 + lane];  // + lo*hi
         xpose8_group(v, lane);                                  // -> v[rg] = dh_{t-1}(row rg*4 + rl, unit c8) without the Dh term
         if (act) {
 #pragma unroll
@@ -722,6 +753,7 @@ r3_bwd_kernel(const __grid_constant__ CUtensorMap m_dpo_hi, const __grid_constan
       } else {
         mbar_wait(&bars->accf[buf], use & 1);
       }
+      if (ehalf == 0) ++xph;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->acce[buf]);
