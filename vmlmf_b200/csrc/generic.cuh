@@ -123,16 +123,34 @@ struct EpiDX {              // dX[m,j] = acc + sum_k dPre[m,kG+j] Dx[k,j]   (G =
 struct EpiDXTC {            // tensor-core epilogue of dX = dZX Ux^T + sum_k dPre_k Dx_k  (lane <-> column, see gemm_tc.cuh)
   float* dx; long long dxs_t, dxs_b; int Bsz; const float* dpre; const float* Dx; int H, I;   // H = gate stride of dPre
   static constexpr bool kGate = false;
-  __device__ void operator()(int m, int n0, int N, int lane, const float (&v)[4]) const {
-    float* o = dx + (long long)(m / Bsz) * dxs_t + (long long)(m % Bsz) * dxs_b;
+  struct Col { float dx[4][4]; };                      // Dx[k][column i]
+  struct In { float dp[4][4]; };                       // dPre[k][column i] of the row
+  __device__ void cols(int n0, int N, int lane, Col& c) const {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int j = n0 + lane + 32 * i;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) c.dx[k][i] = j < N ? __ldg(Dx + k * I + j) : 0.f;
+    }
+  }
+  __device__ void load(int m, int n0, int N, int lane, const Col&, In& in) const {
     const float* dp = dpre + (size_t)m * 4 * H;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int j = n0 + lane + 32 * i;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) in.dp[k][i] = j < N ? __ldg(dp + k * H + j) : 0.f;
+    }
+  }
+  __device__ void finish(int m, int n0, int N, int lane, const float (&v)[4], const Col& c, const In& in) const {
+    float* o = dx + (long long)(m / Bsz) * dxs_t + (long long)(m % Bsz) * dxs_b;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int j = n0 + lane + 32 * i;
       if (j < N) {
         float r = v[i];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) r = fmaf(dp[k * H + j], Dx[k * I + j], r);
+        for (int k = 0; k < 4; ++k) r = fmaf(in.dp[k][i], c.dx[k][i], r);
         o[j] = r;
       }
     }
@@ -864,7 +882,19 @@ inline int generic_bwd_tp(TpArgs& a, cudaStream_t st) {
     if (a.vxt_padded) {
       // pad units of dPre are zero, pad columns of vxt are zero: contract over the whole padded gate axis
       if (!(a.use_tc && tc::tc_operand_ok(a.dpre, 4 * G) && tc::tc_operand_ok(a.dzx, a.zxp))) return VMLMF_EUNSUPPORTED;
-      rc = tc::gemm_tc(a.dpre, 4 * G, a.vxt, 4 * G, (int)rows, RX, 4 * G, tc::EpiStoreTC{a.dzx, a.zxp, 0}, st);
+      // few output tiles, a long contraction (K = 4G): split K over the idle SMs, fixed-order reduce
+      int splits = tc::tc_splits((int)rows, RX, 4 * G, 16);
+      while (splits > 1 && (long long)splits * rows * RX > a.n_part) --splits;
+      if (splits > 1) {
+        const int nkb = ceil_div(4 * G, tc::BK), kbs = ceil_div(nkb, splits), nz = ceil_div(nkb, kbs);
+        rc = tc::gemm_tc(a.dpre, 4 * G, a.vxt, 4 * G, (int)rows, RX, 4 * G, tc::EpiPartialTC{part, (int)rows, RX}, st, splits);
+        if (rc == 0) {
+          splitk_reduce_rows_kernel<<<(unsigned)((rows * RX + 255) / 256), 256, 0, st>>>(part, nz, (int)rows, RX, a.dzx, a.zxp, 0);
+          rc = (int)cudaGetLastError();
+        }
+      } else {
+        rc = tc::gemm_tc(a.dpre, 4 * G, a.vxt, 4 * G, (int)rows, RX, 4 * G, tc::EpiStoreTC{a.dzx, a.zxp, 0}, st);
+      }
       if (rc == tc::kTcNoFit) return VMLMF_EUNSUPPORTED;
     } else if (a.use_tc && tc::tc_operand_ok(a.dpre, 4 * G) && tc::tc_operand_ok(a.dzx, a.zxp)) {
       G_TRY(transpose_launch(a.Vx, 4 * H, RX, a.vxt, 4 * H, st));
