@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Small forward+backward cases, one per kernel family, for compute-sanitizer runs (memcheck / racecheck / synccheck):
    SIMT R1, warp-MMA forward + fused backward (TMEM accumulators), split backward, regime R2 (cooperative tcgen05 recurrence,
-   two group sizes), the tcgen05 GEMMs (NT, TN), softmax-NLL / head / optimizers.   usage: sanitize_cases.py [case ...]"""
+   two group sizes), regime R3 (small batch), the tcgen05 GEMMs (NT, TN), softmax-NLL / head / optimizers.   usage: sanitize_cases.py [case ...]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -28,6 +28,7 @@ CASES = {
     "r1m_fused": lambda: (os.environ.__setitem__("VMLMF_MMA_MIN_BATCH", "1"), seq(3, 40, 9, 64, 8, 6)),
     "r1m_split": lambda: (os.environ.__setitem__("VMLMF_MMA_MIN_BATCH", "1"), os.environ.__setitem__("VMLMF_BWD_SPLIT", "1"), seq(3, 40, 9, 64, 8, 6)),
     "r2_group": lambda: seq(3, 140, 12, 96, 20, 24, 0.08),
+    "r3_small": lambda: seq(3, 20, 12, 96, 20, 40, 0.08),          # B <= 32: weight-stationary regime, 12 CTAs, named-barrier hand-over
     "r2_single": lambda: (os.environ.__setitem__("VMLMF_R2_CLUSTER", "1"), seq(2, 40, 8, 64, 20, 20, 0.08)),
     "gemm": lambda: (gemm_nt(torch.randn(200, 72, device=dev), torch.randn(150, 72, device=dev)),
                      gemm_tn(torch.randn(300, 136, device=dev), torch.randn(300, 40, device=dev)), torch.cuda.synchronize()),

@@ -185,16 +185,18 @@ __device__ __forceinline__ void partial_pass(uint32_t t_main, int cb, int eq, in
                                              float* row_ptr, int c0, int zp, bool row_ok) {
   float* xb = xbuf + (pair * 2 + (xph & 1)) * 1024;
   ++xph;
+  float v[32];
   if (eq == 1) {
-    float v[32];
     tmem_ld32_raw(t_main + (32u << 16) + cb, v);
 #pragma unroll
     for (int i = 0; i < 32; ++i) xb[i * 32 + lane] = v[i];
-    if (pair == 0) asm volatile("bar.sync 1, 64;" ::: "memory"); else asm volatile("bar.sync 2, 64;" ::: "memory");
   } else {
-    float v[32];
     tmem_ld_groups(t_main, t_main + 128, cb, cb + 8, cb + 16, cb + 24, v);      // hi*hi + hi*lo
-    if (pair == 0) asm volatile("bar.sync 1, 64;" ::: "memory"); else asm volatile("bar.sync 2, 64;" ::: "memory");
+  }
+  __syncwarp();
+  // writer and reader warp meet at the same barrier instruction
+  if (pair == 0) asm volatile("bar.sync 1, 64;" ::: "memory"); else asm volatile("bar.sync 2, 64;" ::: "memory");
+  if (eq == 0) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] += xb[i * 32 + lane];
     if (row_ok) {
@@ -385,24 +387,11 @@ r3_fwd_kernel(const __grid_constant__ CUtensorMap m_hop, const __grid_constant__
       ++n_chunk;
     } else if (epi) {
       const int buf = n_chunk & 1, use = n_chunk >> 1;
-      if (ehalf == 0 && eq == 1) {
-        // lo*hi term (accumulator lanes 32..63) -> shared memory, [column][row]: conflict free for writer and reader
-        mbar_wait(&bars->accf[buf], use & 1);
-        tc_fence_after();
-        float v[32];
-        tmem_ld32_raw(tmem_d + (32u << 16) + buf * 256, v);
-        for (int ac = 1; ac < nacc; ++ac) {
-          float w[32];
-          tmem_ld32_raw(tmem_d + (32u << 16) + buf * 256 + ac * 64, w);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] += w[i];
-        }
-        float* xb = xbuf + (xph & 1) * 1024;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) xb[i * 32 + lane] = v[i];
-        asm volatile("bar.sync 1, 64;" ::: "memory");
-      } else if (ehalf == 0) {
-        // lane (c8, rl) owns unit j for the 8 rows rg*4 + rl; the chunk's 32 columns are [gate k][unit]
+      if (ehalf == 0) {
+        // warp 4 (lane quarter 0): lane (c8, rl) owns unit j for the 8 rows rg*4 + rl; the chunk's 32 columns are [gate k][unit].
+        // warp 5 (lane quarter 1) only hands the lo*hi term over.  Both meet at ONE named-barrier instruction.
+        const bool q1 = eq == 1;
+        float* const xb = xbuf + (xph & 1) * 1024;
         const float* hprev = t ? a.y + (size_t)(t - 1) * a.ys_t : a.h0;
         const long long hp_sb = t ? a.ys_b : a.H;
         const float* cprev = SAVE ? (t ? a.cs + (size_t)(t - 1) * a.B * a.H : a.c0) : (t ? a.cs + (size_t)((t - 1) & 1) * a.B * a.H : a.c0);
@@ -410,8 +399,9 @@ r3_fwd_kernel(const __grid_constant__ CUtensorMap m_hop, const __grid_constant__
         float* y_t = a.y + (size_t)t * a.ys_t;
         const bool last = (t == a.T - 1);
         const int j = u0 + c8;
-        const bool act = j < a.H;
+        const bool act = !q1 && j < a.H;
         float dh[4], hp[8], cp[8], xq[8][4];
+        // operands that do not depend on the accumulator: requested before waiting for it
 #pragma unroll
         for (int k = 0; k < 4; ++k) dh[k] = act ? __ldg(a.Dh + k * a.H + j) : 0.f;
 #pragma unroll
@@ -423,46 +413,61 @@ r3_fwd_kernel(const __grid_constant__ CUtensorMap m_hop, const __grid_constant__
 #pragma unroll
           for (int k = 0; k < 4; ++k) xq[rg][k] = ok ? __ldg(a.xp + ((size_t)t * a.B + m) * 4 * a.H + (size_t)k * a.H + j) : 0.f;
         }
-        R3_TRACE(22);
+        if (warp == 4) R3_TRACE(22);
         mbar_wait(&bars->accf[buf], use & 1);
         tc_fence_after();
-        R3_TRACE(23);
+        if (warp == 4) R3_TRACE(23);
         const uint32_t t_main = tmem_d + buf * 256;
         float v[32];
-        tmem_ld_groups(t_main, t_main + 32, 0, 8, 16, 24, v);     // hi*hi + hi*lo of this row, first k-step chain
-        for (int ac = 1; ac < nacc; ++ac) {
-          float w[32];
-          tmem_ld_groups(t_main + ac * 64, t_main + ac * 64 + 32, 0, 8, 16, 24, w);
+        if (q1) {
+          // lo*hi term (accumulator lanes 32..63) -> shared memory, [column][row]: conflict free for writer and reader
+          tmem_ld32_raw(t_main + (32u << 16), v);
+          for (int ac = 1; ac < nacc; ++ac) {
+            float w[32];
+            tmem_ld32_raw(t_main + (32u << 16) + ac * 64, w);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] += w[i];
+            for (int i = 0; i < 32; ++i) v[i] += w[i];
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) xb[i * 32 + lane] = v[i];
+        } else {
+          tmem_ld_groups(t_main, t_main + 32, 0, 8, 16, 24, v);   // hi*hi + hi*lo of this row, first k-step chain
+          for (int ac = 1; ac < nacc; ++ac) {
+            float w[32];
+            tmem_ld_groups(t_main + ac * 64, t_main + ac * 64 + 32, 0, 8, 16, 24, w);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] += w[i];
+          }
         }
-        const float* xb = xbuf + (xph & 1) * 1024;
+        __syncwarp();
         asm volatile("bar.sync 1, 64;" ::: "memory");
+        if (!q1) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] += xb[i * 32 + lane]; // + lo*hi
-        xpose8(v, lane);                                       // -> v[k*8 + rg] = (row rg*4 + rl, unit c8, gate k)
-        if (act) {
-          float* hop_t = a.hop + (size_t)s_rank * kTileFloats;
+          for (int i = 0; i < 32; ++i) v[i] += xb[i * 32 + lane]; // + lo*hi
+          xpose8(v, lane);                                       // -> v[k*8 + rg] = (row rg*4 + rl, unit c8, gate k)
+          if (act) {
+            float* hop_t = a.hop + (size_t)s_rank * kTileFloats;
 #pragma unroll
-          for (int rg = 0; rg < 8; ++rg) {
-            const int m = rg * 4 + rl;
-            if (m < a.B) {
-              float pre[4];
+            for (int rg = 0; rg < 8; ++rg) {
+              const int m = rg * 4 + rl;
+              if (m < a.B) {
+                float pre[4];
 #pragma unroll
-              for (int k = 0; k < 4; ++k) pre[k] = v[k * 8 + rg] + xq[rg][k] + hp[rg] * dh[k];
-              const float gi = sigmoidf_acc(pre[0]), gf = sigmoidf_acc(pre[1]);
-              const float go = sigmoidf_acc(pre[2]), gn = tanhf_acc(pre[3]);
-              const float c = fmaf(gf, cp[rg], gi * gn);
-              const float h = go * tanhf_acc(c);
-              y_t[(size_t)m * a.ys_b + j] = h;
-              hop_t[m * 32 + c8] = h;                            // hi part = the value itself (the tensor core truncates)
-              hop_t[1024 + m * 32 + c8] = split_lo(h, h);
-              cout[(size_t)m * a.H + j] = c;
-              if (SAVE) {
-                float* gp = a.gates + ((size_t)t * a.B + m) * 4 * a.H + j;
-                gp[0] = gi; gp[a.H] = gf; gp[2 * a.H] = go; gp[3 * a.H] = gn;
+                for (int k = 0; k < 4; ++k) pre[k] = v[k * 8 + rg] + xq[rg][k] + hp[rg] * dh[k];
+                const float gi = sigmoidf_acc(pre[0]), gf = sigmoidf_acc(pre[1]);
+                const float go = sigmoidf_acc(pre[2]), gn = tanhf_acc(pre[3]);
+                const float c = fmaf(gf, cp[rg], gi * gn);
+                const float h = go * tanhf_acc(c);
+                y_t[(size_t)m * a.ys_b + j] = h;
+                hop_t[m * 32 + c8] = h;                            // hi part = the value itself (the tensor core truncates)
+                hop_t[1024 + m * 32 + c8] = split_lo(h, h);
+                cout[(size_t)m * a.H + j] = c;
+                if (SAVE) {
+                  float* gp = a.gates + ((size_t)t * a.B + m) * 4 * a.H + j;
+                  gp[0] = gi; gp[a.H] = gf; gp[2 * a.H] = go; gp[3 * a.H] = gn;
+                }
+                if (last) { a.hT[(size_t)m * a.H + j] = h; a.cT[(size_t)m * a.H + j] = c; }
               }
-              if (last) { a.hT[(size_t)m * a.H + j] = h; a.cT[(size_t)m * a.H + j] = c; }
             }
           }
         }
@@ -693,59 +698,61 @@ r3_bwd_kernel(const __grid_constant__ CUtensorMap m_dpo, const __grid_constant__
       ++n_chunk;
     } else if (epi) {
       const int buf = n_chunk & 1, use = n_chunk >> 1;
-      if (ehalf == 0 && eq == 1) {
-        mbar_wait(&bars->accf[buf], use & 1);
-        tc_fence_after();
-        float v[8];
-        tc::tmem_ld8_raw(tmem_d + (32u << 16) + buf * 256, v);   // lo*hi term of the 8 units
-        tc::tmem_ld_wait();
-        for (int ac = 1; ac < nacc; ++ac) {
-          float w[8];
-          tc::tmem_ld8_raw(tmem_d + (32u << 16) + buf * 256 + ac * 32, w);
-          tc::tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] += w[i];
-        }
-        float* xb = xbuf + (xph & 1) * 1024;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) xb[i * 32 + lane] = v[i];
-        asm volatile("bar.sync 1, 64;" ::: "memory");
-      } else if (ehalf == 0) {
+      if (ehalf == 0) {
+        // warp 4: gate-gradient algebra of step t-1; warp 5 hands the lo*hi term over; one named-barrier instruction for both
+        const bool q1 = eq == 1;
+        float* const xb = xbuf + (xph & 1) * 1024;
         // the saved activations of step t-1 are requested before the accumulator is waited for
         PwIn in[8];
-        if (t > 0 && act) {
+        if (!q1 && t > 0 && act) {
 #pragma unroll
           for (int rg = 0; rg < 8; ++rg)
             if (rg * 4 + rl < a.B) pw_load(a, t - 1, rg * 4 + rl, j, false, in[rg]);
         }
-        R3_TRACE(22);
+        if (warp == 4) R3_TRACE(22);
         mbar_wait(&bars->accf[buf], use & 1);
         tc_fence_after();
-        R3_TRACE(23);
+        if (warp == 4) R3_TRACE(23);
         const uint32_t t_main = tmem_d + buf * 256;
         float v[8];
-        tmem_ld_group(t_main, t_main + 16, 0, v);               // hi*hi + hi*lo, first k-step chain
-        for (int ac = 1; ac < nacc; ++ac) {
-          float w[8];
-          tmem_ld_group(t_main + ac * 32, t_main + ac * 32 + 16, 0, w);
+        if (q1) {
+          tc::tmem_ld8_raw(t_main + (32u << 16), v);             // lo*hi term of the 8 units
+          tc::tmem_ld_wait();
+          for (int ac = 1; ac < nacc; ++ac) {
+            float w[8];
+            tc::tmem_ld8_raw(t_main + (32u << 16) + ac * 32, w);
+            tc::tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] += w[i];
+            for (int i = 0; i < 8; ++i) v[i] += w[i];
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) xb[i * 32 + lane] = v[i];
+        } else {
+          tmem_ld_group(t_main, t_main + 16, 0, v);             // hi*hi + hi*lo, first k-step chain
+          for (int ac = 1; ac < nacc; ++ac) {
+            float w[8];
+            tmem_ld_group(t_main + ac * 32, t_main + ac * 32 + 16, 0, w);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] += w[i];
+          }
         }
-        const float* xb = xbuf + (xph & 1) * 1024;
+        __syncwarp();
         asm volatile("bar.sync 1, 64;" ::: "memory");
+        if (!q1) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] += xb[i * 32 + lane];  // + lo*hi
-        xpose8_group(v, lane);                                  // -> v[rg] = dh_{t-1}(row rg*4 + rl, unit c8) without the Dh term
-        if (act) {
+          for (int i = 0; i < 8; ++i) v[i] += xb[i * 32 + lane];  // + lo*hi
+          xpose8_group(v, lane);                                  // -> v[rg] = dh_{t-1}(row rg*4 + rl, unit c8) without the Dh term
+          if (act) {
 #pragma unroll
-          for (int rg = 0; rg < 8; ++rg) {
-            const int m = rg * 4 + rl;
-            if (m < a.B) {
-              if (t > 0) {
-                pw_finish3(a, t - 1, m, j, in[rg], in[rg].dyv + in[rg].dhs + v[rg], dhc);
-              } else {
-                if (a.dh0) a.dh0[(size_t)m * a.H + j] = a.dhrun[(size_t)m * a.Hp + j] + v[rg];
-                if (a.dc0) a.dc0[(size_t)m * a.H + j] = a.dcrun[(size_t)m * a.Hp + j];
+            for (int rg = 0; rg < 8; ++rg) {
+              const int m = rg * 4 + rl;
+              if (m < a.B) {
+                if (t > 0) {
+                  pw_finish3(a, t - 1, m, j, in[rg], in[rg].dyv + in[rg].dhs + v[rg], dhc);
+                } else {
+                  if (a.dh0) a.dh0[(size_t)m * a.H + j] = a.dhrun[(size_t)m * a.Hp + j] + v[rg];
+                  if (a.dc0) a.dc0[(size_t)m * a.H + j] = a.dcrun[(size_t)m * a.Hp + j];
+                }
               }
             }
           }
