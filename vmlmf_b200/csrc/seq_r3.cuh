@@ -19,6 +19,8 @@
 //   phase G   pre[32, 4 x 8] = z * Bm[4 x 8 rows, :]^T                            K = RH, N = 32
 // Backward mirrors it: phase 1 (dz partial = dPre_t[:, 4 x 8] * Bm[4 x 8 rows, :], K = 32), exchange, phase 2
 // (dh_{t-1}[32, 8] = dz_t * A[8 units, :]^T, K = RH, N = 16), gate-gradient algebra of step t-1 in the epilogue.
+// Proxy ordering: every thread that writes an operand tile with ordinary stores executes fence.proxy.async before the (CTA or
+// group) barrier that precedes the TMA read -- the writer-side fence is the documented pattern; the producer adds none.
 // Warp roles as in seq_r2.cuh: warp 0 TMA producer, warp 1 MMA issuer, warps 2-9 epilogue -- only warps 4 and 8 own
 // tensor-memory lanes 0..31 (the batch rows), the others help with the reduce.
 #pragma once
@@ -292,7 +294,6 @@ r3_fwd_kernel(const __grid_constant__ CUtensorMap m_hop, const __grid_constant__
   for (int t = 0; t < a.T; ++t) {
     // ======================================= phase Z =======================================
     if (warp == 0) {
-      fence_proxy_async_all();
       R3_TRACE(1);
       const int s = n_stage % S, it = n_stage / S;
       if (it > 0) mbar_wait(&bars->empty[s], (it - 1) & 1);
@@ -354,7 +355,6 @@ r3_fwd_kernel(const __grid_constant__ CUtensorMap m_hop, const __grid_constant__
     if (warp == 4) R3_TRACE(32);
     // ======================================= phase G =======================================
     if (warp == 0) {
-      fence_proxy_async_all();
       for (int g = 0; g < ngr; ++g, ++n_stage) {
         const int s = n_stage % S, it = n_stage / S;
         if (it > 0) mbar_wait(&bars->empty[s], (it - 1) & 1);
@@ -605,7 +605,6 @@ r3_bwd_kernel(const __grid_constant__ CUtensorMap m_dpo, const __grid_constant__
   for (int t = a.T - 1; t >= 0; --t) {
     // ======================================= phase 1 =======================================
     if (warp == 0) {
-      fence_proxy_async_all();
       R3_TRACE(1);
       const int s = n_stage % S, it = n_stage / S;
       if (it > 0) mbar_wait(&bars->empty[s], (it - 1) & 1);
@@ -666,7 +665,6 @@ r3_bwd_kernel(const __grid_constant__ CUtensorMap m_dpo, const __grid_constant__
     if (warp == 4) R3_TRACE(32);
     // ======================================= phase 2 =======================================
     if (warp == 0) {
-      fence_proxy_async_all();
       for (int g = 0; g < ngr; ++g, ++n_stage) {
         const int s = n_stage % S, it = n_stage / S;
         if (it > 0) mbar_wait(&bars->empty[s], (it - 1) & 1);
