@@ -101,6 +101,34 @@ def test_flat_adam_matches_torch_adam():
     assert list(net1.state_dict().keys()) == list(net2.state_dict().keys())
 
 
+def test_flat_adam_state_dict_resume():
+    """Checkpoint / resume of the flat optimizer (state exported per parameter name): a run interrupted after three steps and
+    resumed in a fresh optimizer continues bit-identically to the uninterrupted run."""
+    def steps(net, opt, n):
+        for _ in range(n):
+            opt.zero_grad()
+            vb.cross_entropy(net(x), y).backward()
+            opt.step()
+    net_a, x, y = _har()
+    opt_a = vb.FlatAdam(net_a, lr=0.002)
+    steps(net_a, opt_a, 3)
+    weights = {k: v.clone() for k, v in net_a.state_dict().items()}
+    state = opt_a.state_dict()
+    assert state["step"] == 3 and set(state["state"]) == {k for k, p in net_a.named_parameters() if not k.startswith("cell.")}
+    steps(net_a, opt_a, 2)                                   # uninterrupted: five steps
+    net_b, _, _ = _har()
+    opt_b = vb.FlatAdam(net_b, lr=0.5)                       # wrong hyper-parameters on purpose: the checkpoint restores them
+    with pytest.raises(RuntimeError, match="before load_state_dict"):
+        opt_b.load_state_dict(state)
+    steps(net_b, opt_b, 1)                                   # builds the flat buffers (live set from the first backward)
+    net_b.load_state_dict(weights)                           # copies into the flat-buffer views
+    opt_b.load_state_dict(state)
+    assert opt_b.lr == 0.002
+    steps(net_b, opt_b, 2)
+    for (k, pa), (_, pb) in zip(net_a.named_parameters(), net_b.named_parameters()):
+        assert torch.equal(pa, pb), k
+
+
 def test_flat_adam_inside_cuda_graph():
     net1, x, y = _har()
     net2, _, _ = _har()

@@ -197,3 +197,25 @@ def test_grad_bucket_pack_zero_semantics_single_process():
     # accumulation across two backwards before a step still works (the second one adds into the slices)
     lin(x).pow(2).sum().backward()
     assert torch.allclose(bucket.pack()[:15].view(3, 5), 2 * ref[0])
+
+
+def test_grad_bucket_reports_empty_and_late_parameters():
+    """GradBucket fixes the live parameter set at the first backward: both misuse cases raise instead of silently skipping
+    (advisor finding, round 1)."""
+    import torch
+    from vmlmf_b200.parallel import GradBucket
+    lin = torch.nn.Sequential(torch.nn.Linear(3, 4), torch.nn.Linear(4, 2))
+    b = GradBucket(lin)
+    with pytest.raises(RuntimeError, match="no parameter has a gradient"):
+        b.pack()
+    for p in lin[1].parameters():
+        p.requires_grad_(False)
+    lin(torch.randn(5, 3)).sum().backward()
+    b.pack()                                              # live set = first layer only
+    assert len(b.params) == 2
+    b.zero()
+    for p in lin[1].parameters():
+        p.requires_grad_(True)
+    lin(torch.randn(5, 3)).sum().backward()
+    with pytest.raises(RuntimeError, match="was not live at the first backward"):
+        b.pack()

@@ -37,7 +37,11 @@ class GraphedTrainStep:
 
     `opt` must be capturable (e.g. torch.optim.Adam(..., capturable=True) or fused=True with capturable=True).
     `zero_fn` replaces `opt.zero_grad(set_to_none=False)` (e.g. GradBucket.zero / FlatAdam.zero_grad); `after_backward` is called between backward and the optimizer step INSIDE the capture
-    (leave None when it would issue a collective)."""
+    (leave None when it would issue a collective).
+
+    Side effect to know about: the `warmup` eager iterations (CUDA requires them before a capture) are REAL training steps on
+    the example batch -- parameters and optimizer state advance `warmup` times before the first replay.  Pass a batch you
+    would train on anyway, or checkpoint / restore around construction when that matters."""
 
     def __init__(self, module, opt, loss_fn, x_example, y_example, warmup=3, zero_fn=None, after_backward=None,
                  static_inputs=False):

@@ -50,6 +50,46 @@ class _FlatOptimizer:
     def all_reduce(self):
         return self.bucket.all_reduce()
 
+    # ---- checkpointing: the flat buffers are private, so the state is exported per parameter NAME (like a module's
+    # state_dict) and can be loaded into a freshly built optimizer of the same model after its first backward / step.
+    # Note: parameters are re-pointed at slices of one flat buffer on the first step; module.to() / .cuda() afterwards
+    # detaches them from it -- move the module first, then build the optimizer.
+    _STATE_TENSORS = ()
+
+    def _named_live(self):
+        names = {id(p): n for n, p in self.bucket.module.named_parameters()}
+        off = 0
+        for p in self.bucket.params:
+            yield names.get(id(p), str(off)), off, p.numel(), p.shape
+            off += p.numel()
+
+    def state_dict(self):
+        if self.pflat is None:
+            return {"state": {}, "hyper": self._hyper()}
+        state = {}
+        for name, off, n, shape in self._named_live():
+            state[name] = {k: getattr(self, k)[off:off + n].view(shape).clone() for k in self._STATE_TENSORS}
+        out = {"state": state, "hyper": self._hyper()}
+        if getattr(self, "t", None) is not None:
+            out["step"] = float(self.t.item())
+        return out
+
+    def load_state_dict(self, sd):
+        if self.pflat is None:
+            raise RuntimeError("vmlmf_b200.optim: run one backward pass and build the optimizer state (a step, or _build()) "
+                               "before load_state_dict(): the live parameter set is taken from the first backward")
+        for name, off, n, shape in self._named_live():
+            if name in sd.get("state", {}):
+                for k in self._STATE_TENSORS:
+                    getattr(self, k)[off:off + n].copy_(sd["state"][name][k].reshape(-1))
+        if "step" in sd and getattr(self, "t", None) is not None:
+            self.t.fill_(sd["step"])
+        for k, v in sd.get("hyper", {}).items():
+            setattr(self, k, tuple(v) if isinstance(v, list) else v)
+
+    def _hyper(self):
+        return {}
+
 
 class FlatAdam(_FlatOptimizer):
     """Adam with torch.optim.Adam's defaults and arithmetic (no amsgrad, no weight decay).  The step counter lives on
@@ -61,6 +101,10 @@ class FlatAdam(_FlatOptimizer):
         self.m = self.v = self.t = None
 
     P2P_MAX_BYTES = 2 << 20      # one-shot all-reduce: every rank reads world x bucket over NVLink
+    _STATE_TENSORS = ("m", "v")
+
+    def _hyper(self):
+        return {"lr": self.lr, "betas": self.betas, "eps": self.eps}
 
     def _build(self):
         super()._build()
@@ -106,6 +150,9 @@ class FlatClipSGD(_FlatOptimizer):
         super().__init__(module_or_bucket, average)
         self.lr, self.max_norm = lr, max_norm
         self.ws = self.norm = None
+
+    def _hyper(self):
+        return {"lr": self.lr, "max_norm": self.max_norm}
 
     def _build(self):
         super()._build()

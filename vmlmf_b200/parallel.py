@@ -35,9 +35,14 @@ class GradBucket:
         self.symmetric = symmetric
         self.symm = None          # torch symmetric-memory handle once rendezvoused
         self.fused_reduce = False # set by an optimizer that performs the reduction itself
+        self._ids = set()
 
     def _build(self):
         self.params = [p for p in self.module.parameters() if p.grad is not None]
+        if not self.params:
+            raise RuntimeError("vmlmf_b200.parallel.GradBucket: no parameter has a gradient yet -- run a backward pass before "
+                               "pack() / all_reduce() / optimizer.step() (the live parameter set is taken from the first backward)")
+        self._ids = {id(p) for p in self.params}
         n = sum(p.numel() for p in self.params)
         ref = self.params[0]
         self.flat = None
@@ -65,6 +70,13 @@ class GradBucket:
         """gather the current .grad tensors into the bucket (no-op for those that already live there)"""
         if self.flat is None:
             self._build()
+        else:
+            # the live set was fixed by the first backward: a parameter that starts receiving gradients later (an unfrozen
+            # layer, a conditional branch) would silently be neither reduced nor updated
+            for name, p in self.module.named_parameters():
+                if p.grad is not None and id(p) not in self._ids:
+                    raise RuntimeError(f"vmlmf_b200.parallel.GradBucket: parameter '{name}' received a gradient but was not live at the "
+                                       "first backward; build a new GradBucket / optimizer after changing which parameters train")
         dst, src = [], []
         for p, v in zip(self.params, self.views):
             if p.grad is None:
