@@ -598,6 +598,21 @@ def test_r3_inference_bitwise_and_agrees_with_r2(monkeypatch, r1_path):
         assert_close(a.cpu().numpy(), t.grad.cpu().numpy().astype(np.float64), TOL, f"d{k} R3 vs R2")
 
 
+def test_randomised_large_regime_shapes(r1_path):
+    """Randomised sweep of the persistent tcgen05 regimes (R2 and the small-batch R3): 16 random (T, B, I, H, RX, RH), with and
+    without carried state, both layouts, every output and gradient within 1e-5 of the fp64 numpy spec
+    (tools/fuzz_regimes.py; a 40-case run is kept in profiles/r02_fuzz_regimes.txt)."""
+    if r1_path != "auto":
+        pytest.skip("the large-shape regimes do not depend on the R1 kernel choice")
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_regimes.py"), "16", "7"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "paths seen" in r.stdout
+
+
 def test_lm_dense_lstm_baseline_runs_through_the_fused_kernels(r1_path):
     """The LM's "custom" dense LSTM layer (V/models/vmlmf_lm.py:283-339) on the canonical kernels against its eager formula."""
     if r1_path != "auto":
