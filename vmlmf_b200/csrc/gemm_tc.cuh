@@ -490,8 +490,12 @@ __host__ __device__ constexpr uint32_t make_idesc_mn(int M, int N) { return make
 
 template <class Epi>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tn_kernel(const __grid_constant__ CUtensorMap mapA,
-                                                              const __grid_constant__ CUtensorMap mapB, int M, int N,
+                                                              const __grid_constant__ CUtensorMap mapB,
+                                                              const __grid_constant__ CUtensorMap mapB2, int nsplitB, int M, int N,
                                                               int K, int kb_per_split, Epi epi, int fast) {
+  // Two B matrices side by side along N: columns [0, nsplitB) come from mapB, columns [nsplitB, N) from mapB2 (nsplitB % 32 == 0;
+  // TMA zero-fills past each matrix's own width).  One pass over A then serves two products that share it (dBm and dVx both
+  // contract dPre: at cfg5 that operand is 4.3 GB).  Single-matrix callers pass nsplitB >= N.
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
@@ -532,7 +536,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tn_kernel(const __grid_const
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           tma_load_2d(st + i * 4096, &mapA, m0 + 32 * i, (kb0 + kb) * BK, &full[s]);
-          tma_load_2d(st + 2 * kTileBytes + i * 4096, &mapB, n0 + 32 * i, (kb0 + kb) * BK, &full[s]);
+          const int nb = n0 + 32 * i;
+          if (nb < nsplitB) tma_load_2d(st + 2 * kTileBytes + i * 4096, &mapB, nb, (kb0 + kb) * BK, &full[s]);
+          else tma_load_2d(st + 2 * kTileBytes + i * 4096, &mapB2, nb - nsplitB, (kb0 + kb) * BK, &full[s]);
         }
       }
     }
@@ -760,7 +766,35 @@ inline int gemm_tn(const float* At, long long lda, const float* Bt, long long ld
   const int nkb = ceil_div((int)K, BK);
   const int kbs = ceil_div(nkb, splits);
   dim3 grid(ceil_div(N, BN), ceil_div(M, BM), ceil_div(nkb, kbs));
-  kern<<<grid, kThreads, kSmemBytes, st>>>(ma, mb, M, N, (int)K, kbs, epi, fast_tf32());
+  kern<<<grid, kThreads, kSmemBytes, st>>>(ma, mb, mb, 0x7fffffff, M, N, (int)K, kbs, epi, fast_tf32());
+  return (int)cudaGetLastError();
+}
+// C[M, N1p + N2] = At^T [B1 | B2] with B1's columns padded to N1p = round_up(N1, 32): two products sharing the A operand
+template <class Epi>
+inline int gemm_tn2(const float* At, long long lda, const float* B1, long long ldb1, int N1, const float* B2, long long ldb2,
+                    int N2, int M, long long K, Epi epi, cudaStream_t st, int splits) {
+  if (M <= 0 || N1 <= 0 || N2 <= 0 || K <= 0) return 0;
+  if (!tc_operand_ok(At, lda) || !tc_operand_ok(B1, ldb1) || !tc_operand_ok(B2, ldb2) || K > 0x7fffffffLL) return kTcNoFit;
+  CUtensorMap ma, mb1, mb2;
+  int rc = make_map_tn(&ma, At, K, M, lda);
+  if (rc) return rc;
+  rc = make_map_tn(&mb1, B1, K, N1, ldb1);
+  if (rc) return rc;
+  rc = make_map_tn(&mb2, B2, K, N2, ldb2);
+  if (rc) return rc;
+  auto kern = gemm_tn_kernel<Epi>;
+  static PerDevice attr_pd;
+  int& attr = attr_pd.cur();
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) return (int)e;
+    attr = 1;
+  }
+  const int N1p = (N1 + 31) / 32 * 32, N = N1p + N2;
+  const int nkb = ceil_div((int)K, BK);
+  const int kbs = ceil_div(nkb, splits);
+  dim3 grid(ceil_div(N, BN), ceil_div(M, BM), ceil_div(nkb, kbs));
+  kern<<<grid, kThreads, kSmemBytes, st>>>(ma, mb1, mb2, N1p, M, N, (int)K, kbs, epi, fast_tf32());
   return (int)cudaGetLastError();
 }
 

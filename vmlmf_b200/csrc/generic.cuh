@@ -429,9 +429,9 @@ constexpr int kColSplits = 256;
 // therefore also bounded below so that one split covers at most kTcMaxKPerSplit of K (<= 64 adds per accumulator),
 // within a 64 MB budget for the partials.
 constexpr long long kTcMaxKPerSplit = 1536;
-inline int tc_accuracy_splits(int M, int N, long long K) {
+inline int tc_accuracy_splits(int M, int N, long long K, long long budget_bytes = 64LL << 20) {
   long long s = (K + kTcMaxKPerSplit - 1) / kTcMaxKPerSplit;
-  const long long cap = (64LL << 20) / ((long long)M * N * 4);
+  const long long cap = budget_bytes / ((long long)M * N * 4);
   if (s > cap) s = cap;
   if (s > 128) s = 128;
   if (s < 1) s = 1;
@@ -466,6 +466,10 @@ inline GenericSizes generic_sizes(int T, int B, int I, int H, int RX, int RH) {
   q = (long long)tc_accuracy_splits(4 * H, RX, rows) * 4 * H * RX; if (q > p) p = q;
   q = (long long)tc_accuracy_splits(H, RH, rows) * H * RH; if (q > p) p = q;
   q = (long long)tc_accuracy_splits(I, RX, rows) * I * RX; if (q > p) p = q;
+  {                                                            // fused dBm | dVx product
+    const long long nv = round_up(RH, 32) + RX;
+    q = (long long)tc_accuracy_splits(4 * H, (int)nv, rows, 128LL << 20) * 4 * H * nv; if (q > p) p = q;
+  }
   s.n_part = p;
   s.hp4 = round_up(H, 4);
   s.ip4 = round_up(I, 4);
@@ -753,6 +757,22 @@ static __global__ void compact_gate_rows_kernel(const float* __restrict__ src, f
   const int k = (int)(row / H), j = (int)(row % H);
   dst[i] = src[((size_t)k * G + j) * R + c];
 }
+// fused dBm | dVx product: part[z][k*G + j][c] over the virtual column axis [RH padded to N1p | RX]  ->  dBm[kH + j, RH], dVx[kH + j, RX]
+// (fixed-order sum over the splits; the gate padding G -> H is dropped on the way)
+static __global__ void splitk_reduce_pair_kernel(const float* __restrict__ part, int nsplit, int H, int G, int RH, int RX, int N1p,
+                                                 float* __restrict__ dBm, float* __restrict__ dVx) {
+  const int W = RH + RX, Nv = N1p + RX;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 4LL * H * W) return;
+  const int c = (int)(i % W);
+  const long long row = i / W;
+  const int k = (int)(row / H), j = (int)(row % H);
+  const size_t src = ((size_t)k * G + j) * Nv + (c < RH ? c : N1p + (c - RH));
+  const size_t zs = (size_t)4 * G * Nv;
+  float s = 0.f;
+  for (int z = 0; z < nsplit; ++z) s += part[(size_t)z * zs + src];
+  if (c < RH) dBm[row * RH + c] = s; else dVx[row * RX + (c - RH)] = s;
+}
 // scratch of generic_bwd_tp for a gate stride G (floats): partials, transposed operands, gate-compaction buffer
 struct TpScratch { long long n_part, ldt, n_tA, n_tB, n_gtmp, total; };
 inline TpScratch tp_scratch(int T, int B, int I, int H, int G, int RX, int RH) {
@@ -767,6 +787,10 @@ inline TpScratch tp_scratch(int T, int B, int I, int H, int G, int RX, int RH) {
   q = (long long)tc_accuracy_splits(4 * G, RX, rows) * 4 * G * RX; if (q > p) p = q;
   q = (long long)tc_accuracy_splits(H, RH, rows) * H * RH; if (q > p) p = q;
   q = (long long)tc_accuracy_splits(I, RX, rows) * I * RX; if (q > p) p = q;
+  {                                                            // fused dBm | dVx product (same budget as the two separate ones)
+    const long long nv = round_up(RH, 32) + RX;
+    q = (long long)tc_accuracy_splits(4 * G, (int)nv, rows, 128LL << 20) * 4 * G * nv; if (q > p) p = q;
+  }
   s.n_part = p;
   s.ldt = (rows + 3) / 4 * 4;
   s.n_tA = 4LL * G * s.ldt;
@@ -823,11 +847,24 @@ inline int generic_bwd_tp(TpArgs& a, cudaStream_t st) {
                       tc::tc_operand_ok(a.zx, a.zxp);
   if (tc_tp) {
     if (direct) {
-      // dBm = dPre^T Z, dVx = dPre^T ZX: no transposed copies
-      G_TRY(tc_direct(a.dpre, 4 * G, a.z, a.zp, 4 * G, RH, gBm));
-      G_TRY(finish_gate(gBm, a.dBm, RH));
-      G_TRY(tc_direct(a.dpre, 4 * G, a.zx, a.zxp, 4 * G, RX, gVx));
-      G_TRY(finish_gate(gVx, a.dVx, RX));
+      // dBm = dPre^T Z, dVx = dPre^T ZX: no transposed copies, and ONE pass over dPre for both (B operand = [Z | ZX])
+      const int N1p = round_up(RH, 32), Nv = N1p + RX, M4 = 4 * G;
+      int splits = tc::tc_splits(M4, Nv, (int)rows, 32);
+      const int acc_splits = tc_accuracy_splits(M4, Nv, rows, 128LL << 20);
+      if (splits < acc_splits) splits = acc_splits;
+      while (splits > 1 && (long long)splits * M4 * Nv > a.n_part) --splits;
+      if ((long long)M4 * Nv <= a.n_part) {
+        const int nkb = ceil_div((int)rows, tc::BK), kbs = ceil_div(nkb, splits), nz = ceil_div(nkb, kbs);
+        G_TRY(tc::gemm_tn2(a.dpre, 4 * G, a.z, a.zp, RH, a.zx, a.zxp, RX, M4, rows, tc::EpiPartialTC{part, M4, Nv}, st, splits));
+        const long long n = 4LL * H * (RH + RX);
+        splitk_reduce_pair_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(part, nz, H, G, RH, RX, N1p, a.dBm, a.dVx);
+        G_TRY((int)cudaGetLastError());
+      } else {
+        G_TRY(tc_direct(a.dpre, 4 * G, a.z, a.zp, 4 * G, RH, gBm));
+        G_TRY(finish_gate(gBm, a.dBm, RH));
+        G_TRY(tc_direct(a.dpre, 4 * G, a.zx, a.zxp, 4 * G, RX, gVx));
+        G_TRY(finish_gate(gVx, a.dVx, RX));
+      }
     } else {
       // dBm = dPre^T Z, dVx = dPre^T ZX share the transposed dPre
       G_TRY(transpose_rows_launch(dPv, nullptr, 0, 0, rows, 4 * G, tA, a.ldt, st));
