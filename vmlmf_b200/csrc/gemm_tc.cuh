@@ -492,7 +492,9 @@ template <class Epi>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tn_kernel(const __grid_constant__ CUtensorMap mapA,
                                                               const __grid_constant__ CUtensorMap mapB,
                                                               const __grid_constant__ CUtensorMap mapB2, int nsplitB, int M, int N,
-                                                              int K, int kb_per_split, Epi epi, int fast) {
+                                                              int K, int kb_per_split, Epi epi, int fast, int a_batch) {
+  // a_batch > 0: A is a rank-3 [T][a_batch][M] view (time-major OR batch-first activations: the two outer strides are free) and
+  // contraction index k = t * a_batch + b; a_batch % 32 == 0, so a 32-row K tile never straddles a timestep.
   // Two B matrices side by side along N: columns [0, nsplitB) come from mapB, columns [nsplitB, N) from mapB2 (nsplitB % 32 == 0;
   // TMA zero-fills past each matrix's own width).  One pass over A then serves two products that share it (dBm and dVx both
   // contract dPre: at cfg5 that operand is 4.3 GB).  Single-matrix callers pass nsplitB >= N.
@@ -535,7 +537,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tn_kernel(const __grid_const
         mbar_arrive_expect_tx(&full[s], 2 * kTileBytes);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          tma_load_2d(st + i * 4096, &mapA, m0 + 32 * i, (kb0 + kb) * BK, &full[s]);
+          if (a_batch > 0) {
+            const int k0 = (kb0 + kb) * BK;
+            tma_load_3d(st + i * 4096, &mapA, m0 + 32 * i, k0 % a_batch, k0 / a_batch, &full[s]);
+          } else {
+            tma_load_2d(st + i * 4096, &mapA, m0 + 32 * i, (kb0 + kb) * BK, &full[s]);
+          }
           const int nb = n0 + 32 * i;
           if (nb < nsplitB) tma_load_2d(st + 2 * kTileBytes + i * 4096, &mapB, nb, (kb0 + kb) * BK, &full[s]);
           else tma_load_2d(st + 2 * kTileBytes + i * 4096, &mapB2, nb - nsplitB, (kb0 + kb) * BK, &full[s]);
@@ -766,7 +773,43 @@ inline int gemm_tn(const float* At, long long lda, const float* Bt, long long ld
   const int nkb = ceil_div((int)K, BK);
   const int kbs = ceil_div(nkb, splits);
   dim3 grid(ceil_div(N, BN), ceil_div(M, BM), ceil_div(nkb, kbs));
-  kern<<<grid, kThreads, kSmemBytes, st>>>(ma, mb, mb, 0x7fffffff, M, N, (int)K, kbs, epi, fast_tf32());
+  kern<<<grid, kThreads, kSmemBytes, st>>>(ma, mb, mb, 0x7fffffff, M, N, (int)K, kbs, epi, fast_tf32(), 0);
+  return (int)cudaGetLastError();
+}
+// C[M, N] = A^T Bt where A is the rank-3 view a[t][b][m] = p[t * s_t + b * s_b + m] (t < Tn, b < Bsz, Bsz % 32 == 0) contracted over
+// k = t * Bsz + b, and Bt is [Tn * Bsz, N] row-major: lets dA = Hprev^T dZ read y in place whatever its layout
+template <class Epi>
+inline int gemm_tn_a3(const float* p, long long s_b, long long s_t, int Bsz, int Tn, const float* Bt, long long ldb, int M, int N,
+                      Epi epi, cudaStream_t st, int splits) {
+  const long long K = (long long)Tn * Bsz;
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  EncodeTiledFn fn = encode_fn();
+  if (!fn || (Bsz & 31) || (s_b & 3) || (s_t & 3) || (reinterpret_cast<uintptr_t>(p) & 15) || !tc_operand_ok(Bt, ldb) || K > 0x7fffffffLL)
+    return kTcNoFit;
+  CUtensorMap ma, mb;
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)M, (cuuint64_t)Bsz, (cuuint64_t)Tn};
+    cuuint64_t strides[2] = {(cuuint64_t)s_b * 4, (cuuint64_t)s_t * 4};
+    cuuint32_t box[3] = {32, BK, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = fn(&ma, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(p), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return kTcNoFit;
+  }
+  int rc = make_map_tn(&mb, Bt, K, N, ldb);
+  if (rc) return rc;
+  auto kern = gemm_tn_kernel<Epi>;
+  static PerDevice attr_pd;
+  int& attr = attr_pd.cur();
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) return (int)e;
+    attr = 1;
+  }
+  const int nkb = ceil_div((int)K, BK);
+  const int kbs = ceil_div(nkb, splits);
+  dim3 grid(ceil_div(N, BN), ceil_div(M, BM), ceil_div(nkb, kbs));
+  kern<<<grid, kThreads, kSmemBytes, st>>>(ma, mb, mb, 0x7fffffff, M, N, (int)K, kbs, epi, fast_tf32(), Bsz);
   return (int)cudaGetLastError();
 }
 // C[M, N1p + N2] = At^T [B1 | B2] with B1's columns padded to N1p = round_up(N1, 32): two products sharing the A operand
@@ -794,7 +837,7 @@ inline int gemm_tn2(const float* At, long long lda, const float* B1, long long l
   const int nkb = ceil_div((int)K, BK);
   const int kbs = ceil_div(nkb, splits);
   dim3 grid(ceil_div(N, BN), ceil_div(M, BM), ceil_div(nkb, kbs));
-  kern<<<grid, kThreads, kSmemBytes, st>>>(ma, mb1, mb2, N1p, M, N, (int)K, kbs, epi, fast_tf32());
+  kern<<<grid, kThreads, kSmemBytes, st>>>(ma, mb1, mb2, N1p, M, N, (int)K, kbs, epi, fast_tf32(), 0);
   return (int)cudaGetLastError();
 }
 

@@ -876,9 +876,34 @@ inline int generic_bwd_tp(TpArgs& a, cudaStream_t st) {
       G_TRY(finish_gate(gVx, a.dVx, RX));
     }
     // dA = Hprev^T dZ: row (t,b) of Hprev is y[t-1,b], or h0[b] / 0 at t = 0
-    G_TRY(transpose_rows_launch(Yv, a.h0, H, B, rows, H, tA, a.ldt, st));
-    G_TRY(transpose_rows_launch(plain_view(a.dz, a.zp), nullptr, 0, 0, rows, RH, tB, a.ldt, st));
-    G_TRY(tc_tn(H, RH, a.dA));
+    int dA_rc = tc::kTcNoFit;
+    if (direct && T > 1 && (H & 3) == 0 && tc::tc_operand_ok(a.dz, a.zp)) {
+      // y read in place as the rank-3 MN-major operand (any layout with 16-byte row pitches): rows t >= 1 pair y[t-1] with
+      // dz[t] -- a pointer offset of B rows on the dz side --, the t = 0 rows pair h0 with dz[0] in one more partial
+      const long long rows1 = rows - B;
+      int splits = tc::tc_splits(H, RH, (int)rows1, 32);
+      const int acc_splits = tc_accuracy_splits(H, RH, rows1);
+      if (splits < acc_splits) splits = acc_splits;
+      while (splits > 1 && (long long)(splits + 1) * H * RH > a.n_part) --splits;
+      const int nkb = ceil_div((int)rows1, tc::BK), kbs = ceil_div(nkb, splits);
+      int nz = ceil_div(nkb, kbs);
+      dA_rc = tc::gemm_tn_a3(a.y, a.ys_b, a.ys_t, B, T - 1, a.dz + (size_t)B * a.zp, a.zp, H, RH, tc::EpiPartialTC{part, H, RH}, st, splits);
+      if (dA_rc == 0) {
+        if (a.h0) {
+          G_TRY((gemm_launch<true, false>(plain_view(a.h0, H), plain_view(a.dz, a.zp), H, RH, B, 1, NIdent{},
+                                          EpiPartial{part + (size_t)nz * H * RH, H, RH}, st)));
+          ++nz;
+        }
+        G_TRY(reduce_to(nz, (long long)H * RH, a.dA));
+      } else if (dA_rc != tc::kTcNoFit) {
+        return dA_rc;
+      }
+    }
+    if (dA_rc == tc::kTcNoFit) {
+      G_TRY(transpose_rows_launch(Yv, a.h0, H, B, rows, H, tA, a.ldt, st));
+      G_TRY(transpose_rows_launch(plain_view(a.dz, a.zp), nullptr, 0, 0, rows, RH, tB, a.ldt, st));
+      G_TRY(tc_tn(H, RH, a.dA));
+    }
   } else {
     // dBm = dPre^T Z   [4G,RH]
     {
