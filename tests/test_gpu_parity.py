@@ -262,7 +262,7 @@ def test_canonical_kernels_vs_numpy_spec(T, B, I, H, RX, RH, bf, state, scale=0.
     (2, 64, 9, 2048, 16, 16, True, False),
     (2, 32, 9, 4096, 256, 256, True, True),
     (3, 200, 77, 256, 32, 32, True, False),      # BASELINE configs[1] at ranks 32/32 (beyond the register-resident regime)
-    (4, 96, 9, 256, 32, 32, True, True),         # B % 32 == 0, H % 4 == 0, T*B >= 256: dA reads y in place (rank-3 MN-major operand), batch-first, h0 term
+    (4, 96, 9, 320, 32, 32, True, True),         # B % 32 == 0, H % 4 == 0, T*B >= 256: dA reads y in place (rank-3 MN-major operand), batch-first, h0 term
     (3, 128, 12, 512, 24, 40, False, True),      # the same path, time-major
 ])
 def test_generic_regime_vs_numpy_spec(T, B, I, H, RX, RH, bf, state, gemm, monkeypatch, r1_path):
