@@ -7,9 +7,11 @@
 //     the 8 hidden units [8s, 8s+8) and keeps ITS rows of the factors in shared memory for the whole call
 //     (forward: Bm rows of its 4 x 8 gate outputs [32 x RH] + its 8 rows of A; backward: the same two slices transposed),
 //     as tf32 hi / lo pairs: ~110 KB per CTA at the LM shape, 9 MB over the group;
-//   * per step only activations move: the CTA's [32 x 8] slice of h (phase Z), the reduced z [32 x RH] (phase G);
-//     TMA boxes are 32 rows (the tensor core still computes 128-row tiles -- rows 32..127 of the A operand are whatever
-//     follows the tile in shared memory, they only reach accumulator lanes 32..127, which nobody reads);
+//   * per step only activations move: the CTA's [32 x 8] slice of h (phase Z), the reduced z [32 x RH] (phase G).  They
+//     live in global memory tile-major ([K tile][hi | lo][32 rows][32 fp32]), so one TMA box brings a group of K tiles;
+//     a tile is 32 rows hi + 32 rows lo (the tensor core still computes 128-row tiles: rows 0..31 = hi, 32..63 = lo of the
+//     SAME instruction -- see "ONE MMA per k-step" below --, rows 64..127 are whatever follows in shared memory and only reach
+//     accumulator lanes nobody reads);
 //   * the x side is taken out of the serial loop: XP = zx Vx^T + bias + x (.) Dx is one time-parallel tcgen05 GEMM before the
 //     launch (700 rows at the LM batch), the gate epilogue adds it; likewise dzx = dPre Vx after the backward launch.
 // Per timestep and CTA (3xTF32, accumulators in tensor memory):
@@ -21,8 +23,9 @@
 // (dh_{t-1}[32, 8] = dz_t * A[8 units, :]^T, K = RH, N = 16), gate-gradient algebra of step t-1 in the epilogue.
 // Proxy ordering: every thread that writes an operand tile with ordinary stores executes fence.proxy.async before the (CTA or
 // group) barrier that precedes the TMA read -- the writer-side fence is the documented pattern; the producer adds none.
-// Warp roles as in seq_r2.cuh: warp 0 TMA producer, warp 1 MMA issuer, warps 2-9 epilogue -- only warps 4 and 8 own
-// tensor-memory lanes 0..31 (the batch rows), the others help with the reduce.
+// Warp roles as in seq_r2.cuh: warp 0 TMA producer, warp 1 MMA issuer (both run warp-uniform and elect one lane per asynchronous
+// instruction), warps 2-9 epilogue -- warps 4 and 8 own tensor-memory lanes 0..31 (hi rows: hi*hi + hi*lo), warps 5 and 9 lanes
+// 32..63 (lo rows: lo*hi, handed to warps 4 / 8 through shared memory); all eight help with the reduce.
 #pragma once
 #include "seq_r2.cuh"
 
