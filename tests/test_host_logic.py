@@ -219,3 +219,13 @@ def test_grad_bucket_reports_empty_and_late_parameters():
     lin(torch.randn(5, 3)).sum().backward()
     with pytest.raises(RuntimeError, match="was not live at the first backward"):
         b.pack()
+
+
+def test_header_and_binding_agree_on_regime_codes():
+    """include/vmlmf_b200.h (the boundary a maintainer binds) and the ctypes binding name the same regimes and ABI version."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "vmlmf_b200.h")).read()
+    codes = {m.group(1): int(m.group(2)) for m in re.finditer(r"VMLMF_PATH_(\w+)\s*=\s*(\d+)", hdr)}
+    assert codes == {"R1": _lib.PATH_R1, "G": _lib.PATH_G, "R1M": _lib.PATH_R1M, "R2": _lib.PATH_R2, "R3": _lib.PATH_R3}
+    assert int(re.search(r"#define VMLMF_ABI_VERSION (\d+)", hdr).group(1)) == _lib.ABI_VERSION
+    assert set(_lib.LARGE_PATHS) == {_lib.PATH_G, _lib.PATH_R2, _lib.PATH_R3}
